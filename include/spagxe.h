@@ -1,0 +1,156 @@
+/*
+ * spagxe.h -- C ABI of libspagxe_cuda.so
+ *
+ * The drop-in boundary for SPAGxECCT's Step-2 per-SNP testing loop on NVIDIA
+ * B200 (sm_100a).  The reference (YuzhuoMa97/SPAGxECCT) is a pure-R package with
+ * no native interface, so each entry point below states which R closure (and which
+ * lines of it) it replaces; the R-side `.Call` shim that binds them is shown in
+ * INTEGRATION.md and spagxecct_b200/R/.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (SPAGXE_OK == 0);
+ *     the message of the last failure is available from spagxe_last_error().
+ *   - no C++ exception and no CUDA error crosses this boundary.
+ *   - matrices are column-major (R layout); outputs are M x ncol column-major.
+ *   - filtered SNPs (MAF < min.maf) carry R's NA_real_ bit pattern
+ *     (0x7FF00000000007A2) in the statistic columns, like `matrix(NA, M, k)`.
+ *   - there is no CPU fallback: every entry point fails with
+ *     SPAGXE_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SPAGXE_H
+#define SPAGXE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spagxe_ctx spagxe_ctx;
+
+enum {
+    SPAGXE_OK = 0,
+    SPAGXE_ERR_CUDA = 1,        /* CUDA runtime failure (message has the detail)          */
+    SPAGXE_ERR_ARG = 2,         /* bad argument (NULL, size mismatch, unknown enum)       */
+    SPAGXE_ERR_STATE = 3,       /* a required spagxe_set_* call is missing                */
+    SPAGXE_ERR_UNSUPPORTED = 4, /* e.g. non-integer dosages, G.model != "Add", survival   */
+    SPAGXE_ERR_CCT_STOP = 5,    /* CCT() would stop(): NA / out-of-range p (ref :2072-2087)*/
+    SPAGXE_ERR_SINGULAR = 6     /* solve(t(W)%*%W) singular (ref :609)                    */
+};
+
+/* traits: the reference's `traits=` argument (R/SPAGxECCT.R:455, :622-677) */
+enum { SPAGXE_TRAIT_BINARY = 1, SPAGXE_TRAIT_QUANTITATIVE = 2 };
+
+/* genotype sources (R/SPAGxECCT.R:483-488: Geno.mtx or GenoFile) */
+enum {
+    SPAGXE_GENO_BED = 0, /* PLINK .bed rows, variant-major, 2 bits/sample, WITHOUT the 3-byte magic */
+    SPAGXE_GENO_F64 = 1, /* R numeric matrix  N x M, NA/NaN = missing, values in {0,1,2}             */
+    SPAGXE_GENO_I32 = 2  /* R integer matrix  N x M, INT_MIN (NA_integer_) = missing                  */
+};
+enum { SPAGXE_LOC_HOST = 0, SPAGXE_LOC_DEVICE = 1 };
+
+typedef struct {
+    int32_t kind;      /* SPAGXE_GENO_*                                                  */
+    int32_t location;  /* SPAGXE_LOC_*: where `data` lives                               */
+    const void *data;  /* first SNP's first byte/element                                 */
+    int64_t n_samples; /* N                                                              */
+    int64_t n_snps;    /* M                                                              */
+    int64_t pitch;     /* BED: bytes between consecutive SNP rows (>= ceil(N/4));
+                          F64/I32: elements between consecutive columns (>= N)           */
+} spagxe_geno;
+
+/* the tuning arguments shared by SPAGxE_CCT / SPAGxEmix_CCT / SPAGxE_Plus
+ * (R/SPAGxECCT.R:464-469, :926-933; R/SPAGxEPlus_functions_MYZ.R:168-173)               */
+typedef struct {
+    double epsilon;          /* 0.001 */
+    double cutoff;           /* 2; NOT used by run_cct, exactly like the reference (:598,:616) */
+    double min_maf;          /* 0.001 */
+    double missing_cutoff;   /* 0.15; accepted and ignored like the reference (never applied)  */
+    double pc_pvalue_cutoff; /* topPCs.pvalue.cutoff = 0.05 (mix only)                  */
+    double neg_ratio_cutoff; /* MAF.est.negative.ratio.cutoff = 0.1 (mix only)          */
+    int32_t g_model;         /* 0 = "Add" (only model implemented on device)            */
+    int32_t impute_method;   /* 0 = "fixed"                                             */
+    int32_t out_location;    /* SPAGXE_LOC_HOST (default) or SPAGXE_LOC_DEVICE for `out` */
+    int32_t reserved;
+} spagxe_params;
+
+/* diagnostics filled by every run (all counters are totals over the call) */
+typedef struct {
+    int64_t n_snps;
+    int64_t n_filtered;     /* MAF < min.maf                                             */
+    int64_t n_branch_a;     /* p.value.betaG >  epsilon                                  */
+    int64_t n_branch_b;     /* p.value.betaG <= epsilon (genotype-adjusted + Wald + CCT) */
+    int64_t n_spa;          /* SNPs whose |z| >= cutoff went through the saddlepoint     */
+    int64_t n_wald_fail;    /* rank-deficient / non-finite IRLS -> NA                    */
+    int64_t n_cct_stop;     /* CCT() stop() conditions met                               */
+    int64_t n_singular;     /* singular W'W                                              */
+    int64_t n_mix_logistic; /* mix: SNPs that used the logistic AF fallback              */
+    int64_t newton_iters;   /* total Newton iterations over all tails                    */
+    int64_t kernel_launches;/* kernels launched by this call                             */
+    int64_t h2d_bytes, d2h_bytes;
+    double ms_total;        /* CUDA-event time of the whole call on the ctx stream       */
+    double ms_score;        /* sum over chunks: unpack + score kernel(s)                 */
+    double ms_tests;        /* sum over chunks: finalize + SPA + branch-B kernels        */
+    int64_t score_bytes;    /* algorithmic bytes of the score pass: M * ceil(N/4)        */
+} spagxe_diag;
+
+/* ---- lifetime ------------------------------------------------------------- */
+/* device: CUDA ordinal. Replaces nothing in the reference (which has no state). */
+int spagxe_ctx_create(int device, spagxe_ctx **out);
+void spagxe_ctx_destroy(spagxe_ctx *ctx);
+const char *spagxe_last_error(const spagxe_ctx *ctx); /* ctx may be NULL: last create error */
+/* run all work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int spagxe_ctx_set_stream(spagxe_ctx *ctx, void *cuda_stream);
+const char *spagxe_version(void);
+
+/* ---- per-analysis inputs --------------------------------------------------- */
+/* R (Step-1 residuals from SPA_G_Get_Resid, R/SPAGxECCT.R:48-96) and E; host pointers,
+ * length N.  Replaces the R/E arguments of SPAGxE_CCT (:460-461) / SPAGxEmix_CCT (:921-922). */
+int spagxe_set_vectors(spagxe_ctx *ctx, int64_t n, const double *R, const double *E);
+/* same with device pointers (multi-GPU: rank 0's copy arrives by one NCCL broadcast) */
+int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const double *dR, const double *dE);
+
+/* data of the Wald model Y ~ Cova + E + g + E:g (R/SPAGxECCT.R:622-677): Phen.mtx$Y and
+ * as.matrix(Cova.mtx) (N x p column-major, p <= 12).  trait = SPAGXE_TRAIT_*.            */
+int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p);
+
+/* topPCs of SPAGxEmix_CCT (R/SPAGxECCT.R:925, :1066): N x k column-major, k <= 15         */
+int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k);
+
+/* obj.SPAGxE_Plus_Nullmodel (R/SPAGxEPlus_functions_MYZ.R:539-545): R via spagxe_set_vectors,
+ * R.new (length N), the three GRM scalars and the sparse GRM as 0-based COO triplets
+ * (lower triangle incl. diagonal, as in data/sparseGRM.SPAGxEPlus.rda).                   */
+int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,
+                   double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew);
+
+/* ---- the Step-2 loops ------------------------------------------------------ */
+/* SPAGxE_CCT loop body, R/SPAGxECCT.R:509-525 -> SPAGxE_CCT_one_SNP :543-683.
+ * out: M x 10 column-major: MAF, missing.rate, p.value.spaGxE, p.value.spaGxE.Wald,
+ * p.value.spaGxE.CCT.Wald, p.value.normGxE, p.value.betaG, Stat.betaG, Var.betaG, z.betaG */
+int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
+                   spagxe_diag *diag);
+/* SPAGxEmix_CCT loop body, R/SPAGxECCT.R:975-997 -> :1013-1269.  out: M x 12 (adds
+ * MAF.est.negative.num, MAC).                                                            */
+int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
+                   spagxe_diag *diag);
+/* SPAGxE_Plus loop body, R/SPAGxEPlus_functions_MYZ.R:214-233 -> :248-405.  out: M x 8:
+ * MAF, missing.rate, p.value.spaGxE.plus, p.value.normGxE.plus, p.value.betaG, Stat.betaG,
+ * Var.betaG, z.betaG                                                                     */
+int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
+                    spagxe_diag *diag);
+
+/* ---- genotype unpack (K1) exposed for the bit-exact decode checks ----------- */
+/* per-SNP code counts of packed rows: counts[4*j + c], c = 00,01,10,11 (GRAB decode: 2,NA,1,0);
+ * replaces the counting part of R/SPAGxECCT.R:557-560.  counts is a HOST array of 4*M int64. */
+int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *geno, int64_t *counts);
+/* decode packed rows into an N x M double matrix (host), NA_real_ for missing: what
+ * GRAB::GRAB.ReadGeno(...)$GenoMat returns (R/SPAGxECCT.R:484-487).                       */
+int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *geno, double *out_host);
+
+/* measured device peaks used by bench.py for the SPA stage's fp64 fraction (DFMA loop)   */
+int spagxe_measure_fp64_peak(spagxe_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPAGXE_H */

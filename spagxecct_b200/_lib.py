@@ -1,0 +1,205 @@
+"""ctypes binding of libspagxe_cuda.so (include/spagxe.h).
+
+There is no CPU fallback: importing the package works anywhere (so host-side logic can be
+tested), but every compute entry point raises if the CUDA library is missing or no sm_100
+device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspagxe_cuda.so")
+
+OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_CCT_STOP, ERR_SINGULAR = range(7)
+TRAIT_BINARY, TRAIT_QUANTITATIVE = 1, 2
+GENO_BED, GENO_F64, GENO_I32 = 0, 1, 2
+LOC_HOST, LOC_DEVICE = 0, 1
+
+EXPORTS = [
+    "spagxe_ctx_create", "spagxe_ctx_destroy", "spagxe_last_error", "spagxe_ctx_set_stream", "spagxe_version",
+    "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
+    "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
+    "spagxe_measure_fp64_peak",
+]
+
+
+class Geno(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("location", C.c_int32), ("data", C.c_void_p), ("n_samples", C.c_int64),
+                ("n_snps", C.c_int64), ("pitch", C.c_int64)]
+
+
+class Params(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("cutoff", C.c_double), ("min_maf", C.c_double),
+                ("missing_cutoff", C.c_double), ("pc_pvalue_cutoff", C.c_double), ("neg_ratio_cutoff", C.c_double),
+                ("g_model", C.c_int32), ("impute_method", C.c_int32), ("out_location", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Diag(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in
+                ["n_snps", "n_filtered", "n_branch_a", "n_branch_b", "n_spa", "n_wald_fail", "n_cct_stop",
+                 "n_singular", "n_mix_logistic", "newton_iters", "kernel_launches", "h2d_bytes", "d2h_bytes"]] + \
+               [("ms_total", C.c_double), ("ms_score", C.c_double), ("ms_tests", C.c_double),
+                ("score_bytes", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SpagxeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[spagxe status {code}] {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library or fail loudly (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). spagxecct_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.spagxe_last_error.restype = C.c_char_p
+    L.spagxe_last_error.argtypes = [C.c_void_p]
+    L.spagxe_version.restype = C.c_char_p
+    L.spagxe_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.spagxe_ctx_destroy.argtypes = [C.c_void_p]
+    L.spagxe_ctx_destroy.restype = None
+    L.spagxe_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.spagxe_set_vectors.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.spagxe_set_vectors_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.spagxe_set_wald.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_set_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                 C.c_double, C.c_void_p]
+    for f in ("spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus"):
+        getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
+    L.spagxe_bed_counts.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
+    L.spagxe_bed_decode.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
+    L.spagxe_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One GPU worth of Step-2 state (device copies of R, E, Wald data, PCs, GRM)."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.spagxe_ctx_create(int(device), C.byref(h))
+        if rc != OK:
+            raise SpagxeError(rc, self.L.spagxe_last_error(None).decode())
+        self.h = h
+        self.n = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.spagxe_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise SpagxeError(rc, self.L.spagxe_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.L.spagxe_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_vectors(self, R, E):
+        R = _f64(R); E = _f64(E)
+        if R.shape != E.shape or R.ndim != 1:
+            raise ValueError("R and E must be vectors of the same length")
+        self._chk(self.L.spagxe_set_vectors(self.h, R.size, R.ctypes.data, E.ctypes.data))
+        self.n = R.size
+
+    def set_vectors_device(self, n, dR_ptr, dE_ptr):
+        self._chk(self.L.spagxe_set_vectors_device(self.h, int(n), C.c_void_p(dR_ptr), C.c_void_p(dE_ptr)))
+        self.n = int(n)
+
+    def set_wald(self, trait, Y, cova):
+        Y = _f64(Y)
+        cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(Y.size, -1))
+        self._chk(self.L.spagxe_set_wald(self.h, int(trait), Y.ctypes.data, cova.ctypes.data, cova.shape[1]))
+
+    def set_pcs(self, pcs):
+        pcs = np.asfortranarray(np.asarray(pcs, dtype=np.float64).reshape(self.n, -1))
+        self._chk(self.L.spagxe_set_pcs(self.h, pcs.ctypes.data, pcs.shape[1]))
+
+    def set_grm(self, gi, gj, gv, R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew, Rnew):
+        gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
+        gv = _f64(gv); Rnew = _f64(Rnew)
+        self._chk(self.L.spagxe_set_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data,
+                                        float(R_GRM_R), float(R_GRM_RE), float(Rnew_GRM_Rnew), Rnew.ctypes.data))
+
+    @staticmethod
+    def geno_desc(kind, data_ptr, n, m, pitch, location=LOC_HOST):
+        return Geno(kind, location, C.c_void_p(data_ptr), int(n), int(m), int(pitch))
+
+    def _run(self, fn, ncol, geno, params, out_ptr=None):
+        prm = params if isinstance(params, Params) else make_params(**(params or {}))
+        diag = Diag()
+        if out_ptr is None:
+            out = np.empty((geno.n_snps, ncol), dtype=np.float64, order="F")
+            rc = fn(self.h, C.byref(geno), C.byref(prm), C.c_void_p(out.ctypes.data), C.byref(diag))
+        else:
+            out = None
+            rc = fn(self.h, C.byref(geno), C.byref(prm), C.c_void_p(out_ptr), C.byref(diag))
+        self.last_diag = diag.asdict()
+        self.last_out = out
+        self._chk(rc)
+        return out, self.last_diag
+
+    def run_cct(self, geno, params=None, out_ptr=None):
+        return self._run(self.L.spagxe_run_cct, 10, geno, params, out_ptr)
+
+    def run_mix(self, geno, params=None, out_ptr=None):
+        return self._run(self.L.spagxe_run_mix, 12, geno, params, out_ptr)
+
+    def run_plus(self, geno, params=None, out_ptr=None):
+        return self._run(self.L.spagxe_run_plus, 8, geno, params, out_ptr)
+
+    def bed_counts(self, geno):
+        counts = np.zeros((geno.n_snps, 4), dtype=np.int64)
+        self._chk(self.L.spagxe_bed_counts(self.h, C.byref(geno), counts.ctypes.data))
+        return counts
+
+    def bed_decode(self, geno):
+        out = np.empty((geno.n_samples, geno.n_snps), dtype=np.float64, order="F")
+        self._chk(self.L.spagxe_bed_decode(self.h, C.byref(geno), out.ctypes.data))
+        return out
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._chk(self.L.spagxe_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+
+def make_params(epsilon=0.001, cutoff=2.0, min_maf=0.001, missing_cutoff=0.15, pc_pvalue_cutoff=0.05,
+                neg_ratio_cutoff=0.1, g_model=0, impute_method=0, out_location=LOC_HOST):
+    return Params(epsilon, cutoff, min_maf, missing_cutoff, pc_pvalue_cutoff, neg_ratio_cutoff, g_model,
+                  impute_method, out_location, 0)

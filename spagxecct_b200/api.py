@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's exported Step-2 functions.
+
+Same names, argument meaning, printed messages, output columns and error behaviour as the R
+closures (R is not available in the build image, so the Python mirror is what the parity tests
+drive; the R wrappers that bind the very same C ABI are in spagxecct_b200/R/).
+
+    SPAGxE_CCT            R/SPAGxECCT.R:455-530
+    SPAGxE_CCT_one_SNP    R/SPAGxECCT.R:543-683
+    SPAGxEmix_CCT(_one_SNP)  R/SPAGxECCT.R:916-1002, :1013-1269
+    SPAGxE_Plus(_one_SNP)    R/SPAGxEPlus_functions_MYZ.R:159-238, :248-405
+    check_input_Resid     R/SPAGxECCT.R:1900-1913
+
+R's `.` in argument names becomes `_` (Geno.mtx -> Geno_mtx).  Phen_mtx is any mapping/DataFrame
+with the columns the reference reads (`ID`, `Y`).  Geno_mtx is an (N, M) array (NaN / INT_MIN =
+NA) or a pandas DataFrame whose index/columns play the role of dimnames.
+"""
+import datetime
+
+import numpy as np
+
+from . import _lib
+from .bedio import BedFile, reorder_samples
+
+COLS_CCT = ["MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
+            "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG"]
+COLS_MIX = COLS_CCT + ["MAF.est.negative.num", "MAC"]
+COLS_PLUS = ["MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG", "Stat.betaG",
+             "Var.betaG", "z.betaG"]
+
+_TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE}
+
+
+class RStop(Exception):
+    """The reference would have called stop() with this message."""
+
+
+class Result:
+    """M x k named matrix (what the R functions return)."""
+
+    def __init__(self, values, rownames, colnames, diag=None):
+        self.values = values
+        self.rownames = list(rownames) if rownames is not None else None
+        self.colnames = list(colnames)
+        self.diag = diag
+
+    def __getitem__(self, col):
+        return self.values[:, self.colnames.index(col)]
+
+    def to_frame(self):
+        import pandas as pd
+        return pd.DataFrame(self.values, index=self.rownames, columns=self.colnames)
+
+
+def _col(df, name):
+    try:
+        v = df[name]
+    except Exception:
+        return None
+    return None if v is None else np.asarray(v)
+
+
+def check_input_Resid(pIDs, gIDs, R, range_=(-100, 100)):
+    """R/SPAGxECCT.R:1900-1913 (same stop() messages)."""
+    if pIDs is None and gIDs is None:
+        raise RStop("Arguments 'pIDs' and 'gIDs' are required in case of potential errors. For more information, "
+                    "please refer to 'Details'.")
+    p = [] if pIDs is None else [str(x) for x in pIDs]
+    g = [] if gIDs is None else [str(x) for x in gIDs]
+    if sorted(set(p)) != sorted(set(g)):
+        raise RStop("unique(pIDs) should be the same as unique(gIDs).")
+    if len(set(g)) != len(g):
+        raise RStop("Argument 'gIDs' should not have a duplicated element.")
+    if range_[1] != -1 * range_[0]:
+        raise RStop("range[2] should be -1*range[1]")
+    if len(R) != len(p):
+        raise RStop("Argument 'pIDs' should be of the same length as input data.")
+    if p == g:
+        return None
+    pos = {s: i for i, s in enumerate(g)}
+    return np.array([pos[s] for s in p])
+
+
+def _split_geno(Geno_mtx):
+    """-> (ndarray (N, M), rownames or None, colnames or None)"""
+    try:
+        import pandas as pd
+        if isinstance(Geno_mtx, pd.DataFrame):
+            return Geno_mtx.to_numpy(), [str(x) for x in Geno_mtx.index], [str(x) for x in Geno_mtx.columns]
+    except ImportError:
+        pass
+    if isinstance(Geno_mtx, tuple):
+        return np.asarray(Geno_mtx[0]), Geno_mtx[1], Geno_mtx[2]
+    return np.asarray(Geno_mtx), None, None
+
+
+def _geno_desc_from_matrix(G):
+    if G.dtype.kind in "iu":
+        G = np.asfortranarray(G, dtype=np.int32)
+        kind = _lib.GENO_I32
+    else:
+        G = np.asfortranarray(G, dtype=np.float64)
+        kind = _lib.GENO_F64
+    n, m = G.shape
+    return G, _lib.Context.geno_desc(kind, G.ctypes.data, n, m, n)
+
+
+def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
+    """The GRAB.ReadGeno step for PLINK input: returns (packed rows, N, M, snp ids, row ids)."""
+    if control not in (None, {"AllMarkers": True}) and dict(control) != {"AllMarkers": True}:
+        raise NotImplementedError("only control=list(AllMarkers=TRUE) is supported for GenoFile input")
+    if not str(GenoFile).endswith(".bed"):
+        raise NotImplementedError("GenoFile must be a PLINK .bed file (BGEN input is not implemented)")
+    bim = fam = None
+    if GenoFileIndex is not None:
+        bim, fam = GenoFileIndex[0], GenoFileIndex[1]
+    bf = BedFile(GenoFile, bim, fam)
+    rows = bf.rows
+    ids = bf.sample_ids
+    if sample_ids is not None:
+        want = [str(x) for x in sample_ids]
+        if want != ids:
+            pos = {s: i for i, s in enumerate(ids)}
+            missing = [s for s in want if s not in pos]
+            if missing:
+                raise RStop(f"SampleIDs not found in the .fam file: {missing[:3]}...")
+            rows = reorder_samples(rows, bf.n, bf.m, [pos[s] for s in want])
+            ids = want
+    rows = np.ascontiguousarray(rows)
+    return rows, len(ids), bf.m, bf.snp_ids, ids
+
+
+def _now():
+    return datetime.datetime.now().strftime('[1] "%Y-%m-%d %H:%M:%S"')
+
+
+def _prep_common(ctx, R, E):
+    R = np.ascontiguousarray(R, dtype=np.float64).ravel()
+    E = np.ascontiguousarray(E, dtype=np.float64).ravel()
+    ctx.set_vectors(R, E)
+    return R, E
+
+
+def _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model, **kw):
+    if impute_method != "fixed":
+        raise NotImplementedError('only impute.method = "fixed" exists in the reference')
+    if G_model != "Add":
+        raise NotImplementedError('only G.model = "Add" is implemented on the device')
+    return _lib.make_params(epsilon=epsilon, cutoff=Cutoff, min_maf=min_maf, missing_cutoff=missing_cutoff, **kw)
+
+
+def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None, GenoFileIndex=None,
+               control=None, Geno_mtx=None, R=None, E=None, Phen_mtx=None, Cova_mtx=None, epsilon=0.001, Cutoff=2,
+               impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0,
+               quiet=False):
+    """Drop-in for SPAGxE_CCT (R/SPAGxECCT.R:455-530): returns an M x 10 named matrix."""
+    if traits not in _TRAITS:
+        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented')
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        pIDs = _col(Phen_mtx, "ID")
+        keep = None
+        if Geno_mtx is None:
+            rows, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
+            keep = rows
+            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+        else:
+            G, gIDs, snp_ids = _split_geno(Geno_mtx)
+            keep, geno = _geno_desc_from_matrix(G)
+            n, m = G.shape
+        check_input_Resid(pIDs, gIDs, R)
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+        _prep_common(ctx, R, E)
+        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        if not quiet:
+            print('[1] "Start Analyzing..."')
+            print(_now())
+        out, diag = ctx.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
+        del keep
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_CCT, diag)
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxE_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, epsilon=0.001, Cutoff=2, impute_method="fixed",
+                       missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0):
+    """Drop-in for SPAGxE_CCT_one_SNP (R/SPAGxECCT.R:543-683): numeric(10). No ID checks, as in R."""
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        g = np.asarray(g)
+        G, geno = _geno_desc_from_matrix(g.reshape(-1, 1))
+        _prep_common(ctx, R, E)
+        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        out, _ = ctx.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
+        return out[0].copy()
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None, GenoFileIndex=None,
+                  control=None, Geno_mtx=None, R=None, E=None, Phen_mtx=None, Cova_mtx=None, topPCs=None,
+                  epsilon=0.001, Cutoff=2, impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add",
+                  topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, ctx=None, device=0, quiet=False):
+    """Drop-in for SPAGxEmix_CCT (R/SPAGxECCT.R:916-1002): M x 12. (No ID check: commented out at :955.)"""
+    if traits not in _TRAITS:
+        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented')
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        if Geno_mtx is None:
+            rows, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
+            keep = rows
+            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+        else:
+            G, _, snp_ids = _split_geno(Geno_mtx)
+            keep, geno = _geno_desc_from_matrix(G)
+            n, m = G.shape
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+        _prep_common(ctx, R, E)
+        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
+        if not quiet:
+            print('[1] "Start Analyzing..."')
+            print(_now())
+        prm = _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model,
+                      pc_pvalue_cutoff=topPCs_pvalue_cutoff, neg_ratio_cutoff=MAF_est_negative_ratio_cutoff)
+        out, diag = ctx.run_mix(geno, prm)
+        del keep
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_MIX, diag)
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxEmix_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, topPCs, epsilon=0.001, Cutoff=2,
+                          impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add",
+                          topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, ctx=None, device=0):
+    """Drop-in for SPAGxEmix_CCT_one_SNP (R/SPAGxECCT.R:1013-1269): numeric(12)."""
+    res = SPAGxEmix_CCT(traits, Geno_mtx=np.asarray(g).reshape(-1, 1), R=R, E=E, Phen_mtx=Phen_mtx,
+                        Cova_mtx=Cova_mtx, topPCs=topPCs, epsilon=epsilon, Cutoff=Cutoff, impute_method=impute_method,
+                        missing_cutoff=missing_cutoff, min_maf=min_maf, G_model=G_model,
+                        topPCs_pvalue_cutoff=topPCs_pvalue_cutoff,
+                        MAF_est_negative_ratio_cutoff=MAF_est_negative_ratio_cutoff, ctx=ctx, device=device, quiet=True)
+    return res.values[0].copy()
+
+
+def SPAGxE_Plus(GenoFile=None, GenoFileIndex=None, control=None, Geno_mtx=None, E=None, Phen_mtx=None,
+                Cova_mtx=None, obj_SPAGxE_Plus_Nullmodel=None, epsilon=0.001, Cutoff=2, impute_method="fixed",
+                missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0, quiet=False):
+    """Drop-in for SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:159-238): M x 8.
+    obj_SPAGxE_Plus_Nullmodel: mapping with R, R_GRM_R, R_GRM_RE, R.new, R.new_GRM_R.new and sparseGRM
+    (ID1/ID2 as 0-based sample indices `i`,`j` or as id strings matched against ResidMat$SubjID, Value)."""
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        obj = obj_SPAGxE_Plus_Nullmodel
+        if Geno_mtx is None:
+            rows, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
+            keep = rows
+            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+        else:
+            G, _, snp_ids = _split_geno(Geno_mtx)
+            keep, geno = _geno_desc_from_matrix(G)
+            n, m = G.shape
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+        _prep_common(ctx, obj["R"], E)
+        gi, gj, gv = _grm_triplets(obj)
+        ctx.set_grm(gi, gj, gv, obj["R_GRM_R"], obj["R_GRM_RE"], obj["R.new_GRM_R.new"], obj["R.new"])
+        if not quiet:
+            print('[1] "Start Analyzing..."')
+            print(_now())
+        out, diag = ctx.run_plus(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
+        del keep
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_PLUS, diag)
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxE_Plus_one_SNP(g, E, Phen_mtx, Cova_mtx, obj_SPAGxE_Plus_Nullmodel, epsilon=0.001, Cutoff=2,
+                        impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0):
+    """Drop-in for SPAGxE_Plus_one_SNP (R/SPAGxEPlus_functions_MYZ.R:248-405): numeric(8)."""
+    res = SPAGxE_Plus(Geno_mtx=np.asarray(g).reshape(-1, 1), E=E, Phen_mtx=Phen_mtx, Cova_mtx=Cova_mtx,
+                      obj_SPAGxE_Plus_Nullmodel=obj_SPAGxE_Plus_Nullmodel, epsilon=epsilon, Cutoff=Cutoff,
+                      impute_method=impute_method, missing_cutoff=missing_cutoff, min_maf=min_maf, G_model=G_model,
+                      ctx=ctx, device=device, quiet=True)
+    return res.values[0].copy()
+
+
+def _grm_triplets(obj):
+    grm = obj["sparseGRM"]
+    if "i" in grm:
+        return np.asarray(grm["i"], dtype=np.int32), np.asarray(grm["j"], dtype=np.int32), np.asarray(grm["Value"])
+    ids = [str(s) for s in obj["ResidMat"]["SubjID"]]
+    pos = {s: k for k, s in enumerate(ids)}
+    gi = np.array([pos[str(s)] for s in grm["ID1"]], dtype=np.int32)
+    gj = np.array([pos[str(s)] for s in grm["ID2"]], dtype=np.int32)
+    return gi, gj, np.asarray(grm["Value"], dtype=np.float64)

@@ -1,0 +1,674 @@
+// kernels.cuh -- Step-2 device kernels (sm_100a).  See DESIGN.md for the data layout.
+//
+//   K0  k_vec_prep1/2     SNP-invariant sums and R.new            (ref :583, :592-594, :2034-2037)
+//   K1  k_pack_dense      R matrix {0,1,2,NA} -> PLINK 2-bit rows  (Geno.mtx input, ref :483, :510)
+//       k_bed_counts      per-code counts (bit-exact decode check)
+//       k_bed_decode      2-bit -> double with NA_real_            (GRAB.ReadGeno, ref :484-487)
+//   K2  score kernels live in score.cuh
+//   K3  k_finalize_*      per-SNP scalar epilogue + routing lists  (ref :557-603, :2000-2045)
+//   K4  k_spa_homo        Newton on the binomial CGF + tail        (ref :1795-1879, :2048-2062)
+//   K5  k_branch_b        G-adjusted residual, SPA, Wald, CCT      (ref :604-678, :2070-2123)
+#pragma once
+#include "dmath.cuh"
+
+namespace spagxe {
+
+// PLINK code -> A1 dosage: 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0 (pinned by inst/GenoMat_*.raw)
+constexpr int kMaxQ = 16;   // Wald design columns: 1 + p + 3, p <= 12
+constexpr int kMaxPC = 15;
+
+struct VecConst {
+    double sumR, sumR2, sumER2, lambda;  // lambda = sum(E R^2)/sum(R^2) (ref :592)
+    double sumV, sumV2;                  // second score vector V (R.new for CCT, E*R for mix/plus)
+    double sumRn, sumRn2;                // R.new = (E - lambda) R (ref :594)
+    double sumE, sumEE, sumER, sumEER, sumEERR;  // branch-B class algebra helpers (unused by v1)
+};
+
+struct SnpStats {  // per-SNP outputs of the score pass (chunk-local index)
+    double *D0, *D1;  // sum over non-missing of dosage * R, dosage * V
+    double *T0, *T1;  // sum over missing samples of R, V
+    int *asum;        // allele sum over non-missing = n_het + 2 n_homA1
+    int *nmiss;       // number of missing calls
+};
+
+struct SpaItem { int snp; int flags; double maf; double S; double Smean; double aux; };
+
+struct Counters {  // device-side diagnostics / work-list cursors
+    unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
+        n_mix_logistic, newton_iters, n_allmissing, n_nonint;
+    int spa_count, spa_cursor, b_count, b_cursor;
+};
+
+// ---------------------------------------------------------------------------
+// K0: SNP-invariant vector statistics.  One CTA (deterministic tree).
+__global__ void __launch_bounds__(1024) k_vec_prep1(const double *__restrict__ R, const double *__restrict__ E,
+                                                    int64_t n, VecConst *vc) {
+    __shared__ double scratch[3 * 32];
+    double v[3] = {0, 0, 0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double r = R[i], e = E[i], r2 = r * r;
+        v[0] += r; v[1] += r2; v[2] += e * r2;
+    }
+    block_sum<3>(v, scratch);
+    if (threadIdx.x == 0) { vc->sumR = v[0]; vc->sumR2 = v[1]; vc->sumER2 = v[2]; vc->lambda = v[2] / v[1]; }
+}
+// mode 0: V = R.new (CCT); mode 1: V = E*R (mix / plus).  Rn_in != NULL: use the caller's R.new (plus).
+__global__ void __launch_bounds__(1024) k_vec_prep2(const double *__restrict__ R, const double *__restrict__ E,
+                                                    const double *__restrict__ Rn_in, int64_t n, int mode,
+                                                    double *__restrict__ Rn, double *__restrict__ V, VecConst *vc) {
+    __shared__ double scratch[4 * 32];
+    const double lambda = vc->lambda;
+    double v[4] = {0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double r = R[i], e = E[i];
+        double rn = Rn_in ? Rn_in[i] : (e - lambda) * r;
+        Rn[i] = rn;
+        double vv = (mode == 0) ? rn : e * r;
+        V[i] = vv;
+        v[0] += rn; v[1] += rn * rn; v[2] += vv; v[3] += vv * vv;
+    }
+    block_sum<4>(v, scratch);
+    if (threadIdx.x == 0) { vc->sumRn = v[0]; vc->sumRn2 = v[1]; vc->sumV = v[2]; vc->sumV2 = v[3]; }
+}
+
+// ---------------------------------------------------------------------------
+// K1 helpers
+// dense column-major matrix -> packed rows. One thread per output 32-bit word (16 samples).
+template <typename T>
+__device__ __forceinline__ int dense_code(T x, int *bad);
+template <>
+__device__ __forceinline__ int dense_code<double>(double x, int *bad) {
+    if (isnan(x)) return 1;
+    if (x == 0.0) return 3;
+    if (x == 1.0) return 2;
+    if (x == 2.0) return 0;
+    *bad = 1; return 1;
+}
+template <>
+__device__ __forceinline__ int dense_code<int>(int x, int *bad) {
+    if (x == INT_MIN) return 1;
+    if (x == 0) return 3;
+    if (x == 1) return 2;
+    if (x == 2) return 0;
+    *bad = 1; return 1;
+}
+template <typename T>
+__global__ void k_pack_dense(const T *__restrict__ G, int64_t ld, int64_t n, int m, uint32_t *__restrict__ bed,
+                             int64_t pitch_words, Counters *ctr) {
+    const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (w >= pitch_words || j >= m) return;
+    const T *col = G + (int64_t)j * ld;
+    uint32_t word = 0xFFFFFFFFu;
+    int bad = 0;
+    const int64_t i0 = w * 16;
+    if (i0 < n) {
+        word = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int c = 3;
+            if (i0 + k < n) c = dense_code<T>(col[i0 + k], &bad);
+            word |= (uint32_t)c << (2 * k);
+        }
+    }
+    bed[(int64_t)j * pitch_words + w] = word;
+    if (bad) atomicAdd(&ctr->n_nonint, 1ULL);
+}
+
+// Make every padding sample (index >= n, up to the row pitch) code 11 (hom-A2: dosage 0, not
+// missing) so that the main kernels need no bounds logic.  One thread per row.
+__global__ void k_sanitize_tail(uint8_t *bed, int64_t pitch, int64_t n, int m) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    uint8_t *row = bed + (int64_t)j * pitch;
+    int64_t full = n >> 2;
+    int rem = (int)(n & 3);
+    int64_t b = full;
+    if (rem) { row[b] |= (uint8_t)(0xFFu << (2 * rem)); b++; }
+    for (; b < pitch; b++) row[b] = 0xFF;
+}
+
+// per-code counts (exact integers). One warp per SNP row; pitch multiple of 4.
+__global__ void k_bed_counts(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, long long *counts) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(bed + (int64_t)warp * pitch);
+    const int64_t nw = (n + 15) >> 4;
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int64_t w = lane; w < nw; w += 32) {
+        uint32_t x = row[w];
+        int64_t rem = n - w * 16;
+        if (rem < 16) x |= 0xFFFFFFFFu << (2 * rem);
+        uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+        c0 += __popc(~lo & ~hi & 0x55555555u);
+        c1 += __popc(lo & ~hi);
+        c2 += __popc(~lo & hi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (lane == 0) {
+        counts[4 * warp + 0] = c0; counts[4 * warp + 1] = c1; counts[4 * warp + 2] = c2;
+        counts[4 * warp + 3] = n - c0 - c1 - c2;
+    }
+}
+
+__global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, double *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= n || j >= m) return;
+    int c = (bed[(int64_t)j * pitch + (i >> 2)] >> (2 * (i & 3))) & 3;
+    out[(int64_t)j * n + i] = (c == 0) ? 2.0 : (c == 2) ? 1.0 : (c == 3) ? 0.0 : d_na_real();
+}
+
+// ---------------------------------------------------------------------------
+// warp-aggregated list append
+__device__ __forceinline__ int list_reserve(int *count, bool want) {
+    unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return -1;
+    int leader = __ffs(mask) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return want ? base + __popc(mask & ((1u << lane) - 1)) : -1;
+}
+
+// genotype prologue from the integer counts (ref :557-577). Returns false if the row is all-missing.
+struct Prologue {
+    double maf_raw, maf, miss_rate, u, sum_g;
+    bool flip;
+};
+__device__ __forceinline__ Prologue make_prologue(int asum, int nmiss, int64_t n) {
+    Prologue p;
+    const double nobs = (double)(n - nmiss);
+    p.maf_raw = ((double)asum / nobs) / 2;  // contract: one correctly rounded division
+    p.miss_rate = (double)nmiss / (double)n;
+    p.u = 2 * p.maf_raw;
+    p.sum_g = (double)asum + p.u * (double)nmiss;
+    p.flip = p.maf_raw > 0.5;
+    p.maf = p.flip ? 1 - p.maf_raw : p.maf_raw;
+    if (p.flip) p.sum_g = 2.0 * (double)n - p.sum_g;
+    return p;
+}
+
+// SPA_G_one_SNP_homo_new's scalar part (ref :2000-2045) given S = sum(g * Rv) and the vector's
+// SNP-invariant sums.  Returns: 0 -> p-values final (normal), 1 -> SPA needed, 2 -> inner min.maf NA.
+__device__ __forceinline__ int homo_scalar(double sum_g, int64_t n, double S_in, double sumRv, double sumRv2,
+                                           double min_maf_inner, double cutoff, double *maf_i, double *S_out,
+                                           double *Smean, double *z) {
+    double mafi = (sum_g / (double)n) / 2;  // mean(g)/2 on the imputed, flipped vector (ref :2000)
+    double S = S_in;
+    if (mafi > 0.5) { mafi = 1 - mafi; S = 2 * sumRv - S; }  // ref :2010-2013 (ties only)
+    *maf_i = mafi; *S_out = S;
+    if (mafi < min_maf_inner) return 2;
+    const double gvar = 2 * mafi * (1 - mafi);
+    const double Svar = sumRv2 * gvar;   // sum(R^2 * g.var.est) (ref :2034)
+    *Smean = 2 * (sumRv * mafi);         // 2 * sum(R * MAF.est)  (ref :2037)
+    *z = (S - *Smean) / sqrt(Svar);
+    return (fabs(*z) < cutoff) ? 0 : 1;
+}
+
+// K3 for SPAGxE_CCT (ref :543-603).  One thread per SNP of the chunk.
+__global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
+                               const VecConst *__restrict__ vcp, double epsilon, double min_maf,
+                               double *__restrict__ out, SpaItem *spa_list, int *b_list, Counters *ctr) {
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = jl < m_chunk;
+    const VecConst vc = *vcp;
+    bool want_spa = false, want_b = false;
+    SpaItem item;
+    const int64_t j = snp0 + jl;
+    if (active) {
+        const double NA = d_na_real();
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        Prologue pr = make_prologue(asum, nmiss, n);
+        double *o = out + j;
+        o[0] = pr.maf; o[1 * m_total] = pr.miss_rate;
+        if (nmiss == n) {  // mean(g, na.rm=T) is NaN; the reference stops at `if(MAF > 0.5)`
+            for (int c = 0; c < 10; c++) o[c * m_total] = NA;
+            o[1 * m_total] = 1.0;
+            atomicAdd(&ctr->n_allmissing, 1ULL);
+        } else if (pr.maf < min_maf) {
+            for (int c = 2; c < 10; c++) o[c * m_total] = NA;
+            atomicAdd(&ctr->n_filtered, 1ULL);
+        } else {
+            double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+            double SV = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
+            if (pr.flip) { S1 = 2 * vc.sumR - S1; SV = 2 * vc.sumV - SV; }
+            const double VarG = 2 * pr.maf * (1 - pr.maf);
+            const double VarS1 = vc.sumR2 * VarG;
+            const double Z1 = S1 / sqrt(VarS1);
+            const double pG = d_pnorm(-fabs(Z1), true) * 2;
+            o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+            if (pG > epsilon) {
+                atomicAdd(&ctr->n_branch_a, 1ULL);
+                double mafi, S, Smean, z;
+                // Cutoff is not forwarded by the reference (:598): always 2, inner min.maf 1e-5
+                int r = homo_scalar(pr.sum_g, n, SV, vc.sumV, vc.sumV2, 0.00001, 2.0, &mafi, &S, &Smean, &z);
+                if (r == 2) {
+                    o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                } else if (r == 0) {
+                    double pn = d_pnorm(fabs(z), false) * 2;
+                    o[2 * m_total] = pn; o[3 * m_total] = pn; o[4 * m_total] = pn; o[5 * m_total] = pn;
+                } else {
+                    o[5 * m_total] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+                    want_spa = true;
+                    item.snp = (int)j; item.flags = 3;  // write p to 3 columns starting at col 2
+                    item.maf = mafi; item.S = S; item.Smean = Smean; item.aux = 0;
+                }
+            } else {
+                atomicAdd(&ctr->n_branch_b, 1ULL);
+                want_b = true;
+            }
+        }
+    }
+    int pos = list_reserve(&ctr->spa_count, want_spa);
+    if (want_spa) spa_list[pos] = item;
+    pos = list_reserve(&ctr->b_count, want_b);
+    if (want_b) b_list[pos] = jl;
+}
+
+// ---------------------------------------------------------------------------
+// K4: saddlepoint approximation.  CGF pieces evaluated exactly as the reference writes them
+// (ref :1652-1681) so overflow/NaN appear in the same places.
+__device__ __forceinline__ void cgf_k12(double tr, double maf, double &k1, double &k2) {
+    const double e = exp(tr);
+    const double x = maf * e;
+    const double u = (1 - maf) + x;
+    const double m0 = u * u;
+    const double m1 = (2 * x) * u;
+    const double m2 = 2 * (x * x) + (2 * x) * u;
+    k1 = m1 / m0;
+    k2 = (m0 * m2 - m1 * m1) / (m0 * m0);
+}
+__device__ __forceinline__ double cgf_k0(double tr, double maf) {
+    const double u = (1 - maf) + maf * exp(tr);
+    return log(u * u);
+}
+
+// Block-collective: fastgetroot_H1_new + GetProb_SPA_G_new (ref :1795-1879). All threads return p.
+template <class Src>
+__device__ double spa_tail(const Src &src, int64_t n, double s, bool lower_tail, double *scratch, int *iters) {
+    const double tol = 0x1p-13;
+    double t = 0, H1 = 0, diff = CUDART_INF, H2e = 0;
+    int iter;
+    for (iter = 1; iter <= 100; iter++) {
+        const double old_t = t, old_diff = diff, old_H1 = H1;
+        double v[2] = {0, 0};
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            double r, maf, k1, k2;
+            src.get(i, r, maf);
+            cgf_k12(t * r, maf, k1, k2);
+            v[0] += r * k1;
+            v[1] += (r * r) * k2;
+        }
+        block_sum<2>(v, scratch);
+        H1 = v[0] - s; H2e = v[1];
+        diff = -1 * H1 / H2e;
+        if (isnan(diff)) diff = 5;
+        if (isnan(H1) || isinf(H1)) { t = d_sign(s) * CUDART_INF; H2e = 0; break; }
+        if (d_sign(H1) != d_sign(old_H1)) {
+            int guard = 0;
+            while (fabs(diff) > fabs(old_diff) - tol && guard++ < 1200) diff = diff / 2;
+        }
+        if (isnan(diff)) diff = 5;
+        if (fabs(diff) < tol) break;
+        t = old_t + diff;
+    }
+    if (iter > 100) iter = 100;
+    *iters = iter;
+    if (iter == 100) t = CUDART_NAN;
+    if (!isfinite(t)) return 0.0;  // every non-finite root yields NA -> 0 in the reference (:1873)
+    double v[2] = {0, 0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double r, maf, k1, k2;
+        src.get(i, r, maf);
+        v[0] += cgf_k0(t * r, maf);
+        cgf_k12(t * r, maf, k1, k2);
+        v[1] += (r * r) * k2;
+    }
+    block_sum<2>(v, scratch);
+    const double temp1 = t * s - v[0];
+    const double w = d_sign(t) * sqrt(2 * temp1);
+    const double vv = t * sqrt(v[1]);
+    double pval = d_pnorm(w + 1 / w * log(vv / w), lower_tail);
+    if (isnan(pval)) pval = 0;
+    return pval;
+}
+
+// two tails (ref :2048-2062). All threads return pval.spa.G
+template <class Src>
+__device__ double spa_two_tail(const Src &src, int64_t n, double s_hi, double s_lo, double *scratch, int *iters) {
+    int i1, i2;
+    double pval1 = spa_tail(src, n, s_hi, false, scratch, &i1);
+    double pval2 = spa_tail(src, n, s_lo, true, scratch, &i2);
+    if (isnan(pval2)) pval2 = pval1;
+    *iters = i1 + i2;
+    return pval1 + pval2;
+}
+
+struct SrcHomo {  // SNP-invariant vector, scalar MAF (SPAGxE_CCT branch A, SPAGxE_Plus)
+    const double *rv; double maf;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m) const { r = rv[i]; m = maf; }
+};
+
+// persistent CTAs popping SPA work items
+constexpr int kSpaThreads = 512;
+__global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restrict__ list, Counters *ctr,
+                                                           const double *__restrict__ rv, int64_t n,
+                                                           int64_t m_total, double *__restrict__ out) {
+    __shared__ double scratch[2 * 32];
+    __shared__ int s_idx;
+    const int count = ctr->spa_count;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_idx = atomicAdd(&ctr->spa_cursor, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= count) break;
+        const SpaItem it = list[idx];
+        SrcHomo src{rv, it.maf};
+        double s_hi, s_lo;
+        if (it.flags & 16) { s_hi = it.S; s_lo = it.Smean; }  // caller supplied both tails (plus)
+        else { s_hi = fmax(it.S, 2 * it.Smean - it.S); s_lo = fmin(it.S, 2 * it.Smean - it.S); }
+        int iters;
+        const double p = spa_two_tail(src, n, s_hi, s_lo, scratch, &iters);
+        if (threadIdx.x == 0) {
+            const int ncol = it.flags & 15;
+            for (int c = 0; c < ncol; c++) out[(int64_t)it.snp + (int64_t)(2 + c) * m_total] = p;
+            atomicAdd(&ctr->n_spa, 1ULL);
+            atomicAdd(&ctr->newton_iters, (unsigned long long)iters);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: branch B (ref :604-678): one CTA per SNP.
+struct WaldData {
+    const double *Y, *cova;  // cova: n x p column-major
+    int p, trait;
+};
+
+struct SrcAdj {  // R.new0_i = E_i * (R_i - fit[class_i]) computed from the packed row (ref :609-612)
+    const uint8_t *row; const double *R, *E; double fit[4]; double maf;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m) const {
+        int c = (row[i >> 2] >> (2 * (i & 3))) & 3;
+        r = E[i] * (R[i] - fit[c]);
+        m = maf;
+    }
+};
+
+// Solve the equilibrated SPD system in place (single thread). A: q x q (row-major, ld kMaxQ),
+// b: rhs.  Returns false when a Cholesky pivot collapses (rank deficient design).
+__device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, double *inv_last) {
+    double sc[kMaxQ];
+    for (int i = 0; i < q; i++) { if (!(A[i][i] > 0)) return false; sc[i] = 1.0 / sqrt(A[i][i]); }
+    for (int i = 0; i < q; i++) for (int j = 0; j < q; j++) A[i][j] *= sc[i] * sc[j];
+    for (int j = 0; j < q; j++) {
+        double d = A[j][j];
+        for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+        if (!(d > 1e-13)) return false;
+        d = sqrt(d); A[j][j] = d;
+        for (int i = j + 1; i < q; i++) {
+            double s = A[i][j];
+            for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
+            A[i][j] = s / d;
+        }
+    }
+    double y[kMaxQ];
+    for (int i = 0; i < q; i++) {
+        double s = b[i] * sc[i];
+        for (int k = 0; k < i; k++) s -= A[i][k] * y[k];
+        y[i] = s / A[i][i];
+    }
+    for (int i = q - 1; i >= 0; i--) {
+        double s = y[i];
+        for (int k = i + 1; k < q; k++) s -= A[k][i] * x[k];
+        x[i] = s / A[i][i];
+    }
+    for (int i = 0; i < q; i++) x[i] *= sc[i];
+    const double l = A[q - 1][q - 1];
+    *inv_last = sc[q - 1] * sc[q - 1] / (l * l);  // ((X'WX)^-1)[q-1][q-1]
+    return true;
+}
+
+constexpr int kBThreads = 512;
+constexpr int kBTile = 256;
+constexpr int kBGroupStride = 160;  // >= (kMaxQ+1)(kMaxQ+2)/2 = 153 entries
+constexpr int kBGroups = kBThreads / kBGroupStride;
+
+// dynamic smem: xs[kBTile][q+1] (x row, z in column q) + xw[kBTile][q]
+__device__ __forceinline__ size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (2 * q + 1); }
+
+// One weighted-least-squares accumulation pass over all samples (block-collective).
+// pass0: eta from mustart; else eta = x . beta.  trait 2 (lm): w = 1, z = y.
+// Outputs (thread 0 valid / smem): NE (q x q), rhs (q), dev (all threads).
+template <class GFun>
+__device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n, int q,
+                            bool pass0, const double *beta_s, double *tile, double (*NE)[kMaxQ], double *rhs,
+                            double *acc_s, double *scratch, int *invalid) {
+    const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
+    const int p = wd.p;
+    const int qs = q + 1;
+    double *xs = tile, *xw = tile + kBTile * qs;
+    const int nent = q * (q + 1) / 2 + q;  // upper triangle + rhs column
+    // entry mapping for this thread
+    const int grp = threadIdx.x / kBGroupStride, e = threadIdx.x % kBGroupStride;
+    int ea = 0, eb = 0;
+    bool has_entry = (grp < kBGroups) && (e < nent);
+    if (has_entry) {
+        int rem = e;
+        for (ea = 0; ea < q; ea++) { int len = q + 1 - ea; if (rem < len) { eb = ea + rem; break; } rem -= len; }
+    }
+    double acc = 0, dev = 0;
+    int bad = 0;
+    for (int64_t base = 0; base < n; base += kBTile) {
+        const int cnt = (int)min((int64_t)kBTile, n - base);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            const int64_t i = base + threadIdx.x;
+            double *xr = xs + threadIdx.x * qs;
+            const double g = gf(i), ev = E[i], y = wd.Y[i];
+            xr[0] = 1.0;
+            for (int c = 0; c < p; c++) xr[1 + c] = wd.cova[i + (int64_t)c * n];
+            xr[p + 1] = ev; xr[p + 2] = g; xr[p + 3] = ev * g;
+            double w2 = 1.0, z = y;
+            if (wd.trait == 1) {
+                double eta, mu;
+                if (pass0) {
+                    double mus = (y + 0.5) / 2;
+                    eta = log(mus / (1 - mus));
+                } else {
+                    eta = 0;
+                    for (int c = 0; c < q; c++) eta += xr[c] * beta_s[c];
+                }
+                double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : exp(eta));
+                mu = tmp / (1 + tmp);
+                if (!(mu > 0 && mu < 1)) bad = 1;
+                double yl = (y != 0.) ? y * log(y / mu) : 0.;
+                double y1 = 1 - y;
+                double yl1 = (y1 != 0.) ? y1 * log(y1 / (1 - mu)) : 0.;
+                dev += 2 * (yl + yl1);
+                double varmu = mu * (1 - mu);
+                double opexp = 1 + exp(eta);
+                double mev = (eta > THRESH || eta < MTHRESH) ? DBL_EPSILON : exp(eta) / (opexp * opexp);
+                z = eta + (y - mu) / mev;
+                w2 = (mev * mev) / varmu;
+            } else if (!pass0) {  // lm second pass: residual sum of squares
+                double fit = 0;
+                for (int c = 0; c < q; c++) fit += xr[c] * beta_s[c];
+                dev += (y - fit) * (y - fit);
+            }
+            xr[q] = z;
+            double *wr = xw + threadIdx.x * q;
+            for (int c = 0; c < q; c++) wr[c] = w2 * xr[c];
+        }
+        __syncthreads();
+        if (has_entry) {
+            for (int s = grp; s < cnt; s += kBGroups) acc = fma(xw[s * q + ea], xs[s * qs + eb], acc);
+        }
+    }
+    __syncthreads();
+    if (has_entry) acc_s[grp * kBGroupStride + e] = acc;
+    __syncthreads();
+    if (threadIdx.x < nent) {
+        double s = 0;
+        for (int g2 = 0; g2 < kBGroups; g2++) s += acc_s[g2 * kBGroupStride + threadIdx.x];
+        int a = 0, b = 0, rem = threadIdx.x;
+        for (a = 0; a < q; a++) { int len = q + 1 - a; if (rem < len) { b = a + rem; break; } rem -= len; }
+        if (b == q) rhs[a] = s; else { NE[a][b] = s; NE[b][a] = s; }
+    }
+    double v[2] = {dev, (double)bad};
+    block_sum<2>(v, scratch);
+    *invalid = v[1] > 0;
+    return v[0];
+}
+
+struct GFromRow {
+    const uint8_t *row; double gval[4];
+    __device__ __forceinline__ double operator()(int64_t i) const { return gval[(row[i >> 2] >> (2 * (i & 3))) & 3]; }
+};
+
+// Block-collective Wald p-value of E:g (ref :636-662).  Returns status in *fail.
+template <class GFun>
+__device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, double *tile,
+                          double *scratch, int *fail) {
+    __shared__ double NE[kMaxQ][kMaxQ];
+    __shared__ double rhs[kMaxQ], beta[kMaxQ];
+    __shared__ double acc_s[kBGroups * kBGroupStride];
+    __shared__ double s_se2, s_ok;
+    const int q = wd.p + 4;
+    *fail = 0;
+    if (wd.trait == 1) {
+        int invalid;
+        double devold = wald_pass(gf, wd, E, n, q, true, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+        double se2 = 0;
+        for (int it = 1; it <= 25; it++) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double x[kMaxQ], il;
+                bool ok = chol_solve(NE, rhs, q, x, &il);
+                for (int c = 0; c < q; c++) beta[c] = ok ? x[c] : 0.0;
+                s_se2 = il; s_ok = ok ? 1.0 : 0.0;
+            }
+            __syncthreads();
+            if (s_ok == 0.0) { *fail = 1; return d_na_real(); }
+            se2 = s_se2;
+            double dev = wald_pass(gf, wd, E, n, q, false, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+            if (!isfinite(dev) || invalid) { *fail = 2; return d_na_real(); }
+            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) break;
+            devold = dev;
+        }
+        const double zst = beta[q - 1] / sqrt(se2);
+        return 2 * d_pnorm(-fabs(zst), true);
+    } else {
+        int invalid;
+        wald_pass(gf, wd, E, n, q, true, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double x[kMaxQ], il;
+            bool ok = chol_solve(NE, rhs, q, x, &il);
+            for (int c = 0; c < q; c++) beta[c] = ok ? x[c] : 0.0;
+            s_se2 = il; s_ok = ok ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (s_ok == 0.0) { *fail = 1; return d_na_real(); }
+        const double il = s_se2;
+        double rss = wald_pass(gf, wd, E, n, q, false, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+        const double rdf = (double)(n - q);
+        const double se = sqrt(il * (rss / rdf));
+        return d_pt2(beta[q - 1] / se, rdf);
+    }
+}
+
+// class sums needed by branch B, computed from the packed row (block-collective).
+// counts n_c and sums over class c of: R, E, E*R, E*E, E*E*R, (E*R)^2 are NOT needed in v1: we do
+// explicit per-sample passes instead (rare branch).
+__global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restrict__ b_list, Counters *ctr,
+                                                             const uint8_t *__restrict__ bed, int64_t pitch,
+                                                             SnpStats st, int64_t snp0, int64_t m_total, int64_t n,
+                                                             const double *__restrict__ R, const double *__restrict__ E,
+                                                             const VecConst *__restrict__ vcp, WaldData wd,
+                                                             double min_maf, double *__restrict__ out) {
+    extern __shared__ double tile[];
+    __shared__ double scratch[4 * 32];
+    __shared__ int s_idx;
+    const int count = ctr->b_count;
+    const VecConst vc = *vcp;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_idx = atomicAdd(&ctr->b_cursor, 1);
+        __syncthreads();
+        if (s_idx >= count) break;
+        const int jl = b_list[s_idx];
+        const int64_t j = snp0 + jl;
+        const uint8_t *row = bed + (int64_t)jl * pitch;
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        const Prologue pr = make_prologue(asum, nmiss, n);
+        GFromRow gf;
+        gf.row = row;
+        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
+        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
+        // W'W, W'R (ref :606-609)
+        double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+        if (pr.flip) S1 = 2 * vc.sumR - S1;
+        double v3[3] = {0, 0, 0};
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
+        block_sum<3>(v3, scratch);
+        const double a = (double)n, b = pr.sum_g, d = v3[0];
+        const double det = a * d - b * b;
+        const double NA = d_na_real();
+        double *o = out + j;
+        if (det == 0 || !isfinite(det)) {
+            if (threadIdx.x == 0) {
+                o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                atomicAdd(&ctr->n_singular, 1ULL);
+            }
+            continue;
+        }
+        const double i00 = d / det, i01 = -b / det, i11 = a / det;
+        SrcAdj src;
+        src.row = row; src.R = R; src.E = E;
+        for (int c = 0; c < 4; c++) {
+            double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
+            src.fit[c] = wi0 * vc.sumR + wi1 * S1;
+        }
+        // S = sum(g * R.new0), sum(R.new0), sum(R.new0^2)
+        v3[0] = v3[1] = v3[2] = 0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            double r, m; src.maf = 0; src.get(i, r, m);
+            double g = gf(i);
+            v3[0] += g * r; v3[1] += r; v3[2] += r * r;
+        }
+        block_sum<3>(v3, scratch);
+        double mafi, S, Smean, z;
+        // branch B forwards min.maf to the inner call (ref :616); Cutoff stays 2
+        int r = homo_scalar(pr.sum_g, n, v3[0], v3[1], v3[2], min_maf, 2.0, &mafi, &S, &Smean, &z);
+        double pspa, pnorm_;
+        int iters = 0;
+        if (r == 2) { pspa = NA; pnorm_ = NA; }
+        else if (r == 0) { pspa = d_pnorm(fabs(z), false) * 2; pnorm_ = pspa; }
+        else {
+            pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            src.maf = mafi;
+            // NB: an inner flip (mafi > .5) only happens on exact ties; S was mirrored by homo_scalar and
+            // the CGF of 2-g with 1-maf is the mirror image, so evaluate with negated residuals.
+            pspa = spa_two_tail(src, n, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), scratch, &iters);
+        }
+        int wfail;
+        double pw = wald_eg(gf, wd, E, n, tile, scratch, &wfail);
+        if (threadIdx.x == 0) {
+            double pc = NA;
+            if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
+            int crc = d_cct2(pspa, pw, &pc);
+            if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
+            o[2 * m_total] = pspa; o[3 * m_total] = pw; o[4 * m_total] = pc; o[5 * m_total] = pnorm_;
+            if (r == 1) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+}
+
+}  // namespace spagxe

@@ -1,0 +1,593 @@
+// spagxe_cuda.cu -- C ABI of libspagxe_cuda.so (include/spagxe.h) and the host-side pipeline.
+//
+// One context drives one GPU.  A run walks the SNP axis in chunks; each chunk is
+//   H2D (copy stream, pinned staging, double-buffered)  ->  score pass  ->  per-SNP epilogue + routing
+//   ->  SPA work list  ->  branch-B work list
+// with no host synchronisation inside the loop: work lists are consumed by persistent CTAs that read
+// their length from device memory.
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/spagxe.h"
+#include "score.cuh"
+
+using namespace spagxe;
+
+static std::string g_create_error;
+
+struct spagxe_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t s_main = nullptr, s_copy = nullptr, s_user = nullptr;
+    bool user_stream = false;
+    int num_sms = 148;
+    // analysis inputs
+    int64_t n = 0;
+    double *d_R = nullptr, *d_E = nullptr, *d_Rn = nullptr, *d_V = nullptr;
+    VecConst *d_vc = nullptr;
+    Counters *d_ctr = nullptr;
+    int vec_mode = -1;  // which V is currently prepared (-1 none)
+    // wald
+    double *d_Y = nullptr, *d_cova = nullptr;
+    int wald_p = 0, wald_trait = 0;
+    // pcs / grm (mix, plus)
+    double *d_pcs = nullptr; int n_pcs = 0;
+    double *d_xtx_inv = nullptr;
+    int64_t grm_nnz = 0; int *d_gi = nullptr, *d_gj = nullptr; double *d_gv = nullptr;
+    double R_GRM_R = 0, R_GRM_RE = 0, Rnew_GRM_Rnew = 0; double *d_Rn_user = nullptr; bool have_grm = false;
+    // chunk scratch
+    int64_t cap_chunk_bytes = 0; uint8_t *d_bed[2] = {nullptr, nullptr};
+    int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
+    int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
+    SpaItem *d_spa_list = nullptr; int *d_b_list = nullptr;
+    int64_t cap_out = 0; double *d_out = nullptr;
+    int64_t cap_dense = 0; void *d_dense = nullptr;
+    // pinned staging
+    uint8_t *h_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    cudaStream_t stream() const { return user_stream ? s_user : s_main; }
+};
+
+static int fail(spagxe_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, SPAGXE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+#define LAUNCH_CHECK()                                                                             \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        cudaError_t e_ = cudaGetLastError();                                                       \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, SPAGXE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_realloc(T **p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void **)p, count * sizeof(T));
+}
+
+extern "C" const char *spagxe_version(void) { return "spagxe-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *spagxe_last_error(const spagxe_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
+    spagxe_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, SPAGXE_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SPAGXE_ERR_CUDA, "no CUDA device: %s (libspagxe_cuda has no CPU fallback)",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SPAGXE_ERR_ARG, "device %d out of range (%d)", device, ndev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, SPAGXE_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SPAGXE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    ctx = new spagxe_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    auto bail = [&](const char *what, cudaError_t ee) {
+        int rc = fail(nullptr, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ee));
+        delete ctx;
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    for (int b = 0; b < 2; b++) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_stage[b], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_done[b], cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    }
+    if ((e = cudaMalloc((void **)&ctx->d_vc, sizeof(VecConst))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
+    // opt in to the large dynamic shared memory of the branch-B kernel
+    e = cudaFuncSetAttribute(k_branch_b_cct, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(double) * kBTile * (2 * kMaxQ + 1)));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    *out = ctx;
+    return SPAGXE_OK;
+}
+
+extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->d_R); cudaFree(ctx->d_E); cudaFree(ctx->d_Rn); cudaFree(ctx->d_V); cudaFree(ctx->d_vc);
+    cudaFree(ctx->d_ctr); cudaFree(ctx->d_Y); cudaFree(ctx->d_cova); cudaFree(ctx->d_pcs); cudaFree(ctx->d_xtx_inv);
+    cudaFree(ctx->d_gi); cudaFree(ctx->d_gj); cudaFree(ctx->d_gv); cudaFree(ctx->d_Rn_user);
+    cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_dense);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
+        if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_done[b]) cudaEventDestroy(ctx->ev_done[b]);
+    }
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+}
+
+extern "C" int spagxe_ctx_set_stream(spagxe_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    ctx->s_user = (cudaStream_t)cuda_stream;
+    ctx->user_stream = true;  // NULL here means the legacy default stream, which torch uses by default
+    return SPAGXE_OK;
+}
+
+static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const double *E, cudaMemcpyKind kind) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (n <= 0 || !R || !E) return fail(ctx, SPAGXE_ERR_ARG, "set_vectors: n=%lld, R=%p, E=%p", (long long)n, R, E);
+    CU(cudaSetDevice(ctx->device));
+    if (n != ctx->n) {
+        CU(dev_realloc(&ctx->d_R, n)); CU(dev_realloc(&ctx->d_E, n));
+        CU(dev_realloc(&ctx->d_Rn, n)); CU(dev_realloc(&ctx->d_V, n));
+        // inputs that depend on N are invalidated
+        cudaFree(ctx->d_Y); ctx->d_Y = nullptr; cudaFree(ctx->d_cova); ctx->d_cova = nullptr; ctx->wald_trait = 0;
+        cudaFree(ctx->d_pcs); ctx->d_pcs = nullptr; ctx->n_pcs = 0;
+        ctx->have_grm = false;
+        ctx->n = n;
+    }
+    cudaStream_t s = ctx->stream();
+    CU(cudaMemcpyAsync(ctx->d_R, R, n * sizeof(double), kind, s));
+    CU(cudaMemcpyAsync(ctx->d_E, E, n * sizeof(double), kind, s));
+    k_vec_prep1<<<1, 1024, 0, s>>>(ctx->d_R, ctx->d_E, n, ctx->d_vc);
+    LAUNCH_CHECK();
+    ctx->vec_mode = -1;
+    CU(cudaStreamSynchronize(s));
+    return SPAGXE_OK;
+}
+extern "C" int spagxe_set_vectors(spagxe_ctx *ctx, int64_t n, const double *R, const double *E) {
+    return set_vectors_common(ctx, n, R, E, cudaMemcpyHostToDevice);
+}
+extern "C" int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const double *dR, const double *dE) {
+    return set_vectors_common(ctx, n, dR, dE, cudaMemcpyDeviceToDevice);
+}
+
+extern "C" int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_wald: call spagxe_set_vectors first");
+    if (trait != SPAGXE_TRAIT_BINARY && trait != SPAGXE_TRAIT_QUANTITATIVE)
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
+                    "traits must be binary(1) or quantitative(2); survival/categorical Wald tests are not implemented");
+    if (!Y || p < 0 || (p > 0 && !cova)) return fail(ctx, SPAGXE_ERR_ARG, "set_wald: bad arguments");
+    if (p + 4 > kMaxQ) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "set_wald: at most %d covariates", kMaxQ - 4);
+    CU(cudaSetDevice(ctx->device));
+    CU(dev_realloc(&ctx->d_Y, ctx->n));
+    CU(dev_realloc(&ctx->d_cova, (size_t)ctx->n * std::max(p, 1)));
+    CU(cudaMemcpy(ctx->d_Y, Y, ctx->n * sizeof(double), cudaMemcpyHostToDevice));
+    if (p > 0) CU(cudaMemcpy(ctx->d_cova, cova, (size_t)ctx->n * p * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->wald_p = p; ctx->wald_trait = trait;
+    return SPAGXE_OK;
+}
+
+// ---------------------------------------------------------------------------
+static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
+    if (ctx->vec_mode == mode) return SPAGXE_OK;
+    k_vec_prep2<<<1, 1024, 0, ctx->stream()>>>(ctx->d_R, ctx->d_E, d_Rn_in, ctx->n, mode, ctx->d_Rn, ctx->d_V, ctx->d_vc);
+    LAUNCH_CHECK();
+    ctx->vec_mode = mode;
+    return SPAGXE_OK;
+}
+
+struct ChunkPlan {
+    int64_t n, m, row_bytes, dpitch;  // dpitch: device pitch of staged rows (multiple of 128)
+    int chunk_m;
+};
+
+static int ensure_chunk_scratch(spagxe_ctx *ctx, const ChunkPlan &pl, bool need_bed_buffers, int64_t out_elems) {
+    const int64_t bytes = pl.dpitch * pl.chunk_m;
+    if (need_bed_buffers && bytes > ctx->cap_chunk_bytes) {
+        CU(dev_realloc(&ctx->d_bed[0], bytes)); CU(dev_realloc(&ctx->d_bed[1], bytes));
+        ctx->cap_chunk_bytes = bytes;
+    }
+    if (pl.chunk_m > ctx->cap_m) {
+        CU(dev_realloc(&ctx->d_stats, (size_t)4 * pl.chunk_m)); CU(dev_realloc(&ctx->d_istats, (size_t)2 * pl.chunk_m));
+        CU(dev_realloc(&ctx->d_spa_list, pl.chunk_m)); CU(dev_realloc(&ctx->d_b_list, pl.chunk_m));
+        ctx->cap_m = pl.chunk_m;
+    }
+    const int tiles_s = (int)((pl.dpitch / 4 + kScoreThreads - 1) / kScoreThreads);
+    const int64_t m_pad = round_up(pl.chunk_m, kScoreRows);
+    const int64_t need = (int64_t)tiles_s * 4 * m_pad;
+    if (need > ctx->cap_partial) {
+        CU(dev_realloc(&ctx->d_partial, need)); CU(dev_realloc(&ctx->d_ipartial, need / 2));
+        ctx->cap_partial = need;
+    }
+    if (out_elems > ctx->cap_out) { CU(dev_realloc(&ctx->d_out, out_elems)); ctx->cap_out = out_elems; }
+    return SPAGXE_OK;
+}
+
+// copy `rows` packed rows from host memory into a pitched device buffer on the copy stream
+static int stage_rows(spagxe_ctx *ctx, const uint8_t *src, int64_t spitch, int64_t row_bytes, int64_t rows,
+                      uint8_t *dst, int64_t dpitch, bool pinned) {
+    if (pinned) {
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyHostToDevice, ctx->s_copy));
+        return SPAGXE_OK;
+    }
+    if (!ctx->h_stage[0]) {
+        ctx->stage_bytes = 32u << 20;
+        for (int b = 0; b < 2; b++) CU(cudaMallocHost((void **)&ctx->h_stage[b], ctx->stage_bytes));
+    }
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)ctx->stage_bytes / row_bytes);
+    if (row_bytes > (int64_t)ctx->stage_bytes) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "row larger than staging buffer");
+    int b = 0;
+    for (int64_t r0 = 0; r0 < rows; r0 += rows_per, b ^= 1) {
+        const int64_t nr = std::min(rows_per, rows - r0);
+        CU(cudaEventSynchronize(ctx->ev_stage[b]));
+        if (spitch == row_bytes) memcpy(ctx->h_stage[b], src + r0 * spitch, nr * row_bytes);
+        else for (int64_t r = 0; r < nr; r++) memcpy(ctx->h_stage[b] + r * row_bytes, src + (r0 + r) * spitch, row_bytes);
+        CU(cudaMemcpy2DAsync(dst + r0 * dpitch, dpitch, ctx->h_stage[b], row_bytes, row_bytes, nr,
+                             cudaMemcpyHostToDevice, ctx->s_copy));
+        CU(cudaEventRecord(ctx->ev_stage[b], ctx->s_copy));
+    }
+    return SPAGXE_OK;
+}
+
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int validate_geno(spagxe_ctx *ctx, const spagxe_geno *g) {
+    if (!g || !g->data) return fail(ctx, SPAGXE_ERR_ARG, "geno is NULL");
+    if (g->n_samples <= 0 || g->n_snps < 0) return fail(ctx, SPAGXE_ERR_ARG, "geno: bad shape");
+    if (g->n_snps > INT_MAX / 2) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "geno: too many SNPs in one call");
+    if (g->kind == SPAGXE_GENO_BED) {
+        if (g->pitch < (g->n_samples + 3) / 4) return fail(ctx, SPAGXE_ERR_ARG, "geno: pitch < ceil(N/4)");
+        if (g->location == SPAGXE_LOC_DEVICE && ((g->pitch & 15) || ((uintptr_t)g->data & 15)))
+            return fail(ctx, SPAGXE_ERR_ARG, "geno: device-resident .bed rows need a 16-byte aligned base and pitch");
+    } else if (g->kind == SPAGXE_GENO_F64 || g->kind == SPAGXE_GENO_I32) {
+        if (g->pitch < g->n_samples) return fail(ctx, SPAGXE_ERR_ARG, "geno: leading dimension < N");
+    } else return fail(ctx, SPAGXE_ERR_ARG, "geno: unknown kind %d", g->kind);
+    if (g->location != SPAGXE_LOC_HOST && g->location != SPAGXE_LOC_DEVICE) return fail(ctx, SPAGXE_ERR_ARG, "geno: bad location");
+    return SPAGXE_OK;
+}
+
+static ChunkPlan make_plan(const spagxe_geno *g) {
+    ChunkPlan pl;
+    pl.n = g->n_samples; pl.m = g->n_snps;
+    pl.row_bytes = (g->n_samples + 3) / 4;
+    if (g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) pl.dpitch = g->pitch;
+    else pl.dpitch = round_up(pl.row_bytes, 128);
+    // ~1 GiB of packed rows per chunk (>> L2), dense inputs are limited by their 8 B/sample staging
+    int64_t budget = (g->kind == SPAGXE_GENO_BED) ? (1ll << 30) : (1ll << 26);
+    int64_t cm = std::max<int64_t>(kScoreRows, budget / pl.dpitch / kScoreRows * kScoreRows);
+    cm = std::min<int64_t>(cm, 65536);
+    pl.chunk_m = (int)std::min<int64_t>(cm, std::max<int64_t>(pl.m, 1));
+    return pl;
+}
+
+// Bring chunk [j0, j0+mc) into packed device rows. Returns the device pointer/pitch to use.
+static int stage_chunk(spagxe_ctx *ctx, const spagxe_geno *g, const ChunkPlan &pl, int64_t j0, int mc, int buf,
+                       const uint8_t **d_rows, int64_t *h2d_bytes) {
+    cudaStream_t s = ctx->stream();
+    if (g->kind == SPAGXE_GENO_BED) {
+        if (g->location == SPAGXE_LOC_DEVICE) {
+            *d_rows = (const uint8_t *)g->data + j0 * g->pitch;
+            return SPAGXE_OK;
+        }
+        const uint8_t *src = (const uint8_t *)g->data + j0 * g->pitch;
+        CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[buf], 0));
+        int rc = stage_rows(ctx, src, g->pitch, pl.row_bytes, mc, ctx->d_bed[buf], pl.dpitch, host_ptr_is_pinned(src));
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_copied[buf], ctx->s_copy));
+        CU(cudaStreamWaitEvent(s, ctx->ev_copied[buf], 0));
+        *h2d_bytes += pl.row_bytes * mc;
+        *d_rows = ctx->d_bed[buf];
+        return SPAGXE_OK;
+    }
+    // dense R matrix: stage (if on host) then pack into 2-bit rows on the device
+    const size_t esz = (g->kind == SPAGXE_GENO_F64) ? 8 : 4;
+    const void *dsrc;
+    if (g->location == SPAGXE_LOC_DEVICE) dsrc = (const uint8_t *)g->data + (size_t)j0 * g->pitch * esz;
+    else {
+        const int64_t need = (int64_t)pl.n * pl.chunk_m * (int64_t)esz;
+        if (need > ctx->cap_dense) {
+            CU(cudaStreamSynchronize(s));
+            if (ctx->d_dense) cudaFree(ctx->d_dense);
+            ctx->d_dense = nullptr;
+            CU(cudaMalloc(&ctx->d_dense, need));
+            ctx->cap_dense = need;
+        }
+        CU(cudaMemcpy2DAsync(ctx->d_dense, pl.n * esz, (const uint8_t *)g->data + (size_t)j0 * g->pitch * esz,
+                             g->pitch * esz, pl.n * esz, mc, cudaMemcpyHostToDevice, s));
+        *h2d_bytes += (int64_t)pl.n * esz * mc;
+        dsrc = ctx->d_dense;
+    }
+    const int64_t ld = (g->location == SPAGXE_LOC_DEVICE) ? g->pitch : pl.n;
+    const int64_t pw = pl.dpitch / 4;
+    dim3 grid((unsigned)((pw + 255) / 256), (unsigned)mc);
+    if (g->kind == SPAGXE_GENO_F64)
+        k_pack_dense<double><<<grid, 256, 0, s>>>((const double *)dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr);
+    else
+        k_pack_dense<int><<<grid, 256, 0, s>>>((const int *)dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr);
+    LAUNCH_CHECK();
+    *d_rows = ctx->d_bed[buf];
+    return SPAGXE_OK;
+}
+
+static SnpStats stats_view(spagxe_ctx *ctx, int cap) {
+    SnpStats st;
+    st.D0 = ctx->d_stats; st.D1 = ctx->d_stats + cap; st.T0 = ctx->d_stats + 2 * (size_t)cap; st.T1 = ctx->d_stats + 3 * (size_t)cap;
+    st.asum = ctx->d_istats; st.nmiss = ctx->d_istats + cap;
+    return st;
+}
+
+static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
+    cudaStream_t s = ctx->stream();
+    const int64_t pw = pl.dpitch / 4;
+    const int tiles_s = (int)((pw + kScoreThreads - 1) / kScoreThreads);
+    const int m_pad = (int)round_up(mc, kScoreRows);
+    dim3 grid((unsigned)tiles_s, (unsigned)(m_pad / kScoreRows));
+    k_score_v1<<<grid, kScoreThreads, 0, s>>>((const uint32_t *)d_rows, pw, pl.n, mc, m_pad, ctx->d_R, ctx->d_V,
+                                               ctx->d_partial, ctx->d_ipartial);
+    LAUNCH_CHECK();
+    k_score_reduce<<<(mc + 127) / 128, 128, 0, s>>>(ctx->d_partial, ctx->d_ipartial, tiles_s, mc, m_pad, st);
+    LAUNCH_CHECK();
+    return SPAGXE_OK;
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+    cudaEvent_t rec(cudaStream_t s) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); return e;
+    }
+};
+
+static void fill_diag(spagxe_diag *diag, const Counters &c, int64_t m) {
+    diag->n_snps = m; diag->n_filtered = c.n_filtered; diag->n_branch_a = c.n_branch_a; diag->n_branch_b = c.n_branch_b;
+    diag->n_spa = c.n_spa; diag->n_wald_fail = c.n_wald_fail; diag->n_cct_stop = c.n_cct_stop;
+    diag->n_singular = c.n_singular; diag->n_mix_logistic = c.n_mix_logistic; diag->newton_iters = c.newton_iters;
+}
+
+static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1, 0, 0, 0, 0};
+
+extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out,
+                              spagxe_diag *diag) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (!prm) prm = &kDefaultParams;
+    int rc = validate_geno(ctx, g);
+    if (rc) return rc;
+    if (!out) return fail(ctx, SPAGXE_ERR_ARG, "out is NULL");
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_cct: call spagxe_set_vectors first");
+    if (g->n_samples != ctx->n) return fail(ctx, SPAGXE_ERR_ARG, "geno has %lld samples but R has %lld",
+                                            (long long)g->n_samples, (long long)ctx->n);
+    if (ctx->wald_trait == 0) return fail(ctx, SPAGXE_ERR_STATE, "run_cct: call spagxe_set_wald first (Wald test data)");
+    if (prm->g_model != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only G.model=\"Add\" is implemented");
+    if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    const int64_t M = g->n_snps, N = g->n_samples;
+    spagxe_diag dg; memset(&dg, 0, sizeof dg);
+    ctx->launches = 0;
+    if (M == 0) { if (diag) *diag = dg; return SPAGXE_OK; }
+    ChunkPlan pl = make_plan(g);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    double *d_out = nullptr;
+    if (prm->out_location == SPAGXE_LOC_DEVICE) { d_out = out; rc = ensure_chunk_scratch(ctx, pl, own_bed, 0); }
+    else { rc = ensure_chunk_scratch(ctx, pl, own_bed, M * 10); d_out = ctx->d_out; }
+    if (rc) return rc;
+    if ((rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    EventPool evp;
+    cudaEvent_t e_begin = evp.rec(s);
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev;
+    SnpStats st = stats_view(ctx, ctx->cap_m);
+    WaldData wd{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
+    const size_t smem_b = sizeof(double) * kBTile * (2 * (ctx->wald_p + 4) + 1);
+    int buf = 0;
+    for (int64_t j0 = 0; j0 < M; j0 += pl.chunk_m, buf ^= 1) {
+        const int mc = (int)std::min<int64_t>(pl.chunk_m, M - j0);
+        const uint8_t *d_rows = nullptr;
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &dg.h2d_bytes))) return rc;
+        // reset per-chunk work-list cursors (counters keep accumulating)
+        CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, 4 * sizeof(int), s));
+        cudaEvent_t a = evp.rec(s);
+        if ((rc = launch_score(ctx, d_rows, pl, mc, st))) return rc;
+        cudaEvent_t b = evp.rec(s);
+        score_ev.push_back({a, b});
+        k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
+                                                        ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
+        LAUNCH_CHECK();
+        k_spa_homo<<<ctx->num_sms * 2, kSpaThreads, 0, s>>>(ctx->d_spa_list, ctx->d_ctr, ctx->d_V, N, M, d_out);
+        LAUNCH_CHECK();
+        k_branch_b_cct<<<ctx->num_sms, kBThreads, smem_b, s>>>(ctx->d_b_list, ctx->d_ctr, d_rows, pl.dpitch, st, j0, M, N,
+                                                               ctx->d_R, ctx->d_E, ctx->d_vc, wd, prm->min_maf, d_out);
+        LAUNCH_CHECK();
+        cudaEvent_t c = evp.rec(s);
+        test_ev.push_back({b, c});
+        if (own_bed) CU(cudaEventRecord(ctx->ev_done[buf], s));
+    }
+    Counters hc;
+    CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
+    if (prm->out_location != SPAGXE_LOC_DEVICE) {
+        CU(cudaMemcpyAsync(out, d_out, M * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        dg.d2h_bytes += M * 10 * sizeof(double);
+    }
+    cudaEvent_t e_end = evp.rec(s);
+    CU(cudaStreamSynchronize(s));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e_begin, e_end); dg.ms_total = ms;
+    for (auto &p : score_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_score += ms; }
+    for (auto &p : test_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_tests += ms; }
+    fill_diag(&dg, hc, M);
+    dg.kernel_launches = ctx->launches;
+    dg.score_bytes = M * pl.row_bytes;
+    if (diag) *diag = dg;
+    if (hc.n_nonint) return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
+                                 "Geno.mtx holds values outside {0,1,2,NA}: imputed dosages are not supported by the 2-bit path");
+    if (hc.n_allmissing) return fail(ctx, SPAGXE_ERR_ARG, "%llu SNP(s) have every genotype missing (the reference stops here)",
+                                     hc.n_allmissing);
+    if (hc.n_singular) return fail(ctx, SPAGXE_ERR_SINGULAR, "solve(t(W)%%*%%W) is singular for %llu SNP(s)", hc.n_singular);
+    if (hc.n_cct_stop) return fail(ctx, SPAGXE_ERR_CCT_STOP, "CCT() would stop() for %llu SNP(s) (NA or out-of-range p-value)",
+                                   hc.n_cct_stop);
+    return SPAGXE_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *g, int64_t *counts) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    int rc = validate_geno(ctx, g);
+    if (rc) return rc;
+    if (!counts) return fail(ctx, SPAGXE_ERR_ARG, "counts is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    ChunkPlan pl = make_plan(g);
+    ctx->launches = 0;
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    long long *d_counts = nullptr;
+    CU(cudaMalloc((void **)&d_counts, sizeof(long long) * 4 * pl.chunk_m));
+    int buf = 0; int64_t h2d = 0;
+    for (int64_t j0 = 0; j0 < g->n_snps; j0 += pl.chunk_m, buf ^= 1) {
+        const int mc = (int)std::min<int64_t>(pl.chunk_m, g->n_snps - j0);
+        const uint8_t *d_rows = nullptr;
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) { cudaFree(d_counts); return rc; }
+        k_bed_counts<<<(mc * 32 + 255) / 256, 256, 0, s>>>(d_rows, pl.dpitch, pl.n, mc, d_counts);
+        ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(counts + 4 * j0, d_counts, sizeof(long long) * 4 * mc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { cudaFree(d_counts); return fail(ctx, SPAGXE_ERR_CUDA, "bed_counts: %s", cudaGetErrorString(e)); }
+        if (own_bed) cudaEventRecord(ctx->ev_done[buf], s);
+    }
+    cudaFree(d_counts);
+    return SPAGXE_OK;
+}
+
+extern "C" int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *g, double *out_host) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    int rc = validate_geno(ctx, g);
+    if (rc) return rc;
+    if (!out_host) return fail(ctx, SPAGXE_ERR_ARG, "out is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    ChunkPlan pl = make_plan(g);
+    // decode expands 32x: keep chunks small
+    pl.chunk_m = (int)std::min<int64_t>(pl.chunk_m, std::max<int64_t>(1, (1ll << 28) / (pl.n * 8)));
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    double *d_dec = nullptr;
+    CU(cudaMalloc((void **)&d_dec, sizeof(double) * pl.n * pl.chunk_m));
+    int buf = 0; int64_t h2d = 0;
+    for (int64_t j0 = 0; j0 < g->n_snps; j0 += pl.chunk_m, buf ^= 1) {
+        const int mc = (int)std::min<int64_t>(pl.chunk_m, g->n_snps - j0);
+        const uint8_t *d_rows = nullptr;
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) { cudaFree(d_dec); return rc; }
+        dim3 grid((unsigned)((pl.n + 255) / 256), (unsigned)mc);
+        k_bed_decode<<<grid, 256, 0, s>>>(d_rows, pl.dpitch, pl.n, mc, d_dec);
+        ctx->launches++;
+        cudaError_t e = cudaMemcpyAsync(out_host + j0 * pl.n, d_dec, sizeof(double) * pl.n * mc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { cudaFree(d_dec); return fail(ctx, SPAGXE_ERR_CUDA, "bed_decode: %s", cudaGetErrorString(e)); }
+        if (own_bed) cudaEventRecord(ctx->ev_done[buf], s);
+    }
+    cudaFree(d_dec);
+    return SPAGXE_OK;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+extern "C" int spagxe_measure_fp64_peak(spagxe_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return SPAGXE_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, 8));
+    const int iters = 1 << 16, blocks = ctx->num_sms * 8, threads = 256;
+    k_dfma_peak<<<blocks, threads, 0, s>>>(d, 1024);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(a, s);
+        k_dfma_peak<<<blocks, threads, 0, s>>>(d, iters);
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        double fl = 2.0 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        best = std::max(best, fl);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "fp64 peak: %s", cudaGetErrorString(e));
+    *tflops = best;
+    return SPAGXE_OK;
+}
+
+// mix / plus entry points are defined in mixplus.cu-style sections below once implemented
+extern "C" int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    (void)pcs; (void)k;
+    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
+}
+extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t, const int32_t *, const int32_t *, const double *, double, double,
+                              double, const double *) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxE_Plus is not implemented yet");
+}
+extern "C" int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *, const spagxe_params *, double *, spagxe_diag *) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
+}
+extern "C" int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *, const spagxe_params *, double *, spagxe_diag *) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxE_Plus is not implemented yet");
+}

@@ -1,0 +1,104 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/spagxe.h declares, fails
+loudly without a GPU, and the host-side mirror of the reference interface behaves like the R code."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from spagxecct_b200 import _lib, api, bedio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "spagxe.h")).read()
+    return sorted(set(re.findall(r"\b(spagxe_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 16
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/spagxe.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms
+    assert b"sm_100a" in _lib.load().spagxe_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.SpagxeError) as ei:
+        _lib.Context(0)
+    assert ei.value.code == _lib.ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "spagxecct_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".R")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("CPU oracle", "").replace("the oracle", "") or f == "harness.py", (dirpath, f)
+
+
+def test_check_input_resid_messages():
+    ids = [f"IID-{i}" for i in range(5)]
+    assert api.check_input_Resid(ids, ids, np.zeros(5)) is None
+    assert list(api.check_input_Resid(ids, ids[::-1], np.zeros(5))) == [4, 3, 2, 1, 0]
+    with pytest.raises(api.RStop, match="unique\\(pIDs\\) should be the same"):
+        api.check_input_Resid(ids, ids[:4] + ["x"], np.zeros(5))
+    with pytest.raises(api.RStop, match="should not have a duplicated element"):
+        api.check_input_Resid(ids, ids + ids[:1], np.zeros(5))
+    with pytest.raises(api.RStop, match="same length as input data"):
+        api.check_input_Resid(ids, ids, np.zeros(4))
+    # the bundled Pheno.mtx has IID, not ID: Phen.mtx$ID is NULL -> this is the stop() the reference hits
+    with pytest.raises(api.RStop, match="unique\\(pIDs\\)"):
+        api.check_input_Resid(None, ids, np.zeros(5))
+
+
+def test_pack_rows_roundtrip_and_reorder(oracle):
+    rng = np.random.default_rng(0)
+    n, m = 1003, 7
+    G = rng.integers(0, 3, (n, m)).astype(float)
+    G[rng.random((n, m)) < 0.05] = np.nan
+    rows = bedio.pack_rows(np.where(np.isnan(G), -1, G))
+    assert rows.size == m * ((n + 3) // 4)
+    back = oracle.bed_decode(rows, n)
+    assert np.array_equal(np.nan_to_num(back, nan=-1), np.nan_to_num(G, nan=-1))
+    perm = rng.permutation(n)[:600]
+    rows2 = bedio.reorder_samples(rows, n, m, perm)
+    back2 = oracle.bed_decode(rows2, 600)
+    assert np.array_equal(np.nan_to_num(back2, nan=-1), np.nan_to_num(G[perm], nan=-1))
+
+
+def test_bedfile_reader(tmp_path, golden_dir, oracle):
+    d = np.load(f"{golden_dir}/bed_SPAGxE.npz")
+    n = int(d["n"])
+    stem = tmp_path / "toy"
+    d["bed"].tofile(str(stem) + ".bed")
+    with open(str(stem) + ".fam", "w") as f:
+        for i in range(n):
+            f.write(f"IID-{i + 1} IID-{i + 1} 0 0 1 -9\n")
+    with open(str(stem) + ".bim", "w") as f:
+        for j, s in enumerate(d["snp_ids"]):
+            f.write(f"1\t{s}\t0\t{j + 1}\tA\tG\n")
+    bf = bedio.BedFile(str(stem) + ".bed")
+    assert (bf.n, bf.m) == (n, 100) and bf.snp_ids[0] == "SNP-1" and bf.sample_ids[1] == "IID-2"
+    assert np.array_equal(bf.rows_array(), d["bed"][3:])
+    with open(str(stem) + ".bed", "r+b") as f:
+        f.write(b"\x6c\x1b\x00")
+    with pytest.raises(ValueError, match="variant-major"):
+        bedio.BedFile(str(stem) + ".bed")
+
+
+def test_output_column_names_match_reference():
+    assert api.COLS_CCT == ["MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
+                            "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG"]  # R/SPAGxECCT.R:499-501
+    assert api.COLS_MIX[10:] == ["MAF.est.negative.num", "MAC"]                                      # :963-966
+    assert api.COLS_PLUS[2:4] == ["p.value.spaGxE.plus", "p.value.normGxE.plus"]                    # Plus :203-205

@@ -1,0 +1,220 @@
+"""GPU parity tests (-m gpu): the CUDA path, driven through the C ABI, against the CPU oracle on the
+same seeded inputs, against the reference's golden decode vectors, and through size-independent
+properties at larger sizes."""
+import numpy as np
+import pytest
+
+from spagxecct_b200 import SPAGxE_CCT, SPAGxE_CCT_one_SNP, _lib
+from spagxecct_b200.harness import get_resid
+from tests._data import assert_parity, make_geno, make_pheno, routes_from_cct_output, to_bed_rows
+
+pytestmark = pytest.mark.gpu
+
+P_COLS = [2, 3, 4, 5, 6]
+S_COLS = [7, 8, 9]
+
+
+def _bed_desc(ctx, rows, n, pitch=None):
+    pitch = pitch or (n + 3) // 4
+    return ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, rows.size // pitch, pitch)
+
+
+@pytest.mark.parametrize("name", ["SPAGxE", "SPAGxEmix", "SPAGxE_Plus"])
+def test_decode_and_counts_bit_exact_vs_plink_raw(gpu_ctx, golden_dir, name):
+    d = np.load(f"{golden_dir}/bed_{name}.npz")
+    rows = np.ascontiguousarray(d["bed"][3:]); raw = d["raw"]; n = int(d["n"])
+    g = _bed_desc(gpu_ctx, rows, n)
+    dec = gpu_ctx.bed_decode(g)
+    want = raw.astype(np.float64); want[raw < 0] = np.nan
+    assert np.array_equal(np.isnan(dec), np.isnan(want))
+    assert np.array_equal(np.nan_to_num(dec, nan=-1), np.nan_to_num(want, nan=-1))
+    # NA_real_ payload (1954) like R's matrix(NA)
+    cnt = gpu_ctx.bed_counts(g)
+    assert np.array_equal(cnt[:, 0], (raw == 2).sum(0)) and np.array_equal(cnt[:, 1], (raw < 0).sum(0))
+    assert np.array_equal(cnt[:, 2], (raw == 1).sum(0)) and np.array_equal(cnt[:, 3], (raw == 0).sum(0))
+
+
+def test_decode_missing_is_r_na_real(gpu_ctx):
+    G = np.array([[2.0, np.nan], [np.nan, 0.0], [1.0, 1.0], [0.0, 2.0], [2.0, 2.0]])
+    rows = to_bed_rows(G)
+    dec = gpu_ctx.bed_decode(_bed_desc(gpu_ctx, rows, 5))
+    assert np.array_equal(np.nan_to_num(dec, nan=-1), np.nan_to_num(G, nan=-1))
+    assert dec.view(np.uint64)[1, 0] == 0x7FF00000000007A2
+
+
+def test_c1_bundled_example_r_matrix_path(gpu_ctx, oracle, golden_dir):
+    """config 1: SPAGxE_CCT on data/Geno.mtx (INTSXP matrix) + Pheno.mtx, binary trait."""
+    d = np.load(f"{golden_dir}/c1.npz")
+    y = d["y"]
+    R = get_resid("binary", y, [d[k] for k in ["Cov1", "Cov2", "E", "PC1", "PC2", "PC3", "PC4"]])
+    cova = np.column_stack([d[k] for k in ["PC1", "PC2", "PC3", "PC4", "Cov1", "Cov2"]])
+    ids = [f"IID-{i + 1}" for i in range(len(y))]
+    G = d["geno"].astype(np.int32)
+    for eps in (0.001, 0.6):
+        res = SPAGxE_CCT("binary", Geno_mtx=(G, ids, list(d["snp_names"])), R=R, E=d["E"],
+                         Phen_mtx={"ID": ids, "Y": y}, Cova_mtx=cova, epsilon=eps, ctx=gpu_ctx, quiet=True)
+        ref, route, iters, rc = oracle.cct_matrix("binary", G.astype(float), R, d["E"], y, cova, epsilon=eps, g_is_int=True)
+        assert rc == 0
+        assert_parity(res.values, ref, P_COLS, S_COLS, label=f"C1 eps={eps}")
+        f, b, s = routes_from_cct_output(res.values, eps)
+        assert np.array_equal(b, (route & 2) > 0) and np.array_equal(s, (route & 4) > 0)
+        assert res.diag["n_branch_b"] == int(((route & 2) > 0).sum()) and res.diag["n_spa"] == int(((route & 4) > 0).sum())
+        assert res.diag["newton_iters"] == int(iters.sum())
+        assert res.rownames[7] == "rs8" and res.colnames[4] == "p.value.spaGxE.CCT.Wald"
+    # the float (REALSXP) matrix path gives identical numbers
+    res2 = SPAGxE_CCT("binary", Geno_mtx=(G.astype(np.float64), ids, None), R=R, E=d["E"],
+                      Phen_mtx={"ID": ids, "Y": y}, Cova_mtx=cova, epsilon=0.6, ctx=gpu_ctx, quiet=True)
+    assert np.array_equal(np.nan_to_num(res2.values, nan=-1), np.nan_to_num(res.values, nan=-1))
+    # the reference stops when Phen.mtx has IID instead of ID
+    from spagxecct_b200 import RStop
+    with pytest.raises(RStop):
+        SPAGxE_CCT("binary", Geno_mtx=(G, ids, None), R=R, E=d["E"], Phen_mtx={"IID": ids, "Y": y}, Cova_mtx=cova,
+                   ctx=gpu_ctx, quiet=True)
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+def test_c2_bed_path(gpu_ctx, oracle, golden_dir, trait, tmp_path):
+    """config 2: SPAGxE_CCT reading inst/GenoMat_SPAGxE.bed, phenotype per roxygen example 6 but seeded."""
+    d = np.load(f"{golden_dir}/bed_SPAGxE.npz")
+    n = int(d["n"])
+    rng = np.random.default_rng(20250101)
+    Cov1 = rng.standard_normal(n); Cov2 = rng.binomial(1, 0.5, n).astype(float); E = rng.standard_normal(n)
+    Y = rng.binomial(1, 0.5, n).astype(float) if trait == "binary" else rng.normal(1, 0.5, n)
+    R = get_resid(trait, Y, [Cov1, Cov2, E])
+    cova = np.column_stack([Cov1, Cov2])
+    stem = str(tmp_path / "GenoMat_SPAGxE")
+    d["bed"].tofile(stem + ".bed")
+    ids = [f"IID-{i + 1}" for i in range(n)]
+    open(stem + ".fam", "w").write("".join(f"{s} {s} 0 0 1 -9\n" for s in ids))
+    open(stem + ".bim", "w").write("".join(f"1\t{s}\t0\t{j + 1}\tA\tG\n" for j, s in enumerate(d["snp_ids"])))
+    for eps in (0.001, 0.3):
+        res = SPAGxE_CCT(trait, GenoFile=stem + ".bed", R=R, E=E, Phen_mtx={"ID": ids, "Y": Y}, Cova_mtx=cova,
+                         epsilon=eps, ctx=gpu_ctx, quiet=True)
+        ref, route, iters, rc = oracle.cct_bed(trait, d["bed"][3:], n, R, E, Y, cova, epsilon=eps)
+        assert rc == 0
+        assert_parity(res.values, ref, P_COLS, S_COLS, label=f"C2 {trait} eps={eps}")
+        f, b, s = routes_from_cct_output(res.values, eps)
+        assert np.array_equal(b, (route & 2) > 0) and np.array_equal(s, (route & 4) > 0)
+        assert res.rownames[:2] == ["SNP-1", "SNP-2"]
+    assert b.sum() >= 10  # eps=0.3 exercises branch B (Wald + CCT) on real fixture genotypes
+
+
+@pytest.mark.parametrize("trait,prev", [("binary", 0.1), ("binary", 0.01), ("quantitative", 0.0)])
+def test_synthetic_missing_flip_filter_branches(gpu_ctx, oracle, trait, prev):
+    """Edge cases no reference fixture exercises: missing calls, MAF > 0.5 flips,
+    min.maf filter incl. an exact tie, ragged N (not a multiple of 4/16/64), SPA-heavy rare variants,
+    strong marginal signals (branch B with SPA inside)."""
+    n = 6007
+    ph = make_pheno(n, 11, prevalence=prev or 0.1, trait=trait)
+    mafs = np.r_[np.full(6, 0.0004), [0.001, 0.002, 0.004, 0.008], np.linspace(0.01, 0.5, 40), np.full(10, 0.02)]
+    m = mafs.size
+    rng = np.random.default_rng(5)
+    miss = np.where(rng.random(m) < 0.5, 0.0, rng.random(m) * 0.08)
+    major = rng.random(m) < 0.5
+    effect = np.zeros(m); effect[-10:] = np.linspace(0.3, 1.2, 10)
+    G = make_geno(n, mafs, 12, miss_rates=miss, count_major=major, effect=effect, Y=ph["Y"])
+    # exact MAF == min.maf tie: (S/n)/2 == min.maf is NOT filtered (`MAF < min.maf`, ref :576)
+    G[:, 6] = 0.0; G[:12, 6] = 1.0
+    min_maf = (12.0 / n) / 2
+    G = np.ascontiguousarray(G)
+    rows = to_bed_rows(G)
+    gpu_ctx.set_vectors(ph["R"], ph["E"])
+    gpu_ctx.set_wald(_lib.TRAIT_BINARY if trait == "binary" else _lib.TRAIT_QUANTITATIVE, ph["Y"], ph["Cova"])
+    for eps in (0.001, 0.05):
+        out, diag = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows, n), dict(epsilon=eps, min_maf=min_maf))
+        ref, route, iters, rc = oracle.cct_bed(trait, rows, n, ph["R"], ph["E"], ph["Y"], ph["Cova"], epsilon=eps,
+                                               min_maf=min_maf)
+        assert rc == 0
+        worst = assert_parity(out, ref, P_COLS, S_COLS, label=f"synthetic {trait} eps={eps}")
+        f, b, s = routes_from_cct_output(out, eps)
+        assert np.array_equal(f, (route & 1) > 0) and np.array_equal(b, (route & 2) > 0) and np.array_equal(s, (route & 4) > 0)
+        assert diag["n_filtered"] == f.sum() and diag["newton_iters"] == iters.sum()
+    assert f.sum() >= 5 and b.sum() >= 8 and s.sum() >= 3
+    assert (out[:, 1] > 0).sum() >= 10          # missing.rate column exercised
+    assert (~np.isnan(out[6, 2]))               # the exact tie row is analysed, like `MAF < min.maf`
+    # dense double matrix input (R matrix with NA) == packed input
+    Gd, gd = np.asfortranarray(G), None
+    gd = gpu_ctx.geno_desc(_lib.GENO_F64, Gd.ctypes.data, n, m, n)
+    out2, _ = gpu_ctx.run_cct(gd, dict(epsilon=0.05, min_maf=min_maf))
+    assert np.array_equal(np.nan_to_num(out2, nan=-1), np.nan_to_num(out, nan=-1))
+
+
+def test_one_snp_entry_point_and_errors(gpu_ctx, oracle):
+    n = 3001
+    ph = make_pheno(n, 21)
+    G = make_geno(n, [0.2, 0.05], 22, miss_rates=[0.02, 0.0])
+    phen = {"Y": ph["Y"]}
+    v = SPAGxE_CCT_one_SNP("binary", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+    ref, *_ = oracle.cct_matrix("binary", G[:, :1], ph["R"], ph["E"], ph["Y"], ph["Cova"])
+    assert_parity(v[None, :], ref, P_COLS, S_COLS, label="one_SNP")
+    # imputed (non-integer) dosages are refused loudly, not silently rounded
+    g = G[:, 1].copy(); g[3] = 0.37
+    with pytest.raises(_lib.SpagxeError) as ei:
+        SPAGxE_CCT_one_SNP("binary", g, ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    # sample-count mismatch
+    with pytest.raises(_lib.SpagxeError) as ei:
+        gpu_ctx.run_cct(gpu_ctx.geno_desc(_lib.GENO_F64, G.ctypes.data, n - 1, 1, n - 1))
+    assert ei.value.code == _lib.ERR_ARG
+    with pytest.raises(NotImplementedError):
+        SPAGxE_CCT_one_SNP("survival", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+
+
+def test_extreme_pvalues_down_to_1e300(gpu_ctx, oracle):
+    """p-values must agree down to p = 1e-300 (north_star): a quantitative trait with a huge G x E effect."""
+    n = 20011
+    rng = np.random.default_rng(31)
+    ph = make_pheno(n, 32, trait="quantitative")
+    g = rng.binomial(2, 0.3, n).astype(float)
+    effs = [0.0, 0.3, 0.8, 1.3]
+    G = np.column_stack([g] * len(effs))
+    outs, refs = [], []
+    for k, b in enumerate(effs):
+        Y = ph["Y"] + b * g * ph["E"] + 0.2 * b * g
+        R = get_resid("quantitative", Y, [ph["Cova"][:, 0], ph["Cova"][:, 1], ph["E"]])
+        gpu_ctx.set_vectors(R, ph["E"]); gpu_ctx.set_wald(_lib.TRAIT_QUANTITATIVE, Y, ph["Cova"])
+        rows = to_bed_rows(G[:, k:k + 1])
+        for eps in (0.0, 1.0):  # branch A and branch B
+            out, _ = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows, n), dict(epsilon=eps))
+            ref, *_ = oracle.cct_bed("quantitative", rows, n, R, ph["E"], Y, ph["Cova"], epsilon=eps)
+            outs.append(out); refs.append(ref)
+    out = np.vstack(outs); ref = np.vstack(refs)
+    assert_parity(out, ref, P_COLS, S_COLS, label="extreme")
+    assert np.nanmin(ref[:, [2, 3, 5]][ref[:, [2, 3, 5]] > 0]) < 1e-250
+
+
+def test_properties_at_scale(gpu_ctx):
+    """Size-independent properties at a size the oracle would take minutes for (N=100k x 2,048 SNPs):
+    (a) device-resident packed input == host input; (b) SNP order permutation permutes the output rows;
+    (c) counting the other allele (2-g) gives the same MAF and p-values (flip symmetry, ref :567-570)."""
+    n, m = 100_003, 2048
+    ph = make_pheno(n, 41, prevalence=0.01)
+    rng = np.random.default_rng(42)
+    mafs = rng.uniform(0.001, 0.5, m)
+    G = (rng.random((n, m)) < mafs).astype(np.int8) + (rng.random((n, m)) < mafs).astype(np.int8)
+    miss = rng.random((n, m)) < (rng.random(m) * 0.03 * (rng.random(m) < 0.5))
+    Gf = G.astype(np.float64); Gf[miss] = np.nan
+    rows = to_bed_rows(Gf)
+    gpu_ctx.set_vectors(ph["R"], ph["E"]); gpu_ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+    base, diag = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows, n))
+    assert diag["n_spa"] > 20 and diag["n_branch_b"] >= 1
+    rb = (n + 3) // 4
+    perm = rng.permutation(m)
+    rows_p = np.ascontiguousarray(rows.reshape(m, rb)[perm]).ravel()
+    outp, _ = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows_p, n))
+    assert np.array_equal(np.nan_to_num(outp, nan=-1), np.nan_to_num(base[perm], nan=-1))
+    rows_f = to_bed_rows(2 - Gf)
+    outf, _ = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows_f, n))
+    ok = ~np.isnan(base[:, 2]) & (np.abs(base[:, 0] - 0.5) > 1e-9)
+    assert np.allclose(outf[ok, 0], base[ok, 0], rtol=1e-13) and np.array_equal(outf[:, 1], base[:, 1])
+    lp = np.abs(np.log10(outf[ok][:, P_COLS]) - np.log10(base[ok][:, P_COLS]))
+    assert np.nanmax(lp / np.maximum(np.abs(np.log10(base[ok][:, P_COLS])), 1e-3)) < 1e-6
+    # device-resident rows with a 128-byte aligned pitch
+    import torch
+    pitch = (rb + 127) // 128 * 128
+    dev = torch.full((m, pitch), 0, dtype=torch.uint8, device="cuda")
+    dev[:, :rb] = torch.from_numpy(rows.reshape(m, rb)).cuda()
+    torch.cuda.synchronize()
+    gd = gpu_ctx.geno_desc(_lib.GENO_BED, dev.data_ptr(), n, m, pitch, _lib.LOC_DEVICE)
+    outd, _ = gpu_ctx.run_cct(gd)
+    assert np.array_equal(np.nan_to_num(outd, nan=-1), np.nan_to_num(base, nan=-1))
