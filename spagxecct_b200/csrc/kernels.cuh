@@ -596,24 +596,26 @@ struct BShared {  // static shared state of the branch-B kernel
 // dynamic smem: xs[kBTile][q+1] (x row, z in column q), ws[kBTile]
 __host__ __device__ inline size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
 
+__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &z,
+                                            double &dev, int &bad);
+
 // One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
 // normal equations land in sh.NE / sh.rhs of EVERY CTA.  Returns the cluster-wide deviance (binary)
 // or residual sum of squares (lm second pass).  pass0: eta from mustart (ref glm.fit), else x.beta.
-template <class GFun>
+template <int NS, class GFun>
 __device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n,
                             int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile, BShared &sh,
                             const ClusterRed &red, int *invalid) {
     namespace cg = cooperative_groups;
-    const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
     const int p = wd.p, qs = (q + 1) | 1;  // odd row stride: conflict-free 64-bit reads
     double *xs = tile, *ws = tile + (size_t)kBTile * qs;
     const int nent = q * (q + 3) / 2;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     // entries grp, grp + kBGroups, ... belong to this warp; all lanes of a warp share (a,b)
-    int ea[kBSlots], eb[kBSlots];
-    double acc[kBSlots];
+    int ea[NS], eb[NS];
+    double acc[NS];
 #pragma unroll
-    for (int k = 0; k < kBSlots; k++) {
+    for (int k = 0; k < NS; k++) {
         acc[k] = 0; ea[k] = -1; eb[k] = 0;
         int e = grp + k * kBGroups;
         if (e < nent) {
@@ -634,36 +636,10 @@ __device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__
             xr[0] = 1.0;
             for (int c = 0; c < p; c++) xr[1 + c] = wd.cova[i + (int64_t)c * n];
             xr[p + 1] = ev; xr[p + 2] = g; xr[p + 3] = ev * g;
-            double w2 = 1.0, z = y;
-            if (wd.trait == 1) {
-                double eta;
-                if (pass0) {
-                    double mus = (y + 0.5) / 2;
-                    eta = log(mus / (1 - mus));
-                } else {
-                    eta = 0;
-                    for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
-                }
-                const bool clampd = (eta > THRESH || eta < MTHRESH);
-                const double ee = exp(eta);
-                const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
-                const double mu = tmp / (1 + tmp);
-                if (!(mu > 0 && mu < 1)) bad = 1;
-                double d;
-                if (y == 1.0) d = log(1.0 / mu);                 // y*log(y/mu), y_log_y(0,.) = 0
-                else if (y == 0.0) d = log(1.0 / (1 - mu));
-                else d = y * log(y / mu) + (1 - y) * log((1 - y) / (1 - mu));
-                dev += 2 * d;
-                const double varmu = mu * (1 - mu);
-                const double opexp = 1 + ee;
-                const double mev = clampd ? DBL_EPSILON : ee / (opexp * opexp);
-                z = eta + (y - mu) / mev;
-                w2 = (mev * mev) / varmu;
-            } else if (!pass0) {  // lm second pass: residual sum of squares
-                double fit = 0;
-                for (int c = 0; c < q; c++) fit += xr[c] * sh.beta[c];
-                dev += (y - fit) * (y - fit);
-            }
+            double eta = 0;
+            if (!pass0) for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
+            double w2, z;
+            irls_sample(wd.trait, pass0, y, eta, w2, z, dev, bad);
             xr[q] = z;
             ws[threadIdx.x] = w2;
         }
@@ -672,13 +648,13 @@ __device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__
             const double w = ws[sidx];
             const double *xr = xs + (size_t)sidx * qs;
 #pragma unroll
-            for (int k = 0; k < kBSlots; k++)
+            for (int k = 0; k < NS; k++)
                 if (ea[k] >= 0) acc[k] = fma(w * xr[ea[k]], xr[eb[k]], acc[k]);
         }
     }
     // warp totals -> CTA partial normal equations -> cluster totals (rank order)
 #pragma unroll
-    for (int k = 0; k < kBSlots; k++) {
+    for (int k = 0; k < NS; k++) {
         double t = warp_sum(acc[k]);
         int e = grp + k * kBGroups;
         if (lane == 0 && e < nent) sh.ne_part[e] = t;
@@ -692,6 +668,105 @@ __device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__
         for (a = 0; a < q; a++) { int len = q + 1 - a; if (rem < len) break; rem -= len; }
         const int b = a + rem;
         if (b == q) sh.rhs[a] = t; else { sh.NE[a][b] = t; sh.NE[b][a] = t; }
+    }
+    cl.sync();
+    double v[2] = {dev, (double)bad};
+    red.template sum<2>(v);
+    *invalid = v[1] > 0;
+    return v[0];
+}
+
+// Per-sample IRLS working quantities (glm.fit binomial/logit restated).
+__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &z,
+                                            double &dev, int &bad) {
+    const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
+    if (trait == 1) {
+        double eta = eta_in;
+        if (pass0) { double mus = (y + 0.5) / 2; eta = log(mus / (1 - mus)); }
+        const bool clampd = (eta > THRESH || eta < MTHRESH);
+        const double ee = exp(eta);
+        const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
+        const double opexp = 1 + ee;
+        const double mu = tmp / (1 + tmp);
+        if (!(mu > 0 && mu < 1)) bad = 1;
+        double d;
+        if (y == 1.0) d = -log(mu);                // y*log(y/mu); y_log_y(0, .) = 0
+        else if (y == 0.0) d = -log(1 - mu);
+        else d = y * log(y / mu) + (1 - y) * log((1 - y) / (1 - mu));
+        dev += 2 * d;
+        const double varmu = mu * (1 - mu);
+        const double mev = clampd ? DBL_EPSILON : ee / (opexp * opexp);
+        z = eta + (y - mu) / mev;
+        w2 = (mev * mev) / varmu;
+    } else {
+        w2 = 1.0; z = y;
+        if (!pass0) dev += (y - eta_in) * (y - eta_in);  // lm second pass: residual sum of squares
+    }
+}
+
+// Register-accumulator variant for narrow designs (Q = p + 4 <= 8): every thread keeps the whole upper
+// triangle of X'WX (+ X'Wz) for its own samples in registers; no shared-memory tile, no per-tile barrier.
+template <int Q, class GFun>
+__device__ double wald_pass_reg(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n,
+                                int64_t i_lo, int64_t i_hi, bool pass0, double *tile, BShared &sh,
+                                const ClusterRed &red, int *invalid) {
+    namespace cg = cooperative_groups;
+    constexpr int NENT = Q * (Q + 3) / 2;
+    constexpr int P = Q - 4;
+    double acc[NENT];
+#pragma unroll
+    for (int e = 0; e < NENT; e++) acc[e] = 0;
+    double beta[Q];
+#pragma unroll
+    for (int c = 0; c < Q; c++) beta[c] = sh.beta[c];
+    double dev = 0;
+    int bad = 0;
+    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        double x[Q];
+        const double g = gf(i), ev = E[i], y = wd.Y[i];
+        x[0] = 1.0;
+#pragma unroll
+        for (int c = 0; c < P; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
+        x[P + 1] = ev; x[P + 2] = g; x[P + 3] = ev * g;
+        double eta = 0;
+        if (!pass0) {
+#pragma unroll
+            for (int c = 0; c < Q; c++) eta += x[c] * beta[c];
+        }
+        double w2, z;
+        irls_sample(wd.trait, pass0, y, eta, w2, z, dev, bad);
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < Q; a++) {
+            const double wa = w2 * x[a];
+#pragma unroll
+            for (int b = a; b < Q; b++) acc[e++] = fma(wa, x[b], acc[e]);
+            acc[e++] = fma(wa, z, acc[e]);
+        }
+    }
+    // warp totals -> per-warp rows in the (otherwise unused) tile -> CTA partial -> cluster total
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < NENT; e++) {
+        const double t = warp_sum(acc[e]);
+        if (lane == 0) tile[warp * NENT + e] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < NENT) {
+        double t = 0;
+        for (int w = 0; w < nw; w++) t += tile[w * NENT + threadIdx.x];
+        sh.ne_part[threadIdx.x] = t;
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (threadIdx.x < NENT) {
+        double t = 0;
+        for (unsigned r = 0; r < cl.num_blocks(); r++) t += cl.map_shared_rank(sh.ne_part, r)[threadIdx.x];
+        int a = 0, rem = threadIdx.x;
+        for (a = 0; a < Q; a++) { int len = Q + 1 - a; if (rem < len) break; rem -= len; }
+        const int b = a + rem;
+        if (b == Q) sh.rhs[a] = t; else { sh.NE[a][b] = t; sh.NE[b][a] = t; }
     }
     cl.sync();
     double v[2] = {dev, (double)bad};
@@ -716,6 +791,29 @@ __device__ __forceinline__ void wald_solve(BShared &sh, int q) {
     __syncthreads();
 }
 
+template <class GFun>
+__device__ __forceinline__ double wald_pass_any(const GFun &gf, const WaldData &wd, const double *E, int64_t n,
+                                                int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile,
+                                                BShared &sh, const ClusterRed &red, int *invalid) {
+    switch (q) {
+        case 4: return wald_pass_reg<4>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 5: return wald_pass_reg<5>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 6: return wald_pass_reg<6>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        default: break;
+    }
+    const int ns = (q * (q + 3) / 2 + kBGroups - 1) / kBGroups;
+    switch (ns) {
+        case 3: return wald_pass<3>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 4: return wald_pass<4>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 5: return wald_pass<5>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 6: return wald_pass<6>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 7: return wald_pass<7>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 8: return wald_pass<8>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 9: return wald_pass<9>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        default: return wald_pass<kBSlots>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+    }
+}
+
 // Cluster-collective Wald p-value of E:g (ref :636-662): glm.fit IRLS for binary, lm for quantitative.
 template <class GFun>
 __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, int64_t i_lo, int64_t i_hi,
@@ -724,13 +822,13 @@ __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, i
     *fail = 0;
     int invalid;
     if (wd.trait == 1) {
-        double devold = wald_pass(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+        double devold = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
         double se2 = 0;
         for (int it = 1; it <= 25; it++) {
             wald_solve(sh, q);
             if (!sh.ok) { *fail = 1; return d_na_real(); }
             se2 = sh.se2;   // covariance of the WLS just solved = the one summary.glm reports on convergence
-            double dev = wald_pass(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+            double dev = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
             if (!isfinite(dev) || invalid) { *fail = 2; return d_na_real(); }
             if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) break;
             devold = dev;
@@ -738,11 +836,11 @@ __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, i
         const double zst = sh.beta[q - 1] / sqrt(se2);
         return 2 * d_pnorm(-fabs(zst), true);
     }
-    wald_pass(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+    wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
     wald_solve(sh, q);
     if (!sh.ok) { *fail = 1; return d_na_real(); }
     const double il = sh.se2, bl = sh.beta[q - 1];
-    double rss = wald_pass(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+    double rss = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
     const double rdf = (double)(n - q);
     const double se = sqrt(il * (rss / rdf));
     return d_pt2(bl / se, rdf);

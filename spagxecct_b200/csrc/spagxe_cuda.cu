@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -221,7 +222,7 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     ctx->vec_mode = mode;
     // SNP-invariant quadrature of the SPA vector (R.new): only worth it when N >> number of nodes
     const double *rv = (mode == 0) ? ctx->d_V : ctx->d_Rn;
-    ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes;
+    ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes && !getenv("SPAGXE_EXACT_SPA");  // env: A/B switch for tests
     if (ctx->quad_on) {
         cudaStream_t s = ctx->stream();
         CU(cudaMemsetAsync(ctx->quad.wfix, 0, sizeof(long long) * kQBins * kQNodes, s));
