@@ -147,6 +147,14 @@ int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *geno, int64_t *counts)
  * GRAB::GRAB.ReadGeno(...)$GenoMat returns (R/SPAGxECCT.R:484-487).                       */
 int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *geno, double *out_host);
 
+/* raw outputs of the fused unpack+score pass (K1+K2) for M SNPs, all HOST arrays of length M:
+ *   D0,D1 = sum over non-missing of dosage*R, dosage*V;  T0,T1 = sum over missing of R, V;
+ *   asum = n_het + 2 n_homA1;  nmiss = #missing.  impl: 0 = tensor-core kernel (default), 1 = fp64
+ *   CUDA-core kernel.  Replaces the vector passes at R/SPAGxECCT.R:557-560, :582, :591; exposed so
+ *   that the two kernels can be checked against each other and against the oracle.            */
+int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *geno, int impl, double *D0, double *D1, double *T0,
+                       double *T1, int32_t *asum, int32_t *nmiss);
+
 /* measured device peaks used by bench.py for the SPA stage's fp64 fraction (DFMA loop)   */
 int spagxe_measure_fp64_peak(spagxe_ctx *ctx, double *tflops);
 

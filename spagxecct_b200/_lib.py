@@ -21,7 +21,7 @@ EXPORTS = [
     "spagxe_ctx_create", "spagxe_ctx_destroy", "spagxe_last_error", "spagxe_ctx_set_stream", "spagxe_version",
     "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
     "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
-    "spagxe_measure_fp64_peak",
+    "spagxe_measure_fp64_peak", "spagxe_score_stats",
 ]
 
 
@@ -85,6 +85,7 @@ def load():
     L.spagxe_bed_counts.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
     L.spagxe_bed_decode.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
     L.spagxe_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.spagxe_score_stats.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_int] + [C.c_void_p] * 6
     _lib = L
     return L
 
@@ -192,6 +193,14 @@ class Context:
         out = np.empty((geno.n_samples, geno.n_snps), dtype=np.float64, order="F")
         self._chk(self.L.spagxe_bed_decode(self.h, C.byref(geno), out.ctypes.data))
         return out
+
+    def score_stats(self, geno, impl=0):
+        m = geno.n_snps
+        d = [np.empty(m) for _ in range(4)]
+        a = np.empty(m, dtype=np.int32); nm = np.empty(m, dtype=np.int32)
+        self._chk(self.L.spagxe_score_stats(self.h, C.byref(geno), int(impl), *[x.ctypes.data for x in d],
+                                            a.ctypes.data, nm.ctypes.data))
+        return dict(D0=d[0], D1=d[1], T0=d[2], T1=d[3], asum=a, nmiss=nm)
 
     def fp64_peak_tflops(self):
         v = C.c_double()

@@ -1,0 +1,349 @@
+// score_tc.cuh -- K1+K2 on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Why tensor cores for a byte-stream kernel: one SNP row is N/4 bytes but needs >= 2N fp64 adds, so
+// a CUDA-core kernel is issue-bound at a few % of HBM bandwidth (measured: score v1 = 4 %).  The
+// contraction  sum_i dosage_i * R_i  is exact in integers once R is written in fixed point:
+//     R_i * 2^s = sum_k d_ik 256^k,  d_ik in [-128,127]  (7 balanced base-256 digits = 56 bits)
+// so   sum_i g_i R_i = 2^-s sum_k 256^k (sum_i g_i d_ik)   with int8 x int8 -> int32 MMAs
+// (tcgen05.mma kind::i8, exact for N < 8.4 M samples), and the result is bit-identical for every
+// tiling, split and GPU count.
+//
+//   A operand (M = 128 SNP rows x K samples, int8): expanded from the packed PLINK codes by the
+//     expander warps with one PRMT per 4 samples and written straight into tensor memory
+//     (tcgen05.st) -- it never touches shared memory.  Thread t of the warp owns SNP row t (TMEM
+//     lane t).  Two A matrices per tile: -dosage (00 -> -2, 10 -> -1) and missing (01 -> 1).
+//     PRMT trick: a selector nibble holds two 2-bit codes [partner | target<<2]; bits 0-2 index an
+//     8-byte LUT {a,a,a,a,b,b,b,b} and bit 3 switches to "replicate the sign of the selected byte",
+//     so   dosage LUT a = 0xFE, b = 0x00:  00 -> 0xFE (-2), 10 -> sign(0xFE) = 0xFF (-1), 01/11 -> 0
+//          missing LUT a = 0x00, b = 0x01:  01 -> 1, 11 -> sign(0x01) = 0, 00/10 -> 0
+//     without any masking; even samples use the selector x << 2.
+//   B operand (K samples x N = 16 columns, int8, K-major, no swizzle) lives in global memory already
+//     tiled in the UMMA canonical layout, one 8 KB block per 512 samples, so one cp.async.bulk per
+//     stage brings it in.  Columns: 7 digits of R, a column of ones (allele / missing counts),
+//     7 digits of V, one zero column.  Samples >= N have all-zero rows: no bounds logic anywhere.
+//   Packed genotypes arrive by TMA (cp.async.bulk.tensor.2d, 128 rows x 128 B, 128B swizzle so that
+//     the thread-per-row 16-byte reads are bank-conflict free).
+//   D accumulators: 2 x (128 lanes x 16 columns) int32 in TMEM; read back with tcgen05.ld at the end
+//     of a work item and added to per-row int64 totals in global memory (integer atomics commute).
+#pragma once
+#include <cuda.h>
+#include "kernels.cuh"
+
+namespace spagxe {
+
+constexpr int kTcRows = 128;          // SNP rows per work item (UMMA M)
+constexpr int kTcTileSamples = 512;   // samples per pipeline stage
+constexpr int kTcTileBytes = kTcTileSamples / 4;   // 128 packed bytes per row per stage
+constexpr int kTcBTileBytes = kTcTileSamples * 16; // 8192 B of B per stage
+constexpr int kTcStages = 6;
+constexpr int kTcExpWarps = 8;
+constexpr int kTcThreads = (kTcExpWarps + 2) * 32;  // + TMA producer warp + MMA warp
+constexpr int kTcDigits = 7;
+constexpr int kTcStageBytes = kTcRows * kTcTileBytes + kTcBTileBytes;  // 24576
+constexpr size_t kTcSmemBytes = (size_t)kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// TMEM columns: A buffers 2 x 128, accumulators at 256 / 272
+constexpr uint32_t kTcColAcc = 256;
+
+struct BmatInfo { int sR, sV; double maxR, maxV; };
+
+// ---- B matrix builder -----------------------------------------------------------------------
+__device__ __forceinline__ int64_t tc_b_offset(int64_t i, int col) {
+    const int64_t tile = i / kTcTileSamples;
+    const int ti = (int)(i % kTcTileSamples);
+    const int chunk = ti >> 6, s = ti & 63, q = s >> 3, r = s & 7;
+    const int reg = 2 * q + ((r & 1) ? 0 : 1), b = r >> 1;
+    const int kin = chunk * 64 + 4 * reg + b;
+    const int kb = kin >> 4, kk = kin & 15;
+    return tile * kTcBTileBytes + (int64_t)kb * 256 + (col >> 3) * 128 + (col & 7) * 16 + kk;
+}
+__global__ void __launch_bounds__(1024) k_tc_scale(const double *__restrict__ R, const double *__restrict__ V,
+                                                   int64_t n, BmatInfo *info) {
+    __shared__ double s0[32], s1[32];
+    double a = 0, b = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { a = fmax(a, fabs(R[i])); b = fmax(b, fabs(V[i])); }
+    for (int o = 16; o > 0; o >>= 1) { a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o)); }
+    if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = a; s1[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; k++) { a = fmax(a, s0[k]); b = fmax(b, s1[k]); }
+        info->maxR = a; info->maxV = b;
+        // |x| * 2^s < 2^54  (7 balanced digits cover +-0.996 * 2^55)
+        info->sR = (a > 0 && isfinite(a)) ? 53 - ilogb(a) : 0;
+        info->sV = (b > 0 && isfinite(b)) ? 53 - ilogb(b) : 0;
+    }
+}
+__global__ void k_tc_build_b(const double *__restrict__ R, const double *__restrict__ V, int64_t n,
+                             const BmatInfo *__restrict__ info, int8_t *__restrict__ B) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long xr = __double2ll_rn(scalbn(R[i], info->sR));
+    long long xv = __double2ll_rn(scalbn(V[i], info->sV));
+#pragma unroll
+    for (int k = 0; k < kTcDigits; k++) {
+        int dr = (int)((xr + 128) & 255) - 128; xr = (xr - dr) >> 8;
+        int dv = (int)((xv + 128) & 255) - 128; xv = (xv - dv) >> 8;
+        B[tc_b_offset(i, k)] = (int8_t)dr;
+        B[tc_b_offset(i, 8 + k)] = (int8_t)dv;
+    }
+    B[tc_b_offset(i, 7)] = 1;
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();  // a protocol bug must fault, not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], kind::i8, M=128, N=16, K=32
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum), "r"(0u) : "memory");
+}
+// K-major, no-swizzle shared-memory descriptor: 8x16B core matrices, LBO = 256 B (next 16 k), SBO = 128 B (next 8 n)
+__device__ __forceinline__ uint64_t tc_bdesc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(256 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    return d;
+}
+constexpr uint32_t kTcIdesc = (2u << 4) /*D = s32*/ | (1u << 7) /*A = s8*/ | (1u << 10) /*B = s8*/ |
+                              ((16u >> 3) << 17) /*N*/ | ((128u >> 4) << 24) /*M*/;
+
+// ---- the kernel ---------------------------------------------------------------------------------
+// work item = (row tile rt, k split ks): rows [128 rt, +128), sample tiles [ks*tiles_per_split, ...)
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+           int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = sbase + kTcStages * kTcStageBytes;
+    // barriers (8 B each): full[6], empty[6], afull[2], aempty[2], accfull, accempty, tmem slot
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (kTcStages + s); };
+    auto bar_afull = [&](int b) { return bars + 8u * (2 * kTcStages + b); };
+    auto bar_aempty = [&](int b) { return bars + 8u * (2 * kTcStages + 2 + b); };
+    const uint32_t bar_accfull = bars + 8u * (2 * kTcStages + 4), bar_accempty = bars + 8u * (2 * kTcStages + 5);
+    const uint32_t tmem_slot = bars + 8u * (2 * kTcStages + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), kTcExpWarps + 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(bar_afull(b), kTcExpWarps); mbar_init(bar_aempty(b), 1); }
+        mbar_init(bar_accfull, 1); mbar_init(bar_accempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kTcExpWarps) {  // TMEM allocation (whole 512 columns: one CTA per SM by construction)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n_items = n_row_tiles * n_splits;
+    if (warp == kTcExpWarps) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t f = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int rt = item / n_splits, ks = item % n_splits;
+                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+                for (int t = t0; t < t1; t++, f++) {
+                    const int s = f % kTcStages;
+                    mbar_wait(bar_empty(s), ((f / kTcStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_full(s), kTcStageBytes);
+                    const uint32_t dst = sbase + s * kTcStageBytes;
+                    tma_load_2d(dst, &bedmap, t * kTcTileBytes, rt * kTcRows, bar_full(s));
+                    bulk_load_1d(dst + kTcRows * kTcTileBytes, Bmat + (int64_t)t * kTcBTileBytes, kTcBTileBytes, bar_full(s));
+                }
+            }
+        }
+    } else if (warp == kTcExpWarps + 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t f = 0, g = 0, it_count = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ks = item % n_splits;
+                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+                if (t1 <= t0) continue;
+                mbar_wait(bar_accempty, (it_count & 1) ^ 1);  // epilogue of the previous item has drained D
+                tc_fence_after();
+                uint32_t accum = 0;
+                for (int t = t0; t < t1; t++, f++) {
+                    const int s = f % kTcStages;
+                    mbar_wait(bar_full(s), (f / kTcStages) & 1);
+                    const uint32_t bsm = sbase + s * kTcStageBytes + kTcRows * kTcTileBytes;
+                    for (int hs = 0; hs < 2; hs++, g++) {
+                        const int buf = g & 1;
+                        mbar_wait(bar_afull(buf), (g >> 1) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const uint64_t bd = tc_bdesc(bsm + (uint32_t)(((hs * 4 + c4) * 4 + 2 * j) * 256));
+                                const uint32_t acol = (uint32_t)(buf * 128 + c4 * 16 + j * 8);
+                                tc_mma_i8_ts(tmem_base + kTcColAcc, tmem_base + acol, bd, kTcIdesc, accum);
+                                tc_mma_i8_ts(tmem_base + kTcColAcc + 16, tmem_base + acol + 64, bd, kTcIdesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc_commit(bar_aempty(buf));
+                    }
+                    tc_commit(bar_empty(s));
+                }
+                tc_commit(bar_accfull);
+                it_count++;
+            }
+        }
+    } else {
+        // ================= expanders (+ epilogue on warps 0-3) =================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;  // SNP row inside the tile == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t swz = (uint32_t)(row & 7);
+        uint32_t f = 0, g = 0, it_count = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int rt = item / n_splits, ks = item % n_splits;
+            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            if (t1 <= t0) continue;
+            for (int t = t0; t < t1; t++, f++) {
+                const int s = f % kTcStages;
+                mbar_wait(bar_full(s), (f / kTcStages) & 1);
+                const uint32_t rowaddr = sbase + s * kTcStageBytes + (uint32_t)row * kTcTileBytes;
+                for (int hs = 0; hs < 2; hs++, g++) {
+                    const int buf = g & 1;
+                    mbar_wait(bar_aempty(buf), ((g >> 1) & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const int c4 = half * 2 + c;          // chunk inside this A buffer
+                        const uint32_t chunk = (uint32_t)(hs * 4 + c4);  // chunk inside the stage
+                        uint32_t x[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                                     : "r"(rowaddr + ((chunk ^ swz) << 4)));
+                        uint32_t d[16], m[16];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t so_lo = x[k], se_lo = x[k] << 2, so_hi = x[k] >> 16, se_hi = x[k] >> 14;
+                            d[4 * k + 0] = prmt(0xFEFEFEFEu, 0u, so_lo); m[4 * k + 0] = prmt(0u, 0x01010101u, so_lo);
+                            d[4 * k + 1] = prmt(0xFEFEFEFEu, 0u, se_lo); m[4 * k + 1] = prmt(0u, 0x01010101u, se_lo);
+                            d[4 * k + 2] = prmt(0xFEFEFEFEu, 0u, so_hi); m[4 * k + 2] = prmt(0u, 0x01010101u, so_hi);
+                            d[4 * k + 3] = prmt(0xFEFEFEFEu, 0u, se_hi); m[4 * k + 3] = prmt(0u, 0x01010101u, se_hi);
+                        }
+                        tmem_st16(lane_addr + (uint32_t)(buf * 128 + c4 * 16), d);
+                        tmem_st16(lane_addr + (uint32_t)(buf * 128 + 64 + c4 * 16), m);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_afull(buf));
+                }
+                if (lane == 0) mbar_arrive(bar_empty(s));
+            }
+            if (half == 0) {
+                // epilogue: D (128 lanes x 2 x 16 int32) -> global int64 totals
+                mbar_wait(bar_accfull, it_count & 1);
+                tc_fence_after();
+                uint32_t dd[16], dm[16];
+                tmem_ld16(lane_addr + kTcColAcc, dd);
+                tmem_ld16(lane_addr + kTcColAcc + 16, dm);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty);
+                const int grow = rt * kTcRows + row;
+                if (grow < m_chunk) {
+                    unsigned long long *dst = (unsigned long long *)(acc + (int64_t)grow * 32);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        if (k != 15) {
+                            atomicAdd(dst + k, (unsigned long long)(long long)(int)dd[k]);
+                            atomicAdd(dst + 16 + k, (unsigned long long)(long long)(int)dm[k]);
+                        }
+                    }
+                }
+            }
+            it_count++;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kTcExpWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// exact integer recombination: value = sum_k acc_k 256^k (two int64 halves -> one rounding), times 2^-s
+__device__ __forceinline__ double tc_combine(const long long *a, int s) {
+    const long long lo = a[0] + (a[1] << 8) + (a[2] << 16) + (a[3] << 24);
+    const long long hi = a[4] + (a[5] << 8) + (a[6] << 16);
+    return scalbn((double)hi * 4294967296.0 + (double)lo, -s);
+}
+__global__ void k_score_tc_reduce(const long long *__restrict__ acc, int m_chunk, const BmatInfo *__restrict__ info, SnpStats st) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_chunk) return;
+    const long long *a = acc + (int64_t)j * 32;
+    // dosage accumulators hold -sum(dosage * digit)
+    st.D0[j] = -tc_combine(a, info->sR);
+    st.D1[j] = -tc_combine(a + 8, info->sV);
+    st.asum[j] = (int)(-a[7]);
+    st.T0[j] = tc_combine(a + 16, info->sR);
+    st.T1[j] = tc_combine(a + 24, info->sV);
+    st.nmiss[j] = (int)a[23];
+}
+
+}  // namespace spagxe

@@ -17,6 +17,7 @@
 
 #include "../../include/spagxe.h"
 #include "score.cuh"
+#include "score_tc.cuh"
 
 using namespace spagxe;
 
@@ -48,6 +49,9 @@ struct spagxe_ctx {
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
     SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
     Quad quad = {nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
+    // tensor-core score pass
+    int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
+    void *encode_tiled = nullptr; bool use_tc = true;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     // pinned staging
@@ -133,6 +137,19 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if ((e = cudaMalloc((void **)&ctx->quad.w, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.range, sizeof(double) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->d_binfo, sizeof(BmatInfo))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_score_tc)", e);
+    {
+        cudaDriverEntryPointQueryResult qres;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ctx->encode_tiled)
+            return bail("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)", e == cudaSuccess ? cudaErrorUnknown : e);
+    }
+    {
+        const char *sv = getenv("SPAGXE_SCORE");   // "v1": fp64 CUDA-core kernel (A/B switch for tests)
+        ctx->use_tc = !(sv && strcmp(sv, "v1") == 0);
+    }
     *out = ctx;
     return SPAGXE_OK;
 }
@@ -147,6 +164,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list);
+    cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
@@ -220,6 +238,17 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     k_vec_prep2<<<1, 1024, 0, ctx->stream()>>>(ctx->d_R, ctx->d_E, d_Rn_in, ctx->n, mode, ctx->d_Rn, ctx->d_V, ctx->d_vc);
     LAUNCH_CHECK();
     ctx->vec_mode = mode;
+    {   // fixed-point int8 digit matrix B of (R, V) for the tensor-core score pass
+        cudaStream_t s = ctx->stream();
+        const int64_t n_tiles = (ctx->n + kTcTileSamples - 1) / kTcTileSamples;
+        const int64_t need = n_tiles * kTcBTileBytes;
+        if (need > ctx->cap_bmat) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_bmat, need)); ctx->cap_bmat = need; }
+        CU(cudaMemsetAsync(ctx->d_bmat, 0, need, s));
+        k_tc_scale<<<1, 1024, 0, s>>>(ctx->d_R, ctx->d_V, ctx->n, ctx->d_binfo);
+        LAUNCH_CHECK();
+        k_tc_build_b<<<(unsigned)((ctx->n + 255) / 256), 256, 0, s>>>(ctx->d_R, ctx->d_V, ctx->n, ctx->d_binfo, ctx->d_bmat);
+        LAUNCH_CHECK();
+    }
     // SNP-invariant quadrature of the SPA vector (R.new): only worth it when N >> number of nodes
     const double *rv = (mode == 0) ? ctx->d_V : ctx->d_Rn;
     ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes && !getenv("SPAGXE_EXACT_SPA");  // env: A/B switch for tests
@@ -417,7 +446,46 @@ static SnpStats stats_view(spagxe_ctx *ctx, int cap) {
     return st;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int launch_score_tc(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
+    cudaStream_t s = ctx->stream();
+    const int m_pad = (int)round_up(mc, kTcRows);
+    if (m_pad > ctx->cap_acc) {
+        CU(cudaStreamSynchronize(s));
+        CU(dev_realloc(&ctx->d_acc, (size_t)m_pad * 32));
+        ctx->cap_acc = m_pad;
+    }
+    CU(cudaMemsetAsync(ctx->d_acc, 0, sizeof(long long) * (size_t)m_pad * 32, s));
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)pl.dpitch, (cuuint64_t)mc};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pl.dpitch};
+    const cuuint32_t box[2] = {kTcTileBytes, kTcRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_rows, gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(ctx, SPAGXE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): pitch=%lld rows=%d", (int)cr,
+                                        (long long)pl.dpitch, mc);
+    const int n_tiles = (int)((pl.n + kTcTileSamples - 1) / kTcTileSamples);
+    const int n_row_tiles = m_pad / kTcRows;
+    int want_splits = std::max(1, (4 * ctx->num_sms + n_row_tiles - 1) / n_row_tiles);
+    want_splits = std::min(want_splits, std::max(1, n_tiles / 16));
+    const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
+    const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    const int n_items = n_row_tiles * n_splits;
+    const int grid = std::min(n_items, ctx->num_sms);
+    k_score_tc<<<grid, kTcThreads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc);
+    LAUNCH_CHECK();
+    k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(ctx->d_acc, mc, ctx->d_binfo, st);
+    LAUNCH_CHECK();
+    return SPAGXE_OK;
+}
+
 static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
+    if (ctx->use_tc) return launch_score_tc(ctx, d_rows, pl, mc, st);
     cudaStream_t s = ctx->stream();
     const int64_t pw = pl.dpitch / 4;
     const int tiles_s = (int)((pw + kScoreThreads - 1) / kScoreThreads);
@@ -523,6 +591,45 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
     if (hc.n_cct_stop) return fail(ctx, SPAGXE_ERR_CCT_STOP, "CCT() would stop() for %llu SNP(s) (NA or out-of-range p-value)",
                                    hc.n_cct_stop);
     return SPAGXE_OK;
+}
+
+// raw per-SNP outputs of the score pass (K1+K2) for cross-checking the two kernels
+extern "C" int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *g, int impl, double *D0, double *D1, double *T0,
+                                  double *T1, int32_t *asum, int32_t *nmiss) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    int rc = validate_geno(ctx, g);
+    if (rc) return rc;
+    if (ctx->n <= 0 || g->n_samples != ctx->n) return fail(ctx, SPAGXE_ERR_STATE, "score_stats: set_vectors first / N mismatch");
+    if (!D0 || !D1 || !T0 || !T1 || !asum || !nmiss) return fail(ctx, SPAGXE_ERR_ARG, "score_stats: NULL output");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    ChunkPlan pl = make_plan(g);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    if (ctx->vec_mode < 0 && (rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    SnpStats st = stats_view(ctx, ctx->cap_m);
+    const bool saved = ctx->use_tc;
+    ctx->use_tc = (impl != 1);
+    int buf = 0; int64_t h2d = 0;
+    for (int64_t j0 = 0; j0 < g->n_snps && rc == 0; j0 += pl.chunk_m, buf ^= 1) {
+        const int mc = (int)std::min<int64_t>(pl.chunk_m, g->n_snps - j0);
+        const uint8_t *d_rows = nullptr;
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) break;
+        if ((rc = launch_score(ctx, d_rows, pl, mc, st))) break;
+        cudaError_t e = cudaSuccess;
+        double *dsts[4] = {D0, D1, T0, T1};
+        const double *srcs[4] = {st.D0, st.D1, st.T0, st.T1};
+        for (int k = 0; k < 4 && e == cudaSuccess; k++)
+            e = cudaMemcpyAsync(dsts[k] + j0, srcs[k], sizeof(double) * mc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(asum + j0, st.asum, sizeof(int) * mc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nmiss + j0, st.nmiss, sizeof(int) * mc, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(ctx, SPAGXE_ERR_CUDA, "score_stats: %s", cudaGetErrorString(e));
+        if (own_bed) cudaEventRecord(ctx->ev_done[buf], s);
+    }
+    ctx->use_tc = saved;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------

@@ -250,3 +250,31 @@ def test_spa_quadrature_matches_oracle_and_exact_kernel(oracle):
     spa = (route & 4) > 0
     d = np.abs(np.log10(outs[0][spa, 2]) - np.log10(outs[1][spa, 2]))
     assert d.max() < 1e-9, d.max()
+
+
+@pytest.mark.parametrize("n,m", [(6007, 70), (1000, 3), (50_021, 300)])
+def test_score_tensor_core_kernel_matches_fp64_kernel(gpu_ctx, n, m):
+    """K1+K2: the tcgen05 int8 fixed-point kernel against the fp64 CUDA-core kernel: integer outputs
+    (allele sums, missing counts) are identical; the exact-integer contraction agrees with the fp64
+    sums to rounding; ragged N and M (not multiples of the 512-sample / 128-row tiles)."""
+    ph = make_pheno(n, 61, prevalence=0.05)
+    rng = np.random.default_rng(62)
+    mafs = rng.uniform(0.001, 0.5, m)
+    G = make_geno(n, mafs, 63, miss_rates=np.where(rng.random(m) < 0.5, 0, rng.random(m) * 0.1), count_major=rng.random(m) < 0.5)
+    rows = to_bed_rows(G)
+    gpu_ctx.set_vectors(ph["R"], ph["E"])
+    g = _bed_desc(gpu_ctx, rows, n)
+    tc = gpu_ctx.score_stats(g, impl=0)
+    v1 = gpu_ctx.score_stats(g, impl=1)
+    assert np.array_equal(tc["asum"], v1["asum"]) and np.array_equal(tc["nmiss"], v1["nmiss"])
+    Gz = np.nan_to_num(G, nan=0.0)
+    assert np.array_equal(tc["asum"], Gz.sum(0).astype(np.int32)) and np.array_equal(tc["nmiss"], np.isnan(G).sum(0))
+    scale = np.sqrt((ph["R"] ** 2).sum())
+    for k in ("D0", "D1", "T0", "T1"):
+        assert np.max(np.abs(tc[k] - v1[k])) <= 1e-11 * scale * 5, (k, np.max(np.abs(tc[k] - v1[k])))
+    # the tensor-core result is exact integer arithmetic: compare with a long-double host sum
+    want = (Gz.astype(np.longdouble) * ph["R"].astype(np.longdouble)[:, None]).sum(0)
+    assert np.max(np.abs(tc["D0"] - want.astype(np.float64))) <= 2e-14 * np.abs(ph["R"]).max() * n
+    # run twice: bit-identical (integer accumulation is order independent)
+    tc2 = gpu_ctx.score_stats(g, impl=0)
+    assert all(np.array_equal(tc[k], tc2[k]) for k in tc)
