@@ -134,6 +134,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %2;\n\t"
+        "@%%px mov.s32 %1, 1;\n\t"
+        "mov.s32 %0, %%rx;\n\t}"
+        : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -191,6 +201,7 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform: UTCIMMA operands stay in uniform registers
 
     const int n_items = n_row_tiles * n_splits;
     if (warp == kTcExpWarps) {
@@ -212,41 +223,48 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
         }
     } else if (warp == kTcExpWarps + 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t f = 0, g = 0, it_count = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int ks = item % n_splits;
-                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
-                if (t1 <= t0) continue;
-                mbar_wait(bar_accempty, (it_count & 1) ^ 1);  // epilogue of the previous item has drained D
-                tc_fence_after();
-                uint32_t accum = 0;
-                for (int t = t0; t < t1; t++, f++) {
-                    const int s = f % kTcStages;
-                    mbar_wait(bar_full(s), (f / kTcStages) & 1);
-                    const uint32_t bsm = sbase + s * kTcStageBytes + kTcRows * kTcTileBytes;
-                    for (int hs = 0; hs < 2; hs++, g++) {
-                        const int buf = g & 1;
-                        mbar_wait(bar_afull(buf), (g >> 1) & 1);
-                        tc_fence_after();
+        // The whole warp walks the (warp-uniform) loop; one elected lane issues tcgen05.mma / commit.
+        uint32_t f = 0, it_count = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int ks = item % n_splits;
+            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            if (t1 <= t0) continue;
+            mbar_wait(bar_accempty, (it_count & 1) ^ 1);  // epilogue of the previous item has drained D
+            tc_fence_after();
+            uint32_t accum = 0;
+            for (int t = t0; t < t1; t++, f++) {
+                const int s = f % kTcStages;
+                mbar_wait(bar_full(s), (f / kTcStages) & 1);
+                const uint32_t bsm = sbase + s * kTcStageBytes + kTcRows * kTcTileBytes;
+                const uint64_t bd0 = tc_bdesc(bsm);
+                // two half-stages: A buffer index == hs and its phase == f & 1 (g == 2 f), so every operand
+                // offset below is a compile-time constant relative to tmem_base / bd0
+#pragma unroll
+                for (int hs = 0; hs < 2; hs++) {
+                    mbar_wait(bar_afull(hs), f & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
 #pragma unroll
                         for (int c4 = 0; c4 < 4; c4++) {
 #pragma unroll
                             for (int j = 0; j < 2; j++) {
-                                const uint64_t bd = tc_bdesc(bsm + (uint32_t)(((hs * 4 + c4) * 4 + 2 * j) * 256));
-                                const uint32_t acol = (uint32_t)(buf * 128 + c4 * 16 + j * 8);
-                                tc_mma_i8_ts(tmem_base + kTcColAcc, tmem_base + acol, bd, kTcIdesc, accum);
-                                tc_mma_i8_ts(tmem_base + kTcColAcc + 16, tmem_base + acol + 64, bd, kTcIdesc, accum);
-                                accum = 1;
+                                const uint64_t bd = bd0 + (uint64_t)((((hs * 4 + c4) * 4 + 2 * j) * 256) >> 4);
+                                const uint32_t acol = (uint32_t)(hs * 128 + c4 * 16 + j * 8);
+                                const uint32_t acc_on = (hs | c4 | j) ? 1u : accum;
+                                tc_mma_i8_ts(tmem_base + kTcColAcc, tmem_base + acol, bd, kTcIdesc, acc_on);
+                                tc_mma_i8_ts(tmem_base + kTcColAcc + 16, tmem_base + acol + 64, bd, kTcIdesc, acc_on);
                             }
                         }
-                        tc_commit(bar_aempty(buf));
+                        tc_commit(bar_aempty(hs));
+                        if (hs == 1) tc_commit(bar_empty(s));
                     }
-                    tc_commit(bar_empty(s));
+                    __syncwarp();
                 }
-                tc_commit(bar_accfull);
-                it_count++;
+                accum = 1;
             }
+            if (elect_one()) tc_commit(bar_accfull);
+            __syncwarp();
+            it_count++;
         }
     } else {
         // ================= expanders (+ epilogue on warps 0-3) =================
