@@ -933,4 +933,160 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
     cl.sync();  // nobody may exit while a peer can still read its shared memory
 }
 
+
+// ===========================================================================
+// SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:248-405)
+struct PlusConst { double R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew; };
+struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
+
+// K3 for SPAGxE_Plus: V = E*R, so D1/T1 carry sum(g*E*R).  One thread per SNP.  out is M x 8.
+__global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
+                                const VecConst *__restrict__ vcp, PlusConst pc, double epsilon, double cutoff,
+                                double min_maf, double *__restrict__ out, SpaItem *spa_list, int *b_list, Counters *ctr) {
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = jl < m_chunk;
+    const VecConst vc = *vcp;
+    bool want_spa = false, want_b = false;
+    SpaItem item;
+    const int64_t j = snp0 + jl;
+    if (active) {
+        const double NA = d_na_real();
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        Prologue pr = make_prologue(asum, nmiss, n);
+        double *o = out + j;
+        o[0] = pr.maf; o[1 * m_total] = pr.miss_rate;
+        if (nmiss == n) {
+            for (int c = 0; c < 8; c++) o[c * m_total] = NA;
+            o[1 * m_total] = 1.0;
+            atomicAdd(&ctr->n_allmissing, 1ULL);
+        } else if (pr.maf < min_maf) {
+            for (int c = 2; c < 8; c++) o[c * m_total] = NA;
+            atomicAdd(&ctr->n_filtered, 1ULL);
+        } else {
+            double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+            double S2 = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
+            if (pr.flip) { S1 = 2 * vc.sumR - S1; S2 = 2 * vc.sumV - S2; }
+            const double gvar = 2 * pr.maf * (1 - pr.maf);
+            const double VarS1 = gvar * pc.R_GRM_R;             // ref :300
+            const double Z1 = (S1 - 0) / sqrt(VarS1);
+            const double pG = d_pnorm(-fabs(Z1), true) * 2;
+            o[4 * m_total] = pG; o[5 * m_total] = S1; o[6 * m_total] = VarS1; o[7 * m_total] = Z1;
+            if (pG > epsilon) {
+                atomicAdd(&ctr->n_branch_a, 1ULL);
+                const double lambda = pc.R_GRM_RE / pc.R_GRM_R;  // ref :310
+                const double S_GxE = S2 - lambda * S1;
+                const double Svar = gvar * pc.Rnew_GRM_Rnew;
+                const double z = S_GxE / sqrt(Svar);
+                if (fabs(z) < cutoff) {
+                    const double pn = d_pnorm(fabs(z), false) * 2;
+                    o[2 * m_total] = pn; o[3 * m_total] = pn;
+                } else {
+                    const double ratio = (vc.sumRn2 * gvar) / Svar;  // sum(R.new^2 * g.var.est) / var (ref :322-323)
+                    const double Snew = S_GxE * sqrt(ratio);
+                    o[3 * m_total] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+                    want_spa = true;
+                    item.snp = (int)j; item.flags = 1 | 16;  // 1 column, explicit tails
+                    item.maf = pr.maf; item.S = fabs(Snew); item.Smean = -fabs(Snew); item.aux = 0;
+                }
+            } else {
+                atomicAdd(&ctr->n_branch_b, 1ULL);
+                want_b = true;
+            }
+        }
+    }
+    int pos = list_reserve(&ctr->spa_count, want_spa);
+    if (want_spa) spa_list[pos] = item;
+    pos = list_reserve(&ctr->b_count, want_b);
+    if (want_b) b_list[pos] = jl;
+}
+
+// branch B of SPAGxE_Plus (ref :342-400): cluster per SNP; K7 = sparse-GRM quadratic form of R.new0
+__global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const int *__restrict__ b_list, Counters *ctr,
+                                                              const uint8_t *__restrict__ bed, int64_t pitch,
+                                                              SnpStats st, int64_t snp0, int64_t m_total, int64_t n,
+                                                              const double *__restrict__ R, const double *__restrict__ E,
+                                                              const VecConst *__restrict__ vcp, GrmCoo grm, double cutoff,
+                                                              double *__restrict__ out) {
+    namespace cg = cooperative_groups;
+    __shared__ BShared sh;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const int count = ctr->b_count;
+    const VecConst vc = *vcp;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const long long eper = (grm.nnz + cs - 1) / cs;
+    const long long e_lo = min(grm.nnz, eper * rank), e_hi = min(grm.nnz, eper * (rank + 1));
+    for (int idx = cluster_id; idx < count; idx += n_clusters) {
+        const int jl = b_list[idx];
+        const int64_t j = snp0 + jl;
+        const uint8_t *row = bed + (int64_t)jl * pitch;
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        const Prologue pr = make_prologue(asum, nmiss, n);
+        GFromRow gf;
+        gf.row = row;
+        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
+        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
+        double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+        if (pr.flip) S1 = 2 * vc.sumR - S1;
+        double v3[3] = {0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
+        red.sum<3>(v3);
+        const double a = (double)n, b = pr.sum_g, d = v3[0];
+        const double det = a * d - b * b;
+        const double NA = d_na_real();
+        double *o = out + j;
+        const bool writer = (rank == 0 && threadIdx.x == 0);
+        if (det == 0 || !isfinite(det)) {
+            if (writer) { o[2 * m_total] = NA; o[3 * m_total] = NA; atomicAdd(&ctr->n_singular, 1ULL); }
+            continue;
+        }
+        const double i00 = d / det, i01 = -b / det, i11 = a / det;
+        SrcAdj src;
+        src.row = row; src.R = R; src.E = E; src.maf = pr.maf;
+        for (int c = 0; c < 4; c++) {
+            double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
+            src.fit[c] = wi0 * vc.sumR + wi1 * S1;
+        }
+        // S0 = sum(g*E*R0), sum(x), sum(x^2) with x = R.new0 = E*R0
+        v3[0] = v3[1] = v3[2] = 0;
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, m, w; src.get(i, r, m, w);
+            v3[0] += gf(i) * r; v3[1] += r; v3[2] += r * r;
+        }
+        red.sum<3>(v3);
+        // K7: sum over the COO entries of Value * x[ID1] * x[ID2] (ref :356-358)
+        double vq[1] = {0};
+        for (long long e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+            double r1, r2, m, w;
+            src.get(grm.gi[e], r1, m, w); src.get(grm.gj[e], r2, m, w);
+            vq[0] += (grm.gv[e] * r1) * r2;
+        }
+        red.sum<1>(vq);
+        const double gvar = 2 * pr.maf * (1 - pr.maf);
+        const double S0 = v3[0];
+        const double Smean = 2 * v3[1] * pr.maf;                       // ref :360
+        const double Svar = 2 * vq[0] * gvar - v3[2] * gvar;          // ref :361
+        const double z = (S0 - Smean) / sqrt(Svar);
+        double pspa, pnorm_;
+        int iters = 0;
+        const bool spa = !(fabs(z) < cutoff);
+        if (!spa) { pnorm_ = d_pnorm(fabs(z), false) * 2; pspa = pnorm_; }
+        else {
+            const double ratio = (v3[2] * gvar) / Svar;
+            const double Snew = S0 * sqrt(ratio), Smean_new = Smean * sqrt(ratio);
+            const double dlt = fabs(Snew - Smean_new);
+            pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            pspa = spa_two_tail(src, red, i_lo, i_hi, Smean + dlt, Smean - dlt, CUDART_INF, &iters);
+        }
+        if (writer) {
+            o[2 * m_total] = pspa; o[3 * m_total] = pnorm_;
+            if (spa) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+    cl.sync();
+}
+
 }  // namespace spagxe

@@ -235,7 +235,7 @@ static int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     if (ctx->vec_mode == mode) return SPAGXE_OK;
-    k_vec_prep2<<<1, 1024, 0, ctx->stream()>>>(ctx->d_R, ctx->d_E, d_Rn_in, ctx->n, mode, ctx->d_Rn, ctx->d_V, ctx->d_vc);
+    k_vec_prep2<<<1, 1024, 0, ctx->stream()>>>(ctx->d_R, ctx->d_E, d_Rn_in, ctx->n, mode == 0 ? 0 : 1, ctx->d_Rn, ctx->d_V, ctx->d_vc);
     LAUNCH_CHECK();
     ctx->vec_mode = mode;
     {   // fixed-point int8 digit matrix B of (R, V) for the tensor-core score pass
@@ -515,17 +515,51 @@ static void fill_diag(spagxe_diag *diag, const Counters &c, int64_t m) {
 
 static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1, 0, 0, 0, 0};
 
-extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out,
-                              spagxe_diag *diag) {
+enum RunMode { RUN_CCT = 0, RUN_PLUS = 1, RUN_MIX = 2 };
+
+static int launch_mix(spagxe_ctx *ctx, const uint8_t *, int64_t, SnpStats, int64_t, int, int64_t, int64_t, WaldData,
+                      const spagxe_params *, double *) {
+    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
+}
+
+static int launch_branch_b_plus(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int64_t M,
+                                int64_t N, double cutoff, double *d_out) {
+    cudaLaunchConfig_t cfg = {};
+    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
+    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int *b_list = ctx->d_b_list;
+    Counters *ctr = ctx->d_ctr;
+    const double *R = ctx->d_R, *E = ctx->d_E;
+    const VecConst *vc = ctx->d_vc;
+    GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
+    CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, b_list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, grm, cutoff, d_out));
+    ctx->launches++;
+    return SPAGXE_OK;
+}
+
+static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag,
+                       RunMode mode) {
     if (!ctx) return SPAGXE_ERR_ARG;
     if (!prm) prm = &kDefaultParams;
     int rc = validate_geno(ctx, g);
     if (rc) return rc;
+    const char *name = mode == RUN_CCT ? "run_cct" : mode == RUN_PLUS ? "run_plus" : "run_mix";
+    const int ncol = mode == RUN_CCT ? 10 : mode == RUN_PLUS ? 8 : 12;
     if (!out) return fail(ctx, SPAGXE_ERR_ARG, "out is NULL");
-    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_cct: call spagxe_set_vectors first");
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_vectors first", name);
     if (g->n_samples != ctx->n) return fail(ctx, SPAGXE_ERR_ARG, "geno has %lld samples but R has %lld",
                                             (long long)g->n_samples, (long long)ctx->n);
-    if (ctx->wald_trait == 0) return fail(ctx, SPAGXE_ERR_STATE, "run_cct: call spagxe_set_wald first (Wald test data)");
+    if (mode != RUN_PLUS && ctx->wald_trait == 0)
+        return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_wald first (Wald test data)", name);
+    if (mode == RUN_PLUS && !ctx->have_grm) return fail(ctx, SPAGXE_ERR_STATE, "run_plus: call spagxe_set_grm first");
+    if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
     if (prm->g_model != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only G.model=\"Add\" is implemented");
     if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
     CU(cudaSetDevice(ctx->device));
@@ -538,15 +572,18 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
     double *d_out = nullptr;
     if (prm->out_location == SPAGXE_LOC_DEVICE) { d_out = out; rc = ensure_chunk_scratch(ctx, pl, own_bed, 0); }
-    else { rc = ensure_chunk_scratch(ctx, pl, own_bed, M * 10); d_out = ctx->d_out; }
+    else { rc = ensure_chunk_scratch(ctx, pl, own_bed, M * ncol); d_out = ctx->d_out; }
     if (rc) return rc;
-    if ((rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
+    // CCT contracts with (R, R.new); plus and mix with (R, E*R); plus takes R.new from the null-model object
+    const int vmode = (mode == RUN_CCT) ? 0 : (mode == RUN_PLUS ? 1 : 2);
+    if ((rc = ensure_vec_mode(ctx, vmode, mode == RUN_PLUS ? ctx->d_Rn_user : nullptr))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     EventPool evp;
     cudaEvent_t e_begin = evp.rec(s);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev;
     SnpStats st = stats_view(ctx, ctx->cap_m);
     WaldData wd{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
+    PlusConst pc{ctx->R_GRM_R, ctx->R_GRM_RE, ctx->Rnew_GRM_Rnew};
     int buf = 0;
     for (int64_t j0 = 0; j0 < M; j0 += pl.chunk_m, buf ^= 1) {
         const int mc = (int)std::min<int64_t>(pl.chunk_m, M - j0);
@@ -558,11 +595,21 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
         if ((rc = launch_score(ctx, d_rows, pl, mc, st))) return rc;
         cudaEvent_t b = evp.rec(s);
         score_ev.push_back({a, b});
-        k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
-                                                        ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
-        LAUNCH_CHECK();
-        if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
-        if ((rc = launch_branch_b(ctx, d_rows, pl.dpitch, st, j0, M, N, wd, prm->min_maf, d_out))) return rc;
+        if (mode == RUN_CCT) {
+            k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
+                                                            ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
+            LAUNCH_CHECK();
+            if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
+            if ((rc = launch_branch_b(ctx, d_rows, pl.dpitch, st, j0, M, N, wd, prm->min_maf, d_out))) return rc;
+        } else if (mode == RUN_PLUS) {
+            k_finalize_plus<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, pc, prm->epsilon, prm->cutoff,
+                                                             prm->min_maf, d_out, ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
+            LAUNCH_CHECK();
+            if ((rc = launch_spa(ctx, ctx->d_Rn, N, M, d_out))) return rc;
+            if ((rc = launch_branch_b_plus(ctx, d_rows, pl.dpitch, st, j0, M, N, prm->cutoff, d_out))) return rc;
+        } else {
+            if ((rc = launch_mix(ctx, d_rows, pl.dpitch, st, j0, mc, M, N, wd, prm, d_out))) return rc;
+        }
         cudaEvent_t c = evp.rec(s);
         test_ev.push_back({b, c});
         if (own_bed) CU(cudaEventRecord(ctx->ev_done[buf], s));
@@ -570,8 +617,8 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
     Counters hc;
     CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
     if (prm->out_location != SPAGXE_LOC_DEVICE) {
-        CU(cudaMemcpyAsync(out, d_out, M * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
-        dg.d2h_bytes += M * 10 * sizeof(double);
+        CU(cudaMemcpyAsync(out, d_out, M * ncol * sizeof(double), cudaMemcpyDeviceToHost, s));
+        dg.d2h_bytes += M * ncol * sizeof(double);
     }
     cudaEvent_t e_end = evp.rec(s);
     CU(cudaStreamSynchronize(s));
@@ -590,6 +637,39 @@ extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagx
     if (hc.n_singular) return fail(ctx, SPAGXE_ERR_SINGULAR, "solve(t(W)%%*%%W) is singular for %llu SNP(s)", hc.n_singular);
     if (hc.n_cct_stop) return fail(ctx, SPAGXE_ERR_CCT_STOP, "CCT() would stop() for %llu SNP(s) (NA or out-of-range p-value)",
                                    hc.n_cct_stop);
+    return SPAGXE_OK;
+}
+
+extern "C" int spagxe_run_cct(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+    return run_generic(ctx, g, prm, out, diag, RUN_CCT);
+}
+extern "C" int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+    return run_generic(ctx, g, prm, out, diag, RUN_PLUS);
+}
+extern "C" int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+    return run_generic(ctx, g, prm, out, diag, RUN_MIX);
+}
+
+extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,
+                              double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_grm: call spagxe_set_vectors first");
+    if (nnz < 0 || (nnz > 0 && (!gi || !gj || !gv)) || !Rnew) return fail(ctx, SPAGXE_ERR_ARG, "set_grm: bad arguments");
+    for (int64_t e = 0; e < nnz; e++)
+        if (gi[e] < 0 || gi[e] >= ctx->n || gj[e] < 0 || gj[e] >= ctx->n)
+            return fail(ctx, SPAGXE_ERR_ARG, "set_grm: index out of range at entry %lld", (long long)e);
+    CU(cudaSetDevice(ctx->device));
+    CU(dev_realloc(&ctx->d_gi, std::max<int64_t>(nnz, 1))); CU(dev_realloc(&ctx->d_gj, std::max<int64_t>(nnz, 1)));
+    CU(dev_realloc(&ctx->d_gv, std::max<int64_t>(nnz, 1))); CU(dev_realloc(&ctx->d_Rn_user, ctx->n));
+    if (nnz > 0) {
+        CU(cudaMemcpy(ctx->d_gi, gi, nnz * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_gj, gj, nnz * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_gv, gv, nnz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(ctx->d_Rn_user, Rnew, ctx->n * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->grm_nnz = nnz; ctx->R_GRM_R = R_GRM_R; ctx->R_GRM_RE = R_GRM_RE; ctx->Rnew_GRM_Rnew = Rnew_GRM_Rnew;
+    ctx->have_grm = true;
+    ctx->vec_mode = -1;
     return SPAGXE_OK;
 }
 
@@ -731,22 +811,8 @@ extern "C" int spagxe_measure_fp64_peak(spagxe_ctx *ctx, double *tflops) {
     return SPAGXE_OK;
 }
 
-// mix / plus entry points are defined in mixplus.cu-style sections below once implemented
 extern "C" int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k) {
     if (!ctx) return SPAGXE_ERR_ARG;
     (void)pcs; (void)k;
     return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
-}
-extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t, const int32_t *, const int32_t *, const double *, double, double,
-                              double, const double *) {
-    if (!ctx) return SPAGXE_ERR_ARG;
-    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxE_Plus is not implemented yet");
-}
-extern "C" int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *, const spagxe_params *, double *, spagxe_diag *) {
-    if (!ctx) return SPAGXE_ERR_ARG;
-    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
-}
-extern "C" int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *, const spagxe_params *, double *, spagxe_diag *) {
-    if (!ctx) return SPAGXE_ERR_ARG;
-    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxE_Plus is not implemented yet");
 }

@@ -278,3 +278,62 @@ def test_score_tensor_core_kernel_matches_fp64_kernel(gpu_ctx, n, m):
     # run twice: bit-identical (integer accumulation is order independent)
     tc2 = gpu_ctx.score_stats(g, impl=0)
     assert all(np.array_equal(tc[k], tc2[k]) for k in tc)
+
+
+P_COLS_PLUS = [2, 3, 4]
+S_COLS_PLUS = [5, 6, 7]
+
+
+def _plus_nullmodel(oracle, golden_dir):
+    d = np.load(f"{golden_dir}/plus.npz")
+    R = get_resid("binary", d["Y"], [d["Cov1"], d["Cov2"], d["E"]])
+    a, b, Rnew, c = oracle.plus_nullmodel_scalars(d["grm_i"], d["grm_j"], d["grm_v"], R, d["E"])
+    obj = {"R": R, "R_GRM_R": a, "R_GRM_RE": b, "R.new": Rnew, "R.new_GRM_R.new": c,
+           "sparseGRM": {"i": d["grm_i"], "j": d["grm_j"], "Value": d["grm_v"]}}
+    return d, obj
+
+
+def test_c5_spagxe_plus_bundled_fixture(gpu_ctx, oracle, golden_dir):
+    """SPAGxE_Plus on inst/GenoMat_SPAGxE_Plus.bed + data/sparseGRM.SPAGxEPlus.rda + the bundled binary
+    phenotype (prevalence 1%), branch A and (epsilon = 0.5) the sparse-GRM branch B."""
+    from spagxecct_b200 import SPAGxE_Plus
+    d, obj = _plus_nullmodel(oracle, golden_dir)
+    bed = np.load(f"{golden_dir}/bed_SPAGxE_Plus.npz")
+    n = int(bed["n"])
+    rows = np.ascontiguousarray(bed["bed"][3:])
+    G = oracle.bed_decode(rows, n)
+    for eps, cutoff in ((0.001, 2.0), (0.5, 2.0), (0.5, 0.5)):
+        res = SPAGxE_Plus(Geno_mtx=G, E=d["E"], Phen_mtx={"Y": d["Y"]}, Cova_mtx=np.column_stack([d["Cov1"], d["Cov2"]]),
+                          obj_SPAGxE_Plus_Nullmodel=obj, epsilon=eps, Cutoff=cutoff, ctx=gpu_ctx, quiet=True)
+        ref, route, iters, _ = oracle.plus_bed(rows, n, obj["R"], d["E"], obj["R.new"], obj["R_GRM_R"], obj["R_GRM_RE"],
+                                              obj["R.new_GRM_R.new"], d["grm_i"], d["grm_j"], d["grm_v"], epsilon=eps,
+                                              cutoff=cutoff)
+        assert_parity(res.values, ref, P_COLS_PLUS, S_COLS_PLUS, label=f"plus eps={eps} cutoff={cutoff}")
+        assert res.diag["n_branch_b"] == ((route & 2) > 0).sum() and res.diag["n_spa"] == ((route & 4) > 0).sum()
+        assert res.diag["newton_iters"] == iters.sum()
+        assert res.colnames[2] == "p.value.spaGxE.plus"
+    assert ((route & 2) > 0).sum() >= 20 and ((route & 4) > 0).sum() >= 10
+
+
+def test_spagxe_plus_synthetic_families_with_missing_and_flips(gpu_ctx, oracle):
+    """Related samples (sib pairs), missing calls, MAF > 0.5 coding, N not a multiple of anything."""
+    n_fam = 3001
+    n = 2 * n_fam + 1001
+    rng = np.random.default_rng(71)
+    ph = make_pheno(n, 72, prevalence=0.05)
+    mafs = rng.uniform(0.005, 0.5, 60)
+    G = make_geno(n, mafs, 73, miss_rates=np.where(rng.random(60) < 0.5, 0, 0.03), count_major=rng.random(60) < 0.5)
+    G[1:2 * n_fam:2] = np.where(rng.random((n_fam, 60)) < 0.5, G[0:2 * n_fam:2], G[1:2 * n_fam:2])  # sibs share alleles
+    gi = np.r_[np.arange(n), np.arange(1, 2 * n_fam, 2)].astype(np.int32)
+    gj = np.r_[np.arange(n), np.arange(0, 2 * n_fam, 2)].astype(np.int32)
+    gv = np.r_[np.ones(n), np.full(n_fam, 0.5)]
+    a, b, Rnew, c = oracle.plus_nullmodel_scalars(gi, gj, gv, ph["R"], ph["E"])
+    rows = to_bed_rows(G)
+    gpu_ctx.set_vectors(ph["R"], ph["E"])
+    gpu_ctx.set_grm(gi, gj, gv, a, b, c, Rnew)
+    for eps in (0.001, 0.3):
+        out, diag = gpu_ctx.run_plus(_bed_desc(gpu_ctx, rows, n), dict(epsilon=eps, cutoff=1.0))
+        ref, route, iters, _ = oracle.plus_bed(rows, n, ph["R"], ph["E"], Rnew, a, b, c, gi, gj, gv, epsilon=eps, cutoff=1.0)
+        assert_parity(out, ref, P_COLS_PLUS, S_COLS_PLUS, label=f"plus synthetic eps={eps}")
+        assert diag["newton_iters"] == iters.sum()
+    assert ((route & 2) > 0).sum() >= 5
