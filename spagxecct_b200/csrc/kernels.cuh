@@ -602,12 +602,12 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
 // One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
 // normal equations land in sh.NE / sh.rhs of EVERY CTA.  Returns the cluster-wide deviance (binary)
 // or residual sum of squares (lm second pass).  pass0: eta from mustart (ref glm.fit), else x.beta.
-template <int NS, class GFun>
-__device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n,
-                            int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile, BShared &sh,
+template <int NS, class Design>
+__device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile, BShared &sh,
                             const ClusterRed &red, int *invalid) {
     namespace cg = cooperative_groups;
-    const int p = wd.p, qs = (q + 1) | 1;  // odd row stride: conflict-free 64-bit reads
+    const int qs = (q + 1) | 1;  // odd row stride: conflict-free 64-bit reads
+    const int trait = ds.trait();
     double *xs = tile, *ws = tile + (size_t)kBTile * qs;
     const int nent = q * (q + 3) / 2;
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -632,14 +632,12 @@ __device__ double wald_pass(const GFun &gf, const WaldData &wd, const double *__
         if (threadIdx.x < cnt) {
             const int64_t i = base + threadIdx.x;
             double *xr = xs + (size_t)threadIdx.x * qs;
-            const double g = gf(i), ev = E[i], y = wd.Y[i];
-            xr[0] = 1.0;
-            for (int c = 0; c < p; c++) xr[1 + c] = wd.cova[i + (int64_t)c * n];
-            xr[p + 1] = ev; xr[p + 2] = g; xr[p + 3] = ev * g;
+            const double y = ds.y(i);
+            ds.fill_rt(i, xr, q);
             double eta = 0;
             if (!pass0) for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
             double w2, z;
-            irls_sample(wd.trait, pass0, y, eta, w2, z, dev, bad);
+            irls_sample(trait, pass0, y, eta, w2, z, dev, bad);
             xr[q] = z;
             ws[threadIdx.x] = w2;
         }
@@ -706,13 +704,12 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
 
 // Register-accumulator variant for narrow designs (Q = p + 4 <= 8): every thread keeps the whole upper
 // triangle of X'WX (+ X'Wz) for its own samples in registers; no shared-memory tile, no per-tile barrier.
-template <int Q, class GFun>
-__device__ double wald_pass_reg(const GFun &gf, const WaldData &wd, const double *__restrict__ E, int64_t n,
-                                int64_t i_lo, int64_t i_hi, bool pass0, double *tile, BShared &sh,
+template <int Q, class Design>
+__device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bool pass0, double *tile, BShared &sh,
                                 const ClusterRed &red, int *invalid) {
     namespace cg = cooperative_groups;
     constexpr int NENT = Q * (Q + 3) / 2;
-    constexpr int P = Q - 4;
+    const int trait = ds.trait();
     double acc[NENT];
 #pragma unroll
     for (int e = 0; e < NENT; e++) acc[e] = 0;
@@ -723,18 +720,15 @@ __device__ double wald_pass_reg(const GFun &gf, const WaldData &wd, const double
     int bad = 0;
     for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
         double x[Q];
-        const double g = gf(i), ev = E[i], y = wd.Y[i];
-        x[0] = 1.0;
-#pragma unroll
-        for (int c = 0; c < P; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
-        x[P + 1] = ev; x[P + 2] = g; x[P + 3] = ev * g;
+        const double y = ds.y(i);
+        ds.template fill<Q>(i, x);
         double eta = 0;
         if (!pass0) {
 #pragma unroll
             for (int c = 0; c < Q; c++) eta += x[c] * beta[c];
         }
         double w2, z;
-        irls_sample(wd.trait, pass0, y, eta, w2, z, dev, bad);
+        irls_sample(trait, pass0, y, eta, w2, z, dev, bad);
         int e = 0;
 #pragma unroll
         for (int a = 0; a < Q; a++) {
@@ -791,56 +785,113 @@ __device__ __forceinline__ void wald_solve(BShared &sh, int q) {
     __syncthreads();
 }
 
-template <class GFun>
-__device__ __forceinline__ double wald_pass_any(const GFun &gf, const WaldData &wd, const double *E, int64_t n,
-                                                int64_t i_lo, int64_t i_hi, int q, bool pass0, double *tile,
-                                                BShared &sh, const ClusterRed &red, int *invalid) {
+__device__ __forceinline__ void wald_solve(BShared &sh, int q);
+
+// Design of the Wald model Y ~ Cova + E + g + E:g (ref :638, :652)
+struct DesignWald {
+    WaldData wd; const double *E; GFromRow gf; int64_t n;
+    __device__ __forceinline__ int q() const { return wd.p + 4; }
+    __device__ __forceinline__ int trait() const { return wd.trait; }
+    __device__ __forceinline__ double y(int64_t i) const { return wd.Y[i]; }
+    template <int Q>
+    __device__ __forceinline__ void fill(int64_t i, double *x) const {
+        constexpr int P = Q - 4;
+        const double g = gf(i), ev = E[i];
+        x[0] = 1.0;
+#pragma unroll
+        for (int c = 0; c < P; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
+        x[P + 1] = ev; x[P + 2] = g; x[P + 3] = ev * g;
+    }
+    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
+        const int p = q - 4;
+        const double g = gf(i), ev = E[i];
+        x[0] = 1.0;
+        for (int c = 0; c < p; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
+        x[p + 1] = ev; x[p + 2] = g; x[p + 3] = ev * g;
+    }
+};
+// Design of the mix fallback glm(1{round(g) != 0} ~ selected PCs, binomial) (ref :1081-1089)
+struct DesignAf {
+    const double *pcs; int64_t n; int nsel; const int *sel; GFromRow gf;
+    __device__ __forceinline__ int q() const { return nsel + 1; }
+    __device__ __forceinline__ int trait() const { return 1; }
+    __device__ __forceinline__ double y(int64_t i) const { return (rint(gf(i)) != 0.0) ? 1.0 : 0.0; }
+    template <int Q>
+    __device__ __forceinline__ void fill(int64_t i, double *x) const {
+        x[0] = 1.0;
+#pragma unroll
+        for (int c = 0; c < Q - 1; c++) x[1 + c] = pcs[i + (int64_t)sel[c] * n];
+    }
+    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
+        x[0] = 1.0;
+        for (int c = 0; c < q - 1; c++) x[1 + c] = pcs[i + (int64_t)sel[c] * n];
+    }
+};
+
+template <class Design>
+__device__ __forceinline__ double wald_pass_any(const Design &ds, int64_t i_lo, int64_t i_hi, int q, bool pass0,
+                                                double *tile, BShared &sh, const ClusterRed &red, int *invalid) {
     switch (q) {
-        case 4: return wald_pass_reg<4>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 5: return wald_pass_reg<5>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 6: return wald_pass_reg<6>(gf, wd, E, n, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 2: return wald_pass_reg<2>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 3: return wald_pass_reg<3>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 4: return wald_pass_reg<4>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 5: return wald_pass_reg<5>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 6: return wald_pass_reg<6>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
         default: break;
     }
     const int ns = (q * (q + 3) / 2 + kBGroups - 1) / kBGroups;
     switch (ns) {
-        case 3: return wald_pass<3>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 4: return wald_pass<4>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 5: return wald_pass<5>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 6: return wald_pass<6>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 7: return wald_pass<7>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 8: return wald_pass<8>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        case 9: return wald_pass<9>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
-        default: return wald_pass<kBSlots>(gf, wd, E, n, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 3: return wald_pass<3>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 4: return wald_pass<4>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 5: return wald_pass<5>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 6: return wald_pass<6>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 7: return wald_pass<7>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 8: return wald_pass<8>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        case 9: return wald_pass<9>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
+        default: return wald_pass<kBSlots>(ds, i_lo, i_hi, q, pass0, tile, sh, red, invalid);
     }
+}
+
+// glm.fit(binomial) IRLS on a design (cluster-collective). On return sh.beta holds the final coefficients and
+// *se2_last the last-WLS variance of the last coefficient. Returns 0 ok, 1 rank deficient, 2 invalid.
+template <class Design>
+__device__ int irls_fit(const Design &ds, int64_t i_lo, int64_t i_hi, double *tile, BShared &sh, const ClusterRed &red,
+                        double *se2_last) {
+    const int q = ds.q();
+    int invalid;
+    double devold = wald_pass_any(ds, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+    for (int it = 1; it <= 25; it++) {
+        wald_solve(sh, q);
+        if (!sh.ok) return 1;
+        *se2_last = sh.se2;   // covariance of the WLS just solved = the one summary.glm reports on convergence
+        double dev = wald_pass_any(ds, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+        if (!isfinite(dev) || invalid) return 2;
+        if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) break;
+        devold = dev;
+    }
+    return 0;
 }
 
 // Cluster-collective Wald p-value of E:g (ref :636-662): glm.fit IRLS for binary, lm for quantitative.
 template <class GFun>
 __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, int64_t i_lo, int64_t i_hi,
                           double *tile, BShared &sh, const ClusterRed &red, int *fail) {
-    const int q = wd.p + 4;
+    DesignWald ds{wd, E, gf, n};
+    const int q = ds.q();
     *fail = 0;
-    int invalid;
     if (wd.trait == 1) {
-        double devold = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
         double se2 = 0;
-        for (int it = 1; it <= 25; it++) {
-            wald_solve(sh, q);
-            if (!sh.ok) { *fail = 1; return d_na_real(); }
-            se2 = sh.se2;   // covariance of the WLS just solved = the one summary.glm reports on convergence
-            double dev = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
-            if (!isfinite(dev) || invalid) { *fail = 2; return d_na_real(); }
-            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) break;
-            devold = dev;
-        }
+        int rc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
+        if (rc) { *fail = rc; return d_na_real(); }
         const double zst = sh.beta[q - 1] / sqrt(se2);
         return 2 * d_pnorm(-fabs(zst), true);
     }
-    wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+    int invalid;
+    wald_pass_any(ds, i_lo, i_hi, q, true, tile, sh, red, &invalid);
     wald_solve(sh, q);
     if (!sh.ok) { *fail = 1; return d_na_real(); }
     const double il = sh.se2, bl = sh.beta[q - 1];
-    double rss = wald_pass_any(gf, wd, E, n, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+    double rss = wald_pass_any(ds, i_lo, i_hi, q, false, tile, sh, red, &invalid);
     const double rdf = (double)(n - q);
     const double se = sqrt(il * (rss / rdf));
     return d_pt2(bl / se, rdf);
@@ -1083,6 +1134,285 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const int *__restri
         }
         if (writer) {
             o[2 * m_total] = pspa; o[3 * m_total] = pnorm_;
+            if (spa) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+    cl.sync();
+}
+
+
+// ===========================================================================
+// SPAGxEmix_CCT (R/SPAGxECCT.R:1013-1269): individual-level allele frequencies from the PCs.
+struct MixData {
+    const double *pcs;      // n x k column-major (topPCs)
+    const double *xtx_inv;  // (k+1) x (k+1) inverse of [1,PCs]'[1,PCs] (SNP-invariant)
+    int k;
+    double pc_pcut, neg_ratio_cut;
+};
+// allele-frequency model of one SNP, kept in shared memory and evaluated on the fly per sample
+struct AfModel {
+    int kind;               // 0 uniform (MAF), 1 clamp(x'beta / 2), 2 logistic 1 - sqrt(1 - mu)
+    int k, nsel;
+    int sel[kMaxPC];
+    double maf;
+    double beta[kMaxPC + 1];
+};
+__device__ __forceinline__ double af_eval(const AfModel &af, const double *__restrict__ pcs, int64_t n, int64_t i) {
+    if (af.kind == 0) return af.maf;
+    if (af.kind == 1) {
+        double f = af.beta[0];
+        for (int c = 0; c < af.k; c++) f += pcs[i + (int64_t)c * n] * af.beta[1 + c];
+        double m = f / 2;                              // Fit.lm$fitted.values/2 (ref :1067)
+        if (m <= 0) m = 0;                             // ref :1095-1096
+        if (m >= 1) m = 1;
+        return m;
+    }
+    double eta = af.beta[0];
+    for (int c = 0; c < af.nsel; c++) eta += pcs[i + (int64_t)af.sel[c] * n] * af.beta[1 + c];
+    const double tmp = (eta < -30.) ? DBL_EPSILON : ((eta > 30.) ? 1 / DBL_EPSILON : exp(eta));
+    const double mu = tmp / (1 + tmp);
+    return 1 - sqrt(1 - mu);                           // ref :1089
+}
+struct SrcMix {  // residual vector (E - lambda) R or E * (R - fit[class]) with per-sample allele frequency
+    const AfModel *af; const double *pcs; int64_t n;
+    const double *R, *E; const uint8_t *row; double fit[4]; double lambda; int adj;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
+        if (adj) { int c = (row[i >> 2] >> (2 * (i & 3))) & 3; r = E[i] * (R[i] - fit[c]); }
+        else r = (E[i] - lambda) * R[i];
+        m = af_eval(*af, pcs, n, i); w = 1.0;
+    }
+};
+
+// K3 for mix: filtered rows are written here; every other SNP goes to the cluster kernel's list
+__global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n, double min_maf,
+                               double *__restrict__ out, int *b_list, Counters *ctr) {
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = jl < m_chunk;
+    bool want = false;
+    if (active) {
+        const double NA = d_na_real();
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        Prologue pr = make_prologue(asum, nmiss, n);
+        double *o = out + snp0 + jl;
+        o[0] = pr.maf; o[1 * m_total] = pr.miss_rate;
+        if (nmiss == n) {
+            for (int c = 0; c < 12; c++) o[c * m_total] = NA;
+            o[1 * m_total] = 1.0;
+            atomicAdd(&ctr->n_allmissing, 1ULL);
+        } else if (pr.maf < min_maf) {
+            for (int c = 2; c < 12; c++) o[c * m_total] = NA;
+            atomicAdd(&ctr->n_filtered, 1ULL);
+        } else want = true;
+    }
+    int pos = list_reserve(&ctr->b_count, want);
+    if (want) b_list[pos] = jl;
+}
+
+struct MixShared { AfModel af; double xg[kMaxPC + 1]; double pv[kMaxPC + 1]; };
+
+__global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ list, Counters *ctr,
+                                                        const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
+                                                        int64_t snp0, int64_t m_total, int64_t n,
+                                                        const double *__restrict__ R, const double *__restrict__ E,
+                                                        const VecConst *__restrict__ vcp, WaldData wd, MixData md,
+                                                        double epsilon, double cutoff, double *__restrict__ out) {
+    namespace cg = cooperative_groups;
+    extern __shared__ double tile[];
+    __shared__ BShared sh;
+    __shared__ MixShared ms;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const int count = ctr->b_count;
+    const VecConst vc = *vcp;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const int k = md.k, k1 = md.k + 1;
+    const double NA = d_na_real();
+    for (int idx = cluster_id; idx < count; idx += n_clusters) {
+        const int jl = list[idx];
+        const int64_t j = snp0 + jl;
+        const uint8_t *row = bed + (int64_t)jl * pitch;
+        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        const Prologue pr = make_prologue(asum, nmiss, n);
+        GFromRow gf;
+        gf.row = row;
+        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
+        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
+        double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+        double S2 = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
+        if (pr.flip) { S1 = 2 * vc.sumR - S1; S2 = 2 * vc.sumV - S2; }
+        const double MAC = pr.maf * 2 * (double)n;                                   // ref :1058
+        double negnum = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) { ms.af.kind = 0; ms.af.maf = pr.maf; ms.af.k = k; ms.af.nsel = 0; }
+        __syncthreads();
+        if (!(MAC <= 20)) {
+            // ---- lm(g ~ topPCs): X'g, beta = (X'X)^-1 X'g (ref :1066) ----
+            for (int c0 = 0; c0 < k1; c0 += 4) {
+                double v4[4] = {0, 0, 0, 0};
+                for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                    const double g = gf(i);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        if (c0 + c < k1) v4[c] += g * ((c0 + c == 0) ? 1.0 : md.pcs[i + (int64_t)(c0 + c - 1) * n]);
+                }
+                red.sum<4>(v4);
+                if (threadIdx.x == 0) for (int c = 0; c < 4; c++) if (c0 + c < k1) ms.xg[c0 + c] = v4[c];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int a = 0; a < k1; a++) {
+                    double b = 0;
+                    for (int c = 0; c < k1; c++) b += md.xtx_inv[a + c * k1] * ms.xg[c];
+                    ms.af.beta[a] = b;
+                }
+                ms.af.kind = 1;
+            }
+            __syncthreads();
+            // fitted values: negative count and residual sum of squares
+            double v2[2] = {0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                double f = ms.af.beta[0];
+                for (int c = 0; c < k; c++) f += md.pcs[i + (int64_t)c * n] * ms.af.beta[1 + c];
+                if (f / 2 < 0) v2[0] += 1.0;
+                const double e = gf(i) - f;
+                v2[1] += e * e;
+            }
+            red.sum<2>(v2);
+            negnum = v2[0];
+            const double negratio = negnum / (double)n;
+            if (negratio > md.neg_ratio_cut) {                                        // ref :1074
+                const double rdf = (double)(n - k1), resvar = v2[1] / rdf;
+                __syncthreads();
+                if (threadIdx.x < k) {                                                // PC p-values (summary.lm)
+                    const int a = 1 + threadIdx.x;
+                    const double se = sqrt(md.xtx_inv[a + a * k1] * resvar);
+                    ms.pv[a] = d_pt2(ms.af.beta[a] / se, rdf);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int ns = 0;
+                    for (int a = 1; a <= k; a++) if (ms.pv[a] < md.pc_pcut) ms.af.sel[ns++] = a - 1;
+                    ms.af.nsel = ns;
+                    // sum(round(g)) == 0 | sum(2 - round(g)) == 0 from the class counts (ref :1084)
+                    ms.af.kind = 0;
+                }
+                __syncthreads();
+                const int nsel = ms.af.nsel;
+                if (nsel > 0) {
+                    double vs[2] = {0, 0};
+                    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double gt = rint(gf(i)); vs[0] += gt; vs[1] += 2 - gt; }
+                    red.sum<2>(vs);
+                    if (!(vs[0] == 0 || vs[1] == 0)) {
+                        DesignAf ds{md.pcs, n, nsel, ms.af.sel, gf};
+                        double se2;
+                        int frc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
+                        (void)frc;   // the reference uses Fit$fitted.values whatever glm() warned about
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            for (int c = 0; c <= nsel; c++) ms.af.beta[c] = sh.beta[c];
+                            ms.af.kind = 2;
+                            if (rank == 0) atomicAdd(&ctr->n_mix_logistic, 1ULL);
+                        }
+                        __syncthreads();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- statistics with per-sample allele frequencies (ref :1102-1108) ----
+        double v4[4] = {0, 0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double m = af_eval(ms.af, md.pcs, n, i), gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
+            v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
+        }
+        red.sum<4>(v4);
+        const double meanS1 = 2 * v4[0], VarS1 = v4[1];
+        const double Z1 = (S1 - meanS1) / sqrt(VarS1);
+        const double pG = d_pnorm(-fabs(Z1), true) * 2;
+        double *o = out + j;
+        const bool writer = (rank == 0 && threadIdx.x == 0);
+        SrcMix src;
+        src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row;
+        double po[4];
+        int iters = 0; bool spa = false;
+        if (pG > epsilon) {
+            const double lambda = v4[2] / v4[1];                                      // ref :1115
+            const double S_GxE = S2 - lambda * S1;
+            src.lambda = lambda; src.adj = 0;
+            double v2[2] = {0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                double r, m, w; src.get(i, r, m, w);
+                v2[0] += r * m; v2[1] += (r * r) * (2 * m * (1 - m));
+            }
+            red.sum<2>(v2);
+            const double Smean = 2 * v2[0], Svar = v2[1];
+            const double z = (S_GxE - Smean) / sqrt(Svar);
+            if (fabs(z) < cutoff) {
+                const double pn = d_pnorm(fabs(z), false) * 2;
+                po[0] = po[1] = po[2] = po[3] = pn;
+            } else {
+                spa = true;
+                const double ps = spa_two_tail(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE),
+                                               CUDART_INF, &iters);
+                po[0] = po[1] = po[2] = ps;
+                po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            }
+            if (writer) atomicAdd(&ctr->n_branch_a, 1ULL);
+        } else {
+            if (writer) atomicAdd(&ctr->n_branch_b, 1ULL);
+            double v3[3] = {0, 0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
+            red.sum<3>(v3);
+            const double a = (double)n, b = pr.sum_g, d = v3[0];
+            const double det = a * d - b * b;
+            if (det == 0 || !isfinite(det)) {
+                if (writer) {
+                    o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                    o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+                    o[10 * m_total] = negnum; o[11 * m_total] = MAC;
+                    atomicAdd(&ctr->n_singular, 1ULL);
+                }
+                continue;
+            }
+            const double i00 = d / det, i01 = -b / det, i11 = a / det;
+            for (int c = 0; c < 4; c++) {
+                double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
+                src.fit[c] = wi0 * vc.sumR + wi1 * S1;
+            }
+            src.adj = 1; src.lambda = 0;
+            v3[0] = v3[1] = v3[2] = 0;
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                double r, m, w; src.get(i, r, m, w);
+                v3[0] += gf(i) * r; v3[1] += r * m; v3[2] += (r * r) * (2 * m * (1 - m));
+            }
+            red.sum<3>(v3);
+            const double S0 = v3[0], Smean = 2 * v3[1], Svar = v3[2];
+            const double z = (S0 - Smean) / sqrt(Svar);
+            double pspa, pn;
+            if (fabs(z) < cutoff) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
+            else {
+                spa = true;
+                pspa = spa_two_tail(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), CUDART_INF, &iters);
+                pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            }
+            int wfail;
+            double pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
+            if (isnan(pw)) pw = pspa;                                                 // ref :1194, :1213, :1232
+            double pc = NA;
+            int crc = d_cct2(pspa, pw, &pc);
+            if (writer) {
+                if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
+                if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
+            }
+            po[0] = pspa; po[1] = pw; po[2] = pc; po[3] = pn;
+        }
+        if (writer) {
+            o[2 * m_total] = po[0]; o[3 * m_total] = po[1]; o[4 * m_total] = po[2]; o[5 * m_total] = po[3];
+            o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+            o[10 * m_total] = negnum; o[11 * m_total] = MAC;
             if (spa) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
         }
     }

@@ -133,6 +133,8 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     // opt in to the large dynamic shared memory of the branch-B kernel
     e = cudaFuncSetAttribute(k_branch_b_cct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    e = cudaFuncSetAttribute(k_mix_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
     if ((e = cudaMalloc((void **)&ctx->quad.x, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.w, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -517,9 +519,29 @@ static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1,
 
 enum RunMode { RUN_CCT = 0, RUN_PLUS = 1, RUN_MIX = 2 };
 
-static int launch_mix(spagxe_ctx *ctx, const uint8_t *, int64_t, SnpStats, int64_t, int, int64_t, int64_t, WaldData,
-                      const spagxe_params *, double *) {
-    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
+static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int mc, int64_t M,
+                      int64_t N, WaldData wd, const spagxe_params *prm, double *d_out) {
+    cudaStream_t s = ctx->stream();
+    k_finalize_mix<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, prm->min_maf, d_out, ctx->d_b_list, ctx->d_ctr);
+    LAUNCH_CHECK();
+    cudaLaunchConfig_t cfg = {};
+    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
+    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = branch_b_smem(kMaxQ);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int *list = ctx->d_b_list;
+    Counters *ctr = ctx->d_ctr;
+    const double *R = ctx->d_R, *E = ctx->d_E;
+    const VecConst *vc = ctx->d_vc;
+    MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff};
+    CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out));
+    ctx->launches++;
+    return SPAGXE_OK;
 }
 
 static int launch_branch_b_plus(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int64_t M,
@@ -813,6 +835,49 @@ extern "C" int spagxe_measure_fp64_peak(spagxe_ctx *ctx, double *tflops) {
 
 extern "C" int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k) {
     if (!ctx) return SPAGXE_ERR_ARG;
-    (void)pcs; (void)k;
-    return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "SPAGxEmix_CCT is not implemented yet");
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_pcs: call spagxe_set_vectors first");
+    if (!pcs || k < 1 || k > kMaxPC) return fail(ctx, SPAGXE_ERR_ARG, "set_pcs: need 1 <= k <= %d principal components", kMaxPC);
+    const int64_t n = ctx->n;
+    const int k1 = k + 1;
+    // (X'X)^-1 for X = [1, PCs] is SNP-invariant: long-double normal matrix + Cholesky on the host, once
+    std::vector<long double> A((size_t)k1 * k1, 0.0L);
+    for (int a = 0; a < k1; a++)
+        for (int b = a; b < k1; b++) {
+            long double sacc = 0;
+            const double *ca = a ? pcs + (size_t)(a - 1) * n : nullptr, *cb = b ? pcs + (size_t)(b - 1) * n : nullptr;
+            for (int64_t i = 0; i < n; i++) sacc += (long double)(ca ? ca[i] : 1.0) * (cb ? cb[i] : 1.0);
+            A[a + (size_t)b * k1] = A[b + (size_t)a * k1] = sacc;
+        }
+    std::vector<long double> L((size_t)k1 * k1, 0.0L), Li((size_t)k1 * k1, 0.0L);
+    for (int j = 0; j < k1; j++) {
+        long double d = A[j + (size_t)j * k1];
+        for (int c = 0; c < j; c++) d -= L[j + (size_t)c * k1] * L[j + (size_t)c * k1];
+        if (!(d > 0)) return fail(ctx, SPAGXE_ERR_SINGULAR, "set_pcs: [1, topPCs] is rank deficient");
+        d = sqrtl(d); L[j + (size_t)j * k1] = d;
+        for (int i = j + 1; i < k1; i++) {
+            long double sacc = A[i + (size_t)j * k1];
+            for (int c = 0; c < j; c++) sacc -= L[i + (size_t)c * k1] * L[j + (size_t)c * k1];
+            L[i + (size_t)j * k1] = sacc / d;
+        }
+    }
+    for (int c = 0; c < k1; c++)   // Li = L^-1 (lower triangular)
+        for (int i = 0; i < k1; i++) {
+            long double sacc = (i == c) ? 1.0L : 0.0L;
+            for (int t = 0; t < i; t++) sacc -= L[i + (size_t)t * k1] * Li[t + (size_t)c * k1];
+            Li[i + (size_t)c * k1] = sacc / L[i + (size_t)i * k1];
+        }
+    std::vector<double> inv((size_t)k1 * k1);
+    for (int a = 0; a < k1; a++)
+        for (int b = 0; b < k1; b++) {
+            long double sacc = 0;
+            for (int t = 0; t < k1; t++) sacc += Li[t + (size_t)a * k1] * Li[t + (size_t)b * k1];
+            inv[a + (size_t)b * k1] = (double)sacc;
+        }
+    CU(cudaSetDevice(ctx->device));
+    CU(dev_realloc(&ctx->d_pcs, (size_t)n * k));
+    CU(dev_realloc(&ctx->d_xtx_inv, (size_t)k1 * k1));
+    CU(cudaMemcpy(ctx->d_pcs, pcs, (size_t)n * k * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_xtx_inv, inv.data(), (size_t)k1 * k1 * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->n_pcs = k;
+    return SPAGXE_OK;
 }

@@ -337,3 +337,59 @@ def test_spagxe_plus_synthetic_families_with_missing_and_flips(gpu_ctx, oracle):
         assert_parity(out, ref, P_COLS_PLUS, S_COLS_PLUS, label=f"plus synthetic eps={eps}")
         assert diag["newton_iters"] == iters.sum()
     assert ((route & 2) > 0).sum() >= 5
+
+
+P_COLS_MIX = [2, 3, 4, 5, 6]
+S_COLS_MIX = [7, 8, 9]
+
+
+def _mix_inputs(golden_dir, trait="binary"):
+    """config-4 recipe at the fixture's scale (N = 10,000): two-way admixture proportions a6 and the bundled
+    top-10 PCs (simulation_studies/SPAGxEmixCCT/data), ancestry-specific allele frequencies and prevalence."""
+    d = np.load(f"{golden_dir}/mix.npz")
+    alpha = d["a6"][:, 0]
+    PCs = d["top10PCs"]
+    n = alpha.size
+    rng = np.random.default_rng(81)
+    pairs = [(0.3, 0.01), (0.1, 0.01), (0.05, 0.4), (0.01, 0.001), (0.2, 0.0), (0.0, 0.15), (0.002, 0.0005), (0.25, 0.25)]
+    m = 64
+    G = np.empty((n, m))
+    for j in range(m):
+        p1, p2 = pairs[j % len(pairs)]
+        p = alpha * p1 + (1 - alpha) * p2
+        g = rng.binomial(2, p).astype(float)
+        if j % 3 == 0:
+            g[rng.random(n) < 0.02] = np.nan
+        if j % 5 == 0:
+            g = 2 - g
+        G[:, j] = g
+    X1 = rng.standard_normal(n); X2 = rng.binomial(1, 0.5, n).astype(float); E = rng.standard_normal(n)
+    eta = 0.5 * X1 + 0.5 * X2 + 0.5 * E + 1.5 * (alpha - alpha.mean())
+    if trait == "binary":
+        Y = rng.binomial(1, 1 / (1 + np.exp(-(-2.5 + eta)))).astype(float)
+    else:
+        Y = eta + rng.standard_normal(n)
+    cova = np.column_stack([X1, X2, PCs[:, 0], PCs[:, 1]])
+    R = get_resid(trait, Y, [X1, X2, PCs[:, 0], PCs[:, 1], E])
+    return dict(G=np.ascontiguousarray(G), R=R, E=E, Y=Y, Cova=cova, PCs=PCs, n=n)
+
+
+@pytest.mark.parametrize("trait", ["binary", "quantitative"])
+def test_c4_spagxemix_admixed(gpu_ctx, oracle, golden_dir, trait):
+    from spagxecct_b200 import SPAGxEmix_CCT
+    x = _mix_inputs(golden_dir, trait)
+    rows = to_bed_rows(x["G"])
+    n = x["n"]
+    for eps in (0.001, 0.2):
+        res = SPAGxEmix_CCT(trait, Geno_mtx=x["G"], R=x["R"], E=x["E"], Phen_mtx={"Y": x["Y"]}, Cova_mtx=x["Cova"],
+                            topPCs=x["PCs"], epsilon=eps, Cutoff=2, ctx=gpu_ctx, quiet=True)
+        ref, route, iters, rc = oracle.mix_bed(trait, rows, n, x["R"], x["E"], x["Y"], x["Cova"], x["PCs"], epsilon=eps,
+                                               nthreads=8)
+        assert rc == 0
+        assert_parity(res.values, ref, P_COLS_MIX, S_COLS_MIX, exact_cols=(0, 1, 10), label=f"mix {trait} eps={eps}")
+        assert np.allclose(res.values[:, 11], ref[:, 11], rtol=1e-14, equal_nan=True)   # MAC
+        d = res.diag
+        assert d["n_branch_b"] == ((route & 2) > 0).sum() and d["n_spa"] == ((route & 4) > 0).sum()
+        assert d["n_mix_logistic"] == ((route & 256) > 0).sum() and d["newton_iters"] == iters.sum()
+        assert res.colnames[10:] == ["MAF.est.negative.num", "MAC"]
+    assert ((route & 256) > 0).sum() >= 3 and ((route & 64) > 0).sum() >= 1 and ((route & 2) > 0).sum() >= 5
