@@ -351,7 +351,7 @@ def _mix_inputs(golden_dir, trait="binary"):
     PCs = d["top10PCs"]
     n = alpha.size
     rng = np.random.default_rng(81)
-    pairs = [(0.3, 0.01), (0.1, 0.01), (0.05, 0.4), (0.01, 0.001), (0.2, 0.0), (0.0, 0.15), (0.002, 0.0005), (0.25, 0.25)]
+    pairs = [(0.3, 0.01), (0.1, 0.01), (0.05, 0.4), (0.01, 0.001), (0.2, 0.0), (0.0, 0.15), (0.0012, 0.0003), (0.25, 0.25)]
     m = 64
     G = np.empty((n, m))
     for j in range(m):
@@ -382,9 +382,9 @@ def test_c4_spagxemix_admixed(gpu_ctx, oracle, golden_dir, trait):
     n = x["n"]
     for eps in (0.001, 0.2):
         res = SPAGxEmix_CCT(trait, Geno_mtx=x["G"], R=x["R"], E=x["E"], Phen_mtx={"Y": x["Y"]}, Cova_mtx=x["Cova"],
-                            topPCs=x["PCs"], epsilon=eps, Cutoff=2, ctx=gpu_ctx, quiet=True)
+                            topPCs=x["PCs"], epsilon=eps, Cutoff=2, min_maf=0.0002, ctx=gpu_ctx, quiet=True)
         ref, route, iters, rc = oracle.mix_bed(trait, rows, n, x["R"], x["E"], x["Y"], x["Cova"], x["PCs"], epsilon=eps,
-                                               nthreads=8)
+                                               min_maf=0.0002, nthreads=8)
         assert rc == 0
         assert_parity(res.values, ref, P_COLS_MIX, S_COLS_MIX, exact_cols=(0, 1, 10), label=f"mix {trait} eps={eps}")
         assert np.allclose(res.values[:, 11], ref[:, 11], rtol=1e-14, equal_nan=True)   # MAC
