@@ -84,7 +84,7 @@ class ClockSampler:
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -171,8 +171,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--batch-snps", type=int, default=16384)
@@ -199,20 +199,18 @@ def main():
     W, K = max(3, args.warmup), args.steps
 
     # ---- inputs: rank 0 owns Step-1 output; ONE NCCL broadcast distributes R and E (north_star) ----
+    from spagxecct_b200.sharded import broadcast_inputs
     vec = torch.empty((2, n), dtype=torch.float64, device=dev)
+    ycov = torch.empty((3, n), dtype=torch.float64, device=dev)   # Wald data (Y, Cova) rides along
     ph = None
     if rank == 0:
         ph = make_pheno(n)
         vec[0] = torch.from_numpy(ph["R"]).to(dev); vec[1] = torch.from_numpy(ph["E"]).to(dev)
+        ycov[0] = torch.from_numpy(ph["Y"]).to(dev); ycov[1:] = torch.from_numpy(ph["Cova"].T.copy()).to(dev)
     if world > 1:
-        dist.broadcast(vec, src=0)
-        ycov = torch.empty((3, n), dtype=torch.float64, device=dev)   # Wald data (Y, Cova) rides along
-        if rank == 0:
-            ycov[0] = torch.from_numpy(ph["Y"]).to(dev); ycov[1:] = torch.from_numpy(ph["Cova"].T.copy()).to(dev)
-        dist.broadcast(ycov, src=0)
-        Y = ycov[0].cpu().numpy(); cova = ycov[1:].cpu().numpy().T.copy()
-    else:
-        Y, cova = ph["Y"], ph["Cova"]
+        vec, ycov = broadcast_inputs(dist, [vec, ycov])           # the ONE collective of the run (NCCL)
+        vec = vec.contiguous(); ycov = ycov.contiguous()
+    Y = ycov[0].cpu().numpy(); cova = ycov[1:].cpu().numpy().T.copy()
     ctx = Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_vectors_device(n, vec[0].data_ptr(), vec[1].data_ptr())
@@ -234,9 +232,9 @@ def main():
 
     # ---- device-resident timing (value) ----
     diags = []
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(W):
         ctx.run_cct(geno_dev, prm_dev, out_ptr=out_dev.data_ptr())
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
