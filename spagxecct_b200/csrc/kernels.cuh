@@ -683,6 +683,18 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
         if (pass0) { double mus = (y + 0.5) / 2; eta = log(mus / (1 - mus)); }
         const bool clampd = (eta > THRESH || eta < MTHRESH);
         const double ee = exp(eta);
+        if (!clampd && (y == 0.0 || y == 1.0)) {
+            // mu = e/(1+e), mu.eta = e/(1+e)^2 = Var(mu) => w = mu.eta; dev_i = -2 log(mu^y (1-mu)^(1-y))
+            //    = 2 (log(1+e) - y eta): one reciprocal, one log, one division (same values to rounding)
+            const double opexp = 1 + ee;
+            const double r = 1.0 / opexp;
+            const double mu = ee * r;
+            const double mev = mu * r;
+            dev += 2 * (log(opexp) - y * eta);
+            z = eta + (y - mu) / mev;
+            w2 = mev;
+            return;
+        }
         const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
         const double opexp = 1 + ee;
         const double mu = tmp / (1 + tmp);
@@ -718,10 +730,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
     for (int c = 0; c < Q; c++) beta[c] = sh.beta[c];
     double dev = 0;
     int bad = 0;
-    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-        double x[Q];
-        const double y = ds.y(i);
-        ds.template fill<Q>(i, x);
+    auto consume = [&](const double (&x)[Q], double y) {
         double eta = 0;
         if (!pass0) {
 #pragma unroll
@@ -734,9 +743,24 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
         for (int a = 0; a < Q; a++) {
             const double wa = w2 * x[a];
 #pragma unroll
-            for (int b = a; b < Q; b++) acc[e++] = fma(wa, x[b], acc[e]);
-            acc[e++] = fma(wa, z, acc[e]);
+            for (int b = a; b < Q; b++) { acc[e] = fma(wa, x[b], acc[e]); e++; }
+            acc[e] = fma(wa, z, acc[e]); e++;
         }
+    };
+    int64_t i = i_lo + threadIdx.x;
+    for (; i + blockDim.x < i_hi; i += 2 * blockDim.x) {   // two samples per trip: both sets of loads in flight
+        double xa[Q], xb[Q];
+        const double ya = ds.y(i), yb = ds.y(i + blockDim.x);
+        ds.template fill<Q>(i, xa);
+        ds.template fill<Q>(i + blockDim.x, xb);
+        consume(xa, ya);
+        consume(xb, yb);
+    }
+    if (i < i_hi) {
+        double xa[Q];
+        const double ya = ds.y(i);
+        ds.template fill<Q>(i, xa);
+        consume(xa, ya);
     }
     // warp totals -> per-warp rows in the (otherwise unused) tile -> CTA partial -> cluster total
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;

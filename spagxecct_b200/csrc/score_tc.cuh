@@ -35,14 +35,15 @@ constexpr int kTcRows = 128;          // SNP rows per work item (UMMA M)
 constexpr int kTcTileSamples = 512;   // samples per pipeline stage
 constexpr int kTcTileBytes = kTcTileSamples / 4;   // 128 packed bytes per row per stage
 constexpr int kTcBTileBytes = kTcTileSamples * 16; // 8192 B of B per stage
-constexpr int kTcStages = 6;
-constexpr int kTcExpWarps = 8;
-constexpr int kTcThreads = (kTcExpWarps + 2) * 32;  // + TMA producer warp + MMA warp
+constexpr int kTcGStages = 10;         // genotype ring (HBM latency x bandwidth needs ~190 KB in flight per SM)
+constexpr int kTcBStages = 6;          // B ring (L2 resident, short latency)
+constexpr int kTcMaxExpWarps = 16;
+constexpr int kTcMaxABufs = 3;
 constexpr int kTcDigits = 7;
-constexpr int kTcStageBytes = kTcRows * kTcTileBytes + kTcBTileBytes;  // 24576
-constexpr size_t kTcSmemBytes = (size_t)kTcStages * kTcStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-// TMEM columns: A buffers 2 x 128, accumulators at 256 / 272
-constexpr uint32_t kTcColAcc = 256;
+constexpr int kTcGStageBytes = kTcRows * kTcTileBytes;  // 16384
+constexpr size_t kTcSmemBytes = (size_t)kTcGStages * kTcGStageBytes + (size_t)kTcBStages * kTcBTileBytes + 1024 /*align*/ + 512 /*barriers*/;
+// TMEM columns: kTcABufs A buffers x 128 columns (256 samples: 64 cols -dosage, 64 cols missing), then accumulators
+constexpr uint32_t kTcColAcc = kTcMaxABufs * 128;
 
 struct BmatInfo { int sR, sV; double maxR, maxV; };
 
@@ -100,15 +101,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
+    auto attempt = [&]() {
+        uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 28)) __trap();  // a protocol bug must fault, not hang the GPU
-    }
+        return done != 0;
+    };
+    if (attempt()) return;
+    for (uint32_t spin = 0; !attempt(); spin++)
+        if (spin > (1u << 26)) __trap();  // a protocol bug must fault, not hang the GPU
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -171,25 +175,33 @@ constexpr uint32_t kTcIdesc = (2u << 4) /*D = s32*/ | (1u << 7) /*A = s8*/ | (1u
 
 // ---- the kernel ---------------------------------------------------------------------------------
 // work item = (row tile rt, k split ks): rows [128 rt, +128), sample tiles [ks*tiles_per_split, ...)
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int kTcExpWarps, int kTcABufs, bool kWithMiss = true, int kProbe = 0>  // kProbe: 1 = no MMAs, 2 = no expansion (timing probes)
+__global__ void __launch_bounds__((kTcExpWarps + 4) * 32, 1)
 k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
            int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
+    constexpr int kTcChunksPerWarp = 4 / (kTcExpWarps / 4);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = sbase + kTcStages * kTcStageBytes;
-    // barriers (8 B each): full[6], empty[6], afull[2], aempty[2], accfull, accempty, tmem slot
-    auto bar_full = [&](int s) { return bars + 8u * s; };
-    auto bar_empty = [&](int s) { return bars + 8u * (kTcStages + s); };
-    auto bar_afull = [&](int b) { return bars + 8u * (2 * kTcStages + b); };
-    auto bar_aempty = [&](int b) { return bars + 8u * (2 * kTcStages + 2 + b); };
-    const uint32_t bar_accfull = bars + 8u * (2 * kTcStages + 4), bar_accempty = bars + 8u * (2 * kTcStages + 5);
-    const uint32_t tmem_slot = bars + 8u * (2 * kTcStages + 6);
+    const uint32_t bbase = sbase + kTcGStages * kTcGStageBytes;            // B ring
+    const uint32_t bars = bbase + kTcBStages * kTcBTileBytes;
+    // barriers (8 B each)
+    auto bar_gfull = [&](int s) { return bars + 8u * s; };
+    auto bar_gempty = [&](int s) { return bars + 8u * (kTcGStages + s); };
+    auto bar_bfull = [&](int s) { return bars + 8u * (2 * kTcGStages + s); };
+    auto bar_bempty = [&](int s) { return bars + 8u * (2 * kTcGStages + kTcBStages + s); };
+    constexpr int kB0 = 2 * kTcGStages + 2 * kTcBStages;
+    auto bar_afull = [&](int b) { return bars + 8u * (kB0 + b); };
+    auto bar_aempty = [&](int b) { return bars + 8u * (kB0 + kTcMaxABufs + b); };
+    const uint32_t bar_accfull = bars + 8u * (kB0 + 2 * kTcMaxABufs), bar_accempty = bars + 8u * (kB0 + 2 * kTcMaxABufs + 1);
+    const uint32_t tmem_slot = bars + 8u * (kB0 + 2 * kTcMaxABufs + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), kTcExpWarps + 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_afull(b), kTcExpWarps); mbar_init(bar_aempty(b), 1); }
-        mbar_init(bar_accfull, 1); mbar_init(bar_accempty, 4);
+        // two MMA warps (dosage / missing) each commit to the stage, A-buffer and accumulator barriers
+        for (int s = 0; s < kTcGStages; s++) { mbar_init(bar_gfull(s), 1); mbar_init(bar_gempty(s), kTcExpWarps); }
+        for (int s = 0; s < kTcBStages; s++) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 2); }
+        for (int b = 0; b < kTcABufs; b++) { mbar_init(bar_afull(b), kTcExpWarps); mbar_init(bar_aempty(b), 2); }
+        mbar_init(bar_accfull, 2); mbar_init(bar_accempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kTcExpWarps) {  // TMEM allocation (whole 512 columns: one CTA per SM by construction)
@@ -205,26 +217,41 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
 
     const int n_items = n_row_tiles * n_splits;
     if (warp == kTcExpWarps) {
-        // ================= TMA producer =================
+        // ================= TMA producer: packed genotype tiles (HBM) =================
         if (lane == 0) {
             uint32_t f = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int rt = item / n_splits, ks = item % n_splits;
                 const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
                 for (int t = t0; t < t1; t++, f++) {
-                    const int s = f % kTcStages;
-                    mbar_wait(bar_empty(s), ((f / kTcStages) & 1) ^ 1);
-                    mbar_expect_tx(bar_full(s), kTcStageBytes);
-                    const uint32_t dst = sbase + s * kTcStageBytes;
-                    tma_load_2d(dst, &bedmap, t * kTcTileBytes, rt * kTcRows, bar_full(s));
-                    bulk_load_1d(dst + kTcRows * kTcTileBytes, Bmat + (int64_t)t * kTcBTileBytes, kTcBTileBytes, bar_full(s));
+                    const int s = f % kTcGStages;
+                    mbar_wait(bar_gempty(s), ((f / kTcGStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_gfull(s), kTcGStageBytes);
+                    tma_load_2d(sbase + s * kTcGStageBytes, &bedmap, t * kTcTileBytes, rt * kTcRows, bar_gfull(s));
                 }
             }
         }
     } else if (warp == kTcExpWarps + 1) {
-        // ================= MMA issuer =================
+        // ================= bulk-copy producer: B tiles (L2) =================
+        if (lane == 0) {
+            uint32_t f = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ks = item % n_splits;
+                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+                for (int t = t0; t < t1; t++, f++) {
+                    const int s = f % kTcBStages;
+                    mbar_wait(bar_bempty(s), ((f / kTcBStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_bfull(s), kTcBTileBytes);
+                    bulk_load_1d(bbase + s * kTcBTileBytes, Bmat + (int64_t)t * kTcBTileBytes, kTcBTileBytes, bar_bfull(s));
+                }
+            }
+        }
+    } else if (warp > kTcExpWarps + 1) {
+        const bool miss_warp = (warp == kTcExpWarps + 3);
+        const uint32_t dcol = kTcColAcc + (miss_warp ? 16u : 0u), aoff = miss_warp ? 64u : 0u;
+        // ================= MMA issuers (one per A matrix) =================
         // The whole warp walks the (warp-uniform) loop; one elected lane issues tcgen05.mma / commit.
-        uint32_t f = 0, it_count = 0;
+        uint32_t f = 0, g = 0, it_count = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int ks = item % n_splits;
             const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
@@ -233,30 +260,29 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
             tc_fence_after();
             uint32_t accum = 0;
             for (int t = t0; t < t1; t++, f++) {
-                const int s = f % kTcStages;
-                mbar_wait(bar_full(s), (f / kTcStages) & 1);
-                const uint32_t bsm = sbase + s * kTcStageBytes + kTcRows * kTcTileBytes;
+                const int s = f % kTcBStages;
+                mbar_wait(bar_bfull(s), (f / kTcBStages) & 1);
+                const uint32_t bsm = bbase + s * kTcBTileBytes;
                 const uint64_t bd0 = tc_bdesc(bsm);
-                // two half-stages: A buffer index == hs and its phase == f & 1 (g == 2 f), so every operand
-                // offset below is a compile-time constant relative to tmem_base / bd0
 #pragma unroll
-                for (int hs = 0; hs < 2; hs++) {
-                    mbar_wait(bar_afull(hs), f & 1);
+                for (int hs = 0; hs < 2; hs++, g++) {
+                    const uint32_t buf = g % kTcABufs, aphase = (g / kTcABufs) & 1;
+                    mbar_wait(bar_afull(buf), aphase);
                     tc_fence_after();
                     if (elect_one()) {
+                        const uint32_t abase = tmem_base + buf * 128u;
 #pragma unroll
                         for (int c4 = 0; c4 < 4; c4++) {
 #pragma unroll
                             for (int j = 0; j < 2; j++) {
                                 const uint64_t bd = bd0 + (uint64_t)((((hs * 4 + c4) * 4 + 2 * j) * 256) >> 4);
-                                const uint32_t acol = (uint32_t)(hs * 128 + c4 * 16 + j * 8);
+                                const uint32_t acol = (uint32_t)(c4 * 16 + j * 8);
                                 const uint32_t acc_on = (hs | c4 | j) ? 1u : accum;
-                                tc_mma_i8_ts(tmem_base + kTcColAcc, tmem_base + acol, bd, kTcIdesc, acc_on);
-                                tc_mma_i8_ts(tmem_base + kTcColAcc + 16, tmem_base + acol + 64, bd, kTcIdesc, acc_on);
+                                if (kProbe != 1 && (kWithMiss || !miss_warp)) tc_mma_i8_ts(tmem_base + dcol, abase + acol + aoff, bd, kTcIdesc, acc_on);
                             }
                         }
-                        tc_commit(bar_aempty(hs));
-                        if (hs == 1) tc_commit(bar_empty(s));
+                        tc_commit(bar_aempty(buf));
+                        if (hs == 1) tc_commit(bar_bempty(s));
                     }
                     __syncwarp();
                 }
@@ -268,7 +294,7 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
         }
     } else {
         // ================= expanders (+ epilogue on warps 0-3) =================
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, part = warp >> 2;
         const int row = quarter * 32 + lane;  // SNP row inside the tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const uint32_t swz = (uint32_t)(row & 7);
@@ -278,41 +304,47 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
             const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
             if (t1 <= t0) continue;
             for (int t = t0; t < t1; t++, f++) {
-                const int s = f % kTcStages;
-                mbar_wait(bar_full(s), (f / kTcStages) & 1);
-                const uint32_t rowaddr = sbase + s * kTcStageBytes + (uint32_t)row * kTcTileBytes;
+                const int s = f % kTcGStages;
+                mbar_wait(bar_gfull(s), (f / kTcGStages) & 1);
+                const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 for (int hs = 0; hs < 2; hs++, g++) {
-                    const int buf = g & 1;
-                    mbar_wait(bar_aempty(buf), ((g >> 1) & 1) ^ 1);
+                    const uint32_t buf = g % kTcABufs;
+                    mbar_wait(bar_aempty(buf), ((g / kTcABufs) & 1) ^ 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int c4 = half * 2 + c;          // chunk inside this A buffer
+                    for (int c = 0; c < (kProbe == 2 ? 0 : kTcChunksPerWarp); c++) {
+                        const int c4 = part * kTcChunksPerWarp + c;  // chunk inside this A buffer
                         const uint32_t chunk = (uint32_t)(hs * 4 + c4);  // chunk inside the stage
-                        uint32_t x[4];
-                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                        uint32_t x[4] = {chunk, chunk + 1, chunk + 2, chunk + 3};
+                        if (kProbe != 4) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                                      : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
                                      : "r"(rowaddr + ((chunk ^ swz) << 4)));
                         uint32_t d[16], m[16];
+                        if (kProbe == 4) {
+#pragma unroll
+                            for (int k = 0; k < 16; k++) { d[k] = x[k & 3] + k; m[k] = x[k & 3] ^ k; }
+                        } else
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const uint32_t so_lo = x[k], se_lo = x[k] << 2, so_hi = x[k] >> 16, se_hi = x[k] >> 14;
+                            // right shifts through IMAD.HI (FMA pipe): the ALU pipe is reserved for PRMT
+                            const uint32_t so_lo = x[k], se_lo = x[k] * 4u, so_hi = __umulhi(x[k], 1u << 16), se_hi = __umulhi(x[k], 1u << 18);
                             d[4 * k + 0] = prmt(0xFEFEFEFEu, 0u, so_lo); m[4 * k + 0] = prmt(0u, 0x01010101u, so_lo);
                             d[4 * k + 1] = prmt(0xFEFEFEFEu, 0u, se_lo); m[4 * k + 1] = prmt(0u, 0x01010101u, se_lo);
                             d[4 * k + 2] = prmt(0xFEFEFEFEu, 0u, so_hi); m[4 * k + 2] = prmt(0u, 0x01010101u, so_hi);
                             d[4 * k + 3] = prmt(0xFEFEFEFEu, 0u, se_hi); m[4 * k + 3] = prmt(0u, 0x01010101u, se_hi);
                         }
-                        tmem_st16(lane_addr + (uint32_t)(buf * 128 + c4 * 16), d);
-                        tmem_st16(lane_addr + (uint32_t)(buf * 128 + 64 + c4 * 16), m);
+                        if (kProbe != 3) tmem_st16(lane_addr + buf * 128u + (uint32_t)(c4 * 16), d);
+                        else if (d[3] == 0x12345678u && m[5] == 0x9abcdef0u) acc[0] = 1;  // keep the expansion alive
+                        if (kWithMiss && kProbe != 3) tmem_st16(lane_addr + buf * 128u + (uint32_t)(64 + c4 * 16), m);
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_afull(buf));
                 }
-                if (lane == 0) mbar_arrive(bar_empty(s));
+                if (lane == 0) mbar_arrive(bar_gempty(s));   // packed bytes are in registers/TMEM: the stage can be refilled
             }
-            if (half == 0) {
+            if (part == 0) {
                 // epilogue: D (128 lanes x 2 x 16 int32) -> global int64 totals
                 mbar_wait(bar_accfull, it_count & 1);
                 tc_fence_after();
@@ -343,6 +375,51 @@ k_score_tc(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict_
     if (warp == kTcExpWarps) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
+}
+
+// ---- access-pattern probe: the same TMA stream as k_score_tc (NBOX adjacent 128 B x 128-row boxes per stage) with the
+// stage released as soon as it lands.  Gives the memory-side ceiling of the tiling, independent of the expansion.
+template <int NBOX>
+__global__ void __launch_bounds__(64, 1)
+k_tma_probe(const __grid_constant__ CUtensorMap bedmap, int n_tiles, int tiles_per_split, int n_splits, int n_row_tiles,
+            unsigned long long *sink) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int kStage = NBOX * kTcRows * kTcTileBytes;
+    constexpr int kSt = (192 * 1024) / kStage;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = sbase + kSt * kStage;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSt; s++) { mbar_init(bars + 8u * s, 1); mbar_init(bars + 8u * (kSt + s), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_items = n_row_tiles * n_splits;
+    unsigned long long acc = 0;
+    uint32_t f = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rt = item / n_splits, ks = item % n_splits;
+        const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+        for (int t = t0; t < t1; t += NBOX, f++) {
+            const int s = f % kSt;
+            if (warp == 0) {
+                if (lane == 0) {
+                    mbar_wait(bars + 8u * (kSt + s), ((f / kSt) & 1) ^ 1);
+                    mbar_expect_tx(bars + 8u * s, kStage);
+                    for (int b = 0; b < NBOX; b++)
+                        tma_load_2d(sbase + s * kStage + b * kTcRows * kTcTileBytes, &bedmap, (t + b) * kTcTileBytes, rt * kTcRows, bars + 8u * s);
+                }
+            } else {
+                mbar_wait(bars + 8u * s, (f / kSt) & 1);
+                uint32_t v;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sbase + s * kStage + lane * 4));
+                acc += v;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8u * (kSt + s));
+            }
+        }
+    }
+    if (acc == 0x123456789ULL) sink[0] = acc;
 }
 
 // exact integer recombination: value = sum_k acc_k 256^k (two int64 halves -> one rounding), times 2^-s

@@ -51,7 +51,7 @@ struct spagxe_ctx {
     Quad quad = {nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
-    void *encode_tiled = nullptr; bool use_tc = true;
+    void *encode_tiled = nullptr; bool use_tc = true; int tc_cfg = 1;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     // pinned staging
@@ -140,8 +140,17 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.range, sizeof(double) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_binfo, sizeof(BmatInfo))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_score_tc<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc<8, 3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        false)
         return bail("cudaFuncSetAttribute(k_score_tc)", e);
+    if (const char *cfg = getenv("SPAGXE_TC_CFG")) ctx->tc_cfg = atoi(cfg);   // tuning switch: expander warps / A buffers
     {
         cudaDriverEntryPointQueryResult qres;
         e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres);
@@ -452,6 +461,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+template <int NBOX>
+static float run_probe(spagxe_ctx *ctx, const CUtensorMap &map, int n_tiles, int tps, int n_splits, int n_row_tiles) {
+    cudaStream_t s = ctx->stream();
+    const size_t smem = 192 * 1024 + 1024 + 256;
+    cudaFuncSetAttribute(k_tma_probe<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    const int grid = std::min(n_row_tiles * n_splits, ctx->num_sms);
+    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)ctx->d_acc);
+    cudaEventRecord(a, s);
+    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)ctx->d_acc);
+    cudaEventRecord(b, s); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms;
+}
+
 static int launch_score_tc(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
     cudaStream_t s = ctx->stream();
     const int m_pad = (int)round_up(mc, kTcRows);
@@ -479,7 +504,24 @@ static int launch_score_tc(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPl
     const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_items = n_row_tiles * n_splits;
     const int grid = std::min(n_items, ctx->num_sms);
-    k_score_tc<<<grid, kTcThreads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc);
+    if (getenv("SPAGXE_TMA_PROBE")) {   // one-off diagnostic of the access pattern (not a product path)
+        const double gb = (double)mc * pl.row_bytes / 1e9;
+        float m1 = run_probe<1>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
+        float m2 = run_probe<2>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
+        float m4 = run_probe<4>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
+        fprintf(stderr, "[tma probe] rows=%d %.3f GB: 1 box %.3f ms (%.0f GB/s), 2 boxes %.3f ms (%.0f GB/s), 4 boxes %.3f ms (%.0f GB/s)\n", mc, gb,
+                m1, gb / m1 * 1e3, m2, gb / m2 * 1e3, m4, gb / m4 * 1e3);
+    }
+    switch (ctx->tc_cfg) {
+        case 1: k_score_tc<8, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 4: k_score_tc<8, 3, false><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 7: k_score_tc<8, 3, true, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 8: k_score_tc<8, 3, true, 4><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 9: k_score_tc<8, 3, false, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 5: k_score_tc<8, 3, true, 1><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 6: k_score_tc<8, 3, true, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        default: k_score_tc<8, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+    }
     LAUNCH_CHECK();
     k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(ctx->d_acc, mc, ctx->d_binfo, st);
     LAUNCH_CHECK();
