@@ -33,6 +33,8 @@ struct SnpStats {  // per-SNP outputs of the score pass (chunk-local index)
 };
 
 struct SpaItem { int snp; int flags; double maf; double S; double Smean; double aux; };
+// deferred branch-B work item: everything the cluster kernel needs, valid until the next flush
+struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0; };
 
 struct Counters {  // device-side diagnostics / work-list cursors
     unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
@@ -215,7 +217,8 @@ __device__ __forceinline__ int homo_scalar(double sum_g, int64_t n, double S_in,
 // K3 for SPAGxE_CCT (ref :543-603).  One thread per SNP of the chunk.
 __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                const VecConst *__restrict__ vcp, double epsilon, double min_maf,
-                               double *__restrict__ out, SpaItem *spa_list, int *b_list, Counters *ctr) {
+                               double *__restrict__ out, SpaItem *spa_list, BItem *b_list, const uint8_t *bed,
+                               int64_t pitch, Counters *ctr) {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = jl < m_chunk;
     const VecConst vc = *vcp;
@@ -269,7 +272,7 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
     int pos = list_reserve(&ctr->spa_count, want_spa);
     if (want_spa) spa_list[pos] = item;
     pos = list_reserve(&ctr->b_count, want_b);
-    if (want_b) b_list[pos] = jl;
+    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl]};
 }
 
 // ---------------------------------------------------------------------------
@@ -596,7 +599,7 @@ struct BShared {  // static shared state of the branch-B kernel
 // dynamic smem: xs[kBTile][q+1] (x row, z in column q), ws[kBTile]
 __host__ __device__ inline size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
 
-__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &z,
+__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
                                             double &dev, int &bad);
 
 // One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
@@ -636,9 +639,9 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
             ds.fill_rt(i, xr, q);
             double eta = 0;
             if (!pass0) for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
-            double w2, z;
-            irls_sample(trait, pass0, y, eta, w2, z, dev, bad);
-            xr[q] = z;
+            double w2, wz;
+            irls_sample(trait, pass0, y, eta, w2, wz, dev, bad);
+            xr[q] = wz;   // column q already carries the weight
             ws[threadIdx.x] = w2;
         }
         __syncthreads();
@@ -647,7 +650,7 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
             const double *xr = xs + (size_t)sidx * qs;
 #pragma unroll
             for (int k = 0; k < NS; k++)
-                if (ea[k] >= 0) acc[k] = fma(w * xr[ea[k]], xr[eb[k]], acc[k]);
+                if (ea[k] >= 0) acc[k] = fma((eb[k] == q ? 1.0 : w) * xr[ea[k]], xr[eb[k]], acc[k]);
         }
     }
     // warp totals -> CTA partial normal equations -> cluster totals (rank order)
@@ -675,7 +678,9 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
 }
 
 // Per-sample IRLS working quantities (glm.fit binomial/logit restated).
-__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &z,
+// Per-sample IRLS working quantities (glm.fit binomial/logit restated).
+// Returns the working weight w and wz = w * z (z = eta + (y - mu)/mu.eta), which is all X'WX and X'Wz need.
+__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
                                             double &dev, int &bad) {
     const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
     if (trait == 1) {
@@ -684,15 +689,15 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
         const bool clampd = (eta > THRESH || eta < MTHRESH);
         const double ee = exp(eta);
         if (!clampd && (y == 0.0 || y == 1.0)) {
-            // mu = e/(1+e), mu.eta = e/(1+e)^2 = Var(mu) => w = mu.eta; dev_i = -2 log(mu^y (1-mu)^(1-y))
-            //    = 2 (log(1+e) - y eta): one reciprocal, one log, one division (same values to rounding)
+            // mu = e/(1+e), mu.eta = e/(1+e)^2 = Var(mu) => w = mu.eta, w z = w eta + (y - mu);
+            // dev_i = -2 log(mu^y (1-mu)^(1-y)) = 2 (log(1+e) - y eta): one reciprocal, one log, no division
             const double opexp = 1 + ee;
             const double r = 1.0 / opexp;
             const double mu = ee * r;
             const double mev = mu * r;
             dev += 2 * (log(opexp) - y * eta);
-            z = eta + (y - mu) / mev;
             w2 = mev;
+            wz = fma(mev, eta, y - mu);
             return;
         }
         const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
@@ -706,10 +711,10 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
         dev += 2 * d;
         const double varmu = mu * (1 - mu);
         const double mev = clampd ? DBL_EPSILON : ee / (opexp * opexp);
-        z = eta + (y - mu) / mev;
         w2 = (mev * mev) / varmu;
+        wz = w2 * (eta + (y - mu) / mev);
     } else {
-        w2 = 1.0; z = y;
+        w2 = 1.0; wz = y;
         if (!pass0) dev += (y - eta_in) * (y - eta_in);  // lm second pass: residual sum of squares
     }
 }
@@ -736,15 +741,15 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
 #pragma unroll
             for (int c = 0; c < Q; c++) eta += x[c] * beta[c];
         }
-        double w2, z;
-        irls_sample(trait, pass0, y, eta, w2, z, dev, bad);
+        double w2, wz;
+        irls_sample(trait, pass0, y, eta, w2, wz, dev, bad);
         int e = 0;
 #pragma unroll
         for (int a = 0; a < Q; a++) {
             const double wa = w2 * x[a];
 #pragma unroll
             for (int b = a; b < Q; b++) { acc[e] = fma(wa, x[b], acc[e]); e++; }
-            acc[e] = fma(wa, z, acc[e]); e++;
+            acc[e] = fma(x[a], wz, acc[e]); e++;
         }
     };
     int64_t i = i_lo + threadIdx.x;
@@ -921,9 +926,8 @@ __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, i
     return d_pt2(bl / se, rdf);
 }
 
-__global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restrict__ b_list, Counters *ctr,
-                                                             const uint8_t *__restrict__ bed, int64_t pitch,
-                                                             SnpStats st, int64_t snp0, int64_t m_total, int64_t n,
+__global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const BItem *__restrict__ b_list, int count, Counters *ctr,
+                                                             int64_t m_total, int64_t n,
                                                              const double *__restrict__ R, const double *__restrict__ E,
                                                              const VecConst *__restrict__ vcp, WaldData wd,
                                                              double min_maf, double *__restrict__ out) {
@@ -933,24 +937,23 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const int *__restric
     cg::cluster_group cl = cg::this_cluster();
     const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
-    const int count = ctr->b_count;
     const VecConst vc = *vcp;
     ClusterRed red{sh.scratch, sh.slot};
     // contiguous sample slice of this CTA (multiple of 4 so that byte loads do not straddle CTAs)
     const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
     const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
     for (int idx = cluster_id; idx < count; idx += n_clusters) {
-        const int jl = b_list[idx];
-        const int64_t j = snp0 + jl;
-        const uint8_t *row = bed + (int64_t)jl * pitch;
-        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        const BItem bi = b_list[idx];
+        const int64_t j = bi.snp;
+        const uint8_t *row = bi.row;
+        const int asum = bi.asum, nmiss = bi.nmiss;
         const Prologue pr = make_prologue(asum, nmiss, n);
         GFromRow gf;
         gf.row = row;
         gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
         if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
         // W'W, W'R (ref :606-609)
-        double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+        double S1 = bi.D0 + ((nmiss > 0) ? pr.u * bi.T0 : 0.0);
         if (pr.flip) S1 = 2 * vc.sumR - S1;
         double v3[3] = {0, 0, 0};
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
@@ -1017,7 +1020,8 @@ struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
 // K3 for SPAGxE_Plus: V = E*R, so D1/T1 carry sum(g*E*R).  One thread per SNP.  out is M x 8.
 __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                 const VecConst *__restrict__ vcp, PlusConst pc, double epsilon, double cutoff,
-                                double min_maf, double *__restrict__ out, SpaItem *spa_list, int *b_list, Counters *ctr) {
+                                double min_maf, double *__restrict__ out, SpaItem *spa_list, BItem *b_list,
+                                const uint8_t *bed, int64_t pitch, Counters *ctr) {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = jl < m_chunk;
     const VecConst vc = *vcp;
@@ -1072,13 +1076,12 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
     int pos = list_reserve(&ctr->spa_count, want_spa);
     if (want_spa) spa_list[pos] = item;
     pos = list_reserve(&ctr->b_count, want_b);
-    if (want_b) b_list[pos] = jl;
+    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl]};
 }
 
 // branch B of SPAGxE_Plus (ref :342-400): cluster per SNP; K7 = sparse-GRM quadratic form of R.new0
-__global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const int *__restrict__ b_list, Counters *ctr,
-                                                              const uint8_t *__restrict__ bed, int64_t pitch,
-                                                              SnpStats st, int64_t snp0, int64_t m_total, int64_t n,
+__global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__restrict__ b_list, int count, Counters *ctr,
+                                                              int64_t m_total, int64_t n,
                                                               const double *__restrict__ R, const double *__restrict__ E,
                                                               const VecConst *__restrict__ vcp, GrmCoo grm, double cutoff,
                                                               double *__restrict__ out) {
@@ -1087,7 +1090,6 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const int *__restri
     cg::cluster_group cl = cg::this_cluster();
     const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
-    const int count = ctr->b_count;
     const VecConst vc = *vcp;
     ClusterRed red{sh.scratch, sh.slot};
     const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
@@ -1095,16 +1097,16 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const int *__restri
     const long long eper = (grm.nnz + cs - 1) / cs;
     const long long e_lo = min(grm.nnz, eper * rank), e_hi = min(grm.nnz, eper * (rank + 1));
     for (int idx = cluster_id; idx < count; idx += n_clusters) {
-        const int jl = b_list[idx];
-        const int64_t j = snp0 + jl;
-        const uint8_t *row = bed + (int64_t)jl * pitch;
-        const int asum = st.asum[jl], nmiss = st.nmiss[jl];
+        const BItem bi = b_list[idx];
+        const int64_t j = bi.snp;
+        const uint8_t *row = bi.row;
+        const int asum = bi.asum, nmiss = bi.nmiss;
         const Prologue pr = make_prologue(asum, nmiss, n);
         GFromRow gf;
         gf.row = row;
         gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
         if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
-        double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
+        double S1 = bi.D0 + ((nmiss > 0) ? pr.u * bi.T0 : 0.0);
         if (pr.flip) S1 = 2 * vc.sumR - S1;
         double v3[3] = {0, 0, 0};
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }

@@ -48,6 +48,7 @@ struct spagxe_ctx {
     int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
     SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
+    BItem *d_bitems = nullptr; int64_t cap_bitems = 0; int *h_count = nullptr;
     Quad quad = {nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
@@ -175,7 +176,8 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list);
-    cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
+    if (ctx->h_count) cudaFreeHost(ctx->h_count);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
@@ -291,24 +293,48 @@ static int launch_spa(spagxe_ctx *ctx, const double *rv, int64_t N, int64_t M, d
     return SPAGXE_OK;
 }
 
-static int launch_branch_b(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int64_t M,
-                           int64_t N, WaldData wd, double min_maf, double *d_out) {
+// Deferred branch B: work items accumulate on the device; a flush reads their number (one small sync), sizes the
+// thread-block clusters so that all SMs are busy, and launches the cluster kernel once.
+static int pick_cluster(int count, int num_sms) {
+    int best = 8; double best_t = 1e300;
+    for (int cs = 1; cs <= kBCluster; cs++) {
+        const int clusters = std::max(1, num_sms / cs);
+        const double t = (double)((count + clusters - 1) / clusters) / cs;   // rounds x time per item (~1/cs)
+        if (t < best_t * 0.999) { best_t = t; best = cs; }
+    }
+    return best;
+}
+static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldData wd, double min_maf, double cutoff,
+                          double *d_out) {
+    cudaStream_t s = ctx->stream();
+    if (!ctx->h_count) CU(cudaMallocHost((void **)&ctx->h_count, sizeof(int)));
+    CU(cudaMemcpyAsync(ctx->h_count, &ctx->d_ctr->b_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const int count = *ctx->h_count;
+    if (count <= 0) return SPAGXE_OK;
+    const int cs = pick_cluster(count, ctx->num_sms);
     cudaLaunchConfig_t cfg = {};
-    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
-    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
+    const int n_clusters = std::min(std::max(1, ctx->num_sms / cs), count);
+    cfg.gridDim = dim3((unsigned)(n_clusters * cs));
     cfg.blockDim = dim3(kBThreads);
-    cfg.dynamicSmemBytes = branch_b_smem(wd.p + 4);
-    cfg.stream = ctx->stream();
+    cfg.dynamicSmemBytes = (mode == 0) ? branch_b_smem(wd.p + 4) : 0;
+    cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const int *b_list = ctx->d_b_list;
+    const BItem *items = ctx->d_bitems;
     Counters *ctr = ctx->d_ctr;
     const double *R = ctx->d_R, *E = ctx->d_E;
     const VecConst *vc = ctx->d_vc;
-    CU(cudaLaunchKernelEx(&cfg, k_branch_b_cct, b_list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, min_maf, d_out));
+    if (mode == 0) {
+        CU(cudaLaunchKernelEx(&cfg, k_branch_b_cct, items, count, ctr, M, N, R, E, vc, wd, min_maf, d_out));
+    } else {
+        GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
+        CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, items, count, ctr, M, N, R, E, vc, grm, cutoff, d_out));
+    }
     ctx->launches++;
+    CU(cudaMemsetAsync(&ctx->d_ctr->b_count, 0, sizeof(int), s));
     return SPAGXE_OK;
 }
 
@@ -586,28 +612,6 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     return SPAGXE_OK;
 }
 
-static int launch_branch_b_plus(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int64_t M,
-                                int64_t N, double cutoff, double *d_out) {
-    cudaLaunchConfig_t cfg = {};
-    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
-    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
-    cfg.blockDim = dim3(kBThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = ctx->stream();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const int *b_list = ctx->d_b_list;
-    Counters *ctr = ctx->d_ctr;
-    const double *R = ctx->d_R, *E = ctx->d_E;
-    const VecConst *vc = ctx->d_vc;
-    GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
-    CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, b_list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, grm, cutoff, d_out));
-    ctx->launches++;
-    return SPAGXE_OK;
-}
-
 static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag,
                        RunMode mode) {
     if (!ctx) return SPAGXE_ERR_ARG;
@@ -640,6 +644,10 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (rc) return rc;
     // CCT contracts with (R, R.new); plus and mix with (R, E*R); plus takes R.new from the null-model object
     const int vmode = (mode == RUN_CCT) ? 0 : (mode == RUN_PLUS ? 1 : 2);
+    {
+        const int64_t need = own_bed ? 2ll * pl.chunk_m : M;
+        if (need > ctx->cap_bitems) { CU(dev_realloc(&ctx->d_bitems, need)); ctx->cap_bitems = need; }
+    }
     if ((rc = ensure_vec_mode(ctx, vmode, mode == RUN_PLUS ? ctx->d_Rn_user : nullptr))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     EventPool evp;
@@ -654,25 +662,30 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         const uint8_t *d_rows = nullptr;
         if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &dg.h2d_bytes))) return rc;
         // reset per-chunk work-list cursors (counters keep accumulating)
-        CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, 4 * sizeof(int), s));
+        CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, (mode == RUN_MIX ? 4 : 2) * sizeof(int), s));  // branch-B items persist until flushed
         cudaEvent_t a = evp.rec(s);
         if ((rc = launch_score(ctx, d_rows, pl, mc, st))) return rc;
         cudaEvent_t b = evp.rec(s);
         score_ev.push_back({a, b});
         if (mode == RUN_CCT) {
             k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
-                                                            ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
+                                                            ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch, ctx->d_ctr);
             LAUNCH_CHECK();
             if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
-            if ((rc = launch_branch_b(ctx, d_rows, pl.dpitch, st, j0, M, N, wd, prm->min_maf, d_out))) return rc;
         } else if (mode == RUN_PLUS) {
             k_finalize_plus<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, pc, prm->epsilon, prm->cutoff,
-                                                             prm->min_maf, d_out, ctx->d_spa_list, ctx->d_b_list, ctx->d_ctr);
+                                                             prm->min_maf, d_out, ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch,
+                                                             ctx->d_ctr);
             LAUNCH_CHECK();
             if ((rc = launch_spa(ctx, ctx->d_Rn, N, M, d_out))) return rc;
-            if ((rc = launch_branch_b_plus(ctx, d_rows, pl.dpitch, st, j0, M, N, prm->cutoff, d_out))) return rc;
         } else {
             if ((rc = launch_mix(ctx, d_rows, pl.dpitch, st, j0, mc, M, N, wd, prm, d_out))) return rc;
+        }
+        // staged rows live in two alternating buffers: pending branch-B items must run before their buffer is reused;
+        // caller-owned device rows stay valid for the whole call, so everything is deferred to one launch at the end
+        const bool last = (j0 + pl.chunk_m >= M);
+        if (mode != RUN_MIX && (last || (own_bed && buf == 1))) {
+            if ((rc = flush_branch_b(ctx, mode == RUN_CCT ? 0 : 1, M, N, wd, prm->min_maf, prm->cutoff, d_out))) return rc;
         }
         cudaEvent_t c = evp.rec(s);
         test_ev.push_back({b, c});
