@@ -599,8 +599,16 @@ struct BShared {  // static shared state of the branch-B kernel
 // dynamic smem: xs[kBTile][q+1] (x row, z in column q), ws[kBTile]
 __host__ __device__ inline size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
 
+struct DevProd {   // prod (1+e^eta) = m * 2^k; log(prod) costs one log per thread instead of one per sample
+    double m = 1.0; int k = 0; int cnt = 0;
+    __device__ __forceinline__ void mul(double x) {
+        m *= x;                                   // x in [1, 1+e^30]: 8 factors stay far below 2^1023
+        if (++cnt == 8) { cnt = 0; int e = ilogb(m); k += e; m = scalbn(m, -e); }
+    }
+    __device__ __forceinline__ double log_value() const { return log(m) + (double)k * 0.693147180559945309417232121458; }
+};
 __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
-                                            double &dev, int &bad);
+                                            double &dev, int &bad, DevProd &dp);
 
 // One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
 // normal equations land in sh.NE / sh.rhs of EVERY CTA.  Returns the cluster-wide deviance (binary)
@@ -617,6 +625,7 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
     // entries grp, grp + kBGroups, ... belong to this warp; all lanes of a warp share (a,b)
     int ea[NS], eb[NS];
     double acc[NS];
+    DevProd dp;
 #pragma unroll
     for (int k = 0; k < NS; k++) {
         acc[k] = 0; ea[k] = -1; eb[k] = 0;
@@ -640,7 +649,7 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
             double eta = 0;
             if (!pass0) for (int c = 0; c < q; c++) eta += xr[c] * sh.beta[c];
             double w2, wz;
-            irls_sample(trait, pass0, y, eta, w2, wz, dev, bad);
+            irls_sample(trait, pass0, y, eta, w2, wz, dev, bad, dp);
             xr[q] = wz;   // column q already carries the weight
             ws[threadIdx.x] = w2;
         }
@@ -653,6 +662,7 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
                 if (ea[k] >= 0) acc[k] = fma((eb[k] == q ? 1.0 : w) * xr[ea[k]], xr[eb[k]], acc[k]);
         }
     }
+    dev += 2 * dp.log_value();
     // warp totals -> CTA partial normal equations -> cluster totals (rank order)
 #pragma unroll
     for (int k = 0; k < NS; k++) {
@@ -681,7 +691,7 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
 // Per-sample IRLS working quantities (glm.fit binomial/logit restated).
 // Returns the working weight w and wz = w * z (z = eta + (y - mu)/mu.eta), which is all X'WX and X'Wz need.
 __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
-                                            double &dev, int &bad) {
+                                            double &dev, int &bad, DevProd &dp) {
     const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
     if (trait == 1) {
         double eta = eta_in;
@@ -695,7 +705,8 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
             const double r = 1.0 / opexp;
             const double mu = ee * r;
             const double mev = mu * r;
-            dev += 2 * (log(opexp) - y * eta);
+            dp.mul(opexp);                 // 2 log(1+e) is added once per thread from the running product
+            dev -= 2 * (y * eta);
             w2 = mev;
             wz = fma(mev, eta, y - mu);
             return;
@@ -733,6 +744,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
     double beta[Q];
 #pragma unroll
     for (int c = 0; c < Q; c++) beta[c] = sh.beta[c];
+    DevProd dp;
     double dev = 0;
     int bad = 0;
     auto consume = [&](const double (&x)[Q], double y) {
@@ -742,7 +754,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
             for (int c = 0; c < Q; c++) eta += x[c] * beta[c];
         }
         double w2, wz;
-        irls_sample(trait, pass0, y, eta, w2, wz, dev, bad);
+        irls_sample(trait, pass0, y, eta, w2, wz, dev, bad, dp);
         int e = 0;
 #pragma unroll
         for (int a = 0; a < Q; a++) {
@@ -767,6 +779,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
         ds.template fill<Q>(i, xa);
         consume(xa, ya);
     }
+    dev += 2 * dp.log_value();
     // warp totals -> per-warp rows in the (otherwise unused) tile -> CTA partial -> cluster total
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __syncthreads();
