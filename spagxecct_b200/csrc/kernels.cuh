@@ -285,8 +285,15 @@ __device__ __forceinline__ void cgf_k12(double tr, double maf, double &k1, doubl
     const double m0 = u * u;
     const double m1 = (2 * x) * u;
     const double m2 = 2 * (x * x) + (2 * x) * u;
-    k1 = m1 / m0;
-    k2 = (m0 * m2 - m1 * m1) / (m0 * m0);
+    const double num = m0 * m2 - m1 * m1;
+    if (m0 < 1e150) {            // common range: one reciprocal instead of two divisions (same values to rounding)
+        const double r = 1.0 / m0;
+        k1 = m1 * r;
+        k2 = (num * r) * r;
+    } else {                     // overflow neighbourhood: keep the reference's exact Inf/NaN behaviour
+        k1 = m1 / m0;
+        k2 = num / (m0 * m0);
+    }
 }
 __device__ __forceinline__ double cgf_k0(double tr, double maf) {
     const double u = (1 - maf) + maf * exp(tr);
@@ -419,6 +426,7 @@ struct Quad {
     double *w;          // [kQBins * kQNodes] weights (double, after conversion)
     long long *wfix;    // fixed-point accumulation buffer
     double *range;      // [0]=rmin, [1]=rmax, [2]=h, [3]=max |t| covered (kQTheta / h; 0 = disabled)
+    int *count;         // number of nodes with non-zero weight (x, w are compacted to that length)
 };
 
 __device__ __forceinline__ double cheb_node(int j) {  // cos((2j+1) pi / (2 kQNodes))
@@ -458,13 +466,32 @@ __global__ void k_quad_accumulate(const double *__restrict__ rv, int64_t n, Quad
         atomicAdd((unsigned long long *)&q.wfix[b * kQNodes + j], (unsigned long long)__double2ll_rn(L * kQScale));
     }
 }
-__global__ void k_quad_finish(Quad q) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= kQBins * kQNodes) return;
-    const int b = idx / kQNodes, j = idx % kQNodes;
+// nodes + weights, compacted in a fixed order to the bins that hold samples (single CTA, deterministic)
+__global__ void __launch_bounds__(1024) k_quad_finish(Quad q) {
+    constexpr int kTotal = kQBins * kQNodes, kPer = (kTotal + 1023) / 1024;
+    __shared__ int s_cnt[1024];
     const double mn = q.range[0], h = q.range[2];
-    q.x[idx] = mn + (b + 0.5) * h + 0.5 * h * cheb_node(j);
-    q.w[idx] = (double)q.wfix[idx] / kQScale;
+    const int i0 = threadIdx.x * kPer;
+    int c = 0;
+    for (int k = 0; k < kPer; k++) { const int idx = i0 + k; if (idx < kTotal && q.wfix[idx] != 0) c++; }
+    s_cnt[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 1024; t++) { int v = s_cnt[t]; s_cnt[t] = run; run += v; }
+        *q.count = run;
+    }
+    __syncthreads();
+    int pos = s_cnt[threadIdx.x];
+    for (int k = 0; k < kPer; k++) {
+        const int idx = i0 + k;
+        if (idx < kTotal && q.wfix[idx] != 0) {
+            const int b = idx / kQNodes, j = idx % kQNodes;
+            q.x[pos] = mn + (b + 0.5) * h + 0.5 * h * cheb_node(j);
+            q.w[pos] = (double)q.wfix[idx] / kQScale;
+            pos++;
+        }
+    }
 }
 struct SrcQuad {
     const double *x, *wq; double maf;
@@ -500,7 +527,7 @@ __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__rest
         double p = -1.0;
         if (max_t > 0) {
             SrcQuad src{q.x, q.w, it.maf};
-            p = spa_two_tail(src, red, 0, (int64_t)kQBins * kQNodes, s_hi, s_lo, max_t, &iters);
+            p = spa_two_tail(src, red, 0, (int64_t)(*q.count), s_hi, s_lo, max_t, &iters);
         }
         if (threadIdx.x == 0) {
             if (p < 0) exact_list[atomicAdd(&ctr->spax_count, 1)] = it;

@@ -49,7 +49,7 @@ struct spagxe_ctx {
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
     SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
     BItem *d_bitems = nullptr; int64_t cap_bitems = 0; int *h_count = nullptr;
-    Quad quad = {nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
+    Quad quad = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
     void *encode_tiled = nullptr; bool use_tc = true; int tc_cfg = 1;
@@ -140,6 +140,7 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if ((e = cudaMalloc((void **)&ctx->quad.w, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.range, sizeof(double) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void **)&ctx->quad.count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_binfo, sizeof(BmatInfo))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaFuncSetAttribute(k_score_tc<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_score_tc<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
@@ -178,7 +179,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
-    cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range);
+    cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range); cudaFree(ctx->quad.count);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
         if (ctx->ev_stage[b]) cudaEventDestroy(ctx->ev_stage[b]);
@@ -272,7 +273,7 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
         LAUNCH_CHECK();
         k_quad_accumulate<<<(unsigned)((ctx->n + 255) / 256), 256, 0, s>>>(rv, ctx->n, ctx->quad);
         LAUNCH_CHECK();
-        k_quad_finish<<<(kQBins * kQNodes + 255) / 256, 256, 0, s>>>(ctx->quad);
+        k_quad_finish<<<1, 1024, 0, s>>>(ctx->quad);
         LAUNCH_CHECK();
     }
     return SPAGXE_OK;
