@@ -18,6 +18,7 @@
 #include "../../include/spagxe.h"
 #include "score.cuh"
 #include "score_tc.cuh"
+#include "score_tc3.cuh"
 
 using namespace spagxe;
 
@@ -52,7 +53,7 @@ struct spagxe_ctx {
     Quad quad = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
-    void *encode_tiled = nullptr; bool use_tc = true; int tc_cfg = 1;
+    void *encode_tiled = nullptr; bool use_tc = true; int tc_cfg = 10;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     // pinned staging
@@ -150,7 +151,9 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
         (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_score_tc<8, 3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        false)
+        (e = cudaFuncSetAttribute(k_score_tc3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_score_tc3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_score_tc)", e);
     if (const char *cfg = getenv("SPAGXE_TC_CFG")) ctx->tc_cfg = atoi(cfg);   // tuning switch: expander warps / A buffers
     {
@@ -544,6 +547,9 @@ static int launch_score_tc(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPl
         case 4: k_score_tc<8, 3, false><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
         case 7: k_score_tc<8, 3, true, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
         case 8: k_score_tc<8, 3, true, 4><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 10: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
+        case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
         case 9: k_score_tc<8, 3, false, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
         case 5: k_score_tc<8, 3, true, 1><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
         case 6: k_score_tc<8, 3, true, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
