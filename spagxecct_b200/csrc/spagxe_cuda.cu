@@ -427,6 +427,7 @@ static ChunkPlan make_plan(const spagxe_geno *g) {
     int64_t budget = (g->kind == SPAGXE_GENO_BED) ? (1ll << 30) : (1ll << 26);
     int64_t cm = std::max<int64_t>(kScoreRows, budget / pl.dpitch / kScoreRows * kScoreRows);
     cm = std::min<int64_t>(cm, 65536);
+    if (const char *ov = getenv("SPAGXE_CHUNK_SNPS")) cm = std::max<int64_t>(1, atoll(ov));   // tests: force many small chunks
     pl.chunk_m = (int)std::min<int64_t>(cm, std::max<int64_t>(pl.m, 1));
     return pl;
 }
@@ -691,12 +692,19 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         // staged rows live in two alternating buffers: pending branch-B items must run before their buffer is reused;
         // caller-owned device rows stay valid for the whole call, so everything is deferred to one launch at the end
         const bool last = (j0 + pl.chunk_m >= M);
+        bool flushed = false;
         if (mode != RUN_MIX && (last || (own_bed && buf == 1))) {
             if ((rc = flush_branch_b(ctx, mode == RUN_CCT ? 0 : 1, M, N, wd, prm->min_maf, prm->cutoff, d_out))) return rc;
+            flushed = true;
         }
         cudaEvent_t c = evp.rec(s);
         test_ev.push_back({b, c});
-        if (own_bed) CU(cudaEventRecord(ctx->ev_done[buf], s));
+        if (own_bed) {
+            CU(cudaEventRecord(ctx->ev_done[buf], s));
+            // the flush also read the OTHER staging buffer (deferred items of the previous chunk): it may only be
+            // refilled after the cluster kernel, so move its release point behind the flush as well
+            if (flushed) CU(cudaEventRecord(ctx->ev_done[buf ^ 1], s));
+        }
     }
     Counters hc;
     CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));

@@ -393,3 +393,41 @@ def test_c4_spagxemix_admixed(gpu_ctx, oracle, golden_dir, trait):
         assert d["n_mix_logistic"] == ((route & 256) > 0).sum() and d["newton_iters"] == iters.sum()
         assert res.colnames[10:] == ["MAF.est.negative.num", "MAC"]
     assert ((route & 256) > 0).sum() >= 3 and ((route & 64) > 0).sum() >= 1 and ((route & 2) > 0).sum() >= 5
+
+
+def test_multi_chunk_streaming_and_deferred_branch_b(oracle):
+    """Many small chunks through the double-buffered host staging path (ragged last chunk): the deferred branch-B
+    items of chunk k must still see their rows when chunk k+2 is staged; result == single-chunk result == oracle."""
+    import os
+    from spagxecct_b200 import Context
+    n, m = 5003, 333
+    ph = make_pheno(n, 91, prevalence=0.1)
+    rng = np.random.default_rng(92)
+    mafs = rng.uniform(0.002, 0.5, m)
+    eff = np.where(rng.random(m) < 0.25, 0.8, 0.0)
+    G = make_geno(n, mafs, 93, miss_rates=np.where(rng.random(m) < 0.5, 0, 0.03), count_major=rng.random(m) < 0.5,
+                  effect=eff, Y=ph["Y"])
+    rows = to_bed_rows(G)
+    outs = []
+    for chunk in (None, "37"):
+        if chunk:
+            os.environ["SPAGXE_CHUNK_SNPS"] = chunk
+        try:
+            with Context(0) as ctx:
+                ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+                out, diag = ctx.run_cct(_bed_desc(ctx, rows, n), dict(epsilon=0.05))
+                Gd = np.asfortranarray(G)
+                out_dense, _ = ctx.run_cct(ctx.geno_desc(_lib.GENO_F64, Gd.ctypes.data, n, m, n), dict(epsilon=0.05))
+        finally:
+            os.environ.pop("SPAGXE_CHUNK_SNPS", None)
+        outs.append(out)
+        assert np.array_equal(np.nan_to_num(out_dense, nan=-1), np.nan_to_num(out, nan=-1))
+    assert diag["n_branch_b"] >= 30
+    # the score pass is exact integer arithmetic (bit-identical under any chunking); branch-B fp64 sums are grouped by
+    # the cluster size chosen per flush, so those columns agree to rounding only
+    a, b = np.nan_to_num(outs[0], nan=-1), np.nan_to_num(outs[1], nan=-1)
+    assert np.array_equal(a[:, [0, 1, 6, 7, 8, 9]], b[:, [0, 1, 6, 7, 8, 9]])
+    assert np.allclose(a, b, rtol=1e-11, atol=0), np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+    ref, route, iters, rc = oracle.cct_bed("binary", rows, n, ph["R"], ph["E"], ph["Y"], ph["Cova"], epsilon=0.05, nthreads=8)
+    assert rc == 0
+    assert_parity(outs[1], ref, P_COLS, S_COLS, label="multi-chunk")
