@@ -431,3 +431,45 @@ def test_multi_chunk_streaming_and_deferred_branch_b(oracle):
     ref, route, iters, rc = oracle.cct_bed("binary", rows, n, ph["R"], ph["E"], ph["Y"], ph["Cova"], epsilon=0.05, nthreads=8)
     assert rc == 0
     assert_parity(outs[1], ref, P_COLS, S_COLS, label="multi-chunk")
+
+
+def test_edge_cases_empty_tiny_and_fatal_inputs(gpu_ctx, oracle):
+    """Empty input, N smaller than one 512-sample tile / one 16-sample word, a SNP with every call missing
+    (the reference stops at `if(MAF > 0.5)`), monomorphic SNPs (filtered), M not a multiple of 128."""
+    n = 13
+    rng = np.random.default_rng(101)
+    R = rng.standard_normal(n); R -= R.mean(); E = rng.standard_normal(n)
+    Y = (rng.random(n) < 0.5).astype(float); cova = rng.standard_normal((n, 1))
+    gpu_ctx.set_vectors(R, E); gpu_ctx.set_wald(_lib.TRAIT_BINARY, Y, cova)
+    G = rng.integers(0, 3, (n, 5)).astype(float)
+    G[:, 2] = 0.0                       # monomorphic -> MAF 0 < min.maf -> NA row
+    G[3, 1] = np.nan
+    rows = to_bed_rows(G)
+    out, diag = gpu_ctx.run_cct(_bed_desc(gpu_ctx, rows, n), dict(epsilon=0.0))
+    ref, route, _, rc = oracle.cct_bed("binary", rows, n, R, E, Y, cova, epsilon=0.0)
+    assert rc == 0
+    assert_parity(out, ref, P_COLS, S_COLS, label="tiny N")
+    assert np.isnan(out[2, 2:]).all() and out[2, 0] == 0.0
+    # M = 0
+    empty = np.zeros(0, dtype=np.uint8)
+    g0 = gpu_ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, 0, (n + 3) // 4)
+    out0, d0 = gpu_ctx.run_cct(g0)
+    assert out0.shape == (0, 10) and d0["n_snps"] == 0
+    # all-missing SNP: fatal, like the reference
+    Gm = G.copy(); Gm[:, 4] = np.nan
+    with pytest.raises(_lib.SpagxeError) as ei:
+        gpu_ctx.run_cct(_bed_desc(gpu_ctx, to_bed_rows(Gm), n))
+    assert ei.value.code == _lib.ERR_ARG and "missing" in str(ei.value)
+    # state errors
+    from spagxecct_b200 import Context
+    with Context(0) as c2:
+        with pytest.raises(_lib.SpagxeError) as ei:
+            c2.run_cct(_bed_desc(c2, rows, n))
+        assert ei.value.code == _lib.ERR_STATE
+        c2.set_vectors(R, E)
+        with pytest.raises(_lib.SpagxeError) as ei:
+            c2.run_plus(_bed_desc(c2, rows, n))
+        assert ei.value.code == _lib.ERR_STATE and "set_grm" in str(ei.value)
+        with pytest.raises(_lib.SpagxeError) as ei:
+            c2.set_wald(3, Y, cova)
+        assert ei.value.code == _lib.ERR_UNSUPPORTED
