@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--batch-snps", type=int, default=16384)
     ap.add_argument("--ref-snps", type=int, default=0)
-    ap.add_argument("--cpu-sample-snps", type=int, default=96)
+    ap.add_argument("--cpu-sample-snps", type=int, default=1536)   # ~15 s of one host core at N = 500k
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -296,6 +296,12 @@ def main():
         ms_score = float(np.mean([d["ms_score"] for d in diags]))
         score_bytes = float(diags[-1]["score_bytes"])
         achieved = score_bytes / (ms_score * 1e-3) / 1e9
+        # one score launch per ~1 GiB chunk of packed rows (csrc/spagxe_cuda.cu make_plan)
+        chunk_rows = max(128, ((1 << 30) // pitch) // 128 * 128)
+        n_launch = -(-m // min(chunk_rows, 65536))
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_ncu_k_score_tc3.txt:
+        # 1.070904 GB read + 5.59 MB written for a launch of 1.024 GB of packed rows), scaled to this launch size
+        traffic = (1.070904e9 + 5.59488e6) / 1.024e9 * (score_bytes / n_launch)
         dg = diags[-1]
         # bounded CPU sample of the very same batch (first rows), single thread
         cpu = None
@@ -323,8 +329,10 @@ def main():
             "config": workload_config(n, m),
             "e2e": e2e, "gpu_launches": int(sum(d["kernel_launches"] for d in diags)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_score (2-bit unpack + score pass)", "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": score_bytes, "ms_per_launch": ms_score,
+                         "traffic": traffic, "kernel": "k_score_tc3 (2-bit unpack + score pass, tcgen05 kind::i8)",
+                         "peak_source": peak_src, "launches_per_step": n_launch,
+                         "algorithmic_bytes_per_launch": score_bytes / n_launch, "ms_per_launch": ms_score / n_launch,
+                         "traffic_source": "ncu --set full of one 1.024 GB launch (profiles/r01_ncu_k_score_tc3.txt), scaled by launch size",
                          "share_of_step": ms_score / (ms_max / K)},
             "cpu_baseline": cpu, "clocks": clocks,
             "stages_ms": {"score": ms_score, "tests(finalize+SPA+branchB)": float(np.mean([d["ms_tests"] for d in diags])),

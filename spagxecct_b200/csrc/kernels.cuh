@@ -10,37 +10,10 @@
 //   K5  k_branch_b        G-adjusted residual, SPA, Wald, CCT      (ref :604-678, :2070-2123)
 #pragma once
 #include "dmath.cuh"
+#include "types.cuh"
 #include <cooperative_groups.h>
 
 namespace spagxe {
-
-// PLINK code -> A1 dosage: 00 -> 2, 01 -> missing, 10 -> 1, 11 -> 0 (pinned by inst/GenoMat_*.raw)
-constexpr int kMaxQ = 16;   // Wald design columns: 1 + p + 3, p <= 12
-constexpr int kMaxPC = 15;
-
-struct VecConst {
-    double sumR, sumR2, sumER2, lambda;  // lambda = sum(E R^2)/sum(R^2) (ref :592)
-    double sumV, sumV2;                  // second score vector V (R.new for CCT, E*R for mix/plus)
-    double sumRn, sumRn2;                // R.new = (E - lambda) R (ref :594)
-    double sumE, sumEE, sumER, sumEER, sumEERR;  // branch-B class algebra helpers (unused by v1)
-};
-
-struct SnpStats {  // per-SNP outputs of the score pass (chunk-local index)
-    double *D0, *D1;  // sum over non-missing of dosage * R, dosage * V
-    double *T0, *T1;  // sum over missing samples of R, V
-    int *asum;        // allele sum over non-missing = n_het + 2 n_homA1
-    int *nmiss;       // number of missing calls
-};
-
-struct SpaItem { int snp; int flags; double maf; double S; double Smean; double aux; };
-// deferred branch-B work item: everything the cluster kernel needs, valid until the next flush
-struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0; };
-
-struct Counters {  // device-side diagnostics / work-list cursors
-    unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
-        n_mix_logistic, newton_iters, n_allmissing, n_nonint;
-    int spa_count, spax_count, b_count, b_cursor;
-};
 
 // ---------------------------------------------------------------------------
 // K0: SNP-invariant vector statistics.  One CTA (deterministic tree).
@@ -350,6 +323,8 @@ __device__ double spa_tail(const Src &src, const Red &red, int64_t i_lo, int64_t
         const double old_t = t, old_diff = diff, old_H1 = H1;
         if (fabs(t) > max_abs_t) { *iters = 0; return -1.0; }
         double v[2] = {0, 0};
+        // two samples in flight: the exp / reciprocal chains interleave, the per-thread order of the adds is unchanged
+#pragma unroll 2
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
             double r, maf, w, k1, k2;
             src.get(i, r, maf, w);
@@ -376,6 +351,7 @@ __device__ double spa_tail(const Src &src, const Red &red, int64_t i_lo, int64_t
     if (!isfinite(t)) return 0.0;  // every non-finite root yields NA -> 0 in the reference (:1873)
     if (fabs(t) > max_abs_t) { *iters = 0; return -1.0; }
     double v[2] = {0, 0};
+#pragma unroll 2
     for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
         double r, maf, w, k1, k2;
         src.get(i, r, maf, w);
@@ -791,16 +767,62 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
             acc[e] = fma(x[a], wz, acc[e]); e++;
         }
     };
+    auto accumulate = [&](const double (&x)[Q], double w2, double wz) {
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < Q; a++) {
+            const double wa = w2 * x[a];
+#pragma unroll
+            for (int b = a; b < Q; b++) { acc[e] = fma(wa, x[b], acc[e]); e++; }
+            acc[e] = fma(x[a], wz, acc[e]); e++;
+        }
+    };
+    // kWS samples per trip.  IRLS passes of a 0/1 response take a branch-free path in which the kWS exp / reciprocal
+    // chains are independent instruction streams (the fp64 pipe is latency-bound at 16 warps per SM); every sum is
+    // still updated in sample order, so the result does not depend on kWS.
+    constexpr int kWS = 2;
     int64_t i = i_lo + threadIdx.x;
-    for (; i + blockDim.x < i_hi; i += 2 * blockDim.x) {   // two samples per trip: both sets of loads in flight
-        double xa[Q], xb[Q];
-        const double ya = ds.y(i), yb = ds.y(i + blockDim.x);
-        ds.template fill<Q>(i, xa);
-        ds.template fill<Q>(i + blockDim.x, xb);
-        consume(xa, ya);
-        consume(xb, yb);
+    for (; i + (kWS - 1) * (int64_t)blockDim.x < i_hi; i += kWS * (int64_t)blockDim.x) {
+        double xs[kWS][Q], ys[kWS], eta[kWS];
+        bool fast = (trait == 1) && !pass0;
+#pragma unroll
+        for (int k = 0; k < kWS; k++) {
+            ys[k] = ds.y(i + k * (int64_t)blockDim.x);
+            ds.template fill<Q>(i + k * (int64_t)blockDim.x, xs[k]);
+            eta[k] = 0;
+            if (!pass0) {
+#pragma unroll
+                for (int c = 0; c < Q; c++) eta[k] += xs[k][c] * beta[c];
+            }
+            fast = fast && (ys[k] == 0.0 || ys[k] == 1.0) && !(eta[k] > 30. || eta[k] < -30.);
+        }
+        if (fast) {
+            double w2[kWS], wz[kWS], ope[kWS];
+#pragma unroll
+            for (int k = 0; k < kWS; k++) {   // same operations as the common branch of irls_sample
+                const double ee = exp(eta[k]);
+                ope[k] = 1 + ee;
+                const double r = 1.0 / ope[k];
+                const double mu = ee * r;
+                w2[k] = mu * r;
+                wz[k] = fma(w2[k], eta[k], ys[k] - mu);
+            }
+#pragma unroll
+            for (int k = 0; k < kWS; k++) {
+                dp.mul(ope[k]);
+                dev -= 2 * (ys[k] * eta[k]);
+                accumulate(xs[k], w2[k], wz[k]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kWS; k++) {
+                double w2, wz;
+                irls_sample(trait, pass0, ys[k], eta[k], w2, wz, dev, bad, dp);
+                accumulate(xs[k], w2, wz);
+            }
+        }
     }
-    if (i < i_hi) {
+    for (; i < i_hi; i += blockDim.x) {
         double xa[Q];
         const double ya = ds.y(i);
         ds.template fill<Q>(i, xa);

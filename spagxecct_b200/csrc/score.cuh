@@ -12,9 +12,15 @@
 // R/V for those samples held in registers, and walks down a tile of SNP rows, so the residual
 // vectors are read once per (CTA, 128 rows) instead of once per SNP.
 #pragma once
-#include "kernels.cuh"
+#include "types.cuh"
+#include <cuda_runtime.h>
 
 namespace spagxe {
+
+__device__ __forceinline__ double score_warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 constexpr int kScoreThreads = 256;
 constexpr int kScoreRows = 128;
@@ -66,7 +72,7 @@ k_score_v1(const uint32_t *__restrict__ bed, int64_t pitch_words, int64_t n, int
                 }
             }
         }
-        d0 = warp_sum(d0); d1 = warp_sum(d1); t0 = warp_sum(t0); t1 = warp_sum(t1);
+        d0 = score_warp_sum(d0); d1 = score_warp_sum(d1); t0 = score_warp_sum(t0); t1 = score_warp_sum(t1);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) {

@@ -1,0 +1,166 @@
+// score_launch.cu -- translation unit of the score pass (K1+K2): tcgen05 kernels, the fp64 cross-check kernel and
+// their launch logic.  See score_tc.cuh for the math; score_launch.h for the interface used by spagxe_cuda.cu.
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "score_launch.h"
+#include "score.cuh"
+#include "score_tc.cuh"
+#include "score_tc3.cuh"
+
+namespace spagxe {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void *g_encode_tiled = nullptr;
+
+static int64_t round_up64(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+cudaError_t score_init(std::string *err) {
+    cudaError_t e;
+#define SMEM_OPT_IN(k)                                                                                          \
+    if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess) { \
+        *err = "cudaFuncSetAttribute(" #k ")"; return e;                                                        \
+    }
+    SMEM_OPT_IN((k_score_tc<8, 3>));
+    SMEM_OPT_IN(k_score_tc3<0>);
+    SMEM_OPT_IN(k_score_tc3<1>);
+    SMEM_OPT_IN(k_score_tc3<2>);
+    SMEM_OPT_IN(k_score_tc3<3>);
+#undef SMEM_OPT_IN
+    if (!g_encode_tiled) {
+        cudaDriverEntryPointQueryResult qres;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &g_encode_tiled, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !g_encode_tiled) {
+            *err = "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)";
+            return e == cudaSuccess ? cudaErrorUnknown : e;
+        }
+    }
+    return cudaSuccess;
+}
+
+int64_t score_bmat_bytes(int64_t n) { return ((n + kTcTileSamples - 1) / kTcTileSamples) * (int64_t)kTcBTileBytes; }
+int score_acc_rows(int mc) { return (int)round_up64(mc, kTcRows); }
+
+cudaError_t score_build_b(cudaStream_t s, const double *R, const double *V, int64_t n, BmatInfo *d_info, int8_t *d_bmat,
+                          int64_t *launches) {
+    cudaError_t e = cudaMemsetAsync(d_bmat, 0, score_bmat_bytes(n), s);
+    if (e != cudaSuccess) return e;
+    k_tc_scale<<<1, 1024, 0, s>>>(R, V, n, d_info);
+    k_tc_build_b<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, V, n, d_info, d_bmat);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+template <int NBOX>
+static float run_probe(cudaStream_t s, int num_sms, const CUtensorMap &map, int n_tiles, int tps, int n_splits, int n_row_tiles,
+                       long long *d_acc) {
+    const size_t smem = 192 * 1024 + 1024 + 256;
+    cudaFuncSetAttribute(k_tma_probe<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    const int grid = std::min(n_row_tiles * n_splits, num_sms);
+    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)d_acc);
+    cudaEventRecord(a, s);
+    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)d_acc);
+    cudaEventRecord(b, s); cudaEventSynchronize(b);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms;
+}
+
+cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8_t *d_rows, const ScoreGeom &g, const int8_t *d_bmat,
+                            const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err) {
+    const int mc = g.mc;
+    const int m_pad = score_acc_rows(mc);
+    cudaError_t e = cudaMemsetAsync(d_acc, 0, sizeof(long long) * (size_t)m_pad * 32, s);
+    if (e != cudaSuccess) { *err = "cudaMemsetAsync(acc)"; return e; }
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)g.dpitch, (cuuint64_t)mc};
+    const cuuint64_t gstr[1] = {(cuuint64_t)g.dpitch};
+    const cuuint32_t box[2] = {kTcTileBytes, kTcRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = ((EncodeTiledFn)g_encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_rows, gdim, gstr, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): pitch=%lld rows=%d", (int)cr, (long long)g.dpitch, mc);
+        *err = buf;
+        return cudaErrorInvalidValue;
+    }
+    const int n_tiles = (int)((g.n + kTcTileSamples - 1) / kTcTileSamples);
+    const int n_row_tiles = m_pad / kTcRows;
+    int want_splits = std::max(1, (4 * num_sms + n_row_tiles - 1) / n_row_tiles);
+    want_splits = std::min(want_splits, std::max(1, n_tiles / 16));
+    const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
+    const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    const int n_items = n_row_tiles * n_splits;
+    const int grid = std::min(n_items, num_sms);
+    if (getenv("SPAGXE_TMA_PROBE")) {   // one-off diagnostic of the access pattern (not a product path)
+        const double gb = (double)mc * g.row_bytes / 1e9;
+        float m1 = run_probe<1>(s, num_sms, map, n_tiles, tiles_per_split, n_splits, n_row_tiles, d_acc);
+        float m2 = run_probe<2>(s, num_sms, map, n_tiles, tiles_per_split, n_splits, n_row_tiles, d_acc);
+        float m4 = run_probe<4>(s, num_sms, map, n_tiles, tiles_per_split, n_splits, n_row_tiles, d_acc);
+        fprintf(stderr, "[tma probe] rows=%d %.3f GB: 1 box %.3f ms (%.0f GB/s), 2 boxes %.3f ms (%.0f GB/s), 4 boxes %.3f ms (%.0f GB/s)\n", mc, gb,
+                m1, gb / m1 * 1e3, m2, gb / m2 * 1e3, m4, gb / m4 * 1e3);
+    }
+#define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
+    switch (tc_cfg) {
+        case 1: k_score_tc<8, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 10: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no MMAs
+        case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no expansion
+        case 16: k_score_tc3<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: hand-over timing trace
+        default: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+    }
+#undef TC_ARGS
+    if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc launch"; return e; }
+    if (tc_cfg == 16) {   // dump the timing trace of CTA 0 (diagnostic, not a product path)
+        static int dumped = 0;
+        cudaStreamSynchronize(s);
+        if (dumped++ == 3) {
+            static unsigned long long h[kT3Warps * kT3TraceRounds * kT3TraceEv];
+            cudaMemcpyFromSymbol(h, g_tc_trace, sizeof h);
+            unsigned long long t0 = ~0ull;
+            for (size_t i = 0; i < sizeof h / sizeof h[0]; i++) if (h[i] && h[i] < t0) t0 = h[i];
+            for (int w = 0; w < kT3Warps; w++) {
+                if (w == kT3ExpWarps || w == kT3ExpWarps + 1) continue;
+                for (int r = 0; r < kT3TraceRounds; r++) {
+                    fprintf(stderr, "[trace] warp %2d round %2d:", w, r);
+                    for (int k = 0; k < 6; k++) {
+                        unsigned long long v = h[((size_t)w * kT3TraceRounds + r) * kT3TraceEv + k];
+                        fprintf(stderr, " %8lld", v ? (long long)(v - t0) : -1ll);
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+    }
+    k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
+    *launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc_reduce launch"; return e; }
+    return cudaSuccess;
+}
+
+int64_t score_v1_partial_elems(const ScoreGeom &g, int chunk_m) {
+    const int tiles_s = (int)((g.dpitch / 4 + kScoreThreads - 1) / kScoreThreads);
+    return (int64_t)tiles_s * 4 * round_up64(chunk_m, kScoreRows);
+}
+
+cudaError_t score_launch_v1(cudaStream_t s, const uint8_t *d_rows, const ScoreGeom &g, const double *R, const double *V,
+                            double *d_partial, int *d_ipartial, SnpStats st, int64_t *launches) {
+    const int64_t pw = g.dpitch / 4;
+    const int tiles_s = (int)((pw + kScoreThreads - 1) / kScoreThreads);
+    const int m_pad = (int)round_up64(g.mc, kScoreRows);
+    dim3 grid((unsigned)tiles_s, (unsigned)(m_pad / kScoreRows));
+    k_score_v1<<<grid, kScoreThreads, 0, s>>>((const uint32_t *)d_rows, pw, g.n, g.mc, m_pad, R, V, d_partial, d_ipartial);
+    k_score_reduce<<<(g.mc + 127) / 128, 128, 0, s>>>(d_partial, d_ipartial, tiles_s, g.mc, m_pad, st);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace spagxe

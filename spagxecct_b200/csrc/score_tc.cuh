@@ -27,7 +27,8 @@
 //     of a work item and added to per-row int64 totals in global memory (integer atomics commute).
 #pragma once
 #include <cuda.h>
-#include "kernels.cuh"
+#include "types.cuh"
+#include <cuda_runtime.h>
 
 namespace spagxe {
 
@@ -45,7 +46,6 @@ constexpr size_t kTcSmemBytes = (size_t)kTcGStages * kTcGStageBytes + (size_t)kT
 // TMEM columns: kTcABufs A buffers x 128 columns (256 samples: 64 cols -dosage, 64 cols missing), then accumulators
 constexpr uint32_t kTcColAcc = kTcMaxABufs * 128;
 
-struct BmatInfo { int sR, sV; double maxR, maxV; };
 
 // ---- B matrix builder -----------------------------------------------------------------------
 __device__ __forceinline__ int64_t tc_b_offset(int64_t i, int col) {

@@ -19,6 +19,13 @@ constexpr int kT3ExpWarps = 4 * kT3Groups;       // 12
 constexpr int kT3Warps = kT3ExpWarps + 2 + kT3Groups;  // + geno producer, B producer, 3 MMA warps = 17
 constexpr int kT3Threads = kT3Warps * 32;
 
+// kProbe == 3: CTA 0 records clock64() at the hand-over points of rounds [16, 64) of every warp (timing trace)
+constexpr int kT3TraceRounds = 48, kT3TraceEv = 8;
+__device__ unsigned long long g_tc_trace[kT3Warps * kT3TraceRounds * kT3TraceEv];
+#define T3_TRACE(k)                                                                                        \
+    if (kProbe == 3 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT3TraceRounds)               \
+        g_tc_trace[((size_t)warp * kT3TraceRounds + (use - 16)) * kT3TraceEv + (k)] = (unsigned long long)clock64();
+
 template <int kProbe = 0>
 __global__ void __launch_bounds__(kT3Threads, 1)
 k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
@@ -110,7 +117,9 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                 if (!waited) { mbar_wait(bar_accempty, (itc & 1) ^ 1); tc_fence_after(); waited = true; }
                 const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages;
                 mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
+                T3_TRACE(0)
                 mbar_wait(bar_afull(q), use & 1);
+                T3_TRACE(1)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
@@ -130,6 +139,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                     tc_commit(bar_bempty(sb));
                 }
                 __syncwarp();
+                T3_TRACE(2)
             }
             if (elect_one()) tc_commit(bar_accfull);
             __syncwarp();
@@ -149,8 +159,11 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
             if (nr == 0) continue;
             for (uint32_t G = gbase + ((q + 3u - gbase % 3u) % 3u); G < gbase + nr; G += 3u, use++) {
                 const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages;
+                T3_TRACE(0)
                 mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
+                T3_TRACE(1)
                 mbar_wait(bar_aempty(q), (use & 1) ^ 1);
+                T3_TRACE(2)
                 tc_fence_after();
                 const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 // all four 16-byte chunks of this row first (loads in flight together), then expand
@@ -179,10 +192,13 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(c4 * 16), d);
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(64 + c4 * 16), m);
                 }
+                T3_TRACE(3)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                T3_TRACE(4)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_afull(q)); mbar_arrive(bar_gempty(s)); }
+                T3_TRACE(5)
             }
             gbase += nr;
             if (q == 0) {

@@ -16,9 +16,8 @@
 #include <algorithm>
 
 #include "../../include/spagxe.h"
-#include "score.cuh"
-#include "score_tc.cuh"
-#include "score_tc3.cuh"
+#include "kernels.cuh"
+#include "score_launch.h"
 
 using namespace spagxe;
 
@@ -53,7 +52,7 @@ struct spagxe_ctx {
     Quad quad = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
-    void *encode_tiled = nullptr; bool use_tc = true; int tc_cfg = 10;
+    bool use_tc = true; int tc_cfg = 10;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     // pinned staging
@@ -143,25 +142,11 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if ((e = cudaMalloc((void **)&ctx->quad.range, sizeof(double) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.count, sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_binfo, sizeof(BmatInfo))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaFuncSetAttribute(k_score_tc<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc<8, 3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_score_tc3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess)
-        return bail("cudaFuncSetAttribute(k_score_tc)", e);
-    if (const char *cfg = getenv("SPAGXE_TC_CFG")) ctx->tc_cfg = atoi(cfg);   // tuning switch: expander warps / A buffers
     {
-        cudaDriverEntryPointQueryResult qres;
-        e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ctx->encode_tiled)
-            return bail("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)", e == cudaSuccess ? cudaErrorUnknown : e);
+        std::string serr;
+        if ((e = score_init(&serr)) != cudaSuccess) return bail(serr.c_str(), e);
     }
+    if (const char *cfg = getenv("SPAGXE_TC_CFG")) ctx->tc_cfg = atoi(cfg);   // tuning switch: score kernel variant
     {
         const char *sv = getenv("SPAGXE_SCORE");   // "v1": fp64 CUDA-core kernel (A/B switch for tests)
         ctx->use_tc = !(sv && strcmp(sv, "v1") == 0);
@@ -257,14 +242,9 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     ctx->vec_mode = mode;
     {   // fixed-point int8 digit matrix B of (R, V) for the tensor-core score pass
         cudaStream_t s = ctx->stream();
-        const int64_t n_tiles = (ctx->n + kTcTileSamples - 1) / kTcTileSamples;
-        const int64_t need = n_tiles * kTcBTileBytes;
+        const int64_t need = score_bmat_bytes(ctx->n);
         if (need > ctx->cap_bmat) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_bmat, need)); ctx->cap_bmat = need; }
-        CU(cudaMemsetAsync(ctx->d_bmat, 0, need, s));
-        k_tc_scale<<<1, 1024, 0, s>>>(ctx->d_R, ctx->d_V, ctx->n, ctx->d_binfo);
-        LAUNCH_CHECK();
-        k_tc_build_b<<<(unsigned)((ctx->n + 255) / 256), 256, 0, s>>>(ctx->d_R, ctx->d_V, ctx->n, ctx->d_binfo, ctx->d_bmat);
-        LAUNCH_CHECK();
+        CU(score_build_b(s, ctx->d_R, ctx->d_V, ctx->n, ctx->d_binfo, ctx->d_bmat, &ctx->launches));
     }
     // SNP-invariant quadrature of the SPA vector (R.new): only worth it when N >> number of nodes
     const double *rv = (mode == 0) ? ctx->d_V : ctx->d_Rn;
@@ -359,13 +339,6 @@ static int ensure_chunk_scratch(spagxe_ctx *ctx, const ChunkPlan &pl, bool need_
         CU(dev_realloc(&ctx->d_spax_list, pl.chunk_m));
         ctx->cap_m = pl.chunk_m;
     }
-    const int tiles_s = (int)((pl.dpitch / 4 + kScoreThreads - 1) / kScoreThreads);
-    const int64_t m_pad = round_up(pl.chunk_m, kScoreRows);
-    const int64_t need = (int64_t)tiles_s * 4 * m_pad;
-    if (need > ctx->cap_partial) {
-        CU(dev_realloc(&ctx->d_partial, need)); CU(dev_realloc(&ctx->d_ipartial, need / 2));
-        ctx->cap_partial = need;
-    }
     if (out_elems > ctx->cap_out) { CU(dev_realloc(&ctx->d_out, out_elems)); ctx->cap_out = out_elems; }
     return SPAGXE_OK;
 }
@@ -425,7 +398,7 @@ static ChunkPlan make_plan(const spagxe_geno *g) {
     else pl.dpitch = round_up(pl.row_bytes, 128);
     // ~1 GiB of packed rows per chunk (>> L2), dense inputs are limited by their 8 B/sample staging
     int64_t budget = (g->kind == SPAGXE_GENO_BED) ? (1ll << 30) : (1ll << 26);
-    int64_t cm = std::max<int64_t>(kScoreRows, budget / pl.dpitch / kScoreRows * kScoreRows);
+    int64_t cm = std::max<int64_t>(kScoreRowsPad, budget / pl.dpitch / kScoreRowsPad * kScoreRowsPad);
     cm = std::min<int64_t>(cm, 65536);
     if (const char *ov = getenv("SPAGXE_CHUNK_SNPS")) cm = std::max<int64_t>(1, atoll(ov));   // tests: force many small chunks
     pl.chunk_m = (int)std::min<int64_t>(cm, std::max<int64_t>(pl.m, 1));
@@ -488,92 +461,28 @@ static SnpStats stats_view(spagxe_ctx *ctx, int cap) {
     return st;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-template <int NBOX>
-static float run_probe(spagxe_ctx *ctx, const CUtensorMap &map, int n_tiles, int tps, int n_splits, int n_row_tiles) {
+static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
     cudaStream_t s = ctx->stream();
-    const size_t smem = 192 * 1024 + 1024 + 256;
-    cudaFuncSetAttribute(k_tma_probe<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const int grid = std::min(n_row_tiles * n_splits, ctx->num_sms);
-    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)ctx->d_acc);
-    cudaEventRecord(a, s);
-    k_tma_probe<NBOX><<<grid, 64, smem, s>>>(map, n_tiles, tps, n_splits, n_row_tiles, (unsigned long long *)ctx->d_acc);
-    cudaEventRecord(b, s); cudaEventSynchronize(b);
-    float ms = 0; cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    return ms;
-}
-
-static int launch_score_tc(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
-    cudaStream_t s = ctx->stream();
-    const int m_pad = (int)round_up(mc, kTcRows);
+    const ScoreGeom sg{pl.n, pl.row_bytes, pl.dpitch, mc};
+    if (!ctx->use_tc) {   // fp64 cross-check kernel: its partial-sum scratch is only allocated when it is used
+        const int64_t need = score_v1_partial_elems(sg, mc);
+        if (need > ctx->cap_partial) {
+            CU(cudaStreamSynchronize(s));
+            CU(dev_realloc(&ctx->d_partial, need)); CU(dev_realloc(&ctx->d_ipartial, need / 2));
+            ctx->cap_partial = need;
+        }
+        CU(score_launch_v1(s, d_rows, sg, ctx->d_R, ctx->d_V, ctx->d_partial, ctx->d_ipartial, st, &ctx->launches));
+        return SPAGXE_OK;
+    }
+    const int m_pad = score_acc_rows(mc);
     if (m_pad > ctx->cap_acc) {
         CU(cudaStreamSynchronize(s));
         CU(dev_realloc(&ctx->d_acc, (size_t)m_pad * 32));
         ctx->cap_acc = m_pad;
     }
-    CU(cudaMemsetAsync(ctx->d_acc, 0, sizeof(long long) * (size_t)m_pad * 32, s));
-    CUtensorMap map;
-    const cuuint64_t gdim[2] = {(cuuint64_t)pl.dpitch, (cuuint64_t)mc};
-    const cuuint64_t gstr[1] = {(cuuint64_t)pl.dpitch};
-    const cuuint32_t box[2] = {kTcTileBytes, kTcRows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult cr = ((EncodeTiledFn)ctx->encode_tiled)(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_rows, gdim, gstr, box, estr,
-                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) return fail(ctx, SPAGXE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): pitch=%lld rows=%d", (int)cr,
-                                        (long long)pl.dpitch, mc);
-    const int n_tiles = (int)((pl.n + kTcTileSamples - 1) / kTcTileSamples);
-    const int n_row_tiles = m_pad / kTcRows;
-    int want_splits = std::max(1, (4 * ctx->num_sms + n_row_tiles - 1) / n_row_tiles);
-    want_splits = std::min(want_splits, std::max(1, n_tiles / 16));
-    const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
-    const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-    const int n_items = n_row_tiles * n_splits;
-    const int grid = std::min(n_items, ctx->num_sms);
-    if (getenv("SPAGXE_TMA_PROBE")) {   // one-off diagnostic of the access pattern (not a product path)
-        const double gb = (double)mc * pl.row_bytes / 1e9;
-        float m1 = run_probe<1>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
-        float m2 = run_probe<2>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
-        float m4 = run_probe<4>(ctx, map, n_tiles, tiles_per_split, n_splits, n_row_tiles);
-        fprintf(stderr, "[tma probe] rows=%d %.3f GB: 1 box %.3f ms (%.0f GB/s), 2 boxes %.3f ms (%.0f GB/s), 4 boxes %.3f ms (%.0f GB/s)\n", mc, gb,
-                m1, gb / m1 * 1e3, m2, gb / m2 * 1e3, m4, gb / m4 * 1e3);
-    }
-    switch (ctx->tc_cfg) {
-        case 1: k_score_tc<8, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 4: k_score_tc<8, 3, false><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 7: k_score_tc<8, 3, true, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 8: k_score_tc<8, 3, true, 4><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 10: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 9: k_score_tc<8, 3, false, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 5: k_score_tc<8, 3, true, 1><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        case 6: k_score_tc<8, 3, true, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-        default: k_score_tc<8, 2><<<grid, 12 * 32, kTcSmemBytes, s>>>(map, ctx->d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, ctx->d_acc); break;
-    }
-    LAUNCH_CHECK();
-    k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(ctx->d_acc, mc, ctx->d_binfo, st);
-    LAUNCH_CHECK();
-    return SPAGXE_OK;
-}
-
-static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
-    if (ctx->use_tc) return launch_score_tc(ctx, d_rows, pl, mc, st);
-    cudaStream_t s = ctx->stream();
-    const int64_t pw = pl.dpitch / 4;
-    const int tiles_s = (int)((pw + kScoreThreads - 1) / kScoreThreads);
-    const int m_pad = (int)round_up(mc, kScoreRows);
-    dim3 grid((unsigned)tiles_s, (unsigned)(m_pad / kScoreRows));
-    k_score_v1<<<grid, kScoreThreads, 0, s>>>((const uint32_t *)d_rows, pw, pl.n, mc, m_pad, ctx->d_R, ctx->d_V,
-                                               ctx->d_partial, ctx->d_ipartial);
-    LAUNCH_CHECK();
-    k_score_reduce<<<(mc + 127) / 128, 128, 0, s>>>(ctx->d_partial, ctx->d_ipartial, tiles_s, mc, m_pad, st);
-    LAUNCH_CHECK();
+    std::string serr;
+    cudaError_t e = score_launch_tc(s, ctx->num_sms, ctx->tc_cfg, d_rows, sg, ctx->d_bmat, ctx->d_binfo, ctx->d_acc, st, &ctx->launches, &serr);
+    if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", serr.c_str(), cudaGetErrorString(e));
     return SPAGXE_OK;
 }
 

@@ -1,0 +1,7 @@
+timeout 200 python bench.py --no-e2e --steps 10 --warmup 3 --cpu-sample-snps 0 2>gpurun_out/err.log | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(round(d['value']), d['stages_ms'], round(d['roofline']['frac'],4))
+"
+timeout 200 python tools/bench_variants.py 2>&1 | tail -3 | cut -c1-200
