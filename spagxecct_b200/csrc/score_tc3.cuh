@@ -97,6 +97,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                 for (int t = t0; t < t1; t++, f++) {
                     const int s = f % kTcBStages;
                     mbar_wait(bar_bempty(s), ((f / kTcBStages) & 1) ^ 1);
+                    if (kProbe == 4) { mbar_arrive(bar_bfull(s)); continue; }   // probe: no B traffic (stale tiles, wrong sums)
                     mbar_expect_tx(bar_bfull(s), kTcBTileBytes);
                     bulk_load_1d(bbase + s * kTcBTileBytes, Bmat + (int64_t)t * kTcBTileBytes, kTcBTileBytes, bar_bfull(s));
                 }
