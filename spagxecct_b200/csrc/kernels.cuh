@@ -754,7 +754,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
         double eta = 0;
         if (!pass0) {
 #pragma unroll
-            for (int c = 0; c < Q; c++) eta += x[c] * beta[c];
+            for (int c = 0; c < Q; c++) eta = fma(x[c], beta[c], eta);
         }
         double w2, wz;
         irls_sample(trait, pass0, y, eta, w2, wz, dev, bad, dp);
@@ -781,10 +781,21 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
     // chains are independent instruction streams (the fp64 pipe is latency-bound at 16 warps per SM); every sum is
     // still updated in sample order, so the result does not depend on kWS.
     constexpr int kWS = 2;
+    // first pass of glm.fit on a 0/1 response: eta = logit((y + 0.5) / 2) = -+log 3, so the working quantities take
+    // two values; they are computed once per thread with the very operations irls_sample applies per sample
+    double p0_eta[2] = {0, 0}, p0_ope[2] = {1, 1}, p0_w2[2] = {0, 0}, p0_wz[2] = {0, 0};
+    if (pass0 && trait == 1) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const double y = (double)b, mus = (y + 0.5) / 2, e0 = log(mus / (1 - mus)), ee = exp(e0);
+            const double opexp = 1 + ee, r = 1.0 / opexp, mu = ee * r, mev = mu * r;
+            p0_eta[b] = e0; p0_ope[b] = opexp; p0_w2[b] = mev; p0_wz[b] = fma(mev, e0, y - mu);
+        }
+    }
     int64_t i = i_lo + threadIdx.x;
     for (; i + (kWS - 1) * (int64_t)blockDim.x < i_hi; i += kWS * (int64_t)blockDim.x) {
         double xs[kWS][Q], ys[kWS], eta[kWS];
-        bool fast = (trait == 1) && !pass0;
+        bool fast = (trait == 1);
 #pragma unroll
         for (int k = 0; k < kWS; k++) {
             ys[k] = ds.y(i + k * (int64_t)blockDim.x);
@@ -792,7 +803,7 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
             eta[k] = 0;
             if (!pass0) {
 #pragma unroll
-                for (int c = 0; c < Q; c++) eta[k] += xs[k][c] * beta[c];
+                for (int c = 0; c < Q; c++) eta[k] = fma(xs[k][c], beta[c], eta[k]);
             }
             fast = fast && (ys[k] == 0.0 || ys[k] == 1.0) && !(eta[k] > 30. || eta[k] < -30.);
         }
@@ -800,6 +811,12 @@ __device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bo
             double w2[kWS], wz[kWS], ope[kWS];
 #pragma unroll
             for (int k = 0; k < kWS; k++) {   // same operations as the common branch of irls_sample
+                if (pass0) {                   // mustart is 0.75 / 0.25: two possible values of everything
+                    const bool one = (ys[k] == 1.0);   // selects, not indexed loads: the table stays in registers
+                    eta[k] = one ? p0_eta[1] : p0_eta[0]; ope[k] = one ? p0_ope[1] : p0_ope[0];
+                    w2[k] = one ? p0_w2[1] : p0_w2[0];    wz[k] = one ? p0_wz[1] : p0_wz[0];
+                    continue;
+                }
                 const double ee = exp(eta[k]);
                 ope[k] = 1 + ee;
                 const double r = 1.0 / ope[k];
