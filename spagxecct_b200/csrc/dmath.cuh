@@ -16,7 +16,7 @@ __device__ __forceinline__ double d_na_real() { return __longlong_as_double(0x7F
 __device__ __forceinline__ double d_sign(double x) { return (x > 0.0) - (x < 0.0); }  // NaN handled by callers
 
 // ---- pnorm (both tails, full relative accuracy down to ~1e-308) -------------
-__device__ __noinline__ double d_pnorm(double x, bool lower_tail) {
+static __device__ __noinline__ double d_pnorm(double x, bool lower_tail) {
     const double a[5] = {2.2352520354606839287, 161.02823106855587881, 1067.6894854603709582,
                          18154.981253343561249, 0.065682337918207449113};
     const double b[4] = {47.20258190468824187, 976.09855173777669322, 10260.932208618978205,
@@ -83,7 +83,7 @@ __device__ __forceinline__ double d_pcauchy(double x) {
 }
 
 // CCT(c(p1, p2)) with equal weights; returns 0 or the stop() code (1 NA, 2 range, 3 both 0 and 1).
-__device__ __noinline__ int d_cct2(double p1, double p2, double *out) {
+static __device__ __noinline__ int d_cct2(double p1, double p2, double *out) {
     *out = d_na_real();
     if (isnan(p1) || isnan(p2)) return 1;
     if ((p1 < 0) || (p2 < 0) || (p1 > 1) || (p2 > 1)) return 2;
@@ -110,7 +110,7 @@ __device__ __noinline__ int d_cct2(double p1, double p2, double *out) {
 }
 
 // ---- regularized incomplete beta by modified Lentz; 2*pt(|t|, df, lower=FALSE) ----
-__device__ __noinline__ double d_betacf(double a, double b, double x) {
+static __device__ __noinline__ double d_betacf(double a, double b, double x) {
     const double FPMIN = 1e-300, EPS = 1e-16;
     double qab = a + b, qap = a + 1, qam = a - 1, c = 1, d = 1 - qab * x / qap;
     if (fabs(d) < FPMIN) d = FPMIN;
@@ -141,7 +141,7 @@ __device__ __forceinline__ double d_lbeta_half(double a) {
     return dlt + 0.57236494292470008707;
 }
 // I_x(a, 1/2) with y = 1 - x supplied separately
-__device__ __noinline__ double d_betainc_half(double a, double x, double y) {
+static __device__ __noinline__ double d_betainc_half(double a, double x, double y) {
     if (x <= 0) return 0;
     if (y <= 0) return 1;
     const double A = a, B = 0.5;
@@ -150,7 +150,7 @@ __device__ __noinline__ double d_betainc_half(double a, double x, double y) {
     return 1 - exp(lbt) * d_betacf(B, A, y) / B;
 }
 // 2*pt(|t|, df, lower=FALSE) = I_{df/(df+t^2)}(df/2, 1/2)
-__device__ __noinline__ double d_pt2(double t, double df) {
+static __device__ __noinline__ double d_pt2(double t, double df) {
     if (isnan(t) || isnan(df)) return t + df;
     const double x2 = t * t, den = df + x2;
     return d_betainc_half(df / 2, df / den, x2 / den);

@@ -1,0 +1,18 @@
+// mix_batch.h -- host interface of the batched SPAGxEmix_CCT common path (mix_batch.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "types.cuh"
+
+namespace spagxe {
+
+struct MixBatchParams { double epsilon, cutoff, neg_ratio_cut; };
+
+// Consumes the candidate list k_finalize_mix left in (b_list, ctr->b_count): writes the output rows of the SNPs that
+// take the common route and leaves the others in (b_list, ctr->b_count) for k_mix_snp.  All work is queued on `s`.
+cudaError_t mix_batch_run(cudaStream_t s, int device, int num_sms, const uint8_t *d_rows, int64_t pitch, SnpStats st, int64_t j0, int mc,
+                          int64_t M, int64_t n, const double *R, const double *E, const VecConst *vc, const double *pcs,
+                          const double *xtx_inv, int k, const MixBatchParams &prm, double *d_out, int *b_list, Counters *ctr,
+                          int64_t *launches);
+
+}  // namespace spagxe

@@ -18,6 +18,7 @@
 #include "../../include/spagxe.h"
 #include "kernels.cuh"
 #include "score_launch.h"
+#include "mix_batch.h"
 
 using namespace spagxe;
 
@@ -509,6 +510,11 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     cudaStream_t s = ctx->stream();
     k_finalize_mix<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, prm->min_maf, d_out, ctx->d_b_list, ctx->d_ctr);
     LAUNCH_CHECK();
+    if (!getenv("SPAGXE_MIX_PER_SNP")) {   // env: A/B switch for tests (every SNP through the cluster kernel)
+        const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff};
+        CU(mix_batch_run(s, ctx->device, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
+                         ctx->d_xtx_inv, ctx->n_pcs, bp, d_out, ctx->d_b_list, ctx->d_ctr, &ctx->launches));
+    }
     cudaLaunchConfig_t cfg = {};
     const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
     cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));

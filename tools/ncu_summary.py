@@ -34,12 +34,26 @@ def main(rep, dst):
                 i = hdr.index(k)
                 lines.append(f"{k:84s} {r[i]:>16s} {units[i]}")
     src = page(rep, "source")
-    if len(src) > 2:
-        h = src[1]
+    # the source page holds one block per kernel: a "Kernel Name" row, a header row, then one row per SASS line
+    blocks, cur = [], None
+    for r in src:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1] if len(r) > 1 else "?", "hdr": None, "rows": []}
+            blocks.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None:
+            cur["rows"].append(r)
+    for blk in blocks:
+        h = blk["hdr"]
+        if not h or "Source" not in h or "# Samples" not in h:
+            continue
         si, ci = h.index("Source"), h.index("# Samples")
         stall = [(i, x) for i, x in enumerate(h) if x.startswith("stall_") and "Not Issued" not in x]
         tot, agg, rows = 0.0, {x: 0.0 for _, x in stall}, []
-        for k, r in enumerate(src[2:]):
+        for k, r in enumerate(blk["rows"]):
+            if len(r) <= max(ci, si):
+                continue
             try:
                 v = float(r[ci])
             except ValueError:
@@ -49,12 +63,12 @@ def main(rep, dst):
             for i, x in stall:
                 try:
                     agg[x] += float(r[i])
-                except ValueError:
+                except (ValueError, IndexError):
                     pass
-        lines.append(f"== warp-state samples: {tot:.0f}")
+        lines.append(f"== warp-state samples of {blk['name'][:70]}: {tot:.0f}")
         lines.append("   " + ", ".join(f"{k[6:]}={v / max(tot, 1):.1%}" for k, v in sorted(agg.items(), key=lambda z: -z[1])[:8]))
         lines.append("== hottest SASS lines")
-        for v, k, s in sorted(rows, reverse=True)[:20]:
+        for v, k, s in sorted(rows, reverse=True)[:12]:
             lines.append(f"{v / max(tot, 1):7.2%}  line {k:5d}  {s}")
     open(dst, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:30]))
