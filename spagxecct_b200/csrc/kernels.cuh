@@ -1252,10 +1252,11 @@ __device__ __forceinline__ double af_eval(const AfModel &af, const double *__res
 struct SrcMix {  // residual vector (E - lambda) R or E * (R - fit[class]) with per-sample allele frequency
     const AfModel *af; const double *pcs; int64_t n;
     const double *R, *E; const uint8_t *row; double fit[4]; double lambda; int adj;
+    const double *mcache;   // m_i of this SNP, written once by the statistics pass (same thread <-> same samples in every pass)
     __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
         if (adj) { int c = (row[i >> 2] >> (2 * (i & 3))) & 3; r = E[i] * (R[i] - fit[c]); }
         else r = (E[i] - lambda) * R[i];
-        m = af_eval(*af, pcs, n, i); w = 1.0;
+        m = mcache ? mcache[i] : af_eval(*af, pcs, n, i); w = 1.0;
     }
 };
 
@@ -1291,7 +1292,8 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                                                         int64_t snp0, int64_t m_total, int64_t n,
                                                         const double *__restrict__ R, const double *__restrict__ E,
                                                         const VecConst *__restrict__ vcp, WaldData wd, MixData md,
-                                                        double epsilon, double cutoff, double *__restrict__ out) {
+                                                        double epsilon, double cutoff, double *__restrict__ out,
+                                                        double *__restrict__ mcache_all) {
     namespace cg = cooperative_groups;
     extern __shared__ double tile[];
     __shared__ BShared sh;
@@ -1400,8 +1402,11 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         __syncthreads();
         // ---- statistics with per-sample allele frequencies (ref :1102-1108) ----
         double v4[4] = {0, 0, 0, 0};
+        // m_i is evaluated once per SNP (k loads + k multiply-adds, or an exp and a sqrt) and kept for the later passes
+        double *mcache = mcache_all ? mcache_all + (int64_t)cluster_id * n : nullptr;
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
             const double m = af_eval(ms.af, md.pcs, n, i), gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
+            if (mcache) mcache[i] = m;
             v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
         }
         red.sum<4>(v4);
@@ -1411,7 +1416,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         double *o = out + j;
         const bool writer = (rank == 0 && threadIdx.x == 0);
         SrcMix src;
-        src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row;
+        src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row; src.mcache = mcache;
         double po[4];
         int iters = 0; bool spa = false;
         if (pG > epsilon) {

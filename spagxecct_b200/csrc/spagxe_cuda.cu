@@ -56,6 +56,7 @@ struct spagxe_ctx {
     bool use_tc = true; int tc_cfg = 10;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
+    int64_t cap_mcache = 0; double *d_mcache = nullptr;   // SPAGxEmix: cached allele frequencies, one vector per cluster
     // pinned staging
     uint8_t *h_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -165,7 +166,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_gi); cudaFree(ctx->d_gj); cudaFree(ctx->d_gv); cudaFree(ctx->d_Rn_user);
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range); cudaFree(ctx->quad.count);
@@ -530,7 +531,12 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     const double *R = ctx->d_R, *E = ctx->d_E;
     const VecConst *vc = ctx->d_vc;
     MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff};
-    CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out));
+    {   // per-cluster cache of the individual allele frequencies m_i (N doubles each)
+        const int64_t need = (int64_t)n_clusters * N;
+        if (need > ctx->cap_mcache) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_mcache, need)); ctx->cap_mcache = need; }
+    }
+    double *mcache = ctx->d_mcache;
+    CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out, mcache));
     ctx->launches++;
     return SPAGXE_OK;
 }
