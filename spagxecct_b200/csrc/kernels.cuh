@@ -706,10 +706,11 @@ __device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, dou
 
 // Register-accumulator variant for narrow designs (Q = p + 4 <= 8): every thread keeps the whole upper
 // triangle of X'WX (+ X'Wz) for its own samples in registers; no shared-memory tile, no per-tile barrier.
-template <int Q, class Design>
-__device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, bool pass0, double *tile, BShared &sh,
+template <int Q, bool PASS0, class Design>
+__device__ double wald_pass_reg(const Design &ds, int64_t i_lo, int64_t i_hi, double *tile, BShared &sh,
                                 const ClusterRed &red, int *invalid) {
     namespace cg = cooperative_groups;
+    constexpr bool pass0 = PASS0;   // compile-time: the first-pass table must not occupy registers in the later passes
     constexpr int NENT = Q * (Q + 3) / 2;
     const int trait = ds.trait();
     double acc[NENT];
@@ -911,11 +912,16 @@ template <class Design>
 __device__ __forceinline__ double wald_pass_any(const Design &ds, int64_t i_lo, int64_t i_hi, int q, bool pass0,
                                                 double *tile, BShared &sh, const ClusterRed &red, int *invalid) {
     switch (q) {
-        case 2: return wald_pass_reg<2>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 3: return wald_pass_reg<3>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 4: return wald_pass_reg<4>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 5: return wald_pass_reg<5>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
-        case 6: return wald_pass_reg<6>(ds, i_lo, i_hi, pass0, tile, sh, red, invalid);
+        case 2: return pass0 ? wald_pass_reg<2, true>(ds, i_lo, i_hi, tile, sh, red, invalid)
+                             : wald_pass_reg<2, false>(ds, i_lo, i_hi, tile, sh, red, invalid);
+        case 3: return pass0 ? wald_pass_reg<3, true>(ds, i_lo, i_hi, tile, sh, red, invalid)
+                             : wald_pass_reg<3, false>(ds, i_lo, i_hi, tile, sh, red, invalid);
+        case 4: return pass0 ? wald_pass_reg<4, true>(ds, i_lo, i_hi, tile, sh, red, invalid)
+                             : wald_pass_reg<4, false>(ds, i_lo, i_hi, tile, sh, red, invalid);
+        case 5: return pass0 ? wald_pass_reg<5, true>(ds, i_lo, i_hi, tile, sh, red, invalid)
+                             : wald_pass_reg<5, false>(ds, i_lo, i_hi, tile, sh, red, invalid);
+        case 6: return pass0 ? wald_pass_reg<6, true>(ds, i_lo, i_hi, tile, sh, red, invalid)
+                             : wald_pass_reg<6, false>(ds, i_lo, i_hi, tile, sh, red, invalid);
         default: break;
     }
     const int ns = (q * (q + 3) / 2 + kBGroups - 1) / kBGroups;
