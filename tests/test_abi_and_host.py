@@ -102,3 +102,27 @@ def test_output_column_names_match_reference():
                             "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG"]  # R/SPAGxECCT.R:499-501
     assert api.COLS_MIX[10:] == ["MAF.est.negative.num", "MAC"]                                      # :963-966
     assert api.COLS_PLUS[2:4] == ["p.value.spaGxE.plus", "p.value.normGxE.plus"]                    # Plus :203-205
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the reference's CPU path: the oracle port on the host cores) prints the driver's JSON
+    line with impl/cpu_baseline/e2e and never touches a GPU; run here at a reduced N so that the contract is checked
+    without one.  Non-zero ranks print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--n-samples", "3000", "--ref-snps", "8",
+           "--steps", "2", "--warmup", "1"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "SNPs/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 2 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "SNPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+    out1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
