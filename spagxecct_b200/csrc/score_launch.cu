@@ -32,6 +32,8 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN(k_score_tc3<2>);
     SMEM_OPT_IN(k_score_tc3<3>);
     SMEM_OPT_IN(k_score_tc3<4>);
+    SMEM_OPT_IN(k_score_tc3<5>);
+    SMEM_OPT_IN(k_score_tc3<6>);
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
         cudaDriverEntryPointQueryResult qres;
@@ -115,6 +117,8 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 10: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
         case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no MMAs
         case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no expansion
+        case 19: k_score_tc3<6><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // expansion token ring
+        case 18: k_score_tc3<5><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: only group 0 expands
         case 17: k_score_tc3<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: B tiles not loaded
         case 16: k_score_tc3<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: hand-over timing trace
         default: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;

@@ -43,6 +43,9 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
     auto bar_aempty = [&](int b) { return bars + 8u * (kB0 + kT3Groups + b); };
     const uint32_t bar_accfull = bars + 8u * (kB0 + 2 * kT3Groups), bar_accempty = bars + 8u * (kB0 + 2 * kT3Groups + 1);
     const uint32_t tmem_slot = bars + 8u * (kB0 + 2 * kT3Groups + 2);
+    // kProbe == 6: expansion token ring.  Round G may start expanding only when round G - 1 has issued its last STTM, so
+    // the three groups take the ALU / MIO in turn instead of all at once (the trace shows them phase-locked).
+    auto bar_tok = [&](uint32_t q) { return bars + 8u * (kB0 + 2 * kT3Groups + 3 + q); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -50,6 +53,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
         for (int s = 0; s < kTcBStages; s++) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 2); }  // 1 commit per round
         for (int b = 0; b < kT3Groups; b++) { mbar_init(bar_afull(b), 4); mbar_init(bar_aempty(b), 1); }
         mbar_init(bar_accfull, kT3Groups); mbar_init(bar_accempty, 4);
+        for (uint32_t b = 0; b < (uint32_t)kT3Groups; b++) mbar_init(bar_tok(b), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kT3ExpWarps) {
@@ -164,12 +168,13 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                 mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
                 T3_TRACE(1)
                 mbar_wait(bar_aempty(q), (use & 1) ^ 1);
+                if (kProbe == 6) mbar_wait(bar_tok(q), q == 0 ? ((use & 1) ^ 1) : (use & 1));   // predecessor round has expanded
                 T3_TRACE(2)
                 tc_fence_after();
                 const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 // all four 16-byte chunks of this row first (loads in flight together), then expand
                 uint4 xv[4];
-                if (kProbe != 2) {
+                if (kProbe != 2 && !(kProbe == 5 && q != 0)) {   // probe 5: only group 0 expands (contention vs. chain latency)
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) {
                         const uint32_t chunk = hs * 4u + (uint32_t)c4;
@@ -179,7 +184,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                     }
                 }
 #pragma unroll
-                for (int c4 = 0; c4 < (kProbe == 2 ? 0 : 4); c4++) {
+                for (int c4 = 0; c4 < ((kProbe == 2 || (kProbe == 5 && q != 0)) ? 0 : 4); c4++) {
                     const uint32_t x[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
                     uint32_t d[16], m[16];
 #pragma unroll
@@ -194,6 +199,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(64 + c4 * 16), m);
                 }
                 T3_TRACE(3)
+                if (kProbe == 6) { __syncwarp(); if (lane == 0) mbar_arrive(bar_tok((q + 1u) % 3u)); }   // pass the token on
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 T3_TRACE(4)
                 tc_fence_before();
