@@ -34,6 +34,10 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN(k_score_tc3<4>);
     SMEM_OPT_IN(k_score_tc3<5>);
     SMEM_OPT_IN(k_score_tc3<6>);
+    SMEM_OPT_IN(k_score_tc3<7>);
+    SMEM_OPT_IN(k_score_tc3<8>);
+    SMEM_OPT_IN(k_score_tc3<9>);
+    SMEM_OPT_IN(k_score_tc3<10>);
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
         cudaDriverEntryPointQueryResult qres;
@@ -114,14 +118,18 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
 #define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
     switch (tc_cfg) {
         case 1: k_score_tc<8, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(TC_ARGS); break;
-        case 10: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 9: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;    // whole-round hand-over (A/B)
         case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no MMAs
         case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no expansion
+        case 29: k_score_tc3<9><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over after 3 of 4 chunks
+        case 30: k_score_tc3<10><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // hand-over after 1 of 4 chunks
+        case 28: k_score_tc3<8><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // per-chunk hand-over
         case 19: k_score_tc3<6><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // expansion token ring
         case 18: k_score_tc3<5><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: only group 0 expands
         case 17: k_score_tc3<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: B tiles not loaded
         case 16: k_score_tc3<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: hand-over timing trace
-        default: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 10:   // product path: half-round hand-over (the MMA warp starts on the first 128 samples of a round early)
+        default: k_score_tc3<7><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
     }
 #undef TC_ARGS
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc launch"; return e; }

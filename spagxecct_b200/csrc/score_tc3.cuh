@@ -46,6 +46,12 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
     // kProbe == 6: expansion token ring.  Round G may start expanding only when round G - 1 has issued its last STTM, so
     // the three groups take the ALU / MIO in turn instead of all at once (the trace shows them phase-locked).
     auto bar_tok = [&](uint32_t q) { return bars + 8u * (kB0 + 2 * kT3Groups + 3 + q); };
+    // kProbe == 7: the first 128 samples of a round are handed to the MMA warp while the second 128 are still expanding
+    // kProbe == 8: the same per 64-sample chunk (three early hand-overs per round)
+    // kProbe == 9 / 10: two parts split after chunk 3 / chunk 1
+    constexpr int kParts = (kProbe == 7 || kProbe == 9 || kProbe == 10) ? 2 : (kProbe == 8 ? 4 : 1);
+    constexpr int kFirst = (kProbe == 9) ? 3 : (kProbe == 10 ? 1 : 4 / kParts);   // chunks in every early part (2-part modes: in the first)
+    auto bar_apart = [&](uint32_t q, uint32_t part) { return bars + 8u * (kB0 + 3 * kT3Groups + 3 + q * 3u + part); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -53,7 +59,7 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
         for (int s = 0; s < kTcBStages; s++) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 2); }  // 1 commit per round
         for (int b = 0; b < kT3Groups; b++) { mbar_init(bar_afull(b), 4); mbar_init(bar_aempty(b), 1); }
         mbar_init(bar_accfull, kT3Groups); mbar_init(bar_accempty, 4);
-        for (uint32_t b = 0; b < (uint32_t)kT3Groups; b++) mbar_init(bar_tok(b), 4);
+        for (uint32_t b = 0; b < (uint32_t)kT3Groups; b++) { mbar_init(bar_tok(b), 4); for (uint32_t c = 0; c < 3; c++) mbar_init(bar_apart(b, c), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kT3ExpWarps) {
@@ -123,13 +129,34 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                 const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages;
                 mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
                 T3_TRACE(0)
+                if (kParts > 1) {   // early parts as soon as they are in TMEM
+#pragma unroll
+                    for (int part = 0; part < kParts - 1; part++) {
+                        mbar_wait(bar_apart(q, (uint32_t)part), use & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
+#pragma unroll
+                            for (int c4 = part * kFirst; c4 < (part + 1) * kFirst; c4++) {
+#pragma unroll
+                                for (int j = 0; j < 2; j++) {
+                                    const uint64_t bd = bd0 + (uint64_t)(((c4 * 4 + 2 * j) * 256) >> 4);
+                                    const uint32_t acol = (uint32_t)(c4 * 16 + j * 8);
+                                    tc_mma_i8_ts(dd, abase + acol, bd, kTcIdesc, 1u);
+                                    tc_mma_i8_ts(dm, abase + acol + 64, bd, kTcIdesc, 1u);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
                 mbar_wait(bar_afull(q), use & 1);
                 T3_TRACE(1)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; c4++) {
+                    for (int c4 = (kParts - 1) * kFirst; c4 < 4; c4++) {
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
                             const uint64_t bd = bd0 + (uint64_t)(((c4 * 4 + 2 * j) * 256) >> 4);
@@ -197,6 +224,12 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                     }
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(c4 * 16), d);
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(64 + c4 * 16), m);
+                    if (kParts > 1 && (c4 + 1) % kFirst == 0 && (c4 + 1) / kFirst <= kParts - 1) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_apart(q, (uint32_t)((c4 + 1) / kFirst - 1)));
+                    }
                 }
                 T3_TRACE(3)
                 if (kProbe == 6) { __syncwarp(); if (lane == 0) mbar_arrive(bar_tok((q + 1u) % 3u)); }   // pass the token on
