@@ -299,9 +299,9 @@ def main():
         # one score launch per ~1 GiB chunk of packed rows (csrc/spagxe_cuda.cu make_plan)
         chunk_rows = max(128, ((1 << 30) // pitch) // 128 * 128)
         n_launch = -(-m // min(chunk_rows, 65536))
-        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_ncu_k_score_tc3_halfround.txt:
-        # 1.070477 GB read + 7.49 MB written for a launch of 1.024 GB of packed rows), scaled to this launch size
-        traffic = (1.070477e9 + 7.4944e6) / 1.024e9 * (score_bytes / n_launch)
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_ncu_k_score_tc3_final.txt:
+        # 1.070415 GB read + 7.95 MB written for a launch of 1.024 GB of packed rows), scaled to this launch size
+        traffic = (1.070415e9 + 7.950592e6) / 1.024e9 * (score_bytes / n_launch)
         dg = diags[-1]
         # bounded CPU sample of the very same batch (first rows), single thread
         cpu = None
@@ -332,7 +332,7 @@ def main():
                          "traffic": traffic, "kernel": "k_score_tc3 (2-bit unpack + score pass, tcgen05 kind::i8)",
                          "peak_source": peak_src, "launches_per_step": n_launch,
                          "algorithmic_bytes_per_launch": score_bytes / n_launch, "ms_per_launch": ms_score / n_launch,
-                         "traffic_source": "ncu --set full of one 1.024 GB launch (profiles/r01_ncu_k_score_tc3_halfround.txt), scaled by launch size",
+                         "traffic_source": "ncu --set full of one 1.024 GB launch (profiles/r01_ncu_k_score_tc3_final.txt), scaled by launch size",
                          "share_of_step": ms_score / (ms_max / K)},
             "cpu_baseline": cpu, "clocks": clocks,
             "stages_ms": {"score": ms_score, "tests(finalize+SPA+branchB)": float(np.mean([d["ms_tests"] for d in diags])),

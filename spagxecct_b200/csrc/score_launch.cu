@@ -38,6 +38,8 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN(k_score_tc3<8>);
     SMEM_OPT_IN(k_score_tc3<9>);
     SMEM_OPT_IN(k_score_tc3<10>);
+    SMEM_OPT_IN(k_score_tc3<11>);
+    SMEM_OPT_IN(k_score_tc3<12>);
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
         cudaDriverEntryPointQueryResult qres;
@@ -121,6 +123,8 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 9: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;    // whole-round hand-over (A/B)
         case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no MMAs
         case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no expansion
+        case 32: k_score_tc3<12><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // + first chunk expanded before the A-buffer wait
+        case 27: k_score_tc3<7><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // half-round hand-over only
         case 29: k_score_tc3<9><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over after 3 of 4 chunks
         case 30: k_score_tc3<10><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // hand-over after 1 of 4 chunks
         case 28: k_score_tc3<8><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // per-chunk hand-over
@@ -129,7 +133,8 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 17: k_score_tc3<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: B tiles not loaded
         case 16: k_score_tc3<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: hand-over timing trace
         case 10:   // product path: half-round hand-over (the MMA warp starts on the first 128 samples of a round early)
-        default: k_score_tc3<7><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+                   // and packed bytes read before the wait for the A buffer
+        default: k_score_tc3<11><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
     }
 #undef TC_ARGS
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc launch"; return e; }

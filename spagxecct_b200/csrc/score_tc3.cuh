@@ -49,7 +49,11 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
     // kProbe == 7: the first 128 samples of a round are handed to the MMA warp while the second 128 are still expanding
     // kProbe == 8: the same per 64-sample chunk (three early hand-overs per round)
     // kProbe == 9 / 10: two parts split after chunk 3 / chunk 1
-    constexpr int kParts = (kProbe == 7 || kProbe == 9 || kProbe == 10) ? 2 : (kProbe == 8 ? 4 : 1);
+    // kProbe == 11: as 7, and the packed bytes are read before waiting for the A buffer (their latency hides in that wait)
+    constexpr int kParts = (kProbe == 7 || kProbe == 9 || kProbe == 10 || kProbe == 11 || kProbe == 12) ? 2 : (kProbe == 8 ? 4 : 1);
+    // kProbe == 12: as 11, and the first chunk is expanded into registers before that wait as well
+    constexpr bool kLoadEarly = (kProbe == 11 || kProbe == 12);
+    constexpr bool kExpandEarly = (kProbe == 12);
     constexpr int kFirst = (kProbe == 9) ? 3 : (kProbe == 10 ? 1 : 4 / kParts);   // chunks in every early part (2-part modes: in the first)
     auto bar_apart = [&](uint32_t q, uint32_t part) { return bars + 8u * (kB0 + 3 * kT3Groups + 3 + q * 3u + part); };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,10 +198,12 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                 T3_TRACE(0)
                 mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
                 T3_TRACE(1)
-                mbar_wait(bar_aempty(q), (use & 1) ^ 1);
-                if (kProbe == 6) mbar_wait(bar_tok(q), q == 0 ? ((use & 1) ^ 1) : (use & 1));   // predecessor round has expanded
-                T3_TRACE(2)
-                tc_fence_after();
+                if (!kLoadEarly) {
+                    mbar_wait(bar_aempty(q), (use & 1) ^ 1);
+                    if (kProbe == 6) mbar_wait(bar_tok(q), q == 0 ? ((use & 1) ^ 1) : (use & 1));   // predecessor round has expanded
+                    T3_TRACE(2)
+                    tc_fence_after();
+                }
                 const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 // all four 16-byte chunks of this row first (loads in flight together), then expand
                 uint4 xv[4];
@@ -210,10 +216,8 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                                      : "r"(rowaddr + ((chunk ^ swz) << 4)));
                     }
                 }
-#pragma unroll
-                for (int c4 = 0; c4 < ((kProbe == 2 || (kProbe == 5 && q != 0)) ? 0 : 4); c4++) {
-                    const uint32_t x[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
-                    uint32_t d[16], m[16];
+                auto expand = [&](const uint4 &v, uint32_t (&d)[16], uint32_t (&m)[16]) {
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         const uint32_t so_lo = x[k], se_lo = x[k] * 4u, so_hi = __umulhi(x[k], 1u << 16), se_hi = __umulhi(x[k], 1u << 18);
@@ -222,6 +226,17 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
                         d[4 * k + 2] = prmt(0xFEFEFEFEu, 0u, so_hi); m[4 * k + 2] = prmt(0u, 0x01010101u, so_hi);
                         d[4 * k + 3] = prmt(0xFEFEFEFEu, 0u, se_hi); m[4 * k + 3] = prmt(0u, 0x01010101u, se_hi);
                     }
+                };
+                uint32_t d0[16], m0[16];
+                if (kExpandEarly) expand(xv[0], d0, m0);
+                if (kLoadEarly) { mbar_wait(bar_aempty(q), (use & 1) ^ 1); tc_fence_after(); }
+#pragma unroll
+                for (int c4 = 0; c4 < ((kProbe == 2 || (kProbe == 5 && q != 0)) ? 0 : 4); c4++) {
+                    uint32_t d[16], m[16];
+                    if (kExpandEarly && c4 == 0) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) { d[k] = d0[k]; m[k] = m0[k]; }
+                    } else expand(xv[c4], d, m);
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(c4 * 16), d);
                     tmem_st16(lane_addr + q * 128u + (uint32_t)(64 + c4 * 16), m);
                     if (kParts > 1 && (c4 + 1) % kFirst == 0 && (c4 + 1) / kFirst <= kParts - 1) {
