@@ -212,7 +212,12 @@ __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, i
 
 // ---- host side ----------------------------------------------------------------------------------
 struct MixScratch { uint8_t *want = nullptr; double *part = nullptr, *beta = nullptr; int64_t cap_want = 0, cap_part = 0, cap_beta = 0; };
-static MixScratch g_ms[16];
+MixScratch *mix_scratch_create() { return new MixScratch(); }
+void mix_scratch_destroy(MixScratch *ms) {
+    if (!ms) return;
+    cudaFree(ms->want); cudaFree(ms->part); cudaFree(ms->beta);
+    delete ms;
+}
 
 template <typename T>
 static cudaError_t grow(T **p, int64_t *cap, int64_t need) {
@@ -247,11 +252,12 @@ static cudaError_t run_k(cudaStream_t s, int num_sms, MixScratch &ms, const uint
     return cudaGetLastError();
 }
 
-cudaError_t mix_batch_run(cudaStream_t s, int device, int num_sms, const uint8_t *d_rows, int64_t pitch, SnpStats st, int64_t j0, int mc,
+cudaError_t mix_batch_run(cudaStream_t s, MixScratch *scratch, int num_sms, const uint8_t *d_rows, int64_t pitch, SnpStats st, int64_t j0, int mc,
                           int64_t M, int64_t n, const double *R, const double *E, const VecConst *vc, const double *pcs,
                           const double *xtx_inv, int k, const MixBatchParams &prm, double *d_out, int *b_list, Counters *ctr,
                           int64_t *launches) {
-    MixScratch &ms = g_ms[device & 15];
+    if (!scratch) return cudaErrorInvalidValue;
+    MixScratch &ms = *scratch;
     cudaError_t e;
     if ((e = grow(&ms.want, &ms.cap_want, (int64_t)mc)) != cudaSuccess) return e;
     // the candidate list written by k_finalize_mix becomes a per-SNP flag; the list is then refilled with the slow SNPs

@@ -56,6 +56,7 @@ struct spagxe_ctx {
     bool use_tc = true; int tc_cfg = 10;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
+    MixScratch *mix_scratch = nullptr;                    // SPAGxEmix: scratch of the batched common path
     int64_t cap_mcache = 0; double *d_mcache = nullptr;   // SPAGxEmix: cached allele frequencies, one vector per cluster
     // pinned staging
     uint8_t *h_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -167,6 +168,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
+    mix_scratch_destroy(ctx->mix_scratch);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range); cudaFree(ctx->quad.count);
@@ -513,7 +515,8 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     LAUNCH_CHECK();
     if (!getenv("SPAGXE_MIX_PER_SNP")) {   // env: A/B switch for tests (every SNP through the cluster kernel)
         const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff};
-        CU(mix_batch_run(s, ctx->device, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
+        if (!ctx->mix_scratch) ctx->mix_scratch = mix_scratch_create();
+        CU(mix_batch_run(s, ctx->mix_scratch, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
                          ctx->d_xtx_inv, ctx->n_pcs, bp, d_out, ctx->d_b_list, ctx->d_ctr, &ctx->launches));
     }
     cudaLaunchConfig_t cfg = {};
