@@ -102,6 +102,17 @@ const char *spagxe_last_error(const spagxe_ctx *ctx); /* ctx may be NULL: last c
 /* run all work on a caller-owned cudaStream_t (e.g. torch's current stream); NULL = own stream */
 int spagxe_ctx_set_stream(spagxe_ctx *ctx, void *cuda_stream);
 const char *spagxe_version(void);
+/* Test / tuning hooks -- NOT part of the reference-facing surface and never needed by a caller of the R functions.
+ * Each option switches between implementations that must give the same results (the tests compare them); the
+ * defaults are the product configuration.  The library reads no environment variable.                       */
+enum {
+    SPAGXE_OPT_CHUNK_SNPS = 1,  /* SNPs per pipeline chunk (0 = automatic, ~1 GiB of packed rows)             */
+    SPAGXE_OPT_EXACT_SPA = 2,   /* 1: per-sample CGF sums instead of the SNP-invariant quadrature (K4 vs K4c) */
+    SPAGXE_OPT_MIX_PER_SNP = 3, /* 1: every SPAGxEmix SNP through the per-SNP kernel (K6b) instead of K6a      */
+    SPAGXE_OPT_SCORE_IMPL = 4,  /* 0: tcgen05 score kernel (default), 1: fp64 CUDA-core cross-check kernel    */
+    SPAGXE_OPT_PROBE_CFG = 100  /* builds with -DSPAGXE_PROBES only (tools/): score-kernel timing probes       */
+};
+int spagxe_ctx_set_option(spagxe_ctx *ctx, int option, int64_t value);
 
 /* ---- per-analysis inputs --------------------------------------------------- */
 /* R (Step-1 residuals from SPA_G_Get_Resid, R/SPAGxECCT.R:48-96) and E; host pointers,
@@ -122,6 +133,13 @@ int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k);
  * (lower triangle incl. diagonal, as in data/sparseGRM.SPAGxEPlus.rda).                   */
 int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,
                    double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew);
+
+/* The three sparse-GRM quadratic forms and R.new of SPAGxE_Plus_Nullmodel (R/SPAGxEPlus_functions_MYZ.R:490-537:
+ * the dplyr match()/mutate() block), computed on the device with the same COO kernel family as the Step-2 branch B.
+ * All pointers are HOST arrays; gi/gj are 0-based sample indices (the R shim does the match() on SubjID once).
+ * scalars3 = {R_GRM_R, R_GRM_RE, R.new_GRM_R.new}; Rnew has length n.  Does not change the context's analysis state. */
+int spagxe_plus_nullmodel(spagxe_ctx *ctx, int64_t n, const double *R, const double *E, int64_t nnz, const int32_t *gi,
+                          const int32_t *gj, const double *gv, double *scalars3, double *Rnew);
 
 /* ---- the Step-2 loops ------------------------------------------------------ */
 /* SPAGxE_CCT loop body, R/SPAGxECCT.R:509-525 -> SPAGxE_CCT_one_SNP :543-683.

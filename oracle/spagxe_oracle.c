@@ -14,8 +14,11 @@
  * inst/GenoMat_*.raw fixtures (tests/test_oracle_golden.py).  No statistic
  * or p-value is pinned by any file in the reference and R is not installed
  * in the build container, so for every numeric output this oracle is
- * "parity unpinned": it is cross-checked only against an independent
- * numpy/mpmath restatement (tests/_npref.py).
+ * "parity unpinned": it is cross-checked only against independent
+ * numpy / scipy / mpmath restatements written inside
+ * tests/test_oracle_golden.py, and -- whenever an Rscript is on PATH --
+ * against the reference itself (tools/run_reference.R driven by
+ * tests/test_vs_rscript.py).
  *
  * R numeric semantics mirrored here:
  *   - sum(x): sequential long-double accumulation of doubles that were

@@ -21,8 +21,10 @@ EXPORTS = [
     "spagxe_ctx_create", "spagxe_ctx_destroy", "spagxe_last_error", "spagxe_ctx_set_stream", "spagxe_version",
     "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
     "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
-    "spagxe_measure_fp64_peak", "spagxe_score_stats",
+    "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
 ]
+# test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
+OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL = 1, 2, 3, 4
 
 
 class Geno(C.Structure):
@@ -74,12 +76,15 @@ def load():
     L.spagxe_ctx_destroy.argtypes = [C.c_void_p]
     L.spagxe_ctx_destroy.restype = None
     L.spagxe_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.spagxe_ctx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     L.spagxe_set_vectors.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.spagxe_set_vectors_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.spagxe_set_wald.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_set_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_void_p]
+    L.spagxe_plus_nullmodel.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
     L.spagxe_bed_counts.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
@@ -131,6 +136,10 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.L.spagxe_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, option, value):
+        """Test / tuning hook (never needed by a caller of the R-mirroring functions)."""
+        self._chk(self.L.spagxe_ctx_set_option(self.h, int(option), int(value)))
+
     def set_vectors(self, R, E):
         R = _f64(R); E = _f64(E)
         if R.shape != E.shape or R.ndim != 1:
@@ -156,6 +165,15 @@ class Context:
         gv = _f64(gv); Rnew = _f64(Rnew)
         self._chk(self.L.spagxe_set_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data,
                                         float(R_GRM_R), float(R_GRM_RE), float(Rnew_GRM_Rnew), Rnew.ctypes.data))
+
+    def plus_nullmodel(self, gi, gj, gv, R, E):
+        """(R_GRM_R, R_GRM_RE, R.new, R.new_GRM_R.new) of SPAGxE_Plus_Nullmodel, computed on the device."""
+        gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
+        gv = _f64(gv); R = _f64(R); E = _f64(E)
+        out3 = np.empty(3); Rnew = np.empty(R.size)
+        self._chk(self.L.spagxe_plus_nullmodel(self.h, R.size, R.ctypes.data, E.ctypes.data, gi.size, gi.ctypes.data,
+                                               gj.ctypes.data, gv.ctypes.data, out3.ctypes.data, Rnew.ctypes.data))
+        return float(out3[0]), float(out3[1]), Rnew, float(out3[2])
 
     @staticmethod
     def geno_desc(kind, data_ptr, n, m, pitch, location=LOC_HOST):

@@ -73,7 +73,10 @@ def check_input_Resid(pIDs, gIDs, R, range_=(-100, 100)):
                     "please refer to 'Details'.")
     p = [] if pIDs is None else [str(x) for x in pIDs]
     g = [] if gIDs is None else [str(x) for x in gIDs]
-    if sorted(set(p)) != sorted(set(g)):
+    # `any(sort(unique(pIDs)) != sort(unique(gIDs)))` (:1904): with rownames(Geno.mtx) NULL the comparison is
+    # against logical(0) and any() is FALSE, so R passes silently; a length mismatch of two non-empty sets recycles
+    # with a warning and (practically always) trips the test, which is the behaviour kept here
+    if gIDs is not None and pIDs is not None and sorted(set(p)) != sorted(set(g)):
         raise RStop("unique(pIDs) should be the same as unique(gIDs).")
     if len(set(g)) != len(g):
         raise RStop("Argument 'gIDs' should not have a duplicated element.")
@@ -81,7 +84,7 @@ def check_input_Resid(pIDs, gIDs, R, range_=(-100, 100)):
         raise RStop("range[2] should be -1*range[1]")
     if len(R) != len(p):
         raise RStop("Argument 'pIDs' should be of the same length as input data.")
-    if p == g:
+    if gIDs is None or p == g:
         return None
     pos = {s: i for i, s in enumerate(g)}
     return np.array([pos[s] for s in p])

@@ -22,12 +22,15 @@ __global__ void __launch_bounds__(1024) k_vec_prep1(const double *__restrict__ R
                                                     int64_t n, VecConst *vc) {
     __shared__ double scratch[3 * 32];
     double v[3] = {0, 0, 0};
+    int bad = 0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
         double r = R[i], e = E[i], r2 = r * r;
+        if (!isfinite(r) || !isfinite(e)) bad++;
         v[0] += r; v[1] += r2; v[2] += e * r2;
     }
     block_sum<3>(v, scratch);
-    if (threadIdx.x == 0) { vc->sumR = v[0]; vc->sumR2 = v[1]; vc->sumER2 = v[2]; vc->lambda = v[2] / v[1]; }
+    bad = __syncthreads_count(bad);
+    if (threadIdx.x == 0) { vc->sumR = v[0]; vc->sumR2 = v[1]; vc->sumER2 = v[2]; vc->lambda = v[2] / v[1]; vc->nonfinite = bad; }
 }
 // mode 0: V = R.new (CCT); mode 1: V = E*R (mix / plus).  Rn_in != NULL: use the caller's R.new (plus).
 __global__ void __launch_bounds__(1024) k_vec_prep2(const double *__restrict__ R, const double *__restrict__ E,
@@ -90,19 +93,6 @@ __global__ void k_pack_dense(const T *__restrict__ G, int64_t ld, int64_t n, int
     }
     bed[(int64_t)j * pitch_words + w] = word;
     if (bad) atomicAdd(&ctr->n_nonint, 1ULL);
-}
-
-// Make every padding sample (index >= n, up to the row pitch) code 11 (hom-A2: dosage 0, not
-// missing) so that the main kernels need no bounds logic.  One thread per row.
-__global__ void k_sanitize_tail(uint8_t *bed, int64_t pitch, int64_t n, int m) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    uint8_t *row = bed + (int64_t)j * pitch;
-    int64_t full = n >> 2;
-    int rem = (int)(n & 3);
-    int64_t b = full;
-    if (rem) { row[b] |= (uint8_t)(0xFFu << (2 * rem)); b++; }
-    for (; b < pitch; b++) row[b] = 0xFF;
 }
 
 // per-code counts (exact integers). One warp per SNP row; pitch multiple of 4.
@@ -1072,6 +1062,40 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const BItem *__restr
 // SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:248-405)
 struct PlusConst { double R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew; };
 struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
+
+// Step-1 scalars of SPAGxE_Plus_Nullmodel (ref R/SPAGxEPlus_functions_MYZ.R:490-537): the three sparse-GRM quadratic
+// forms and R.new = (E - lambda) R with lambda = R_GRM_RE / R_GRM_R.  One CTA, fixed-order sums (runs once per analysis).
+__global__ void __launch_bounds__(1024) k_plus_nullmodel(const double *__restrict__ R, const double *__restrict__ E,
+                                                         int64_t n, GrmCoo grm, double *__restrict__ Rnew,
+                                                         double *__restrict__ out3) {
+    __shared__ double scratch[5 * 32];
+    __shared__ double s_lambda;
+    double v[5] = {0, 0, 0, 0, 0};
+    for (long long e = threadIdx.x; e < grm.nnz; e += blockDim.x) {
+        const int i = grm.gi[e], j = grm.gj[e];
+        const double val = grm.gv[e], ri = R[i], rj = R[j], rei = ri * E[i], rej = rj * E[j];
+        v[0] += (val * ri) * rj;          // Cov_R          (:507)
+        v[1] += (val * ri) * rej;         // Cov_R_RE_part1 (:515)
+        v[2] += (val * rj) * rei;         // Cov_R_RE_part2 (:516)
+    }
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double r = R[i], re = r * E[i];
+        v[3] += r * r; v[4] += re * r;
+    }
+    block_sum<5>(v, scratch);
+    const double R_GRM_R = v[0] * 2 - v[3];                  // :510
+    const double R_GRM_RE = v[1] + v[2] - v[4];              // :523-525
+    if (threadIdx.x == 0) { out3[0] = R_GRM_R; out3[1] = R_GRM_RE; s_lambda = R_GRM_RE / R_GRM_R; }
+    __syncthreads();
+    const double lambda = s_lambda;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) Rnew[i] = (E[i] - lambda) * R[i];   // :530
+    __syncthreads();   // the COO pass below gathers R.new written by other threads of this CTA
+    double w[2] = {0, 0};
+    for (long long e = threadIdx.x; e < grm.nnz; e += blockDim.x) w[0] += (grm.gv[e] * Rnew[grm.gi[e]]) * Rnew[grm.gj[e]];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double r = Rnew[i]; w[1] += r * r; }
+    block_sum<2>(w, scratch);
+    if (threadIdx.x == 0) out3[2] = w[0] * 2 - w[1];         // :537
+}
 
 // K3 for SPAGxE_Plus: V = E*R, so D1/T1 carry sum(g*E*R).  One thread per SNP.  out is M x 8.
 __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,

@@ -26,20 +26,22 @@ cudaError_t score_init(std::string *err) {
     if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes)) != cudaSuccess) { \
         *err = "cudaFuncSetAttribute(" #k ")"; return e;                                                        \
     }
+    SMEM_OPT_IN(k_score_unpack_mma);
+#ifdef SPAGXE_PROBES
     SMEM_OPT_IN((k_score_tc<8, 3>));
-    SMEM_OPT_IN(k_score_tc3<0>);
-    SMEM_OPT_IN(k_score_tc3<1>);
-    SMEM_OPT_IN(k_score_tc3<2>);
-    SMEM_OPT_IN(k_score_tc3<3>);
-    SMEM_OPT_IN(k_score_tc3<4>);
-    SMEM_OPT_IN(k_score_tc3<5>);
-    SMEM_OPT_IN(k_score_tc3<6>);
-    SMEM_OPT_IN(k_score_tc3<7>);
-    SMEM_OPT_IN(k_score_tc3<8>);
-    SMEM_OPT_IN(k_score_tc3<9>);
-    SMEM_OPT_IN(k_score_tc3<10>);
-    SMEM_OPT_IN(k_score_tc3<11>);
-    SMEM_OPT_IN(k_score_tc3<12>);
+    SMEM_OPT_IN(k_score_tc3_probe<0>);
+    SMEM_OPT_IN(k_score_tc3_probe<1>);
+    SMEM_OPT_IN(k_score_tc3_probe<2>);
+    SMEM_OPT_IN(k_score_tc3_probe<3>);
+    SMEM_OPT_IN(k_score_tc3_probe<4>);
+    SMEM_OPT_IN(k_score_tc3_probe<5>);
+    SMEM_OPT_IN(k_score_tc3_probe<6>);
+    SMEM_OPT_IN(k_score_tc3_probe<7>);
+    SMEM_OPT_IN(k_score_tc3_probe<8>);
+    SMEM_OPT_IN(k_score_tc3_probe<9>);
+    SMEM_OPT_IN(k_score_tc3_probe<10>);
+    SMEM_OPT_IN(k_score_tc3_probe<12>);
+#endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
         cudaDriverEntryPointQueryResult qres;
@@ -65,6 +67,7 @@ cudaError_t score_build_b(cudaStream_t s, const double *R, const double *V, int6
     return cudaGetLastError();
 }
 
+#ifdef SPAGXE_PROBES
 template <int NBOX>
 static float run_probe(cudaStream_t s, int num_sms, const CUtensorMap &map, int n_tiles, int tps, int n_splits, int n_row_tiles,
                        long long *d_acc) {
@@ -80,6 +83,8 @@ static float run_probe(cudaStream_t s, int num_sms, const CUtensorMap &map, int 
     cudaEventDestroy(a); cudaEventDestroy(b);
     return ms;
 }
+
+#endif
 
 cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8_t *d_rows, const ScoreGeom &g, const int8_t *d_bmat,
                             const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err) {
@@ -105,11 +110,15 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
     const int n_row_tiles = m_pad / kTcRows;
     int want_splits = std::max(1, (4 * num_sms + n_row_tiles - 1) / n_row_tiles);
     want_splits = std::min(want_splits, std::max(1, n_tiles / 16));
+    // int32 TMEM accumulators are exact while samples per split * 2 * 128 < 2^31: at most 16,383 tiles of 512 samples
+    want_splits = std::max(want_splits, (n_tiles + 16382) / 16383);
     const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
     const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_items = n_row_tiles * n_splits;
     const int grid = std::min(n_items, num_sms);
-    if (getenv("SPAGXE_TMA_PROBE")) {   // one-off diagnostic of the access pattern (not a product path)
+#define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
+#ifdef SPAGXE_PROBES
+    if (tc_cfg == 99) {   // one-off diagnostic of the access pattern
         const double gb = (double)mc * g.row_bytes / 1e9;
         float m1 = run_probe<1>(s, num_sms, map, n_tiles, tiles_per_split, n_splits, n_row_tiles, d_acc);
         float m2 = run_probe<2>(s, num_sms, map, n_tiles, tiles_per_split, n_splits, n_row_tiles, d_acc);
@@ -117,28 +126,30 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         fprintf(stderr, "[tma probe] rows=%d %.3f GB: 1 box %.3f ms (%.0f GB/s), 2 boxes %.3f ms (%.0f GB/s), 4 boxes %.3f ms (%.0f GB/s)\n", mc, gb,
                 m1, gb / m1 * 1e3, m2, gb / m2 * 1e3, m4, gb / m4 * 1e3);
     }
-#define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
-    switch (tc_cfg) {
+    switch (tc_cfg) {   // probe builds only: schedule variants and timing probes (several give WRONG sums by design)
         case 1: k_score_tc<8, 3><<<grid, 12 * 32, kTcSmemBytes, s>>>(TC_ARGS); break;
-        case 9: k_score_tc3<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;    // whole-round hand-over (A/B)
-        case 11: k_score_tc3<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no MMAs
-        case 12: k_score_tc3<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: no expansion
-        case 32: k_score_tc3<12><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // + first chunk expanded before the A-buffer wait
-        case 27: k_score_tc3<7><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // half-round hand-over only
-        case 29: k_score_tc3<9><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over after 3 of 4 chunks
-        case 30: k_score_tc3<10><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // hand-over after 1 of 4 chunks
-        case 28: k_score_tc3<8><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // per-chunk hand-over
-        case 19: k_score_tc3<6><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // expansion token ring
-        case 18: k_score_tc3<5><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: only group 0 expands
-        case 17: k_score_tc3<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: B tiles not loaded
-        case 16: k_score_tc3<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // probe: hand-over timing trace
-        case 10:   // product path: half-round hand-over (the MMA warp starts on the first 128 samples of a round early)
-                   // and packed bytes read before the wait for the A buffer
-        default: k_score_tc3<11><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 9: k_score_tc3_probe<0><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;    // whole-round hand-over
+        case 11: k_score_tc3_probe<1><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // no MMAs
+        case 12: k_score_tc3_probe<2><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // no expansion
+        case 32: k_score_tc3_probe<12><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // first chunk expanded early
+        case 27: k_score_tc3_probe<7><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // half-round hand-over only
+        case 29: k_score_tc3_probe<9><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over after 3 of 4 chunks
+        case 30: k_score_tc3_probe<10><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;  // hand-over after 1 of 4 chunks
+        case 28: k_score_tc3_probe<8><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // per-chunk hand-over
+        case 19: k_score_tc3_probe<6><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // expansion token ring
+        case 18: k_score_tc3_probe<5><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // only group 0 expands
+        case 17: k_score_tc3_probe<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // B tiles not loaded
+        case 16: k_score_tc3_probe<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over timing trace
+        default: k_score_unpack_mma<<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
     }
+#else
+    (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
+    k_score_unpack_mma<<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS);
+#endif
 #undef TC_ARGS
-    if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc launch"; return e; }
-    if (tc_cfg == 16) {   // dump the timing trace of CTA 0 (diagnostic, not a product path)
+    if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_unpack_mma launch"; return e; }
+#ifdef SPAGXE_PROBES
+    if (tc_cfg == 16) {   // dump the timing trace of CTA 0
         static int dumped = 0;
         cudaStreamSynchronize(s);
         if (dumped++ == 3) {
@@ -159,6 +170,7 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
             }
         }
     }
+#endif
     k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
     *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc_reduce launch"; return e; }

@@ -173,6 +173,7 @@ __device__ __forceinline__ uint64_t tc_bdesc(uint32_t saddr) {
 constexpr uint32_t kTcIdesc = (2u << 4) /*D = s32*/ | (1u << 7) /*A = s8*/ | (1u << 10) /*B = s8*/ |
                               ((16u >> 3) << 17) /*N*/ | ((128u >> 4) << 24) /*M*/;
 
+#ifdef SPAGXE_PROBES   // first-generation kernel and the TMA access-pattern probe: tools builds only
 // ---- the kernel ---------------------------------------------------------------------------------
 // work item = (row tile rt, k split ks): rows [128 rt, +128), sample tiles [ks*tiles_per_split, ...)
 template <int kTcExpWarps, int kTcABufs, bool kWithMiss = true, int kProbe = 0>  // kProbe: 1 = no MMAs, 2 = no expansion (timing probes)
@@ -421,6 +422,8 @@ k_tma_probe(const __grid_constant__ CUtensorMap bedmap, int n_tiles, int tiles_p
     }
     if (acc == 0x123456789ULL) sink[0] = acc;
 }
+
+#endif  // SPAGXE_PROBES
 
 // exact integer recombination: value = sum_k acc_k 256^k (two int64 halves -> one rounding), times 2^-s
 __device__ __forceinline__ double tc_combine(const long long *a, int s) {

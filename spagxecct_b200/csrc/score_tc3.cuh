@@ -21,15 +21,24 @@ constexpr int kT3Threads = kT3Warps * 32;
 
 // kProbe == 3: CTA 0 records clock64() at the hand-over points of rounds [16, 64) of every warp (timing trace)
 constexpr int kT3TraceRounds = 48, kT3TraceEv = 8;
+#ifdef SPAGXE_PROBES
 __device__ unsigned long long g_tc_trace[kT3Warps * kT3TraceRounds * kT3TraceEv];
 #define T3_TRACE(k)                                                                                        \
     if (kProbe == 3 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT3TraceRounds)               \
         g_tc_trace[((size_t)warp * kT3TraceRounds + (use - 16)) * kT3TraceEv + (k)] = (unsigned long long)clock64();
+#else
+#define T3_TRACE(k)
+#endif
 
-template <int kProbe = 0>
-__global__ void __launch_bounds__(kT3Threads, 1)
-k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
-            int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
+// The kernel body is a template over the schedule variant.  The library ships exactly one instantiation
+// (kT3Product, as the plain kernel k_score_unpack_mma below); every other value is a timing probe or an A/B
+// variant and only exists in builds with -DSPAGXE_PROBES (tools/, never the product .so).
+constexpr int kT3Product = 11;   // half-round hand-over + packed bytes read before the A-buffer wait
+
+template <int kProbe>
+__device__ __forceinline__ void
+score_tc3_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+               int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bbase = sbase + kTcGStages * kTcGStageBytes;
@@ -289,5 +298,21 @@ k_score_tc3(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
+
+// K1+K2 product kernel: 2-bit unpack + exact int8 contraction on tcgen05 (the only score kernel in the product .so
+// besides the fp64 cross-check kernel k_score_v1)
+__global__ void __launch_bounds__(kT3Threads, 1)
+k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
+    score_tc3_body<kT3Product>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc);
+}
+#ifdef SPAGXE_PROBES
+template <int kProbe>
+__global__ void __launch_bounds__(kT3Threads, 1)
+k_score_tc3_probe(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+                  int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
+    score_tc3_body<kProbe>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc);
+}
+#endif
 
 }  // namespace spagxe

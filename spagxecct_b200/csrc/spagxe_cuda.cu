@@ -53,7 +53,9 @@ struct spagxe_ctx {
     Quad quad = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
-    bool use_tc = true; int tc_cfg = 10;
+    bool use_tc = true; int tc_cfg = 0;
+    // test / tuning hooks (spagxe_ctx_set_option); no environment variable is ever read by this library
+    int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     MixScratch *mix_scratch = nullptr;                    // SPAGxEmix: scratch of the batched common path
@@ -61,10 +63,14 @@ struct spagxe_ctx {
     // pinned staging
     uint8_t *h_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;   // timing events, created once and reused by every call
+    int64_t cap_util = 0; void *d_util = nullptr;            // scratch of spagxe_bed_counts / spagxe_bed_decode
+    int *h_flag = nullptr;                                   // pinned word for small device -> host flags
     int64_t launches = 0;
     cudaStream_t stream() const { return user_stream ? s_user : s_main; }
 };
 
+static int check_grm_indices(spagxe_ctx *ctx, const char *who, int64_t nnz, const int32_t *gi, const int32_t *gj, int64_t n);
 static int fail(spagxe_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -149,11 +155,7 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
         std::string serr;
         if ((e = score_init(&serr)) != cudaSuccess) return bail(serr.c_str(), e);
     }
-    if (const char *cfg = getenv("SPAGXE_TC_CFG")) ctx->tc_cfg = atoi(cfg);   // tuning switch: score kernel variant
-    {
-        const char *sv = getenv("SPAGXE_SCORE");   // "v1": fp64 CUDA-core kernel (A/B switch for tests)
-        ctx->use_tc = !(sv && strcmp(sv, "v1") == 0);
-    }
+    if ((e = cudaMallocHost((void **)&ctx->h_flag, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMallocHost", e);
     *out = ctx;
     return SPAGXE_OK;
 }
@@ -171,6 +173,9 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     mix_scratch_destroy(ctx->mix_scratch);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_count) cudaFreeHost(ctx->h_count);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    cudaFree(ctx->d_util);
+    for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range); cudaFree(ctx->quad.count);
     for (int b = 0; b < 2; b++) {
         if (ctx->h_stage[b]) cudaFreeHost(ctx->h_stage[b]);
@@ -188,6 +193,24 @@ extern "C" int spagxe_ctx_set_stream(spagxe_ctx *ctx, void *cuda_stream) {
     ctx->s_user = (cudaStream_t)cuda_stream;
     ctx->user_stream = true;  // NULL here means the legacy default stream, which torch uses by default
     return SPAGXE_OK;
+}
+
+// Test / tuning hooks.  They select between bit-compatible implementations (chunking, exact vs quadrature SPA sums,
+// batched vs per-SNP SPAGxEmix route, fp64 vs tensor-core score kernel) so that the tests can compare them; defaults are
+// the product configuration.  Nothing here is read from the environment.
+extern "C" int spagxe_ctx_set_option(spagxe_ctx *ctx, int option, int64_t value) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    switch (option) {
+        case SPAGXE_OPT_CHUNK_SNPS: if (value < 0) break; ctx->opt_chunk_snps = value; return SPAGXE_OK;
+        case SPAGXE_OPT_EXACT_SPA: ctx->opt_exact_spa = value != 0; ctx->vec_mode = -1; return SPAGXE_OK;
+        case SPAGXE_OPT_MIX_PER_SNP: ctx->opt_mix_per_snp = value != 0; return SPAGXE_OK;
+        case SPAGXE_OPT_SCORE_IMPL: if (value != 0 && value != 1) break; ctx->use_tc = (value == 0); return SPAGXE_OK;
+#ifdef SPAGXE_PROBES
+        case SPAGXE_OPT_PROBE_CFG: ctx->tc_cfg = (int)value; return SPAGXE_OK;
+#endif
+        default: break;
+    }
+    return fail(ctx, SPAGXE_ERR_ARG, "set_option: unknown option %d or bad value %lld", option, (long long)value);
 }
 
 static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const double *E, cudaMemcpyKind kind) {
@@ -209,7 +232,14 @@ static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const
     k_vec_prep1<<<1, 1024, 0, s>>>(ctx->d_R, ctx->d_E, n, ctx->d_vc);
     LAUNCH_CHECK();
     ctx->vec_mode = -1;
+    // R and E must be finite: the fixed-point digits of the score pass and the SPA sums are undefined otherwise
+    // (R would carry the NaN through sum() and stop in the first `if`)
+    CU(cudaMemcpyAsync(ctx->h_flag, &ctx->d_vc->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    if (ctx->h_flag[0]) {
+        ctx->n = 0;
+        return fail(ctx, SPAGXE_ERR_ARG, "set_vectors: R or E holds %d non-finite value(s)", ctx->h_flag[0]);
+    }
     return SPAGXE_OK;
 }
 extern "C" int spagxe_set_vectors(spagxe_ctx *ctx, int64_t n, const double *R, const double *E) {
@@ -252,7 +282,7 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
     }
     // SNP-invariant quadrature of the SPA vector (R.new): only worth it when N >> number of nodes
     const double *rv = (mode == 0) ? ctx->d_V : ctx->d_Rn;
-    ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes && !getenv("SPAGXE_EXACT_SPA");  // env: A/B switch for tests
+    ctx->quad_on = ctx->n >= 8ll * kQBins * kQNodes && !ctx->opt_exact_spa;
     if (ctx->quad_on) {
         cudaStream_t s = ctx->stream();
         CU(cudaMemsetAsync(ctx->quad.wfix, 0, sizeof(long long) * kQBins * kQNodes, s));
@@ -394,7 +424,7 @@ static int validate_geno(spagxe_ctx *ctx, const spagxe_geno *g) {
     return SPAGXE_OK;
 }
 
-static ChunkPlan make_plan(const spagxe_geno *g) {
+static ChunkPlan make_plan(const spagxe_geno *g, int64_t chunk_override) {
     ChunkPlan pl;
     pl.n = g->n_samples; pl.m = g->n_snps;
     pl.row_bytes = (g->n_samples + 3) / 4;
@@ -404,7 +434,7 @@ static ChunkPlan make_plan(const spagxe_geno *g) {
     int64_t budget = (g->kind == SPAGXE_GENO_BED) ? (1ll << 30) : (1ll << 26);
     int64_t cm = std::max<int64_t>(kScoreRowsPad, budget / pl.dpitch / kScoreRowsPad * kScoreRowsPad);
     cm = std::min<int64_t>(cm, 65536);
-    if (const char *ov = getenv("SPAGXE_CHUNK_SNPS")) cm = std::max<int64_t>(1, atoll(ov));   // tests: force many small chunks
+    if (chunk_override > 0) cm = chunk_override;   // test hook: force many small chunks
     pl.chunk_m = (int)std::min<int64_t>(cm, std::max<int64_t>(pl.m, 1));
     return pl;
 }
@@ -490,11 +520,14 @@ static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan 
     return SPAGXE_OK;
 }
 
-struct EventPool {
-    std::vector<cudaEvent_t> ev;
-    ~EventPool() { for (auto e : ev) cudaEventDestroy(e); }
+struct EventPool {   // view of the context's reusable timing events for one call
+    spagxe_ctx *ctx;
+    explicit EventPool(spagxe_ctx *c) : ctx(c) { c->ev_used = 0; }
     cudaEvent_t rec(cudaStream_t s) {
-        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); return e;
+        if (ctx->ev_used == ctx->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+        cudaEvent_t e = ctx->ev_pool[ctx->ev_used++];
+        cudaEventRecord(e, s);
+        return e;
     }
 };
 
@@ -513,7 +546,7 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     cudaStream_t s = ctx->stream();
     k_finalize_mix<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, prm->min_maf, d_out, ctx->d_b_list, ctx->d_ctr);
     LAUNCH_CHECK();
-    if (!getenv("SPAGXE_MIX_PER_SNP")) {   // env: A/B switch for tests (every SNP through the cluster kernel)
+    if (!ctx->opt_mix_per_snp) {   // test hook: every SNP through the cluster kernel
         const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff};
         if (!ctx->mix_scratch) ctx->mix_scratch = mix_scratch_create();
         CU(mix_batch_run(s, ctx->mix_scratch, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
@@ -568,7 +601,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     spagxe_diag dg; memset(&dg, 0, sizeof dg);
     ctx->launches = 0;
     if (M == 0) { if (diag) *diag = dg; return SPAGXE_OK; }
-    ChunkPlan pl = make_plan(g);
+    ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
     double *d_out = nullptr;
     if (prm->out_location == SPAGXE_LOC_DEVICE) { d_out = out; rc = ensure_chunk_scratch(ctx, pl, own_bed, 0); }
@@ -582,7 +615,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     }
     if ((rc = ensure_vec_mode(ctx, vmode, mode == RUN_PLUS ? ctx->d_Rn_user : nullptr))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-    EventPool evp;
+    EventPool evp(ctx);
     cudaEvent_t e_begin = evp.rec(s);
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev;
     SnpStats st = stats_view(ctx, ctx->cap_m);
@@ -671,9 +704,7 @@ extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, c
     if (!ctx) return SPAGXE_ERR_ARG;
     if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_grm: call spagxe_set_vectors first");
     if (nnz < 0 || (nnz > 0 && (!gi || !gj || !gv)) || !Rnew) return fail(ctx, SPAGXE_ERR_ARG, "set_grm: bad arguments");
-    for (int64_t e = 0; e < nnz; e++)
-        if (gi[e] < 0 || gi[e] >= ctx->n || gj[e] < 0 || gj[e] >= ctx->n)
-            return fail(ctx, SPAGXE_ERR_ARG, "set_grm: index out of range at entry %lld", (long long)e);
+    { int rc = check_grm_indices(ctx, "set_grm", nnz, gi, gj, ctx->n); if (rc) return rc; }
     CU(cudaSetDevice(ctx->device));
     CU(dev_realloc(&ctx->d_gi, std::max<int64_t>(nnz, 1))); CU(dev_realloc(&ctx->d_gj, std::max<int64_t>(nnz, 1)));
     CU(dev_realloc(&ctx->d_gv, std::max<int64_t>(nnz, 1))); CU(dev_realloc(&ctx->d_Rn_user, ctx->n));
@@ -689,6 +720,49 @@ extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, c
     return SPAGXE_OK;
 }
 
+static int check_grm_indices(spagxe_ctx *ctx, const char *who, int64_t nnz, const int32_t *gi, const int32_t *gj, int64_t n) {
+    for (int64_t e = 0; e < nnz; e++)
+        if (gi[e] < 0 || gi[e] >= n || gj[e] < 0 || gj[e] >= n)
+            return fail(ctx, SPAGXE_ERR_ARG, "%s: index out of range at entry %lld", who, (long long)e);
+    return SPAGXE_OK;
+}
+
+// SPAGxE_Plus_Nullmodel's quadratic forms on the device (ref R/SPAGxEPlus_functions_MYZ.R:490-537)
+extern "C" int spagxe_plus_nullmodel(spagxe_ctx *ctx, int64_t n, const double *R, const double *E, int64_t nnz,
+                                     const int32_t *gi, const int32_t *gj, const double *gv, double *scalars3, double *Rnew) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (n <= 0 || !R || !E || nnz < 0 || (nnz > 0 && (!gi || !gj || !gv)) || !scalars3 || !Rnew)
+        return fail(ctx, SPAGXE_ERR_ARG, "plus_nullmodel: bad arguments");
+    int rc = check_grm_indices(ctx, "plus_nullmodel", nnz, gi, gj, n);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    // one scratch block: R | E | Rnew | out3 (8-byte items), then gv, then gi | gj
+    const int64_t nz = std::max<int64_t>(nnz, 1);
+    const int64_t need = (3 * n + 4 + nz) * (int64_t)sizeof(double) + 2 * nz * (int64_t)sizeof(int);
+    if (need > ctx->cap_util) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_util); ctx->d_util = nullptr; ctx->cap_util = 0;
+        CU(cudaMalloc(&ctx->d_util, need)); ctx->cap_util = need;
+    }
+    double *dR = (double *)ctx->d_util, *dE = dR + n, *dRn = dE + n, *dout = dRn + n, *dgv = dout + 4;
+    int *dgi = (int *)(dgv + nz), *dgj = dgi + nz;
+    CU(cudaMemcpyAsync(dR, R, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dE, E, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (nnz > 0) {
+        CU(cudaMemcpyAsync(dgv, gv, nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dgi, gi, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(dgj, gj, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    GrmCoo grm{dgi, dgj, dgv, (long long)nnz};
+    k_plus_nullmodel<<<1, 1024, 0, s>>>(dR, dE, n, grm, dRn, dout);
+    LAUNCH_CHECK();
+    CU(cudaMemcpyAsync(scalars3, dout, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(Rnew, dRn, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SPAGXE_OK;
+}
+
 // raw per-SNP outputs of the score pass (K1+K2) for cross-checking the two kernels
 extern "C" int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *g, int impl, double *D0, double *D1, double *T0,
                                   double *T1, int32_t *asum, int32_t *nmiss) {
@@ -699,7 +773,7 @@ extern "C" int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *g, int imp
     if (!D0 || !D1 || !T0 || !T1 || !asum || !nmiss) return fail(ctx, SPAGXE_ERR_ARG, "score_stats: NULL output");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
-    ChunkPlan pl = make_plan(g);
+    ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     if (ctx->vec_mode < 0 && (rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
@@ -736,26 +810,29 @@ extern "C" int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *g, int64_t 
     if (!counts) return fail(ctx, SPAGXE_ERR_ARG, "counts is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
-    ChunkPlan pl = make_plan(g);
+    ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     ctx->launches = 0;
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     long long *d_counts = nullptr;
-    CU(cudaMalloc((void **)&d_counts, sizeof(long long) * 4 * pl.chunk_m));
+    {
+        const int64_t need = (int64_t)sizeof(long long) * 4 * pl.chunk_m;
+        if (need > ctx->cap_util) { cudaFree(ctx->d_util); ctx->d_util = nullptr; ctx->cap_util = 0; CU(cudaMalloc(&ctx->d_util, need)); ctx->cap_util = need; }
+        d_counts = (long long *)ctx->d_util;
+    }
     int buf = 0; int64_t h2d = 0;
     for (int64_t j0 = 0; j0 < g->n_snps; j0 += pl.chunk_m, buf ^= 1) {
         const int mc = (int)std::min<int64_t>(pl.chunk_m, g->n_snps - j0);
         const uint8_t *d_rows = nullptr;
-        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) { cudaFree(d_counts); return rc; }
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) return rc;
         k_bed_counts<<<(mc * 32 + 255) / 256, 256, 0, s>>>(d_rows, pl.dpitch, pl.n, mc, d_counts);
         ctx->launches++;
         cudaError_t e = cudaMemcpyAsync(counts + 4 * j0, d_counts, sizeof(long long) * 4 * mc, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { cudaFree(d_counts); return fail(ctx, SPAGXE_ERR_CUDA, "bed_counts: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "bed_counts: %s", cudaGetErrorString(e));
         if (own_bed) cudaEventRecord(ctx->ev_done[buf], s);
     }
-    cudaFree(d_counts);
     return SPAGXE_OK;
 }
 
@@ -766,27 +843,30 @@ extern "C" int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *g, double *
     if (!out_host) return fail(ctx, SPAGXE_ERR_ARG, "out is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
-    ChunkPlan pl = make_plan(g);
+    ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     // decode expands 32x: keep chunks small
     pl.chunk_m = (int)std::min<int64_t>(pl.chunk_m, std::max<int64_t>(1, (1ll << 28) / (pl.n * 8)));
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     double *d_dec = nullptr;
-    CU(cudaMalloc((void **)&d_dec, sizeof(double) * pl.n * pl.chunk_m));
+    {
+        const int64_t need = (int64_t)sizeof(double) * pl.n * pl.chunk_m;
+        if (need > ctx->cap_util) { cudaFree(ctx->d_util); ctx->d_util = nullptr; ctx->cap_util = 0; CU(cudaMalloc(&ctx->d_util, need)); ctx->cap_util = need; }
+        d_dec = (double *)ctx->d_util;
+    }
     int buf = 0; int64_t h2d = 0;
     for (int64_t j0 = 0; j0 < g->n_snps; j0 += pl.chunk_m, buf ^= 1) {
         const int mc = (int)std::min<int64_t>(pl.chunk_m, g->n_snps - j0);
         const uint8_t *d_rows = nullptr;
-        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) { cudaFree(d_dec); return rc; }
+        if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &h2d))) return rc;
         dim3 grid((unsigned)((pl.n + 255) / 256), (unsigned)mc);
         k_bed_decode<<<grid, 256, 0, s>>>(d_rows, pl.dpitch, pl.n, mc, d_dec);
         ctx->launches++;
         cudaError_t e = cudaMemcpyAsync(out_host + j0 * pl.n, d_dec, sizeof(double) * pl.n * mc, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { cudaFree(d_dec); return fail(ctx, SPAGXE_ERR_CUDA, "bed_decode: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "bed_decode: %s", cudaGetErrorString(e));
         if (own_bed) cudaEventRecord(ctx->ev_done[buf], s);
     }
-    cudaFree(d_dec);
     return SPAGXE_OK;
 }
 

@@ -13,7 +13,7 @@ struct VecConst {
     double sumR, sumR2, sumER2, lambda;  // lambda = sum(E R^2)/sum(R^2) (ref :592)
     double sumV, sumV2;                  // second score vector V (R.new for CCT, E*R for mix/plus)
     double sumRn, sumRn2;                // R.new = (E - lambda) R (ref :594)
-    double sumE, sumEE, sumER, sumEER, sumEERR;  // branch-B class algebra helpers (unused by v1)
+    int nonfinite, pad_;                 // number of non-finite entries of R and E (set_vectors refuses them)
 };
 
 struct SnpStats {  // per-SNP outputs of the score pass (chunk-local index)
@@ -30,7 +30,7 @@ struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0
 struct Counters {  // device-side diagnostics / work-list cursors
     unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
         n_mix_logistic, newton_iters, n_allmissing, n_nonint;
-    int spa_count, spax_count, b_count, b_cursor;
+    int spa_count, spax_count, b_count, pad_;
 };
 
 struct BmatInfo { int sR, sV; double maxR, maxV; };   // fixed-point scales of the tensor-core B matrix

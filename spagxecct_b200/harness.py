@@ -42,3 +42,47 @@ def get_resid(traits, y, covars):
         return np.asarray(y, dtype=np.float64) - mu
     beta, *_ = np.linalg.lstsq(X, np.asarray(y, dtype=np.float64), rcond=None)
     return np.asarray(y, dtype=np.float64) - X @ beta
+
+
+def cox_fit_breslow(time, event, X, maxit=50, tol=1e-10):
+    """Cox proportional-hazards fit by Newton-Raphson with Breslow's treatment of ties (stand-in for the Step-1
+    `coxph` of SPA_G_Get_Resid, R/SPAGxECCT.R:72-80, used only to give test / bench residuals the right shape).
+    Returns (beta, martingale residuals)."""
+    time = np.asarray(time, dtype=np.float64); event = np.asarray(event, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64).reshape(len(time), -1)
+    Xc = X - X.mean(axis=0)
+    order = np.argsort(-time, kind="stable")                # descending: risk set of i = prefix ending at i's tie group
+    t = time[order]; d = event[order]; Z = Xc[order]
+    # index of the last element of each tie group (in descending order) for every position
+    last = np.r_[np.nonzero(np.diff(t))[0], len(t) - 1]
+    grp_end = last[np.searchsorted(last, np.arange(len(t)))]
+    beta = np.zeros(Z.shape[1])
+    for _ in range(maxit):
+        r = np.exp(Z @ beta)
+        S0 = np.cumsum(r)[grp_end]
+        S1 = np.cumsum(Z * r[:, None], axis=0)[grp_end]
+        ZZ = Z[:, :, None] * Z[:, None, :] * r[:, None, None]
+        S2 = np.cumsum(ZZ, axis=0)[grp_end]
+        m1 = S1 / S0[:, None]
+        grad = (d[:, None] * (Z - m1)).sum(axis=0)
+        hess = (d[:, None, None] * (S2 / S0[:, None, None] - m1[:, :, None] * m1[:, None, :])).sum(axis=0)
+        step = np.linalg.solve(hess, grad)
+        beta = beta + step
+        if np.max(np.abs(step)) < tol:
+            break
+    r = np.exp(Z @ beta)
+    S0 = np.cumsum(r)[grp_end]
+    # cumulative baseline hazard at each subject's time: sum over events with time <= t_i, i.e. a reversed cumsum
+    inc = d / S0
+    H = np.cumsum(inc[::-1])[::-1]
+    first = np.r_[0, np.nonzero(np.diff(t))[0] + 1]
+    grp_start = first[np.searchsorted(first, np.arange(len(t)), side="right") - 1]
+    H = H[grp_start]
+    mart_sorted = d - r * H
+    mart = np.empty_like(mart_sorted)
+    mart[order] = mart_sorted
+    return beta, mart
+
+
+def cox_martingale_resid(time, event, X):
+    return cox_fit_breslow(time, event, X)[1]

@@ -57,9 +57,14 @@ def test_check_input_resid_messages():
         api.check_input_Resid(ids, ids + ids[:1], np.zeros(5))
     with pytest.raises(api.RStop, match="same length as input data"):
         api.check_input_Resid(ids, ids, np.zeros(4))
-    # the bundled Pheno.mtx has IID, not ID: Phen.mtx$ID is NULL -> this is the stop() the reference hits
-    with pytest.raises(api.RStop, match="unique\\(pIDs\\)"):
+    # the bundled Pheno.mtx has IID, not ID: Phen.mtx$ID is NULL.  `sort(unique(NULL)) != ...` is logical(0), so
+    # any() is FALSE and the stop() the reference hits is the length check (SURVEY.md section 4, R/SPAGxECCT.R:1906)
+    with pytest.raises(api.RStop, match="same length as input data"):
         api.check_input_Resid(None, ids, np.zeros(5))
+    # rownames(Geno.mtx) NULL: every comparison is against logical(0) and R passes silently
+    assert api.check_input_Resid(ids, None, np.zeros(5)) is None
+    with pytest.raises(api.RStop, match="are required"):
+        api.check_input_Resid(None, None, np.zeros(5))
 
 
 def test_pack_rows_roundtrip_and_reorder(oracle):

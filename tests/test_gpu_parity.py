@@ -224,7 +224,6 @@ def test_properties_at_scale(gpu_ctx):
 def test_spa_quadrature_matches_oracle_and_exact_kernel(oracle):
     """N large enough for the SNP-invariant quadrature of the CGF sums (K4c): p-values and Newton
     iteration counts must match the per-sample oracle, and the exact per-sample kernel."""
-    import os
     from spagxecct_b200 import Context
     n, m = 120_011, 400
     ph = make_pheno(n, 51, prevalence=0.01)
@@ -236,14 +235,10 @@ def test_spa_quadrature_matches_oracle_and_exact_kernel(oracle):
     assert rc == 0 and ((route & 4) > 0).sum() >= 10
     outs = []
     for exact in (False, True):
-        if exact:
-            os.environ["SPAGXE_EXACT_SPA"] = "1"
-        try:
-            with Context(0) as ctx:
-                ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
-                out, diag = ctx.run_cct(_bed_desc(ctx, rows, n))
-        finally:
-            os.environ.pop("SPAGXE_EXACT_SPA", None)
+        with Context(0) as ctx:
+            ctx.set_option(_lib.OPT_EXACT_SPA, int(exact))
+            ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+            out, diag = ctx.run_cct(_bed_desc(ctx, rows, n))
         assert_parity(out, ref, P_COLS, S_COLS, label=f"quad exact={exact}")
         assert diag["newton_iters"] == iters.sum() and diag["n_spa"] == ((route & 4) > 0).sum()
         outs.append(out)
@@ -284,10 +279,14 @@ P_COLS_PLUS = [2, 3, 4]
 S_COLS_PLUS = [5, 6, 7]
 
 
-def _plus_nullmodel(oracle, golden_dir):
+def _plus_nullmodel(gpu_ctx, oracle, golden_dir):
+    """Step-1 object of SPAGxE_Plus: the GRM quadratic forms come from the device (spagxe_plus_nullmodel) and are
+    checked against the oracle's restatement of R/SPAGxEPlus_functions_MYZ.R:490-537."""
     d = np.load(f"{golden_dir}/plus.npz")
     R = get_resid("binary", d["Y"], [d["Cov1"], d["Cov2"], d["E"]])
-    a, b, Rnew, c = oracle.plus_nullmodel_scalars(d["grm_i"], d["grm_j"], d["grm_v"], R, d["E"])
+    a, b, Rnew, c = gpu_ctx.plus_nullmodel(d["grm_i"], d["grm_j"], d["grm_v"], R, d["E"])
+    a0, b0, Rnew0, c0 = oracle.plus_nullmodel_scalars(d["grm_i"], d["grm_j"], d["grm_v"], R, d["E"])
+    assert np.allclose([a, b, c], [a0, b0, c0], rtol=1e-12) and np.allclose(Rnew, Rnew0, rtol=1e-12, atol=1e-15)
     obj = {"R": R, "R_GRM_R": a, "R_GRM_RE": b, "R.new": Rnew, "R.new_GRM_R.new": c,
            "sparseGRM": {"i": d["grm_i"], "j": d["grm_j"], "Value": d["grm_v"]}}
     return d, obj
@@ -297,7 +296,7 @@ def test_c5_spagxe_plus_bundled_fixture(gpu_ctx, oracle, golden_dir):
     """SPAGxE_Plus on inst/GenoMat_SPAGxE_Plus.bed + data/sparseGRM.SPAGxEPlus.rda + the bundled binary
     phenotype (prevalence 1%), branch A and (epsilon = 0.5) the sparse-GRM branch B."""
     from spagxecct_b200 import SPAGxE_Plus
-    d, obj = _plus_nullmodel(oracle, golden_dir)
+    d, obj = _plus_nullmodel(gpu_ctx, oracle, golden_dir)
     bed = np.load(f"{golden_dir}/bed_SPAGxE_Plus.npz")
     n = int(bed["n"])
     rows = np.ascontiguousarray(bed["bed"][3:])
@@ -327,7 +326,9 @@ def test_spagxe_plus_synthetic_families_with_missing_and_flips(gpu_ctx, oracle):
     gi = np.r_[np.arange(n), np.arange(1, 2 * n_fam, 2)].astype(np.int32)
     gj = np.r_[np.arange(n), np.arange(0, 2 * n_fam, 2)].astype(np.int32)
     gv = np.r_[np.ones(n), np.full(n_fam, 0.5)]
-    a, b, Rnew, c = oracle.plus_nullmodel_scalars(gi, gj, gv, ph["R"], ph["E"])
+    a, b, Rnew, c = gpu_ctx.plus_nullmodel(gi, gj, gv, ph["R"], ph["E"])
+    a0, b0, Rnew0, c0 = oracle.plus_nullmodel_scalars(gi, gj, gv, ph["R"], ph["E"])
+    assert np.allclose([a, b, c], [a0, b0, c0], rtol=1e-12) and np.allclose(Rnew, Rnew0, rtol=1e-12, atol=1e-15)
     rows = to_bed_rows(G)
     gpu_ctx.set_vectors(ph["R"], ph["E"])
     gpu_ctx.set_grm(gi, gj, gv, a, b, c, Rnew)
@@ -398,7 +399,6 @@ def test_c4_spagxemix_admixed(gpu_ctx, oracle, golden_dir, trait):
 def test_multi_chunk_streaming_and_deferred_branch_b(oracle):
     """Many small chunks through the double-buffered host staging path (ragged last chunk): the deferred branch-B
     items of chunk k must still see their rows when chunk k+2 is staged; result == single-chunk result == oracle."""
-    import os
     from spagxecct_b200 import Context
     n, m = 5003, 333
     ph = make_pheno(n, 91, prevalence=0.1)
@@ -409,17 +409,13 @@ def test_multi_chunk_streaming_and_deferred_branch_b(oracle):
                   effect=eff, Y=ph["Y"])
     rows = to_bed_rows(G)
     outs = []
-    for chunk in (None, "37"):
-        if chunk:
-            os.environ["SPAGXE_CHUNK_SNPS"] = chunk
-        try:
-            with Context(0) as ctx:
-                ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
-                out, diag = ctx.run_cct(_bed_desc(ctx, rows, n), dict(epsilon=0.05))
-                Gd = np.asfortranarray(G)
-                out_dense, _ = ctx.run_cct(ctx.geno_desc(_lib.GENO_F64, Gd.ctypes.data, n, m, n), dict(epsilon=0.05))
-        finally:
-            os.environ.pop("SPAGXE_CHUNK_SNPS", None)
+    for chunk in (0, 37):
+        with Context(0) as ctx:
+            ctx.set_option(_lib.OPT_CHUNK_SNPS, chunk)
+            ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+            out, diag = ctx.run_cct(_bed_desc(ctx, rows, n), dict(epsilon=0.05))
+            Gd = np.asfortranarray(G)
+            out_dense, _ = ctx.run_cct(ctx.geno_desc(_lib.GENO_F64, Gd.ctypes.data, n, m, n), dict(epsilon=0.05))
         outs.append(out)
         assert np.array_equal(np.nan_to_num(out_dense, nan=-1), np.nan_to_num(out, nan=-1))
     assert diag["n_branch_b"] >= 30
@@ -475,7 +471,7 @@ def test_edge_cases_empty_tiny_and_fatal_inputs(gpu_ctx, oracle):
         assert ei.value.code == _lib.ERR_UNSUPPORTED
 
 
-def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir, monkeypatch):
+def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir):
     """SPAGxEmix_CCT: the batched common path (mix_batch.cu) against the per-SNP cluster kernel on the same inputs
     (tiled 3x so that the sample axis spans several splits and a ragged last tile)."""
     from spagxecct_b200 import SPAGxEmix_CCT
@@ -492,9 +488,11 @@ def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir, mon
                 Phen_mtx={"Y": tile(x["Y"])}, Cova_mtx=tile(x["Cova"]), topPCs=PCs, epsilon=0.001, Cutoff=2, min_maf=0.0002,
                 ctx=gpu_ctx, quiet=True)
     fast = SPAGxEmix_CCT("binary", **args)
-    monkeypatch.setenv("SPAGXE_MIX_PER_SNP", "1")
-    slow = SPAGxEmix_CCT("binary", **args)
-    monkeypatch.delenv("SPAGXE_MIX_PER_SNP")
+    gpu_ctx.set_option(_lib.OPT_MIX_PER_SNP, 1)
+    try:
+        slow = SPAGxEmix_CCT("binary", **args)
+    finally:
+        gpu_ctx.set_option(_lib.OPT_MIX_PER_SNP, 0)
     assert_parity(fast.values, slow.values, P_COLS_MIX, S_COLS_MIX, exact_cols=(0, 1, 10, 11), label="mix batched vs per-SNP")
     for key in ("n_branch_a", "n_branch_b", "n_spa", "n_mix_logistic", "newton_iters", "n_filtered"):
         assert fast.diag[key] == slow.diag[key], key

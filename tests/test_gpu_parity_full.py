@@ -1,0 +1,157 @@
+"""GPU parity at BASELINE.json's full sizes (-m gpu): the CUDA path through the C ABI against the multi-threaded CPU
+oracle on identical packed rows.
+
+    C3  N = 500,000 x 2,048 SNPs of the very batch bench.py times (quadrature SPA, branch B, flips, missing calls)
+    C4  N = 200,000 x 512 SNPs, 10 PCs: all four allele-frequency routes of SPAGxEmix_CCT
+    C5  N = 100,000, 20,000 four-member families (sparse GRM nnz = 200,000), skewed Cox martingale residuals
+    +   an exactness bound of the int8 fixed-point score sums at N = 500,000 (long-double host sums)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from spagxecct_b200 import _lib
+from tests._data import assert_parity, routes_from_cct_output
+
+pytestmark = pytest.mark.gpu
+
+P_COLS = [2, 3, 4, 5, 6]
+S_COLS = [7, 8, 9]
+NTHREADS = os.cpu_count() or 8
+
+
+@pytest.fixture(scope="module")
+def c3():
+    """The bench batch: rows [0, 2048) of rank 0's shard (bench.make_batch_device) and the bench phenotype."""
+    import torch
+    import bench
+    n, m = bench.N_SAMPLES, 2048
+    rb = (n + 3) // 4
+    pitch = (rb + 127) // 128 * 128
+    ph = bench.make_pheno(n)
+    bed = bench.make_batch_device(n, m, 0, torch.device("cuda", 0), pitch)
+    torch.cuda.synchronize()
+    rows = np.ascontiguousarray(bed[:, :rb].cpu().numpy())
+    return dict(n=n, m=m, rb=rb, pitch=pitch, ph=ph, bed=bed, rows=rows)
+
+
+def test_c3_bench_batch_2048_snps_at_500k(gpu_ctx, oracle, c3):
+    """routing sets, Newton iteration totals and p-values of a 2,048-SNP slice of the timed batch at the
+    headline N.  epsilon = 0.001 is the product setting; epsilon = 0.01 pushes ~20 SNPs through branch B
+    (genotype-adjusted residual + SPA + logistic Wald + CCT) at the same N."""
+    n, m, ph = c3["n"], c3["m"], c3["ph"]
+    gpu_ctx.set_vectors(ph["R"], ph["E"]); gpu_ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+    gd = gpu_ctx.geno_desc(_lib.GENO_BED, c3["bed"].data_ptr(), n, m, c3["pitch"], _lib.LOC_DEVICE)
+    seen_b = 0
+    for eps in (0.001, 0.01):
+        out, diag = gpu_ctx.run_cct(gd, dict(epsilon=eps))
+        ref, route, iters, rc = oracle.cct_bed("binary", c3["rows"].ravel(), n, ph["R"], ph["E"], ph["Y"], ph["Cova"],
+                                               epsilon=eps, nthreads=NTHREADS)
+        assert rc == 0
+        worst = assert_parity(out, ref, P_COLS, S_COLS, label=f"C3 500k eps={eps}")
+        f, b, s = routes_from_cct_output(out, eps)
+        assert np.array_equal(f, (route & 1) > 0) and np.array_equal(b, (route & 2) > 0) and np.array_equal(s, (route & 4) > 0)
+        assert diag["n_spa"] == int(s.sum()) and diag["n_branch_b"] == int(b.sum())
+        assert diag["newton_iters"] == int(iters.sum())
+        assert s.sum() >= 80, s.sum()                       # SPA SNPs: these go through the SNP-invariant quadrature
+        seen_b = max(seen_b, int(b.sum()))
+        print(f"C3 eps={eps}: spa={int(s.sum())} branchB={int(b.sum())} newton={int(iters.sum())} worst rel dlog10p={worst:.2e}")
+    assert seen_b >= 3
+    # host rows through the staging path == device-resident rows
+    gh = gpu_ctx.geno_desc(_lib.GENO_BED, c3["rows"].ctypes.data, n, m, c3["rb"])
+    out_h, _ = gpu_ctx.run_cct(gh, dict(epsilon=0.01))
+    assert np.array_equal(np.nan_to_num(out_h, nan=-1), np.nan_to_num(out, nan=-1))
+
+
+def test_c3_quadrature_vs_exact_spa_at_500k(c3, oracle):
+    """K4c (SNP-invariant Chebyshev quadrature of the CGF sums) against the per-sample kernel K4 at N = 500,000."""
+    from spagxecct_b200 import Context
+    n, m, ph = c3["n"], 512, c3["ph"]
+    outs, diags = [], []
+    for exact in (0, 1):
+        with Context(0) as ctx:
+            ctx.set_option(_lib.OPT_EXACT_SPA, exact)
+            ctx.set_vectors(ph["R"], ph["E"]); ctx.set_wald(_lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
+            gd = ctx.geno_desc(_lib.GENO_BED, c3["bed"].data_ptr(), n, m, c3["pitch"], _lib.LOC_DEVICE)
+            out, diag = ctx.run_cct(gd)
+        outs.append(out); diags.append(diag)
+    assert diags[0]["newton_iters"] == diags[1]["newton_iters"] and diags[0]["n_spa"] == diags[1]["n_spa"] >= 15
+    spa = outs[0][:, 2] != outs[0][:, 5]
+    d = np.abs(np.log10(outs[0][spa, 2]) - np.log10(outs[1][spa, 2]))
+    assert d.max() < 1e-9, d.max()
+
+
+def test_c3_fixed_point_score_sums_exactness_bound(gpu_ctx, c3):
+    """The tensor-core score pass quantises R (and V) to 2^-s with s = 53 - ilogb(max|R|) and is exact from there on:
+    |D0 - sum(dosage_i R_i)| <= nnz * 2^-s / 2 * max dosage + one final rounding.  Checked against long-double host
+    sums at the headline N, and put in proportion to the statistic (sqrt(Var) of the score)."""
+    n, ph = c3["n"], c3["ph"]
+    m = 64
+    gpu_ctx.set_vectors(ph["R"], ph["E"])
+    gd = gpu_ctx.geno_desc(_lib.GENO_BED, c3["bed"].data_ptr(), n, m, c3["pitch"], _lib.LOC_DEVICE)
+    st = gpu_ctx.score_stats(gd, impl=0)
+    rows = c3["rows"][:m]
+    code = np.stack([(rows >> (2 * k)) & 3 for k in range(4)], axis=2).reshape(m, -1)[:, :n]
+    dos = np.where(code == 0, 2, np.where(code == 2, 1, 0)).astype(np.int8)
+    Rl = ph["R"].astype(np.longdouble)
+    s = 53 - int(np.floor(np.log2(np.abs(ph["R"]).max())))
+    for j in range(m):
+        exact = (dos[j].astype(np.longdouble) * Rl).sum()
+        nnz = int((dos[j] != 0).sum())
+        bound = nnz * 2.0 ** (-s) + abs(float(exact)) * 2.0 ** -52
+        err = abs(float(np.longdouble(st["D0"][j]) - exact))
+        assert err <= bound, (j, err, bound)
+        miss = (code[j] == 1)
+        exact_t = Rl[miss].sum()
+        assert abs(float(np.longdouble(st["T0"][j]) - exact_t)) <= miss.sum() * 2.0 ** (-s - 1) + abs(float(exact_t)) * 2.0 ** -52
+        assert st["asum"][j] == int(dos[j].sum()) and st["nmiss"][j] == int(miss.sum())
+    # in units of the statistic: the worst-case quantisation error over sqrt(sum R^2 * 2 maf (1 - maf)) at maf = 0.001
+    scale = np.sqrt((ph["R"] ** 2).sum() * 2 * 0.001 * 0.999)
+    assert n * 2.0 ** (-s) / scale < 1e-9
+
+
+def test_c4_spagxemix_full_size(gpu_ctx, oracle):
+    """N = 200,000, 10 PCs, 512 SNPs covering MAC <= 20, the clamped OLS route, the
+    no-significant-PC route and the logistic fallback."""
+    from tests._configs import c4_admixed
+    x = c4_admixed()
+    n, m = x["n"], x["m"]
+    gpu_ctx.set_vectors(x["R"], x["E"]); gpu_ctx.set_wald(_lib.TRAIT_BINARY, x["Y"], x["Cova"]); gpu_ctx.set_pcs(x["PCs"])
+    g = gpu_ctx.geno_desc(_lib.GENO_BED, x["rows"].ctypes.data, n, m, (n + 3) // 4)
+    prm = dict(epsilon=0.001, cutoff=2.0, min_maf=1e-5)
+    out, diag = gpu_ctx.run_mix(g, prm)
+    ref, route, iters, rc = oracle.mix_bed("binary", x["rows"], n, x["R"], x["E"], x["Y"], x["Cova"], x["PCs"],
+                                           epsilon=0.001, min_maf=1e-5, nthreads=NTHREADS)
+    assert rc == 0
+    worst = assert_parity(out, ref, [2, 3, 4, 5, 6], [7, 8, 9], exact_cols=(0, 1, 10), label="C4 200k")
+    assert np.allclose(out[:, 11], ref[:, 11], rtol=1e-14, equal_nan=True)
+    assert diag["n_branch_b"] == ((route & 2) > 0).sum() and diag["n_spa"] == ((route & 4) > 0).sum()
+    assert diag["n_mix_logistic"] == ((route & 256) > 0).sum() and diag["newton_iters"] == iters.sum()
+    n_mac, n_neg, n_log = ((route & 64) > 0).sum(), ((route & 128) > 0).sum(), ((route & 256) > 0).sum()
+    print(f"C4: MAC<=20 {n_mac}, negative-ratio fallback {n_neg}, logistic {n_log}, spa {diag['n_spa']}, "
+          f"branchB {diag['n_branch_b']}, worst rel dlog10p={worst:.2e}")
+    assert n_mac >= 5 and n_log >= 5 and n_neg > n_log and diag["n_spa"] >= 5
+
+
+def test_c5_spagxe_plus_full_size(gpu_ctx, oracle):
+    """N = 100,000 with related samples (sparse GRM) and Cox martingale residuals (bounded above by 1,
+    long left tail); epsilon = 0.01 sends ~5 SNPs through the sparse-GRM branch B."""
+    from tests._configs import c5_families
+    x = c5_families()
+    n, m = x["n"], x["m"]
+    assert x["grm_i"].size == n + 5 * 20_000 and x["R"].max() <= 1.0 and x["R"].min() < -2.0
+    a, b, Rnew, c = gpu_ctx.plus_nullmodel(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
+    a0, b0, Rnew0, c0 = oracle.plus_nullmodel_scalars(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
+    assert np.allclose([a, b, c], [a0, b0, c0], rtol=1e-12) and np.allclose(Rnew, Rnew0, rtol=1e-12, atol=1e-15)
+    gpu_ctx.set_vectors(x["R"], x["E"]); gpu_ctx.set_grm(x["grm_i"], x["grm_j"], x["grm_v"], a0, b0, c0, Rnew0)
+    g = gpu_ctx.geno_desc(_lib.GENO_BED, x["rows"].ctypes.data, n, m, (n + 3) // 4)
+    for eps in (0.001, 0.02):
+        out, diag = gpu_ctx.run_plus(g, dict(epsilon=eps, cutoff=2.0))
+        ref, route, iters, _ = oracle.plus_bed(x["rows"], n, x["R"], x["E"], Rnew0, a0, b0, c0, x["grm_i"], x["grm_j"], x["grm_v"],
+                                              epsilon=eps, cutoff=2.0, nthreads=NTHREADS)
+        worst = assert_parity(out, ref, [2, 3, 4], [5, 6, 7], label=f"C5 100k eps={eps}")
+        assert diag["n_branch_b"] == ((route & 2) > 0).sum() and diag["n_spa"] == ((route & 4) > 0).sum()
+        assert diag["newton_iters"] == iters.sum()
+        print(f"C5 eps={eps}: spa={diag['n_spa']} branchB={diag['n_branch_b']} worst rel dlog10p={worst:.2e}")
+    assert diag["n_branch_b"] >= 3 and diag["n_spa"] >= 10
