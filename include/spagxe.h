@@ -92,6 +92,14 @@ typedef struct {
     double ms_score;        /* sum over chunks: unpack + score kernel(s)                 */
     double ms_tests;        /* sum over chunks: finalize + SPA + branch-B kernels        */
     int64_t score_bytes;    /* algorithmic bytes of the score pass: M * ceil(N/4)        */
+    /* stage split of ms_tests and the work counted on the device (fp64 rooflines of the SPA and branch-B stages) */
+    double ms_spa;          /* sum over chunks: per-SNP epilogue + SPA kernels           */
+    double ms_branch_b;     /* deferred branch-B launches (solver farm / cluster kernel) */
+    int64_t spa_nodes;      /* quadrature nodes per CGF evaluation (0: per-sample sums)  */
+    int64_t bb_irls_sample_passes; /* samples x IRLS / lm passes swept by the farm       */
+    int64_t bb_tail_sample_passes; /* samples x CGF evaluations of branch-B SPA tails    */
+    int64_t bb_prep_sample_passes; /* samples x preparation passes (counts, R.new0 sums) */
+    int64_t bb_iterations;  /* lock-step iterations (grid barriers) of the farm          */
 } spagxe_diag;
 
 /* ---- lifetime ------------------------------------------------------------- */

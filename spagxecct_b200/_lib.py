@@ -44,7 +44,9 @@ class Diag(C.Structure):
                 ["n_snps", "n_filtered", "n_branch_a", "n_branch_b", "n_spa", "n_wald_fail", "n_cct_stop",
                  "n_singular", "n_mix_logistic", "newton_iters", "kernel_launches", "h2d_bytes", "d2h_bytes"]] + \
                [("ms_total", C.c_double), ("ms_score", C.c_double), ("ms_tests", C.c_double),
-                ("score_bytes", C.c_int64)]
+                ("score_bytes", C.c_int64), ("ms_spa", C.c_double), ("ms_branch_b", C.c_double),
+                ("spa_nodes", C.c_int64), ("bb_irls_sample_passes", C.c_int64), ("bb_tail_sample_passes", C.c_int64),
+                ("bb_prep_sample_passes", C.c_int64), ("bb_iterations", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -15,6 +15,41 @@ namespace spagxe {
 __device__ __forceinline__ double d_na_real() { return __longlong_as_double(0x7FF00000000007A2LL); }
 __device__ __forceinline__ double d_sign(double x) { return (x > 0.0) - (x < 0.0); }  // NaN handled by callers
 
+// ---- branch-free exp / reciprocal for the per-sample hot loops ---------------------------------------------------
+// exp(x) for |x| < 700 (result normal): k = round(x / ln 2), r = x - k ln 2 in two parts, e^r by a degree-11 polynomial
+// (Chebyshev interpolant on |r| <= 0.3466, relative error 1.7e-17 before rounding), 2^k through the exponent field.
+// The CUDA library exp() computes the same thing but wraps it in range branches (BSSY/BSYNC pairs) that keep ptxas
+// from interleaving the chains of neighbouring samples; the callers guard the range instead.
+__device__ __forceinline__ double d_exp_fast(double x) {
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);   // 1.5 * 2^52: the low word is round(x / ln 2)
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 2.5110049204818658e-08;
+    p = fma(p, r, 2.763265472252779e-07);
+    p = fma(p, r, 2.755724088722987e-06);
+    p = fma(p, r, 2.4801485441561313e-05);
+    p = fma(p, r, 0.00019841269890076403);
+    p = fma(p, r, 0.0013888888952352863);
+    p = fma(p, r, 0.008333333333319589);
+    p = fma(p, r, 0.04166666666648795);
+    p = fma(p, r, 0.1666666666666668);
+    p = fma(p, r, 0.5000000000000019);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+// 1 / x for normal x with a normal reciprocal: hardware seed (2^-23) + two Newton steps, no special-case branch
+__device__ __forceinline__ double d_rcp_fast(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 // ---- pnorm (both tails, full relative accuracy down to ~1e-308) -------------
 static __device__ __noinline__ double d_pnorm(double x, bool lower_tail) {
     const double a[5] = {2.2352520354606839287, 161.02823106855587881, 1067.6894854603709582,

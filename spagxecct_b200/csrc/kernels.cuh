@@ -7,11 +7,12 @@
 //   K2  score kernels live in score.cuh
 //   K3  k_finalize_*      per-SNP scalar epilogue + routing lists  (ref :557-603, :2000-2045)
 //   K4  k_spa_homo        Newton on the binomial CGF + tail        (ref :1795-1879, :2048-2062)
-//   K5  k_branch_b        G-adjusted residual, SPA, Wald, CCT      (ref :604-678, :2070-2123)
+//   K5  bb_farm.cu        G-adjusted residual, SPA, Wald, CCT      (ref :604-678, :2070-2123)
 #pragma once
 #include "dmath.cuh"
 #include "types.cuh"
 #include "snp_common.cuh"
+#include "stat_common.cuh"
 #include <cooperative_groups.h>
 
 namespace spagxe {
@@ -131,23 +132,6 @@ __global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int
     out[(int64_t)j * n + i] = (c == 0) ? 2.0 : (c == 2) ? 1.0 : (c == 3) ? 0.0 : d_na_real();
 }
 
-// SPA_G_one_SNP_homo_new's scalar part (ref :2000-2045) given S = sum(g * Rv) and the vector's
-// SNP-invariant sums.  Returns: 0 -> p-values final (normal), 1 -> SPA needed, 2 -> inner min.maf NA.
-__device__ __forceinline__ int homo_scalar(double sum_g, int64_t n, double S_in, double sumRv, double sumRv2,
-                                           double min_maf_inner, double cutoff, double *maf_i, double *S_out,
-                                           double *Smean, double *z) {
-    double mafi = (sum_g / (double)n) / 2;  // mean(g)/2 on the imputed, flipped vector (ref :2000)
-    double S = S_in;
-    if (mafi > 0.5) { mafi = 1 - mafi; S = 2 * sumRv - S; }  // ref :2010-2013 (ties only)
-    *maf_i = mafi; *S_out = S;
-    if (mafi < min_maf_inner) return 2;
-    const double gvar = 2 * mafi * (1 - mafi);
-    const double Svar = sumRv2 * gvar;   // sum(R^2 * g.var.est) (ref :2034)
-    *Smean = 2 * (sumRv * mafi);         // 2 * sum(R * MAF.est)  (ref :2037)
-    *z = (S - *Smean) / sqrt(Svar);
-    return (fabs(*z) < cutoff) ? 0 : 1;
-}
-
 // K3 for SPAGxE_CCT (ref :543-603).  One thread per SNP of the chunk.
 __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                const VecConst *__restrict__ vcp, double epsilon, double min_maf,
@@ -207,31 +191,6 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
     if (want_spa) spa_list[pos] = item;
     pos = list_reserve(&ctr->b_count, want_b);
     if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl]};
-}
-
-// ---------------------------------------------------------------------------
-// K4: saddlepoint approximation.  CGF pieces evaluated exactly as the reference writes them
-// (ref :1652-1681) so overflow/NaN appear in the same places.
-__device__ __forceinline__ void cgf_k12(double tr, double maf, double &k1, double &k2) {
-    const double e = exp(tr);
-    const double x = maf * e;
-    const double u = (1 - maf) + x;
-    const double m0 = u * u;
-    const double m1 = (2 * x) * u;
-    const double m2 = 2 * (x * x) + (2 * x) * u;
-    const double num = m0 * m2 - m1 * m1;
-    if (m0 < 1e150) {            // common range: one reciprocal instead of two divisions (same values to rounding)
-        const double r = 1.0 / m0;
-        k1 = m1 * r;
-        k2 = (num * r) * r;
-    } else {                     // overflow neighbourhood: keep the reference's exact Inf/NaN behaviour
-        k1 = m1 / m0;
-        k2 = num / (m0 * m0);
-    }
-}
-__device__ __forceinline__ double cgf_k0(double tr, double maf) {
-    const double u = (1 - maf) + maf * exp(tr);
-    return log(u * u);
 }
 
 // Reduction policies: every thread of every participating CTA gets the same fixed-order total.
@@ -353,19 +312,6 @@ struct SrcHomo {  // SNP-invariant vector, scalar MAF (SPAGxE_CCT branch A, SPAG
 // basis on kQNodes Chebyshev points of bin b).  For the CGF terms phi(r) = r K1(tr), r^2 K2(tr), K0(tr)
 // the error is <= (|t| h / 2)^kQNodes / (2^(kQNodes-1) kQNodes!) * O(|r|) per sample, i.e. below 1e-12
 // relative while |t| h <= kQTheta; beyond that the item is re-done by the exact kernel.
-constexpr int kQNodes = 6;
-constexpr int kQBins = 2048;
-constexpr double kQTheta = 0.1;
-constexpr double kQScale = 274877906944.0;  // 2^38 fixed-point weights (exact integer atomics => deterministic)
-
-struct Quad {
-    double *x;          // [kQBins * kQNodes] nodes
-    double *w;          // [kQBins * kQNodes] weights (double, after conversion)
-    long long *wfix;    // fixed-point accumulation buffer
-    double *range;      // [0]=rmin, [1]=rmax, [2]=h, [3]=max |t| covered (kQTheta / h; 0 = disabled)
-    int *count;         // number of nodes with non-zero weight (x, w are compacted to that length)
-};
-
 __device__ __forceinline__ double cheb_node(int j) {  // cos((2j+1) pi / (2 kQNodes))
     return cospi((2.0 * j + 1.0) / (2.0 * kQNodes));
 }
@@ -448,7 +394,6 @@ __device__ __forceinline__ void spa_item_write(const SpaItem &it, double p, int 
 }
 
 // quadrature SPA: one CTA per item; items whose |t| leaves the covered range go to the exact list
-constexpr int kSpaQThreads = 256;
 __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__restrict__ list, Counters *ctr, Quad q,
                                                             SpaItem *__restrict__ exact_list, int64_t m_total,
                                                             double *__restrict__ out) {
@@ -474,7 +419,6 @@ __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__rest
 }
 
 // exact SPA: persistent CTAs popping work items, N exp() per CGF evaluation
-constexpr int kSpaThreads = 512;
 __global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restrict__ list, const int *count_ptr,
                                                            Counters *ctr, const double *__restrict__ rv, int64_t n,
                                                            int64_t m_total, double *__restrict__ out) {
@@ -496,11 +440,6 @@ __global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restr
 // K5: branch B (ref :604-678).  One thread-block CLUSTER per SNP: each CTA owns a contiguous slice of
 // the samples, CTA totals meet through distributed shared memory (ClusterRed), every CTA then runs
 // the same scalar logic, so no broadcast is needed.
-struct WaldData {
-    const double *Y, *cova;  // cova: n x p column-major
-    int p, trait;
-};
-
 struct SrcAdj {  // R.new0_i = E_i * (R_i - fit[class_i]) computed from the packed row (ref :609-612)
     const uint8_t *row; const double *R, *E; double fit[4]; double maf;
     __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
@@ -544,13 +483,6 @@ __device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, doub
     return true;
 }
 
-constexpr int kBThreads = 512;
-constexpr int kBTile = 512;                 // samples staged per tile (one per thread)
-constexpr int kBCluster = 8;                // CTAs cooperating on one SNP
-constexpr int kBGroups = kBThreads / 32;    // entry groups (one warp each) in the accumulation phase
-constexpr int kBMaxEnt = (kMaxQ * (kMaxQ + 3)) / 2;          // 152 normal-equation entries incl. rhs
-constexpr int kBSlots = (kBMaxEnt + kBGroups - 1) / kBGroups; // <= 10 accumulators per thread
-
 struct BShared {  // static shared state of the branch-B kernel
     double NE[kMaxQ][kMaxQ];
     double rhs[kMaxQ], beta[kMaxQ];
@@ -561,19 +493,6 @@ struct BShared {  // static shared state of the branch-B kernel
 };
 
 // dynamic smem: xs[kBTile][q+1] (x row, z in column q), ws[kBTile]
-__host__ __device__ inline size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
-
-struct DevProd {   // prod (1+e^eta) = m * 2^k; log(prod) costs one log per thread instead of one per sample
-    double m = 1.0; int k = 0; int cnt = 0;
-    __device__ __forceinline__ void mul(double x) {
-        m *= x;                                   // x in [1, 1+e^30]: 8 factors stay far below 2^1023
-        if (++cnt == 8) { cnt = 0; int e = ilogb(m); k += e; m = scalbn(m, -e); }
-    }
-    __device__ __forceinline__ double log_value() const { return log(m) + (double)k * 0.693147180559945309417232121458; }
-};
-__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
-                                            double &dev, int &bad, DevProd &dp);
-
 // One weighted-least-squares accumulation pass over this CTA's sample slice, then the cluster-wide
 // normal equations land in sh.NE / sh.rhs of EVERY CTA.  Returns the cluster-wide deviance (binary)
 // or residual sum of squares (lm second pass).  pass0: eta from mustart (ref glm.fit), else x.beta.
@@ -649,49 +568,6 @@ __device__ double wald_pass(const Design &ds, int64_t i_lo, int64_t i_hi, int q,
     red.template sum<2>(v);
     *invalid = v[1] > 0;
     return v[0];
-}
-
-// Per-sample IRLS working quantities (glm.fit binomial/logit restated).
-// Per-sample IRLS working quantities (glm.fit binomial/logit restated).
-// Returns the working weight w and wz = w * z (z = eta + (y - mu)/mu.eta), which is all X'WX and X'Wz need.
-__device__ __forceinline__ void irls_sample(int trait, bool pass0, double y, double eta_in, double &w2, double &wz,
-                                            double &dev, int &bad, DevProd &dp) {
-    const double THRESH = 30., MTHRESH = -30., INVEPS = 1 / DBL_EPSILON;
-    if (trait == 1) {
-        double eta = eta_in;
-        if (pass0) { double mus = (y + 0.5) / 2; eta = log(mus / (1 - mus)); }
-        const bool clampd = (eta > THRESH || eta < MTHRESH);
-        const double ee = exp(eta);
-        if (!clampd && (y == 0.0 || y == 1.0)) {
-            // mu = e/(1+e), mu.eta = e/(1+e)^2 = Var(mu) => w = mu.eta, w z = w eta + (y - mu);
-            // dev_i = -2 log(mu^y (1-mu)^(1-y)) = 2 (log(1+e) - y eta): one reciprocal, one log, no division
-            const double opexp = 1 + ee;
-            const double r = 1.0 / opexp;
-            const double mu = ee * r;
-            const double mev = mu * r;
-            dp.mul(opexp);                 // 2 log(1+e) is added once per thread from the running product
-            dev -= 2 * (y * eta);
-            w2 = mev;
-            wz = fma(mev, eta, y - mu);
-            return;
-        }
-        const double tmp = (eta < MTHRESH) ? DBL_EPSILON : ((eta > THRESH) ? INVEPS : ee);
-        const double opexp = 1 + ee;
-        const double mu = tmp / (1 + tmp);
-        if (!(mu > 0 && mu < 1)) bad = 1;
-        double d;
-        if (y == 1.0) d = -log(mu);                // y*log(y/mu); y_log_y(0, .) = 0
-        else if (y == 0.0) d = -log(1 - mu);
-        else d = y * log(y / mu) + (1 - y) * log((1 - y) / (1 - mu));
-        dev += 2 * d;
-        const double varmu = mu * (1 - mu);
-        const double mev = clampd ? DBL_EPSILON : ee / (opexp * opexp);
-        w2 = (mev * mev) / varmu;
-        wz = w2 * (eta + (y - mu) / mev);
-    } else {
-        w2 = 1.0; wz = y;
-        if (!pass0) dev += (y - eta_in) * (y - eta_in);  // lm second pass: residual sum of squares
-    }
 }
 
 // Register-accumulator variant for narrow designs (Q = p + 4 <= 8): every thread keeps the whole upper
@@ -972,97 +848,11 @@ __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, i
     return d_pt2(bl / se, rdf);
 }
 
-__global__ void __launch_bounds__(kBThreads) k_branch_b_cct(const BItem *__restrict__ b_list, int count, Counters *ctr,
-                                                             int64_t m_total, int64_t n,
-                                                             const double *__restrict__ R, const double *__restrict__ E,
-                                                             const VecConst *__restrict__ vcp, WaldData wd,
-                                                             double min_maf, double *__restrict__ out) {
-    namespace cg = cooperative_groups;
-    extern __shared__ double tile[];
-    __shared__ BShared sh;
-    cg::cluster_group cl = cg::this_cluster();
-    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
-    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
-    const VecConst vc = *vcp;
-    ClusterRed red{sh.scratch, sh.slot};
-    // contiguous sample slice of this CTA (multiple of 4 so that byte loads do not straddle CTAs)
-    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
-    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
-    for (int idx = cluster_id; idx < count; idx += n_clusters) {
-        const BItem bi = b_list[idx];
-        const int64_t j = bi.snp;
-        const uint8_t *row = bi.row;
-        const int asum = bi.asum, nmiss = bi.nmiss;
-        const Prologue pr = make_prologue(asum, nmiss, n);
-        GFromRow gf;
-        gf.row = row;
-        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
-        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
-        // W'W, W'R (ref :606-609)
-        double S1 = bi.D0 + ((nmiss > 0) ? pr.u * bi.T0 : 0.0);
-        if (pr.flip) S1 = 2 * vc.sumR - S1;
-        double v3[3] = {0, 0, 0};
-        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
-        red.sum<3>(v3);
-        const double a = (double)n, b = pr.sum_g, d = v3[0];
-        const double det = a * d - b * b;
-        const double NA = d_na_real();
-        double *o = out + j;
-        const bool writer = (rank == 0 && threadIdx.x == 0);
-        if (det == 0 || !isfinite(det)) {
-            if (writer) {
-                o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
-                atomicAdd(&ctr->n_singular, 1ULL);
-            }
-            continue;
-        }
-        const double i00 = d / det, i01 = -b / det, i11 = a / det;
-        SrcAdj src;
-        src.row = row; src.R = R; src.E = E; src.maf = 0;
-        for (int c = 0; c < 4; c++) {
-            double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
-            src.fit[c] = wi0 * vc.sumR + wi1 * S1;
-        }
-        // S = sum(g * R.new0), sum(R.new0), sum(R.new0^2)
-        v3[0] = v3[1] = v3[2] = 0;
-        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-            double r, m, w; src.get(i, r, m, w);
-            double g = gf(i);
-            v3[0] += g * r; v3[1] += r; v3[2] += r * r;
-        }
-        red.sum<3>(v3);
-        double mafi, S, Smean, z;
-        // branch B forwards min.maf to the inner call (ref :616); Cutoff stays 2
-        int r = homo_scalar(pr.sum_g, n, v3[0], v3[1], v3[2], min_maf, 2.0, &mafi, &S, &Smean, &z);
-        double pspa, pnorm_;
-        int iters = 0;
-        if (r == 2) { pspa = NA; pnorm_ = NA; }
-        else if (r == 0) { pspa = d_pnorm(fabs(z), false) * 2; pnorm_ = pspa; }
-        else {
-            pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
-            src.maf = mafi;
-            pspa = spa_two_tail(src, red, i_lo, i_hi, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), CUDART_INF, &iters);
-        }
-        int wfail;
-        double pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
-        if (writer) {
-            double pc = NA;
-            if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
-            int crc = d_cct2(pspa, pw, &pc);
-            if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
-            o[2 * m_total] = pspa; o[3 * m_total] = pw; o[4 * m_total] = pc; o[5 * m_total] = pnorm_;
-            if (r == 1) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
-        }
-    }
-    cl.sync();  // nobody may exit while a peer can still read its shared memory
-}
+// (branch B of SPAGxE_CCT is the solver farm in bb_farm.cu)
 
 
 // ===========================================================================
 // SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:248-405)
-struct PlusConst { double R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew; };
-struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
-
 // Step-1 scalars of SPAGxE_Plus_Nullmodel (ref R/SPAGxEPlus_functions_MYZ.R:490-537): the three sparse-GRM quadratic
 // forms and R.new = (E - lambda) R with lambda = R_GRM_RE / R_GRM_R.  One CTA, fixed-order sums (runs once per analysis).
 __global__ void __launch_bounds__(1024) k_plus_nullmodel(const double *__restrict__ R, const double *__restrict__ E,
@@ -1160,7 +950,7 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
 }
 
 // branch B of SPAGxE_Plus (ref :342-400): cluster per SNP; K7 = sparse-GRM quadratic form of R.new0
-__global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__restrict__ b_list, int count, Counters *ctr,
+__global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__restrict__ b_list, const int *__restrict__ count_ptr, Counters *ctr,
                                                               int64_t m_total, int64_t n,
                                                               const double *__restrict__ R, const double *__restrict__ E,
                                                               const VecConst *__restrict__ vcp, GrmCoo grm, double cutoff,
@@ -1171,6 +961,7 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__rest
     const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
     const VecConst vc = *vcp;
+    const int count = *count_ptr;   // read on the device: the host never synchronises to size this launch
     ClusterRed red{sh.scratch, sh.slot};
     const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
     const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
@@ -1249,12 +1040,6 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__rest
 
 // ===========================================================================
 // SPAGxEmix_CCT (R/SPAGxECCT.R:1013-1269): individual-level allele frequencies from the PCs.
-struct MixData {
-    const double *pcs;      // n x k column-major (topPCs)
-    const double *xtx_inv;  // (k+1) x (k+1) inverse of [1,PCs]'[1,PCs] (SNP-invariant)
-    int k;
-    double pc_pcut, neg_ratio_cut;
-};
 // allele-frequency model of one SNP, kept in shared memory and evaluated on the fly per sample
 struct AfModel {
     int kind;               // 0 uniform (MAF), 1 clamp(x'beta / 2), 2 logistic 1 - sqrt(1 - mu)

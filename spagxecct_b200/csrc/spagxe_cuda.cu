@@ -16,9 +16,10 @@
 #include <algorithm>
 
 #include "../../include/spagxe.h"
-#include "kernels.cuh"
+#include "snp_kernels.h"
 #include "score_launch.h"
 #include "mix_batch.h"
+#include "bb_farm.h"
 
 using namespace spagxe;
 
@@ -49,7 +50,7 @@ struct spagxe_ctx {
     int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
     SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
-    BItem *d_bitems = nullptr; int64_t cap_bitems = 0; int *h_count = nullptr;
+    BItem *d_bitems = nullptr; int64_t cap_bitems = 0;
     Quad quad = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool quad_on = false;
     // tensor-core score pass
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
@@ -58,6 +59,7 @@ struct spagxe_ctx {
     int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
+    BbFarm *farm = nullptr;                                // SPAGxE_CCT branch-B solver farm (K5)
     MixScratch *mix_scratch = nullptr;                    // SPAGxEmix: scratch of the batched common path
     int64_t cap_mcache = 0; double *d_mcache = nullptr;   // SPAGxEmix: cached allele frequencies, one vector per cluster
     // pinned staging
@@ -140,9 +142,8 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     }
     if ((e = cudaMalloc((void **)&ctx->d_vc, sizeof(VecConst))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
-    // opt in to the large dynamic shared memory of the branch-B kernel
-    e = cudaFuncSetAttribute(k_branch_b_cct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
-    if (e != cudaSuccess) return bail("cudaFuncSetAttribute", e);
+    if ((e = bb_farm_create(&ctx->farm, device, ctx->num_sms)) != cudaSuccess) return bail("bb_farm_create", e);
+    // opt in to the large dynamic shared memory of the per-SNP SPAGxEmix kernel
     e = cudaFuncSetAttribute(k_mix_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
     if ((e = cudaMalloc((void **)&ctx->quad.x, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -171,8 +172,8 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
     mix_scratch_destroy(ctx->mix_scratch);
+    bb_farm_destroy(ctx->farm);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
-    if (ctx->h_count) cudaFreeHost(ctx->h_count);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_util);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
@@ -311,47 +312,40 @@ static int launch_spa(spagxe_ctx *ctx, const double *rv, int64_t N, int64_t M, d
     return SPAGXE_OK;
 }
 
-// Deferred branch B: work items accumulate on the device; a flush reads their number (one small sync), sizes the
-// thread-block clusters so that all SMs are busy, and launches the cluster kernel once.
-static int pick_cluster(int count, int num_sms) {
-    int best = 8; double best_t = 1e300;
-    for (int cs = 1; cs <= kBCluster; cs++) {
-        const int clusters = std::max(1, num_sms / cs);
-        const double t = (double)((count + clusters - 1) / clusters) / cs;   // rounds x time per item (~1/cs)
-        if (t < best_t * 0.999) { best_t = t; best = cs; }
-    }
-    return best;
-}
+// Deferred branch B: work items accumulate on the device; a flush launches the kernel that drains them.  The item count
+// is read ON THE DEVICE (persistent grids), so the host never synchronises here and the next chunk's copies keep flowing.
 static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldData wd, double min_maf, double cutoff,
                           double *d_out) {
     cudaStream_t s = ctx->stream();
-    if (!ctx->h_count) CU(cudaMallocHost((void **)&ctx->h_count, sizeof(int)));
-    CU(cudaMemcpyAsync(ctx->h_count, &ctx->d_ctr->b_count, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const int count = *ctx->h_count;
-    if (count <= 0) return SPAGXE_OK;
-    const int cs = pick_cluster(count, ctx->num_sms);
-    cudaLaunchConfig_t cfg = {};
-    const int n_clusters = std::min(std::max(1, ctx->num_sms / cs), count);
-    cfg.gridDim = dim3((unsigned)(n_clusters * cs));
-    cfg.blockDim = dim3(kBThreads);
-    cfg.dynamicSmemBytes = (mode == 0) ? branch_b_smem(wd.p + 4) : 0;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    const BItem *items = ctx->d_bitems;
-    Counters *ctr = ctx->d_ctr;
-    const double *R = ctx->d_R, *E = ctx->d_E;
-    const VecConst *vc = ctx->d_vc;
-    if (mode == 0) {
-        CU(cudaLaunchKernelEx(&cfg, k_branch_b_cct, items, count, ctr, M, N, R, E, vc, wd, min_maf, d_out));
-    } else {
+    if (mode == 0) {   // SPAGxE_CCT: the solver farm (cooperative persistent kernel, one CTA per SM)
+        BbFarmArgs a;
+        a.items = ctx->d_bitems; a.count = &ctx->d_ctr->b_count; a.m_total = M; a.n = N;
+        a.R = ctx->d_R; a.E = ctx->d_E; a.vc = ctx->d_vc; a.Y = wd.Y; a.cova = wd.cova; a.p = wd.p; a.trait = wd.trait;
+        a.min_maf = min_maf; a.out = d_out; a.ctr = ctx->d_ctr;
+        const char *what = "bb_farm_launch";
+        cudaError_t e = bb_farm_launch(ctx->farm, s, a, &ctx->launches, &what);
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    } else {           // SPAGxE_Plus: one 4-CTA cluster per item, persistent over the device-side list
+        constexpr int cs = 4;
+        cudaLaunchConfig_t cfg = {};
+        const int n_clusters = std::max(1, ctx->num_sms / cs);
+        cfg.gridDim = dim3((unsigned)(n_clusters * cs));
+        cfg.blockDim = dim3(kBThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const BItem *items = ctx->d_bitems;
+        const int *count = &ctx->d_ctr->b_count;
+        Counters *ctr = ctx->d_ctr;
+        const double *R = ctx->d_R, *E = ctx->d_E;
+        const VecConst *vc = ctx->d_vc;
         GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
         CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, items, count, ctr, M, N, R, E, vc, grm, cutoff, d_out));
+        ctx->launches++;
     }
-    ctx->launches++;
     CU(cudaMemsetAsync(&ctx->d_ctr->b_count, 0, sizeof(int), s));
     return SPAGXE_OK;
 }
@@ -478,12 +472,8 @@ static int stage_chunk(spagxe_ctx *ctx, const spagxe_geno *g, const ChunkPlan &p
     }
     const int64_t ld = (g->location == SPAGXE_LOC_DEVICE) ? g->pitch : pl.n;
     const int64_t pw = pl.dpitch / 4;
-    dim3 grid((unsigned)((pw + 255) / 256), (unsigned)mc);
-    if (g->kind == SPAGXE_GENO_F64)
-        k_pack_dense<double><<<grid, 256, 0, s>>>((const double *)dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr);
-    else
-        k_pack_dense<int><<<grid, 256, 0, s>>>((const int *)dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr);
-    LAUNCH_CHECK();
+    CU(launch_pack_dense(s, g->kind == SPAGXE_GENO_F64, dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr));
+    ctx->launches++;
     *d_rows = ctx->d_bed[buf];
     return SPAGXE_OK;
 }
@@ -617,7 +607,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     EventPool evp(ctx);
     cudaEvent_t e_begin = evp.rec(s);
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> score_ev, test_ev, spa_ev, bb_ev;
     SnpStats st = stats_view(ctx, ctx->cap_m);
     WaldData wd{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
     PlusConst pc{ctx->R_GRM_R, ctx->R_GRM_RE, ctx->Rnew_GRM_Rnew};
@@ -650,12 +640,15 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         // caller-owned device rows stay valid for the whole call, so everything is deferred to one launch at the end
         const bool last = (j0 + pl.chunk_m >= M);
         bool flushed = false;
+        cudaEvent_t c = evp.rec(s);
+        spa_ev.push_back({b, c});
         if (mode != RUN_MIX && (last || (own_bed && buf == 1))) {
             if ((rc = flush_branch_b(ctx, mode == RUN_CCT ? 0 : 1, M, N, wd, prm->min_maf, prm->cutoff, d_out))) return rc;
             flushed = true;
         }
-        cudaEvent_t c = evp.rec(s);
-        test_ev.push_back({b, c});
+        cudaEvent_t d = evp.rec(s);
+        test_ev.push_back({b, d});
+        if (flushed) bb_ev.push_back({c, d});
         if (own_bed) {
             CU(cudaEventRecord(ctx->ev_done[buf], s));
             // the flush also read the OTHER staging buffer (deferred items of the previous chunk): it may only be
@@ -665,6 +658,8 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     }
     Counters hc;
     CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
+    int h_nodes = 0;
+    if (ctx->quad_on && mode != RUN_MIX) CU(cudaMemcpyAsync(&h_nodes, ctx->quad.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (prm->out_location != SPAGXE_LOC_DEVICE) {
         CU(cudaMemcpyAsync(out, d_out, M * ncol * sizeof(double), cudaMemcpyDeviceToHost, s));
         dg.d2h_bytes += M * ncol * sizeof(double);
@@ -675,6 +670,15 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     cudaEventElapsedTime(&ms, e_begin, e_end); dg.ms_total = ms;
     for (auto &p : score_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_score += ms; }
     for (auto &p : test_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_tests += ms; }
+    for (auto &p : spa_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_spa += ms; }
+    for (auto &p : bb_ev) { cudaEventElapsedTime(&ms, p.first, p.second); dg.ms_branch_b += ms; }
+    dg.spa_nodes = h_nodes;
+    if (mode == RUN_CCT) {
+        BbFarmWork w;
+        CU(bb_farm_read_work(ctx->farm, s, &w, true));
+        dg.bb_irls_sample_passes = (int64_t)w.irls_sample_passes; dg.bb_tail_sample_passes = (int64_t)w.tail_sample_passes;
+        dg.bb_prep_sample_passes = (int64_t)w.prep_sample_passes; dg.bb_iterations = (int64_t)w.iterations;
+    }
     fill_diag(&dg, hc, M);
     dg.kernel_launches = ctx->launches;
     dg.score_bytes = M * pl.row_bytes;

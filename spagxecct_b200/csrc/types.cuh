@@ -2,6 +2,7 @@
 // kernels (kernels.cuh / spagxe_cuda.cu).
 #pragma once
 #include <cstdint>
+#include <cstddef>
 
 namespace spagxe {
 
@@ -34,5 +35,46 @@ struct Counters {  // device-side diagnostics / work-list cursors
 };
 
 struct BmatInfo { int sR, sV; double maxR, maxV; };   // fixed-point scales of the tensor-core B matrix
+
+
+// ---- launch geometry and kernel argument structs shared by the host pipeline (spagxe_cuda.cu) and the per-SNP test
+// kernels (kernels.cuh, compiled in snp_kernels.cu) ---------------------------------------------------------------
+struct WaldData {
+    const double *Y, *cova;  // cova: n x p column-major
+    int p, trait;
+};
+
+constexpr int kQNodes = 6;
+constexpr int kQBins = 2048;
+constexpr double kQTheta = 0.1;
+constexpr double kQScale = 274877906944.0;  // 2^38 fixed-point weights (exact integer atomics => deterministic)
+
+struct Quad {
+    double *x;          // [kQBins * kQNodes] nodes
+    double *w;          // [kQBins * kQNodes] weights (double, after conversion)
+    long long *wfix;    // fixed-point accumulation buffer
+    double *range;      // [0]=rmin, [1]=rmax, [2]=h, [3]=max |t| covered (kQTheta / h; 0 = disabled)
+    int *count;         // number of nodes with non-zero weight (x, w are compacted to that length)
+};
+
+constexpr int kSpaQThreads = 256;   // k_spa_quad
+constexpr int kSpaThreads = 512;    // k_spa_homo
+constexpr int kBThreads = 512;
+constexpr int kBTile = 512;                 // samples staged per tile (one per thread)
+constexpr int kBCluster = 8;                // CTAs cooperating on one SNP
+constexpr int kBGroups = kBThreads / 32;    // entry groups (one warp each) in the accumulation phase
+constexpr int kBMaxEnt = (kMaxQ * (kMaxQ + 3)) / 2;          // 152 normal-equation entries incl. rhs
+constexpr int kBSlots = (kBMaxEnt + kBGroups - 1) / kBGroups; // <= 10 accumulators per thread
+inline __host__ __device__ size_t branch_b_smem(int q) { return sizeof(double) * kBTile * (size_t)(((q + 1) | 1) + 1); }
+
+struct PlusConst { double R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew; };
+struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
+
+struct MixData {
+    const double *pcs;      // n x k column-major (topPCs)
+    const double *xtx_inv;  // (k+1) x (k+1) inverse of [1,PCs]'[1,PCs] (SNP-invariant)
+    int k;
+    double pc_pcut, neg_ratio_cut;
+};
 
 }  // namespace spagxe

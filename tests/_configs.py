@@ -76,7 +76,7 @@ def c4_admixed(n=200_000, m=512, k=10, seed=20251104, device="cuda", golden_dir=
 
     # ---- test SNPs ----
     pairs = [(0.3, 0.01), (0.1, 0.01), (0.05, 0.4), (0.01, 0.001), (0.2, 0.0), (0.0, 0.15), (0.0012, 0.0003),
-             (0.25, 0.25), (0.00004, 0.00002), (0.002, 0.0)]
+             (0.25, 0.25), (0.00004, 0.00002), (0.002, 0.0), (0.00008, 0.00008)]
     p1 = torch.tensor([pairs[j % len(pairs)][0] for j in range(m)], dtype=torch.float64, device=device)
     p2 = torch.tensor([pairs[j % len(pairs)][1] for j in range(m)], dtype=torch.float64, device=device)
     dos = draw(p1, p2, m)

@@ -131,16 +131,33 @@ def test_c4_spagxemix_full_size(gpu_ctx, oracle):
     n_mac, n_neg, n_log = ((route & 64) > 0).sum(), ((route & 128) > 0).sum(), ((route & 256) > 0).sum()
     print(f"C4: MAC<=20 {n_mac}, negative-ratio fallback {n_neg}, logistic {n_log}, spa {diag['n_spa']}, "
           f"branchB {diag['n_branch_b']}, worst rel dlog10p={worst:.2e}")
-    assert n_mac >= 5 and n_log >= 5 and n_neg > n_log and diag["n_spa"] >= 5
+    assert n_mac >= 5 and n_log >= 5 and n_neg >= n_log and diag["n_spa"] >= 5
+    # the fourth route (more than the allowed share of negative fitted frequencies but NO principal component below the
+    # p-value cut-off -> uniform allele frequency, ref :1076-1079) is not reachable with the default cut-offs at this N;
+    # tighten both so that it is exercised on the first 160 SNPs
+    m2 = 160
+    g2 = gpu_ctx.geno_desc(_lib.GENO_BED, x["rows"].ctypes.data, n, m2, (n + 3) // 4)
+    out2, diag2 = gpu_ctx.run_mix(g2, dict(epsilon=0.001, cutoff=2.0, min_maf=1e-5, neg_ratio_cutoff=0.005, pc_pvalue_cutoff=1e-12))
+    ref2, route2, iters2, rc2 = oracle.mix_bed("binary", x["rows"][:m2 * ((n + 3) // 4)], n, x["R"], x["E"], x["Y"], x["Cova"],
+                                               x["PCs"], epsilon=0.001, min_maf=1e-5, neg_ratio_cut=0.005, pc_pcut=1e-12,
+                                               nthreads=NTHREADS)
+    assert rc2 == 0
+    assert_parity(out2, ref2, [2, 3, 4, 5, 6], [7, 8, 9], exact_cols=(0, 1, 10), label="C4 200k tight cut-offs")
+    no_pc = ((route2 & 128) > 0) & ((route2 & 256) == 0)
+    print(f"C4 tight cut-offs: negative-ratio fallback {((route2 & 128) > 0).sum()}, of which without a significant PC {no_pc.sum()}")
+    assert no_pc.sum() >= 3 and diag2["n_mix_logistic"] == ((route2 & 256) > 0).sum()
 
 
 def test_c5_spagxe_plus_full_size(gpu_ctx, oracle):
-    """N = 100,000 with related samples (sparse GRM) and Cox martingale residuals (bounded above by 1,
-    long left tail); epsilon = 0.01 sends ~5 SNPs through the sparse-GRM branch B."""
+    """N = 100,000 with related samples (sparse GRM) and Cox martingale residuals at a 1 % event rate
+    (bounded above by 1, almost all mass just below 0: skewness > 5); epsilon = 0.02 sends ~10 SNPs through the
+    sparse-GRM branch B."""
     from tests._configs import c5_families
     x = c5_families()
     n, m = x["n"], x["m"]
-    assert x["grm_i"].size == n + 5 * 20_000 and x["R"].max() <= 1.0 and x["R"].min() < -2.0
+    R = x["R"]
+    skew = float(np.mean((R - R.mean()) ** 3) / R.std() ** 3)
+    assert x["grm_i"].size == n + 5 * 20_000 and 0.9 < R.max() <= 1.0 and np.median(R) < 0 and skew > 5   # martingale shape
     a, b, Rnew, c = gpu_ctx.plus_nullmodel(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
     a0, b0, Rnew0, c0 = oracle.plus_nullmodel_scalars(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
     assert np.allclose([a, b, c], [a0, b0, c0], rtol=1e-12) and np.allclose(Rnew, Rnew0, rtol=1e-12, atol=1e-15)
