@@ -336,7 +336,11 @@ def main():
                          "share_of_step": ms_score / (ms_max / K)},
             "cpu_baseline": cpu, "clocks": clocks,
             "stages_ms": {"score": ms_score, "tests(finalize+SPA+branchB)": float(np.mean([d["ms_tests"] for d in diags])),
+                          "spa(finalize+quadrature SPA)": float(np.mean([d["ms_spa"] for d in diags])),
+                          "branch_b(solver farm)": float(np.mean([d["ms_branch_b"] for d in diags])),
                           "total_device": float(np.mean([d["ms_total"] for d in diags]))},
+            "farm_work": {k: int(dg[k]) for k in ["bb_irls_sample_passes", "bb_tail_sample_passes", "bb_prep_sample_passes",
+                                                  "bb_iterations", "spa_nodes"]},
             "routing": {k: int(dg[k]) for k in ["n_filtered", "n_branch_a", "n_branch_b", "n_spa", "newton_iters"]},
             "fp64_peak_tflops_measured": fp64,
         }

@@ -46,6 +46,7 @@ struct FItem {   // per-item state in shared memory (identical in every CTA)
     int w_it, w_status;                  // Wald: 0 active, 1 done, 2 rank deficient, 3 invalid
     int spa_kind;                        // homo_scalar: 0 normal, 1 SPA, 2 inner min.maf NA, 3 singular W'W
     int asum, nmiss, flip;
+    int prep, pad_;                      // preparation stage: 0 class counts pending, 1 adjusted-residual sums pending, 2 done
 };
 
 static_assert(sizeof(FItem) % 8 == 0, "item states are published as 8-byte words");
@@ -55,8 +56,7 @@ struct FGeom {
     int q, p, trait;
     int ncols;               // columns: R, E, Y, cova[0..p)
     int n_staged;            // the first n_staged of them live in shared memory (all of them in the BASELINE configs)
-    int wscr;                // doubles of scratch per warp: 160 partial totals + the LD x LD Cholesky matrix
-    int ld;                  // 8 or 16: leading dimension of that matrix
+    int ld;                  // 8 or 16: leading dimension of the Cholesky matrix of wide designs
     int kw;                  // doubles per partial row
     int rows;                // partial rows per solver = gridDim.x * kFJ
     int tile_stride;         // generic path: doubles per tile row
@@ -75,7 +75,6 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &phase)
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
             if (++spins > (1u << 24)) __trap();   // a protocol bug must fault (after a few seconds), not hang the GPU
-            __nanosleep(40);
         } while (v < target);
         __threadfence();
     }
@@ -154,7 +153,7 @@ template <int Q, int MODE, class CT>
 __device__ void sweep_wald_reg(const CT &cols, const FItem &it, int64_t g0, int a, int b, double *prow, int lane) {
     constexpr int P = Q - 4;
     constexpr int NENT = Q * (Q + 3) / 2;
-    constexpr int U = 2;
+    constexpr int U = 4;
     double acc[NENT];
 #pragma unroll
     for (int e = 0; e < NENT; e++) acc[e] = 0;
@@ -206,16 +205,28 @@ __device__ void sweep_wald_reg(const CT &cols, const FItem &it, int64_t g0, int 
     };
     int i = a + lane;
     if (MODE <= 1) {
+        // U samples per trip.  Phase 1 builds eta (the design row is consumed as it is loaded), phase 2 runs the U
+        // exp / reciprocal chains side by side, phase 3 re-reads each row from shared memory and accumulates: the rows
+        // are not kept live across the chains, which is what lets four samples fit into 128 registers.
         for (; i + 32 * (U - 1) < b; i += 32 * U) {
-            double xs[U][Q], ys[U], eta[U];
+            double ys[U], gs[U], eta[U];
             bool fast = true;
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                load(i + 32 * u, xs[u], ys[u]);
+                const int ii = i + 32 * u;
+                const int c = code_at(it.row, g0 + ii);
+                gs[u] = it.gval[c];
+                ys[u] = cols.get(2, ii);
                 eta[u] = 0;
                 if (MODE == 1) {
+                    const double ev = cols.get(1, ii);
+                    double e = beta[0];
 #pragma unroll
-                    for (int c = 0; c < Q; c++) eta[u] = fma(xs[u][c], beta[c], eta[u]);
+                    for (int k = 0; k < P; k++) e = fma(cols.get(3 + k, ii), beta[1 + k], e);
+                    e = fma(ev, beta[P + 1], e);
+                    e = fma(gs[u], beta[P + 2], e);
+                    e = fma(ev * gs[u], beta[P + 3], e);
+                    eta[u] = e;
                 }
                 fast = fast && (ys[u] == 0.0 || ys[u] == 1.0) && !(eta[u] > 30. || eta[u] < -30.);
             }
@@ -238,13 +249,24 @@ __device__ void sweep_wald_reg(const CT &cols, const FItem &it, int64_t g0, int 
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
+                    const int ii = i + 32 * u;
                     dp.mul(ope[u]);
                     dev -= 2 * (ys[u] * eta[u]);
-                    accumulate(xs[u], w2[u], wz[u]);
+                    double x[Q];
+                    const double ev = cols.get(1, ii);
+                    x[0] = 1.0;
+#pragma unroll
+                    for (int k = 0; k < P; k++) x[1 + k] = cols.get(3 + k, ii);
+                    x[P + 1] = ev; x[P + 2] = gs[u]; x[P + 3] = ev * gs[u];
+                    accumulate(x, w2[u], wz[u]);
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < U; u++) one(xs[u], ys[u]);
+                for (int u = 0; u < U; u++) {
+                    double x[Q], y;
+                    load(i + 32 * u, x, y);
+                    one(x, y);
+                }
             }
         }
     }
@@ -254,15 +276,26 @@ __device__ void sweep_wald_reg(const CT &cols, const FItem &it, int64_t g0, int 
         one(x, y);
     }
     if (MODE <= 1) dev += 2 * dp.log_value();
-    // totals: every lane gets them, lane e stores entry e
-#pragma unroll
-    for (int e = 0; e < NENT; e++) {
-        const double t = wsum(acc[e]);
-        if (lane == (e & 31)) prow[e] = t;
-    }
-    dev = wsum(dev);
+    // warp totals by a transposing butterfly: at every step a lane hands over the half of the vector its partner keeps,
+    // so 31 exchanges instead of 5 per entry; lane e ends with the total of entry e (fixed tree => deterministic)
+    static_assert(NENT + 2 <= 32, "one entry per lane");
     bad = __reduce_add_sync(0xffffffffu, bad);
-    if (lane == 0) { prow[NENT] = dev; prow[NENT + 1] = (double)bad; }
+    double v[32];
+#pragma unroll
+    for (int e = 0; e < 32; e++) v[e] = (e < NENT) ? acc[e] : 0.0;
+    v[NENT] = dev;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int k = 0; k < half; k++) {
+            const double send = up ? v[k] : v[k + half];
+            const double keep = up ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    if (lane <= NENT) prow[lane] = v[0];
+    if (lane == NENT + 1) prow[lane] = (double)bad;
 }
 
 // Wald pass for wide designs (7..16 columns): the warp stages 32 samples' rows [x, w x, wz] in its tile, then lane L
@@ -380,18 +413,92 @@ __device__ __forceinline__ void reduce_rows(const double *__restrict__ part, int
     for (int k = 0; k < NV; k++) tot[k] = wsum(tot[k]);
 }
 
-// Wald state machine step after sweep number it.w_it (ref: glm.fit / summary.glm, lm / summary.lm)
-__device__ void update_wald(FItem &it, const FGeom &gm, const double *part, double *wscr, int lane) {
-    const int q = gm.q, nent = q * (q + 3) / 2;
-    for (int e0 = 0; e0 < nent + 2; e0 += 32) {   // kw is a multiple of 32: whole blocks are always readable
-        double tot[32];
-        reduce_rows<32>(part + e0, gm.rows, gm.kw, lane, tot);
-        if (lane == 0) {
+// The same solve with every index known at compile time (Q <= 6): the matrix lives in registers.
+// ent: upper triangle row by row, each row followed by its right-hand side (the order the sweeps accumulate in).
+template <int Q>
+__device__ bool chol_solve_reg(const double *ent, double *x_out, double *inv_last) {
+    double A[Q][Q], b[Q], sc[Q], y[Q], x[Q];
+    {
+        int e = 0;
 #pragma unroll
-            for (int k = 0; k < 32; k++) if (e0 + k < nent + 2) wscr[e0 + k] = tot[k];
+        for (int r = 0; r < Q; r++) {
+#pragma unroll
+            for (int c = r; c < Q; c++) { A[r][c] = ent[e]; A[c][r] = ent[e]; e++; }
+            b[r] = ent[e]; e++;
         }
     }
-    __syncwarp();
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < Q; i++) { if (!(A[i][i] > 0)) ok = false; sc[i] = 1.0 / sqrt(A[i][i]); }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < Q; i++)
+#pragma unroll
+        for (int j = 0; j < Q; j++) A[i][j] *= sc[i] * sc[j];
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        double d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+        if (!(d > 1e-13)) ok = false;
+        d = sqrt(d); A[j][j] = d;
+#pragma unroll
+        for (int i = j + 1; i < Q; i++) {
+            double sacc = A[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) sacc -= A[i][k] * A[j][k];
+            A[i][j] = sacc / d;
+        }
+    }
+    if (!ok) return false;
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        double sacc = b[i] * sc[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) sacc -= A[i][k] * y[k];
+        y[i] = sacc / A[i][i];
+    }
+#pragma unroll
+    for (int i = Q - 1; i >= 0; i--) {
+        double sacc = y[i];
+#pragma unroll
+        for (int k = i + 1; k < Q; k++) sacc -= A[k][i] * x[k];
+        x[i] = sacc / A[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < Q; i++) x_out[i] = x[i] * sc[i];
+    const double l = A[Q - 1][Q - 1];
+    *inv_last = sc[Q - 1] * sc[Q - 1] / (l * l);
+    return true;
+}
+
+// CTA-cooperative sum of one solver's partial rows: thread (g, e) = (tid / 32, tid % 32) adds entry e of the rows of
+// group g (rows split into 16 contiguous groups), the 16 group sums meet in shared memory and are added in group order.
+// Every thread of the CTA must call it; out[0 .. nval) is valid after it returns.  Fixed order => same bits everywhere.
+__device__ void cta_reduce_rows(const double *__restrict__ part, int rows, int kw, int nval, double *s_red, double *out) {
+    const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int per = (rows + kFWarps - 1) / kFWarps;
+    const int r0 = min(rows, g * per), r1 = min(rows, r0 + per);
+    for (int e0 = 0; e0 < nval; e0 += 32) {
+        double acc = 0;
+        const double *p = part + e0 + e;
+#pragma unroll 8
+        for (int r = r0; r < r1; r++) acc += __ldcg(p + (size_t)r * kw);
+        s_red[g * 32 + e] = acc;
+        __syncthreads();
+        if (g == 0 && e0 + e < nval) {
+            double t = 0;
+#pragma unroll
+            for (int k = 0; k < kFWarps; k++) t += s_red[k * 32 + e];
+            out[e0 + e] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// Wald state machine step after sweep number it.w_it (ref: glm.fit / summary.glm, lm / summary.lm)
+__device__ void update_wald(FItem &it, const FGeom &gm, double *wscr, int lane) {   // wscr[0 .. nent + 2): the totals
+    const int q = gm.q, nent = q * (q + 3) / 2;
     if (lane == 0) {
         const double dev = wscr[nent];
         const bool bad = wscr[nent + 1] > 0;
@@ -413,7 +520,10 @@ __device__ void update_wald(FItem &it, const FGeom &gm, const double *part, doub
         if (need_solve) {
             double rhs[kMaxQ], x[kMaxQ], il = 0;
             bool ok;
-            if (gm.ld == 8) {
+            if (q == 6) ok = chol_solve_reg<6>(wscr, x, &il);
+            else if (q == 5) ok = chol_solve_reg<5>(wscr, x, &il);
+            else if (q == 4) ok = chol_solve_reg<4>(wscr, x, &il);
+            else if (gm.ld == 8) {
                 double (*A)[8] = reinterpret_cast<double (*)[8]>(wscr + 160);
                 int e = 0;
                 for (int r = 0; r < q; r++) {
@@ -525,7 +635,8 @@ struct FarmWorkCounters { unsigned long long irls, tail, prep, iters, items; };
 // ---- the kernel -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFThreads, 1)
 k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x kw*/,
-          double *__restrict__ tpart /*2 x batch x 2 x rows x 2*/, FItem *__restrict__ gitems /*batch*/, unsigned *barrier,
+          double *__restrict__ tpart /*2 x batch x 2 x rows x 2*/, double *__restrict__ qpart /*2 x batch x rows x 4*/,
+          FItem *__restrict__ gitems /*batch*/, unsigned *barrier,
           FarmWorkCounters *work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -535,10 +646,13 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
     double *s_cols = reinterpret_cast<double *>(smem_raw);
     const size_t cols_doubles = (size_t)gm.n_staged * gm.len;
     FItem *s_items = reinterpret_cast<FItem *>(s_cols + cols_doubles);
-    double *s_wscr = reinterpret_cast<double *>(s_items + kFBatch);            // per warp: gm.wscr doubles
-    int *s_act = reinterpret_cast<int *>(s_wscr + (size_t)kFWarps * gm.wscr);  // per item: bit 0 Wald, bit 1/2 SPA tails active
-    double *s_tiles = reinterpret_cast<double *>(s_act + kFBatch);             // per warp: 32 x tile_stride (wide designs)
-    double *wscr = s_wscr + (size_t)warp * gm.wscr;
+    int *s_act = reinterpret_cast<int *>(s_items + kFBatch);                   // per item: who takes part in this iteration
+    int *s_units = s_act + kFBatch;                                             // unit list of the iteration (kFBatch x 4 kinds x kFJ)
+    int *s_ctl = s_units + kFBatch * 4 * kFJ;                                   // [0] units, [1] next unit, [2] active items (+ pad)
+    double *s_red = reinterpret_cast<double *>(s_ctl + 4);                      // 16 x 32 group sums of the cooperative reduction
+    double *s_tot = s_red + kFWarps * 32;                                       // 160 totals of the solver being updated,
+                                                                                // then kMaxQ x kMaxQ for the wide-design Cholesky
+    double *s_tiles = s_tot + 160 + kMaxQ * kMaxQ;                              // per warp: 32 x tile_stride (wide designs)
     double *tile = s_tiles + (size_t)warp * 32 * gm.tile_stride;
 
     const int64_t g0 = (int64_t)blockIdx.x * gm.len;                            // first sample of this CTA's slice
@@ -564,6 +678,9 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
     auto prow_of = [&](int buf, int item, int j) {
         return part + (((size_t)buf * kFBatch + item) * gm.rows + (size_t)blockIdx.x * kFJ + j) * gm.kw;
     };
+    auto qrow_of = [&](int buf, int item, int j) {
+        return qpart + (((size_t)buf * kFBatch + item) * gm.rows + (size_t)blockIdx.x * kFJ + j) * 4;
+    };
     auto trow_of = [&](int buf, int item, int h, int j) {
         return tpart + ((((size_t)buf * kFBatch + item) * 2 + h) * gm.rows + (size_t)blockIdx.x * kFJ + j) * 2;
     };
@@ -580,153 +697,153 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
             it.row = bi.row; it.snp = bi.snp; it.asum = bi.asum; it.nmiss = bi.nmiss; it.D0 = bi.D0; it.T0 = bi.T0;
             it.gval[0] = 2.0; it.gval[1] = pr.u; it.gval[2] = 1.0; it.gval[3] = 0.0;
             if (pr.flip) for (int c = 0; c < 4; c++) it.gval[c] = 2 - it.gval[c];
+            for (int c = 0; c < 4; c++) it.fit[c] = 0;
             it.flip = pr.flip; it.sum_g = pr.sum_g; it.u = pr.u;
             for (int c = 0; c < kMaxQ; c++) it.beta[c] = 0;
             it.devold = 0; it.se2 = 0; it.bl = 0; it.pw = d_na_real();
-            it.w_it = 0; it.w_status = 0; it.spa_kind = 0;
+            it.w_it = 0; it.w_status = 0; it.spa_kind = 0; it.prep = 0; it.pad_ = 0;
+            it.mafi = 0; it.S = 0; it.Smean = 0; it.z = 0;
             it.pspa = d_na_real(); it.pnorm_ = d_na_real();
             for (int h = 0; h < 2; h++) { it.tail_phase[h] = 2; it.tail_iter[h] = 0; it.tail_p[h] = 0; it.tail_t[h] = 0; it.tail_H1[h] = 0; it.tail_diff[h] = CUDART_INF; it.tail_s[h] = 0; }
         }
-        __syncthreads();
-        // ---- phase B: class counts ----
-        for (int u = warp; u < nb * kFJ; u += kFWarps) {
-            const int item = u / kFJ, j = u % kFJ;
-            int a, b; unit_range(j, a, b);
-            sweep_counts(s_items[item], g0, a, b, prow_of(pbuf, item, j), lane);
-            w_prep += (unsigned long long)(b - a);
-        }
-        grid_barrier(barrier, bphase);
-        // ---- W'W, W'R -> fitted value per genotype class (ref :606-611) ----
-        for (int item = warp; item < nb; item += kFWarps) {
-            FItem &it = s_items[item];
-            double tot[2];
-            reduce_rows<2>(part + ((size_t)pbuf * kFBatch + item) * gm.rows * gm.kw, gm.rows, gm.kw, lane, tot);
-            const double n00 = tot[0], n10 = tot[1];
-            if (lane == 0) {
-                const double n01 = (double)it.nmiss, n11 = (double)gm.n - n00 - n10 - n01;
-                // sum(g^2) class by class, in the order 00, 01, 10, 11
-                double sg2 = ((n00 * (it.gval[0] * it.gval[0]) + n01 * (it.gval[1] * it.gval[1])) + n10 * (it.gval[2] * it.gval[2])) +
-                             n11 * (it.gval[3] * it.gval[3]);
-                double S1 = it.D0 + ((it.nmiss > 0) ? it.u * it.T0 : 0.0);   // sum(g R) from the score pass (ref :582)
-                if (it.flip) S1 = 2 * vc.sumR - S1;
-                const double a_ = (double)gm.n, b_ = it.sum_g, d_ = sg2;
-                const double det = a_ * d_ - b_ * b_;
-                if (det == 0 || !isfinite(det)) { it.spa_kind = 3; it.w_status = 1; it.pw = d_na_real(); }
-                else {
-                    const double i00 = d_ / det, i01 = -b_ / det, i11 = a_ / det;
-                    for (int c = 0; c < 4; c++) {
-                        const double wi0 = i00 + it.gval[c] * i01, wi1 = i01 + it.gval[c] * i11;
-                        it.fit[c] = wi0 * vc.sumR + wi1 * S1;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        pbuf ^= 1;
-        // ---- phase C: statistics of the adjusted residual ----
-        for (int u = warp; u < nb * kFJ; u += kFWarps) {
-            const int item = u / kFJ, j = u % kFJ;
-            if (s_items[item].spa_kind == 3) continue;
-            int a, b; unit_range(j, a, b);
-            sweep_adj(colsB, s_items[item], g0, a, b, prow_of(pbuf, item, j), lane);
-            w_prep += (unsigned long long)(b - a);
-        }
-        grid_barrier(barrier, bphase);
-        for (int item = warp; item < nb; item += kFWarps) {
-            FItem &it = s_items[item];
-            if (it.spa_kind == 3) continue;
-            double tot[4];
-            reduce_rows<4>(part + ((size_t)pbuf * kFBatch + item) * gm.rows * gm.kw, gm.rows, gm.kw, lane, tot);
-            const double v0 = tot[0], v1 = tot[1], v2 = tot[2];
-            if (lane == 0) {
-                double mafi, S, Smean = 0, z = 0;
-                // branch B forwards min.maf to the inner call (ref :616); Cutoff stays 2
-                const int r = homo_scalar(it.sum_g, gm.n, v0, v1, v2, A.min_maf, 2.0, &mafi, &S, &Smean, &z);
-                it.spa_kind = r; it.mafi = mafi; it.S = S; it.Smean = Smean; it.z = z;
-                if (r == 2) { it.pspa = d_na_real(); it.pnorm_ = d_na_real(); }
-                else if (r == 0) { it.pspa = d_pnorm(fabs(z), false) * 2; it.pnorm_ = it.pspa; }
-                else {
-                    it.pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
-                    it.tail_s[0] = fmax(S, 2 * Smean - S); it.tail_s[1] = fmin(S, 2 * Smean - S);
-                    it.tail_phase[0] = 0; it.tail_phase[1] = 0;
-                }
-            }
-        }
-        __syncthreads();
-        pbuf ^= 1;
-        // ---- the iteration loop: all active solvers advance one step per grid barrier ----
+        // ---- the iteration loop: every active solver of every item advances one step per pair of grid barriers ----
+        // solvers of an item: preparation (class counts -> fitted values -> adjusted-residual sums -> SPA set-up), the Wald
+        // fit (runs from the first iteration on: it only needs the genotypes) and, once the preparation is done, the tails
         for (;;) {
-            // snapshot of the solvers that take part in this iteration: the unit / solver numbering below must not move
-            // while other warps of the CTA are already updating item state
+            __syncthreads();
+            // snapshot of who takes part in this iteration: unit numbering and ownership must not move while item
+            // states are being updated
             if (threadIdx.x < nb) {
                 const FItem &it = s_items[threadIdx.x];
-                s_act[threadIdx.x] = (it.w_status == 0 ? 1 : 0) | (it.tail_phase[0] < 2 ? 2 : 0) | (it.tail_phase[1] < 2 ? 4 : 0);
+                s_act[threadIdx.x] = ((it.w_status == 0 && it.spa_kind != 3) ? 1 : 0) | (it.tail_phase[0] < 2 ? 2 : 0) |
+                                     (it.tail_phase[1] < 2 ? 4 : 0) | (it.prep == 0 ? 8 : 0) | (it.prep == 1 ? 16 : 0);
             }
             __syncthreads();
-            int n_active = 0;
-            int u = 0;
-            for (int item = 0; item < nb; item++) {
-                const FItem &it = s_items[item];
-                const int act = s_act[item];
-                const bool wact = (act & 1) != 0;
-                n_active += __popc(act);
-                if (wact) {
-                    for (int j = 0; j < kFJ; j++, u++) {
-                        if (u % kFWarps != warp) continue;
-                        int a, b; unit_range(j, a, b);
-                        double *pr = prow_of(pbuf, item, j);
-                        const int mode = (gm.trait == 1) ? (it.w_it == 0 ? 0 : 1) : (it.w_it == 0 ? 2 : 3);
-                        if (all_staged) run_wald_unit(colsA, it, gm, mode, g0, a, b, pr, tile, lane);
-                        else run_wald_unit(colsB, it, gm, mode, g0, a, b, pr, tile, lane);
-                        w_irls += (unsigned long long)(b - a);
+            // unit list of this iteration, most expensive kinds first (Wald, tails, preparation); one warp builds it,
+            // then the warps of the CTA take units from it dynamically (the partial row of a unit does not depend on
+            // which warp computes it, so the results stay reproducible)
+            if (warp == 0) {
+                int n_units = 0, n_act = 0;
+                for (int pass = 0; pass < 3; pass++) {
+                    for (int i0 = 0; i0 < nb; i0 += 32) {
+                        const int item = i0 + lane;
+                        const int act = (item < nb) ? s_act[item] : 0;
+                        if (pass == 0) n_act += __popc(__ballot_sync(0xffffffffu, act != 0));
+                        const int kinds = (pass == 0) ? (act & 1) : (pass == 1) ? ((act >> 1) & 3) : ((act >> 3) & 3);
+                        // per lane: number of solver kinds of this pass that are active (0..2), kFJ units each
+                        const int mine = __popc(kinds) * kFJ;
+                        int pre = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+                        int pos = n_units + pre - mine;
+                        for (int bit = 0; bit < 2; bit++) {
+                            if (!(kinds & (1 << bit))) continue;
+                            const int kind = (pass == 0) ? 0 : (pass == 1) ? 1 + bit : 3 + bit;   // 0 Wald, 1/2 tails, 3 counts, 4 sums
+                            for (int j = 0; j < kFJ; j++) s_units[pos++] = (item << 8) | (kind << 4) | j;
+                        }
+                        n_units += __shfl_sync(0xffffffffu, pre, 31);
                     }
                 }
-                for (int h = 0; h < 2; h++) {
-                    if (!(act & (2 << h))) continue;
-                    for (int j = 0; j < kFJ; j++, u++) {
-                        if (u % kFWarps != warp) continue;
-                        int a, b; unit_range(j, a, b);
-                        double *tr = trow_of(pbuf, item, h, j);
-                        if (all_staged) {
-                            if (it.tail_phase[h] == 0) sweep_tail<false>(colsA, it, h, g0, a, b, tr, lane);
-                            else sweep_tail<true>(colsA, it, h, g0, a, b, tr, lane);
-                        } else {
-                            if (it.tail_phase[h] == 0) sweep_tail<false>(colsB, it, h, g0, a, b, tr, lane);
-                            else sweep_tail<true>(colsB, it, h, g0, a, b, tr, lane);
-                        }
-                        w_tail += (unsigned long long)(b - a);
+                if (lane == 0) { s_ctl[0] = n_units; s_ctl[1] = 0; s_ctl[2] = n_act; }
+            }
+            __syncthreads();
+            const int n_units = s_ctl[0], n_active = s_ctl[2];
+            for (;;) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&s_ctl[1], 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k >= n_units) break;
+                const int desc = s_units[k];
+                const int item = desc >> 8, kind = (desc >> 4) & 15, j = desc & 15;
+                const FItem &it = s_items[item];
+                int a, b; unit_range(j, a, b);
+                if (kind == 0) {
+                    double *pr = prow_of(pbuf, item, j);
+                    const int mode = (gm.trait == 1) ? (it.w_it == 0 ? 0 : 1) : (it.w_it == 0 ? 2 : 3);
+                    if (all_staged) run_wald_unit(colsA, it, gm, mode, g0, a, b, pr, tile, lane);
+                    else run_wald_unit(colsB, it, gm, mode, g0, a, b, pr, tile, lane);
+                    w_irls += (unsigned long long)(b - a);
+                } else if (kind <= 2) {
+                    const int h = kind - 1;
+                    double *tr = trow_of(pbuf, item, h, j);
+                    if (all_staged) {
+                        if (it.tail_phase[h] == 0) sweep_tail<false>(colsA, it, h, g0, a, b, tr, lane);
+                        else sweep_tail<true>(colsA, it, h, g0, a, b, tr, lane);
+                    } else {
+                        if (it.tail_phase[h] == 0) sweep_tail<false>(colsB, it, h, g0, a, b, tr, lane);
+                        else sweep_tail<true>(colsB, it, h, g0, a, b, tr, lane);
                     }
+                    w_tail += (unsigned long long)(b - a);
+                } else {
+                    double *qr = qrow_of(pbuf, item, j);
+                    if (kind == 3) sweep_counts(it, g0, a, b, qr, lane);
+                    else sweep_adj(colsB, it, g0, a, b, qr, lane);
+                    w_prep += (unsigned long long)(b - a);
                 }
             }
-            if (n_active == 0) break;                     // identical state in every CTA: a uniform decision
+            if (n_active == 0) break;                     // identical item tables in every CTA: a uniform decision
             w_iters++;
             grid_barrier(barrier, bphase);
-            // scalar updates: item k of the batch belongs to CTA k mod grid, which adds the partial rows once (fixed
-            // order), advances the item's solvers (one warp each) and publishes the new state; after a second barrier
-            // every CTA copies the states of the items that took part, so all CTAs keep identical item tables
-            {
-                int owned = 0;
-                for (int item = 0; item < nb; item++) {
-                    const int act = s_act[item];
-                    if (!act || (item % (int)gridDim.x) != (int)blockIdx.x) continue;
-                    FItem &it = s_items[item];
-                    if ((act & 1) && (3 * owned) % kFWarps == warp)
-                        update_wald(it, gm, part + ((size_t)pbuf * kFBatch + item) * gm.rows * gm.kw, wscr, lane);
-                    for (int h = 0; h < 2; h++)
-                        if ((act & (2 << h)) && (3 * owned + 1 + h) % kFWarps == warp)
-                            update_tail(it, h, gm, tpart + (((size_t)pbuf * kFBatch + item) * 2 + h) * gm.rows * 2, lane);
-                    owned++;
+            // ---- scalar updates: item k of the batch belongs to CTA k mod grid.  The owner adds the partial rows once
+            // (fixed order), advances the item's solvers and publishes the new state; after the second barrier every
+            // CTA copies the states of the items that took part, so all CTAs keep identical item tables.
+            for (int item = blockIdx.x; item < nb; item += gridDim.x) {   // the items this CTA owns
+                const int act = s_act[item];
+                if (!act) continue;                                           // uniform in the CTA
+                FItem &it = s_items[item];
+                if (act & 1)
+                    cta_reduce_rows(part + ((size_t)pbuf * kFBatch + item) * gm.rows * gm.kw, gm.rows, gm.kw,
+                                    gm.q * (gm.q + 3) / 2 + 2, s_red, s_tot);
+                if (warp == 0) {
+                    if (act & 1) update_wald(it, gm, s_tot, lane);
+                } else if (warp == 1 || warp == 2) {
+                    const int h = warp - 1;
+                    if (act & (2 << h)) update_tail(it, h, gm, tpart + (((size_t)pbuf * kFBatch + item) * 2 + h) * gm.rows * 2, lane);
+                } else if (warp == 3 && (act & 24)) {
+                    double tot[4];
+                    reduce_rows<4>(qpart + ((size_t)pbuf * kFBatch + item) * gm.rows * 4, gm.rows, 4, lane, tot);
+                    if (lane == 0) {
+                        if (act & 8) {
+                            // W'W, W'R -> fitted value per genotype class (ref :606-611); sum(g^2) from the exact class counts
+                            const double n00 = tot[0], n10 = tot[1];
+                            const double n01 = (double)it.nmiss, n11 = (double)gm.n - n00 - n10 - n01;
+                            const double sg2 = ((n00 * (it.gval[0] * it.gval[0]) + n01 * (it.gval[1] * it.gval[1])) +
+                                                n10 * (it.gval[2] * it.gval[2])) + n11 * (it.gval[3] * it.gval[3]);
+                            double S1 = it.D0 + ((it.nmiss > 0) ? it.u * it.T0 : 0.0);   // sum(g R) from the score pass (ref :582)
+                            if (it.flip) S1 = 2 * vc.sumR - S1;
+                            const double a_ = (double)gm.n, b_ = it.sum_g, d_ = sg2;
+                            const double det = a_ * d_ - b_ * b_;
+                            if (det == 0 || !isfinite(det)) { it.spa_kind = 3; it.prep = 2; }   // solve() would stop (ref :609)
+                            else {
+                                const double i00 = d_ / det, i01 = -b_ / det, i11 = a_ / det;
+                                for (int c = 0; c < 4; c++) {
+                                    const double wi0 = i00 + it.gval[c] * i01, wi1 = i01 + it.gval[c] * i11;
+                                    it.fit[c] = wi0 * vc.sumR + wi1 * S1;
+                                }
+                                it.prep = 1;
+                            }
+                        } else {
+                            double mafi, S, Smean = 0, z = 0;
+                            // branch B forwards min.maf to the inner call (ref :616); Cutoff stays 2
+                            const int r = homo_scalar(it.sum_g, gm.n, tot[0], tot[1], tot[2], A.min_maf, 2.0, &mafi, &S, &Smean, &z);
+                            it.spa_kind = r; it.mafi = mafi; it.S = S; it.Smean = Smean; it.z = z;
+                            if (r == 2) { it.pspa = d_na_real(); it.pnorm_ = d_na_real(); }
+                            else if (r == 0) { it.pspa = d_pnorm(fabs(z), false) * 2; it.pnorm_ = it.pspa; }
+                            else {
+                                it.pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+                                it.tail_s[0] = fmax(S, 2 * Smean - S); it.tail_s[1] = fmin(S, 2 * Smean - S);
+                                it.tail_phase[0] = 0; it.tail_phase[1] = 0;
+                            }
+                            it.prep = 2;
+                        }
+                    }
                 }
                 __syncthreads();
-                owned = 0;
-                for (int item = 0; item < nb; item++) {
-                    if (!s_act[item] || (item % (int)gridDim.x) != (int)blockIdx.x) continue;
-                    if (owned % kFWarps == warp) {
-                        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&s_items[item]);
-                        unsigned long long *dst = reinterpret_cast<unsigned long long *>(gitems + item);
-                        for (int k = lane; k < (int)(sizeof(FItem) / 8); k += 32) dst[k] = src[k];
-                    }
-                    owned++;
+                // publish (one warp copies the whole state)
+                if (warp == 4) {
+                    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&s_items[item]);
+                    unsigned long long *dst = reinterpret_cast<unsigned long long *>(gitems + item);
+                    for (int k = lane; k < (int)(sizeof(FItem) / 8); k += 32) dst[k] = src[k];
                 }
             }
             grid_barrier(barrier, bphase);
@@ -736,7 +853,6 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
                 unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s_items[item]);
                 for (int k = lane; k < (int)(sizeof(FItem) / 8); k += 32) dst[k] = __ldcg(src + k);
             }
-            __syncthreads();
             pbuf ^= 1;
         }
         // ---- results (CTA 0 writes; every CTA holds the same values) ----
@@ -778,7 +894,7 @@ struct BbFarm {
     int device = 0, num_sms = 0, grid = 0;
     size_t smem_max = 0;
     double *d_part = nullptr; size_t cap_part = 0;
-    double *d_tpart = nullptr; size_t cap_tpart = 0;
+    double *d_tpart = nullptr; size_t cap_tpart = 0;   // tails (2 doubles per row) followed by the preparation rows (4)
     unsigned *d_barrier = nullptr;
     FarmWorkCounters *d_work = nullptr;
     FItem *d_items = nullptr;
@@ -824,8 +940,8 @@ cudaError_t bb_farm_launch(BbFarm *f, cudaStream_t s, const BbFarmArgs &args, in
     gm.kw = (nent + 2 + 31) / 32 * 32;
     gm.tile_stride = (gm.q <= kFRegQ) ? 0 : ((2 * gm.q + 1) | 1);
     gm.ld = (gm.q <= 8) ? 8 : kMaxQ;
-    gm.wscr = 160 + gm.ld * gm.ld;
-    const size_t fixed = sizeof(FItem) * kFBatch + sizeof(double) * kFWarps * (size_t)gm.wscr + sizeof(int) * kFBatch +
+    const size_t fixed = sizeof(FItem) * kFBatch + sizeof(int) * (kFBatch + kFBatch * 4 * kFJ + 4) +
+                         sizeof(double) * (kFWarps * 32 + 160 + kMaxQ * kMaxQ) +
                          sizeof(double) * kFWarps * 32 * (size_t)gm.tile_stride + 64;
     if (fixed > f->smem_max) { *what = "bb_farm: shared-memory layout"; return cudaErrorInvalidConfiguration; }
     // as many SNP-invariant columns of the slice as fit (R, E, Y first); the rest is read through L1/L2
@@ -838,7 +954,7 @@ cudaError_t bb_farm_launch(BbFarm *f, cudaStream_t s, const BbFarmArgs &args, in
         if ((e = cudaMalloc((void **)&f->d_part, need_part * sizeof(double))) != cudaSuccess) { *what = "cudaMalloc(part)"; return e; }
         f->cap_part = need_part;
     }
-    const size_t need_t = (size_t)2 * kFBatch * 2 * gm.rows * 2;
+    const size_t need_t = (size_t)2 * kFBatch * 2 * gm.rows * 2 + (size_t)2 * kFBatch * gm.rows * 4;
     if (need_t > f->cap_tpart) {
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) { *what = "sync"; return e; }
         cudaFree(f->d_tpart); f->d_tpart = nullptr; f->cap_tpart = 0;
@@ -851,7 +967,8 @@ cudaError_t bb_farm_launch(BbFarm *f, cudaStream_t s, const BbFarmArgs &args, in
     unsigned *bar = f->d_barrier;
     FarmWorkCounters *work = f->d_work;
     FItem *gitems = f->d_items;
-    void *kargs[] = {&a, &gm, &part, &tpart, &gitems, &bar, &work};
+    double *qpart = f->d_tpart + (size_t)2 * kFBatch * 2 * gm.rows * 2;
+    void *kargs[] = {&a, &gm, &part, &tpart, &qpart, &gitems, &bar, &work};
     e = cudaLaunchCooperativeKernel((const void *)k_bb_farm, dim3((unsigned)grid), dim3(kFThreads), kargs, smem, s);
     if (e != cudaSuccess) { *what = "cudaLaunchCooperativeKernel(k_bb_farm)"; return e; }
     (*launches)++;
