@@ -310,8 +310,8 @@ struct SrcHomo {  // SNP-invariant vector, scalar MAF (SPAGxE_CCT branch A, SPAG
 // ---- K4c: the same sums through a SNP-invariant piecewise-Chebyshev quadrature ----------------
 // sum_i phi(R_i) = sum_{b,j} W[b][j] * phi(x[b][j]) + err, W[b][j] = sum_{i in bin b} L_j(R_i) (Lagrange
 // basis on kQNodes Chebyshev points of bin b).  For the CGF terms phi(r) = r K1(tr), r^2 K2(tr), K0(tr)
-// the error is <= (|t| h / 2)^kQNodes / (2^(kQNodes-1) kQNodes!) * O(|r|) per sample, i.e. below 1e-12
-// relative while |t| h <= kQTheta; beyond that the item is re-done by the exact kernel.
+// the error per sample is ~ (|t| h / (2 pi))^kQNodes / 2^(kQNodes-1) (see types.cuh), i.e. ~1e-13 relative while
+// |t| h <= kQTheta; beyond that the item is re-done by the exact kernel.
 __device__ __forceinline__ double cheb_node(int j) {  // cos((2j+1) pi / (2 kQNodes))
     return cospi((2.0 * j + 1.0) / (2.0 * kQNodes));
 }
