@@ -72,6 +72,8 @@ typedef struct {
     int32_t impute_method;   /* 0 = "fixed"                                             */
     int32_t out_location;    /* SPAGXE_LOC_HOST (default) or SPAGXE_LOC_DEVICE for `out` */
     int32_t reserved;
+    int64_t out_ld;          /* rows of the caller's (host) result matrix when it is larger than this call's M: the
+                                call writes a row block of it (0 = M; used by the multi-GPU driver)              */
 } spagxe_params;
 
 /* diagnostics filled by every run (all counters are totals over the call) */
@@ -133,6 +135,9 @@ int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const double *dR, cons
  * as.matrix(Cova.mtx) (N x p column-major, p <= 12).  trait = SPAGXE_TRAIT_*.            */
 int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p);
 
+/* same with device pointers (the multi-GPU driver hands over what arrived by the NCCL broadcast) */
+int spagxe_set_wald_device(spagxe_ctx *ctx, int trait, const double *dY, const double *dcova, int p);
+
 /* topPCs of SPAGxEmix_CCT (R/SPAGxECCT.R:925, :1066): N x k column-major, k <= 15         */
 int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k);
 
@@ -164,6 +169,27 @@ int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params
  * Var.betaG, z.betaG                                                                     */
 int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
                     spagxe_diag *diag);
+
+/* ---- the same loop on several GPUs of one node ----------------------------------
+ * One process, one host thread + stream per GPU.  SNPs are independent, so the M SNPs of a call are cut into contiguous
+ * ranges (a .bed file is variant-major: a range of SNPs is a range of bytes); the per-analysis vectors are uploaded to
+ * the first GPU and reach the others through ONE ncclBroadcast of [R | E | Y | Cova]; every GPU copies its result rows
+ * into its own row block of the caller's M x ncol matrix.  No other collective, no reduction across GPUs.  NCCL is
+ * loaded with dlopen("libnccl.so.2") when the first multi-GPU context is created (single-GPU use never needs it).
+ * Replaces the serial for-loop of SPAGxE_CCT (R/SPAGxECCT.R:509-525) exactly like spagxe_run_cct.               */
+typedef struct spagxe_mgpu spagxe_mgpu;
+int spagxe_mgpu_create(int n_gpus, const int *devices /* NULL: 0 .. n_gpus-1 */, spagxe_mgpu **out);
+void spagxe_mgpu_destroy(spagxe_mgpu *mg);
+const char *spagxe_mgpu_last_error(const spagxe_mgpu *mg);   /* mg may be NULL: last create error */
+int spagxe_mgpu_n_gpus(const spagxe_mgpu *mg);
+/* R, E (length n) and the Wald data (trait, Y, Cova n x p) of SPAGxE_CCT; host pointers.  One broadcast. */
+int spagxe_mgpu_set_inputs(spagxe_mgpu *mg, int64_t n, const double *R, const double *E, int trait, const double *Y,
+                           const double *cova, int p);
+/* geno: n_shards == 1: one HOST genotype source, cut into contiguous SNP ranges, one per GPU;
+ *       n_shards == n_gpus: shard k is tested on GPU k and may live on the host or in that GPU's memory.
+ * out: HOST matrix (sum of the shards' SNPs) x 10, column-major, rows in shard order.  diag: totals (times: maximum). */
+int spagxe_mgpu_run_cct(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                        spagxe_diag *diag);
 
 /* ---- genotype unpack (K1) exposed for the bit-exact decode checks ----------- */
 /* per-SNP code counts of packed rows: counts[4*j + c], c = 00,01,10,11 (GRAB decode: 2,NA,1,0);

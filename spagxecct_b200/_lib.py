@@ -22,6 +22,8 @@ EXPORTS = [
     "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
     "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
     "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
+    "spagxe_set_wald_device", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
+    "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
 OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL = 1, 2, 3, 4
@@ -36,7 +38,7 @@ class Params(C.Structure):
     _fields_ = [("epsilon", C.c_double), ("cutoff", C.c_double), ("min_maf", C.c_double),
                 ("missing_cutoff", C.c_double), ("pc_pvalue_cutoff", C.c_double), ("neg_ratio_cutoff", C.c_double),
                 ("g_model", C.c_int32), ("impute_method", C.c_int32), ("out_location", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("out_ld", C.c_int64)]
 
 
 class Diag(C.Structure):
@@ -82,6 +84,15 @@ def load():
     L.spagxe_set_vectors.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.spagxe_set_vectors_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.spagxe_set_wald.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_set_wald_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_mgpu_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.spagxe_mgpu_destroy.argtypes = [C.c_void_p]
+    L.spagxe_mgpu_destroy.restype = None
+    L.spagxe_mgpu_last_error.argtypes = [C.c_void_p]
+    L.spagxe_mgpu_last_error.restype = C.c_char_p
+    L.spagxe_mgpu_n_gpus.argtypes = [C.c_void_p]
+    L.spagxe_mgpu_set_inputs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_mgpu_run_cct.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
     L.spagxe_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_set_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_void_p]
@@ -158,6 +169,9 @@ class Context:
         cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(Y.size, -1))
         self._chk(self.L.spagxe_set_wald(self.h, int(trait), Y.ctypes.data, cova.ctypes.data, cova.shape[1]))
 
+    def set_wald_device(self, trait, dY_ptr, dcova_ptr, p):
+        self._chk(self.L.spagxe_set_wald_device(self.h, int(trait), C.c_void_p(dY_ptr), C.c_void_p(dcova_ptr), int(p)))
+
     def set_pcs(self, pcs):
         pcs = np.asfortranarray(np.asarray(pcs, dtype=np.float64).reshape(self.n, -1))
         self._chk(self.L.spagxe_set_pcs(self.h, pcs.ctypes.data, pcs.shape[1]))
@@ -228,7 +242,71 @@ class Context:
         return v.value
 
 
+class MultiContext:
+    """SPAGxE_CCT on several GPUs of one node through the C ABI (spagxe_mgpu_*): one process, one host thread + stream
+    per GPU, ONE ncclBroadcast of [R | E | Y | Cova], contiguous SNP ranges, results copied into disjoint row blocks."""
+
+    def __init__(self, n_gpus, devices=None):
+        self.L = load()
+        h = C.c_void_p()
+        dev = None
+        if devices is not None:
+            dev = (C.c_int * n_gpus)(*[int(d) for d in devices])
+        rc = self.L.spagxe_mgpu_create(int(n_gpus), dev, C.byref(h))
+        if rc != OK:
+            raise SpagxeError(rc, self.L.spagxe_mgpu_last_error(None).decode())
+        self.h = h
+        self.n_gpus = int(n_gpus)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.spagxe_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise SpagxeError(rc, self.L.spagxe_mgpu_last_error(self.h).decode())
+
+    def set_inputs(self, R, E, trait, Y, cova):
+        R = _f64(R); E = _f64(E); Y = _f64(Y)
+        cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(Y.size, -1))
+        self._chk(self.L.spagxe_mgpu_set_inputs(self.h, R.size, R.ctypes.data, E.ctypes.data, int(trait), Y.ctypes.data,
+                                                cova.ctypes.data, cova.shape[1]))
+
+    def run_cct(self, geno, params=None, out_ptr=None):
+        """geno: one host Geno (cut into SNP ranges) or a list of n_gpus Geno shards (host or that GPU's memory)."""
+        prm = params if isinstance(params, Params) else make_params(**(params or {}))
+        diag = Diag()
+        if isinstance(geno, (list, tuple)):
+            arr = (Geno * len(geno))(*geno)
+            n_sh, m = len(geno), sum(g.n_snps for g in geno)
+            gp = C.cast(arr, C.POINTER(Geno))
+        else:
+            n_sh, m = 1, geno.n_snps
+            gp = C.byref(geno)
+        out = None
+        if out_ptr is None:
+            out = np.empty((m, 10), dtype=np.float64, order="F")
+            out_ptr = out.ctypes.data
+        rc = self.L.spagxe_mgpu_run_cct(self.h, gp, n_sh, C.byref(prm), C.c_void_p(out_ptr), C.byref(diag))
+        self.last_diag = diag.asdict()
+        self._chk(rc)
+        return out, self.last_diag
+
+
 def make_params(epsilon=0.001, cutoff=2.0, min_maf=0.001, missing_cutoff=0.15, pc_pvalue_cutoff=0.05,
                 neg_ratio_cutoff=0.1, g_model=0, impute_method=0, out_location=LOC_HOST):
     return Params(epsilon, cutoff, min_maf, missing_cutoff, pc_pvalue_cutoff, neg_ratio_cutoff, g_model,
-                  impute_method, out_location, 0)
+                  impute_method, out_location, 0, 0)

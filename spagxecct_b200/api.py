@@ -161,9 +161,14 @@ def _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model, **
 def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None, GenoFileIndex=None,
                control=None, Geno_mtx=None, R=None, E=None, Phen_mtx=None, Cova_mtx=None, epsilon=0.001, Cutoff=2,
                impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0,
-               quiet=False):
-    """Drop-in for SPAGxE_CCT (R/SPAGxECCT.R:455-530): returns an M x 10 named matrix."""
+               quiet=False, n_gpus=1):
+    """Drop-in for SPAGxE_CCT (R/SPAGxECCT.R:455-530): returns an M x 10 named matrix.
+    n_gpus > 1 (an addition to the reference's formals, like `n.gpus` of the R wrapper): the SNPs are cut into contiguous
+    ranges over that many GPUs of the node (spagxe_mgpu_*: one NCCL broadcast of R/E/Y/Cova, no other collective)."""
     _trait_code(traits)
+    if n_gpus > 1 and ctx is None:
+        return _spagxe_cct_multi(traits, GenoFile, GenoFileIndex, control, Geno_mtx, R, E, Phen_mtx, Cova_mtx, epsilon, Cutoff,
+                                 impute_method, missing_cutoff, min_maf, G_model, quiet, n_gpus)
     own = ctx is None
     ctx = ctx or _lib.Context(device)
     try:
@@ -195,6 +200,33 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
     finally:
         if own:
             ctx.close()
+
+
+def _spagxe_cct_multi(traits, GenoFile, GenoFileIndex, control, Geno_mtx, R, E, Phen_mtx, Cova_mtx, epsilon, Cutoff,
+                      impute_method, missing_cutoff, min_maf, G_model, quiet, n_gpus):
+    with _lib.MultiContext(n_gpus) as mg:
+        pIDs = _col(Phen_mtx, "ID")
+        if Geno_mtx is None:
+            rows, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
+            keep = rows
+            geno = _lib.Context.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+        else:
+            G, gIDs, snp_ids = _split_geno(Geno_mtx)
+            keep, geno = _geno_desc_from_matrix(G)
+            n, m = G.shape
+        check_input_Resid(pIDs, gIDs, R)
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+            print('[1] "Start Analyzing..."')
+            print(_now())
+        mg.set_inputs(R, E, _trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        out, diag = mg.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
+        del keep
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_CCT, diag)
 
 
 def SPAGxE_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, epsilon=0.001, Cutoff=2, impute_method="fixed",

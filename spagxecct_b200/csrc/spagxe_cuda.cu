@@ -250,7 +250,14 @@ extern "C" int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const doubl
     return set_vectors_common(ctx, n, dR, dE, cudaMemcpyDeviceToDevice);
 }
 
+static int set_wald_common(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p, cudaMemcpyKind kind);
 extern "C" int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p) {
+    return set_wald_common(ctx, trait, Y, cova, p, cudaMemcpyHostToDevice);
+}
+extern "C" int spagxe_set_wald_device(spagxe_ctx *ctx, int trait, const double *dY, const double *dcova, int p) {
+    return set_wald_common(ctx, trait, dY, dcova, p, cudaMemcpyDeviceToDevice);
+}
+static int set_wald_common(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p, cudaMemcpyKind kind) {
     if (!ctx) return SPAGXE_ERR_ARG;
     if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_wald: call spagxe_set_vectors first");
     if (trait != SPAGXE_TRAIT_BINARY && trait != SPAGXE_TRAIT_QUANTITATIVE)
@@ -261,8 +268,9 @@ extern "C" int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, cons
     CU(cudaSetDevice(ctx->device));
     CU(dev_realloc(&ctx->d_Y, ctx->n));
     CU(dev_realloc(&ctx->d_cova, (size_t)ctx->n * std::max(p, 1)));
-    CU(cudaMemcpy(ctx->d_Y, Y, ctx->n * sizeof(double), cudaMemcpyHostToDevice));
-    if (p > 0) CU(cudaMemcpy(ctx->d_cova, cova, (size_t)ctx->n * p * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(ctx->d_Y, Y, ctx->n * sizeof(double), kind, ctx->stream()));
+    if (p > 0) CU(cudaMemcpyAsync(ctx->d_cova, cova, (size_t)ctx->n * p * sizeof(double), kind, ctx->stream()));
+    CU(cudaStreamSynchronize(ctx->stream()));
     ctx->wald_p = p; ctx->wald_trait = trait;
     return SPAGXE_OK;
 }
@@ -527,7 +535,7 @@ static void fill_diag(spagxe_diag *diag, const Counters &c, int64_t m) {
     diag->n_singular = c.n_singular; diag->n_mix_logistic = c.n_mix_logistic; diag->newton_iters = c.newton_iters;
 }
 
-static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1, 0, 0, 0, 0};
+static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1, 0, 0, 0, 0, 0};
 
 enum RunMode { RUN_CCT = 0, RUN_PLUS = 1, RUN_MIX = 2 };
 
@@ -585,6 +593,8 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
     if (prm->g_model != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only G.model=\"Add\" is implemented");
     if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
+    if (prm->out_ld != 0 && (prm->out_ld < g->n_snps || prm->out_location == SPAGXE_LOC_DEVICE))
+        return fail(ctx, SPAGXE_ERR_ARG, "out_ld must be 0 or >= M, and only applies to a host result matrix");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
     const int64_t M = g->n_snps, N = g->n_samples;
@@ -661,7 +671,9 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     int h_nodes = 0;
     if (ctx->quad_on && mode != RUN_MIX) CU(cudaMemcpyAsync(&h_nodes, ctx->quad.count, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (prm->out_location != SPAGXE_LOC_DEVICE) {
-        CU(cudaMemcpyAsync(out, d_out, M * ncol * sizeof(double), cudaMemcpyDeviceToHost, s));
+        const int64_t ld = prm->out_ld ? prm->out_ld : M;
+        CU(cudaMemcpy2DAsync(out, ld * sizeof(double), d_out, M * sizeof(double), M * sizeof(double), ncol,
+                             cudaMemcpyDeviceToHost, s));
         dg.d2h_bytes += M * ncol * sizeof(double);
     }
     cudaEvent_t e_end = evp.rec(s);
