@@ -4,6 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port, all host threads)
 
+    python bench.py --workload mix|plus ...                  # configs 4 / 5 (SPAGxEmix_CCT, SPAGxE_Plus), same JSON contract
+
 A "step" is one pass of the hot path (2-bit unpack + score + routing + SPA + genotype-adjusted
 branch) over one batch of synthetic UK-Biobank-shaped SNPs that is already resident in HBM.  The
 batch (default 16,384 SNPs x 500,000 samples = 2.05 GB packed) is far larger than the 126 MB L2, so
@@ -26,6 +28,8 @@ N_SAMPLES = 500_000
 PREVALENCE = 0.01
 SEED_PHENO = 12345
 SEED_GENO = 20251019
+# DRAM bytes per algorithmic byte of the score kernel: 1.070415 GB read + 7.95 MB written per 1.024 GB launch (ncu --set full)
+SCORE_TRAFFIC_PER_ALGORITHMIC_BYTE = (1.070415e9 + 7.950592e6) / 1.024e9
 
 
 def make_pheno(n=N_SAMPLES):
@@ -118,6 +122,61 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# fp64-pipe instructions per unit of work, counted in the SASS of the shipped kernels (ncu source page of
+# profiles/r02_ncu_k_bb_farm.txt: DFMA + DMUL + DADD + DSETP of one loop trip / samples per trip); DESIGN.md section 4.
+FP64_INSTR = {"irls_pass": 70.5, "irls_pass0": 46.5, "tail_eval": 44.0, "prep": 8.0, "quad_eval": 46.0}
+
+
+def fp64_stage(instr, ms, peak_tflops):
+    """fp64 'roofline' of a stage: issued fp64 instructions x 2 flop (the DFMA-equivalent the peak loop counts) over time."""
+    if not ms or not peak_tflops:
+        return None
+    ach = instr * 2.0 / (ms * 1e-3) / 1e12
+    return {"bound": "fp64", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s (fp64 instructions x 2)", "frac": ach / peak_tflops,
+            "fp64_instructions": instr, "ms": ms}
+
+
+def pin_to_gpu_numa(local):
+    """Bind this rank (and the pinned buffers it allocates afterwards) to the CPUs of its GPU's NUMA node."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        info = {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as ex:   # affinity is best effort
+        info["error"] = str(ex)[:80]
+    return info
+
+
+def r_reference_rate(ph, rows_host, n, m_sample):
+    """When an Rscript and the reference sources are reachable, time the UNMODIFIED R SPAGxE_CCT on a slice of the
+    batch (tools/run_reference.R); None otherwise (the GPU box has neither)."""
+    try:
+        from tests import _rscript
+        if not _rscript.available():
+            return None
+        from oracle import oracle as O
+        rb = (n + 3) // 4
+        G = O.bed_decode(rows_host[: m_sample * rb], n)
+        out, secs = _rscript.run("cct", "binary", G, ph["R"], ph["E"], ph["Y"], ph["Cova"])
+        return {"value": m_sample / secs, "unit": "SNPs/s", "cores": 1, "kind": "R",
+                "sample": f"{m_sample} SNPs of the timed batch at N={n} through the reference's own SPAGxE_CCT ({secs:.1f} s in R)"}
+    except Exception:
+        return None
+
+
 def oracle_sample_rate(ph, rows_host, n, nthreads):
     """reference CPU path (oracle port of SPAGxE_CCT_one_SNP) on a bounded sample of the same batch."""
     from oracle import oracle as O
@@ -180,20 +239,140 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def workload_config_other(kind, n, m, extra):
+    rb = (n + 3) // 4
+    base = {"mix": "C4: SPAGxEmix_CCT, two-way admixed population, 10 PCs, binary trait with ancestry-specific prevalence 0.1 / 0.01",
+            "plus": "C5: SPAGxE_Plus, 20,000 four-member families + 20,000 singletons, sparse GRM (200,000 entries), Cox martingale residuals"}[kind]
+    return {"workload": f"{base}, N={n}, {m} SNPs/step/GPU ({m * rb / 1e6:.0f} MB packed .bed rows resident in HBM)", "n_samples": n,
+            "snps_per_step_per_gpu": m, "l2_policy": "L2 flushed by a 256 MB write between steps" if m * rb < 3e8 else "inputs larger than L2",
+            "sharding": "SNP ranges per rank, no data-path collective", **extra}
+
+
+def run_other(args, kind):
+    """configs 4 and 5 (SPAGxEmix_CCT / SPAGxE_Plus): same contract, device-resident rows; not the headline."""
+    import torch
+    from spagxecct_b200 import Context, _lib
+    from tests._configs import c4_admixed, c5_families
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    W, K = max(3, args.warmup), args.steps
+    m = args.batch_snps if args.batch_snps != 16384 else (4096 if kind == "mix" else 8192)
+    x = c4_admixed(m=m, device=dev) if kind == "mix" else c5_families(m=m, device=dev)
+    n = x["n"]
+    rb = (n + 3) // 4
+    ctx = Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_vectors(x["R"], x["E"])
+    if kind == "mix":
+        ctx.set_wald(_lib.TRAIT_BINARY, x["Y"], x["Cova"]); ctx.set_pcs(x["PCs"])
+        run, ncol, prm_kw = ctx.run_mix, 12, dict(min_maf=1e-5)
+        metric = "SNPs/sec at N=200k, 10 PCs (SPAGxEmix_CCT Step-2 loop, device-timed)"
+    else:
+        a, b, Rnew, c = ctx.plus_nullmodel(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
+        ctx.set_grm(x["grm_i"], x["grm_j"], x["grm_v"], a, b, c, Rnew)
+        run, ncol, prm_kw = ctx.run_plus, 8, dict()
+        metric = "SNPs/sec at N=100k with a sparse GRM (SPAGxE_Plus Step-2 loop, device-timed)"
+    pitch = (rb + 127) // 128 * 128
+    bed = torch.full((m, pitch), 0xFF, dtype=torch.uint8, device=dev)
+    bed[:, :rb] = torch.from_numpy(x["rows"].reshape(m, rb)).to(dev)
+    out_dev = torch.empty((m, ncol), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    geno = ctx.geno_desc(_lib.GENO_BED, bed.data_ptr(), n, m, pitch, _lib.LOC_DEVICE)
+    prm = _lib.make_params(out_location=_lib.LOC_DEVICE, **prm_kw)
+    sampler = ClockSampler(local); sampler.start()
+    for _ in range(W):
+        run(geno, prm, out_ptr=out_dev.data_ptr())
+    torch.cuda.synchronize()
+    ms_sum, diags = 0.0, []
+    for _ in range(K):
+        flush.fill_(1)                                   # 256 MB > 126 MB L2
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, dg = run(geno, prm, out_ptr=out_dev.data_ptr())
+        e1.record(); torch.cuda.synchronize()
+        ms_sum += e0.elapsed_time(e1); diags.append(dg)
+    clocks = sampler.stop()
+    # end to end: pinned host rows in, host matrix out
+    host_rows = torch.from_numpy(x["rows"].reshape(m, rb)).pin_memory()
+    host_out = torch.empty((ncol, m), dtype=torch.float64).pin_memory()
+    geno_h = ctx.geno_desc(_lib.GENO_BED, host_rows.data_ptr(), n, m, rb, _lib.LOC_HOST)
+    prm_h = _lib.make_params(**prm_kw)
+    run(geno_h, prm_h, out_ptr=host_out.data_ptr())
+    ke = max(3, min(K, 10))
+    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(ke):
+        _, dge = run(geno_h, prm_h, out_ptr=host_out.data_ptr())
+    e3.record(); torch.cuda.synchronize()
+    ms_e = e2.elapsed_time(e3)
+    peak, peak_src = hbm_peak()
+    try:
+        fp64 = ctx.fp64_peak_tflops()
+    except Exception:
+        fp64 = None
+    ms_score = float(np.mean([d["ms_score"] for d in diags]))
+    ms_tests = float(np.mean([d["ms_tests"] for d in diags]))
+    dg = diags[-1]
+    k1 = x["PCs"].shape[1] + 1 if kind == "mix" else 0
+    line = {"metric": metric, "value": m * K / (ms_sum * 1e-3), "unit": "SNPs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_sum / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config_other(kind, n, m, {"n_pcs": k1 - 1} if kind == "mix" else {"grm_nnz": int(x["grm_i"].size)}),
+            "e2e": {"value": m * ke / (ms_e * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": int(dge["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(dge["d2h_bytes"]), "steps": ke},
+            "gpu_launches": int(sum(d["kernel_launches"] for d in diags)),
+            "roofline": ({"bound": "tensor", "achieved": 2.0 * n * k1 * 2 * m / (ms_tests * 1e-3) / 1e12, "peak": fp64, "unit": "TFLOP/s",
+                          "frac": (2.0 * n * k1 * 2 * m / (ms_tests * 1e-3) / 1e12 / fp64) if fp64 else None, "traffic": None,
+                          "kernel": "k_mix_tile + k_mix_finish (allele-frequency projection, fp64 CUDA cores; 'tensor' = compute bound)",
+                          "flop_model": "2 passes x 2 N (k+1) flop per SNP (X'g and x_i'beta)", "peak_source": "DFMA loop measured in this run"}
+                         if kind == "mix" else
+                         {"bound": "hbm", "achieved": float(dg["score_bytes"]) / (ms_score * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": float(dg["score_bytes"]) / (ms_score * 1e-3) / 1e9 / peak, "traffic": None,
+                          "kernel": "k_score_unpack_mma", "peak_source": peak_src}),
+            "cpu_baseline": None, "clocks": clocks,
+            "stages_ms": {"score": ms_score, "tests": ms_tests, "total_device": float(np.mean([d["ms_total"] for d in diags]))},
+            "routing": {k: int(dg[k]) for k in ["n_filtered", "n_branch_a", "n_branch_b", "n_spa", "n_mix_logistic", "newton_iters"]},
+            "fp64_peak_tflops_measured": fp64}
+    if args.cpu_sample_snps > 0:
+        from oracle import oracle as O
+        O.build()
+        ns = min(64 if kind == "mix" else 256, m)
+        t0 = time.perf_counter()
+        if kind == "mix":
+            ref, *_ = O.mix_bed("binary", x["rows"][: ns * rb], n, x["R"], x["E"], x["Y"], x["Cova"], x["PCs"], min_maf=1e-5)
+        else:
+            ref, *_ = O.plus_bed(x["rows"][: ns * rb], n, x["R"], x["E"], Rnew, a, b, c, x["grm_i"], x["grm_j"], x["grm_v"])
+        dt = time.perf_counter() - t0
+        got = out_dev.cpu().numpy().reshape(ncol, m).T[:ns]
+        pc = [2, 3, 4, 5, 6] if kind == "mix" else [2, 3, 4]
+        with np.errstate(all="ignore"):
+            chk = float(np.nanmax(np.abs(np.log10(got[:, pc]) - np.log10(ref[:, pc])) / np.maximum(np.abs(np.log10(ref[:, pc])), 1e-3)))
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "SNPs/s", "cores": 1, "kind": "port",
+                                "sample": f"first {ns} SNPs of the timed batch ({dt:.1f} s); restated reference (C oracle, -O2)",
+                                "max_rel_dlog10p_vs_gpu": chk}
+    if rank == 0:
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cct", choices=["cct", "mix", "plus"])
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--batch-snps", type=int, default=16384)
     ap.add_argument("--ref-snps", type=int, default=0)
     ap.add_argument("--cpu-sample-snps", type=int, default=1536)   # ~15 s of one host core at N = 500k
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "cct":
+        return run_other(args, args.workload)
 
     import torch
     import torch.distributed as dist
@@ -205,12 +384,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device (spagxecct_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {"numa_node": None} if args.no_affinity else pin_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, m = args.n_samples, args.batch_snps
     W, K = max(3, args.warmup), args.steps
 
-    # ---- inputs: rank 0 owns Step-1 output; ONE NCCL broadcast distributes R and E (north_star) ----
+    # ---- inputs: rank 0 owns Step-1 output; ONE NCCL broadcast distributes R, E and the Wald data (north_star) ----
     from spagxecct_b200.sharded import broadcast_inputs
     vec = torch.empty((2, n), dtype=torch.float64, device=dev)
     ycov = torch.empty((3, n), dtype=torch.float64, device=dev)   # Wald data (Y, Cova) rides along
@@ -222,11 +402,10 @@ def main():
     if world > 1:
         vec, ycov = broadcast_inputs(dist, [vec, ycov])           # the ONE collective of the run (NCCL)
         vec = vec.contiguous(); ycov = ycov.contiguous()
-    Y = ycov[0].cpu().numpy(); cova = ycov[1:].cpu().numpy().T.copy()
     ctx = Context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_vectors_device(n, vec[0].data_ptr(), vec[1].data_ptr())
-    ctx.set_wald(_lib.TRAIT_BINARY, Y, cova)
+    ctx.set_wald_device(_lib.TRAIT_BINARY, ycov[0].data_ptr(), ycov[1].data_ptr(), 2)
 
     rb = (n + 3) // 4
     pitch = (rb + 127) // 128 * 128
@@ -242,6 +421,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_floats(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(v)]
+        outl = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outl, t)
+        return [float(o.item()) for o in outl]
+
     # ---- device-resident timing (value) ----
     diags = []
     sampler = ClockSampler(local); sampler.start()
@@ -256,11 +443,8 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_all = gather_floats(e0.elapsed_time(e1))
+    ms_max = max(ms_all)
     value = world * m * K / (ms_max * 1e-3)
 
     # ---- end-to-end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
@@ -276,17 +460,20 @@ def main():
         barrier()
         e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
         e2.record()
-        ke = max(2, min(K, 3))
+        ke = max(3, min(K, args.e2e_steps))
         for _ in range(ke):
             _, dge = ctx.run_cct(geno_host, prm_host, out_ptr=host_out.data_ptr())
         e3.record()
         barrier()
-        ms_e = e2.elapsed_time(e3)
-        te = torch.tensor([ms_e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * m * ke / (float(te.item()) * 1e-3), "unit": "SNPs/s",
-               "h2d_bytes_per_step": int(dge["h2d_bytes"]), "d2h_bytes_per_step": int(dge["d2h_bytes"]), "steps": ke}
+        ms_e_all = gather_floats(e2.elapsed_time(e3))
+        h2d = int(dge["h2d_bytes"])
+        e2e = {"value": world * m * ke / (max(ms_e_all) * 1e-3), "unit": "SNPs/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(dge["d2h_bytes"]), "steps": ke,
+               "per_rank_h2d_gbs": [h2d * ke / (t * 1e-3) / 1e9 for t in ms_e_all],
+               "aggregate_h2d_gbs": world * h2d * ke / (max(ms_e_all) * 1e-3) / 1e9,
+               "device_ms_per_step_inside_e2e": float(dge["ms_total"]),
+               "copy_compute_overlap": "chunks of 1 GiB double-buffered: H2D of chunk k+1 on the copy stream while chunk k is tested",
+               "numa": numa}
         # e2e output must equal the device-resident output
         same = np.array_equal(np.nan_to_num(host_out.numpy().T, nan=-1), np.nan_to_num(out_dev.cpu().numpy().reshape(10, m).T, nan=-1))
         e2e["matches_device_path"] = bool(same)
@@ -299,9 +486,9 @@ def main():
         # one score launch per ~1 GiB chunk of packed rows (csrc/spagxe_cuda.cu make_plan)
         chunk_rows = max(128, ((1 << 30) // pitch) // 128 * 128)
         n_launch = -(-m // min(chunk_rows, 65536))
-        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r01_ncu_k_score_tc3_final.txt:
-        # 1.070415 GB read + 7.95 MB written for a launch of 1.024 GB of packed rows), scaled to this launch size
-        traffic = (1.070415e9 + 7.950592e6) / 1.024e9 * (score_bytes / n_launch)
+        # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/r02_ncu_k_score_unpack_mma.txt),
+        # scaled to this launch size
+        traffic = SCORE_TRAFFIC_PER_ALGORITHMIC_BYTE * (score_bytes / n_launch)
         dg = diags[-1]
         # bounded CPU sample of the very same batch (first rows), single thread
         cpu = None
@@ -310,18 +497,31 @@ def main():
             rows_host = bed[:ns, :rb].contiguous().cpu().numpy().ravel()
             rate, dt, mm = oracle_sample_rate(ph, rows_host, n, 1)
             from oracle import oracle as O
-            ref_out, *_ = O.cct_bed("binary", rows_host[: 8 * rb], n, ph["R"], ph["E"], ph["Y"], ph["Cova"])
-            got = out_dev.cpu().numpy().reshape(10, m).T[:8]
+            nchk = min(ns, 256)
+            ref_out, route, *_ = O.cct_bed("binary", rows_host[: nchk * rb], n, ph["R"], ph["E"], ph["Y"], ph["Cova"], nthreads=os.cpu_count())
+            got = out_dev.cpu().numpy().reshape(10, m).T[:nchk]
             pc = [2, 3, 4, 5, 6]
             with np.errstate(all="ignore"):
                 chk = float(np.nanmax(np.abs(np.log10(got[:, pc]) - np.log10(ref_out[:, pc])) / np.maximum(np.abs(np.log10(ref_out[:, pc])), 1e-3)))
             cpu = {"value": rate, "unit": "SNPs/s", "cores": 1, "kind": "port",
                    "sample": f"first {mm} SNPs of the timed batch at N={n} ({dt:.1f} s); restated reference (C oracle, -O2), not the R interpreter",
-                   "max_rel_dlog10p_vs_gpu_first8": chk}
+                   "parity_first_snps": {"snps": nchk, "max_rel_dlog10p_vs_gpu": chk, "n_spa": int(((route & 4) > 0).sum()),
+                                         "n_branch_b": int(((route & 2) > 0).sum())}}
+            rr = r_reference_rate(ph, rows_host, n, min(32, ns))
+            if rr:
+                cpu["r_interpreter"] = rr
         try:
             fp64 = ctx.fp64_peak_tflops()
         except Exception:
             fp64 = None
+        ms_spa = float(np.mean([d["ms_spa"] for d in diags])); ms_bb = float(np.mean([d["ms_branch_b"] for d in diags]))
+        n_items = max(1, int(dg["n_branch_b"]))
+        pass0 = float(n_items) * n                                   # one mustart pass per work item
+        irls = max(0.0, float(dg["bb_irls_sample_passes"]) - pass0)
+        bb_instr = (irls * FP64_INSTR["irls_pass"] + pass0 * FP64_INSTR["irls_pass0"] +
+                    float(dg["bb_tail_sample_passes"]) * FP64_INSTR["tail_eval"] + float(dg["bb_prep_sample_passes"]) * FP64_INSTR["prep"])
+        farm_tail_iters = float(dg["bb_tail_sample_passes"]) / n
+        quad_evals = max(0.0, float(dg["newton_iters"]) + 2.0 * float(dg["n_spa"]) - farm_tail_iters) * float(dg["spa_nodes"])
         line = {
             "metric": "SNPs/sec at N=500k (SPAGxE_CCT Step-2 loop, device-timed)", "value": value, "unit": "SNPs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
@@ -329,19 +529,24 @@ def main():
             "config": workload_config(n, m),
             "e2e": e2e, "gpu_launches": int(sum(d["kernel_launches"] for d in diags)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_score_tc3 (2-bit unpack + score pass, tcgen05 kind::i8)",
+                         "traffic": traffic, "kernel": "k_score_unpack_mma (2-bit unpack + score pass, tcgen05 kind::i8)",
                          "peak_source": peak_src, "launches_per_step": n_launch,
                          "algorithmic_bytes_per_launch": score_bytes / n_launch, "ms_per_launch": ms_score / n_launch,
-                         "traffic_source": "ncu --set full of one 1.024 GB launch (profiles/r01_ncu_k_score_tc3_final.txt), scaled by launch size",
+                         "traffic_source": "ncu --set full of one 1.024 GB launch (profiles/r02_ncu_k_score_unpack_mma.txt), scaled by launch size",
                          "share_of_step": ms_score / (ms_max / K)},
+            "roofline_stages": {
+                "spa_quadrature(k_spa_quad)": fp64_stage(quad_evals * FP64_INSTR["quad_eval"], ms_spa, fp64),
+                "branch_b(k_bb_farm)": fp64_stage(bb_instr, ms_bb, fp64),
+                "model": "fp64 instructions per unit counted in the SASS loops (bench.py FP64_INSTR) x units counted on the device",
+            },
             "cpu_baseline": cpu, "clocks": clocks,
             "stages_ms": {"score": ms_score, "tests(finalize+SPA+branchB)": float(np.mean([d["ms_tests"] for d in diags])),
-                          "spa(finalize+quadrature SPA)": float(np.mean([d["ms_spa"] for d in diags])),
-                          "branch_b(solver farm)": float(np.mean([d["ms_branch_b"] for d in diags])),
+                          "spa(finalize+quadrature SPA)": ms_spa, "branch_b(solver farm)": ms_bb,
                           "total_device": float(np.mean([d["ms_total"] for d in diags]))},
             "farm_work": {k: int(dg[k]) for k in ["bb_irls_sample_passes", "bb_tail_sample_passes", "bb_prep_sample_passes",
                                                   "bb_iterations", "spa_nodes"]},
             "routing": {k: int(dg[k]) for k in ["n_filtered", "n_branch_a", "n_branch_b", "n_spa", "newton_iters"]},
+            "per_rank_ms": ms_all,
             "fp64_peak_tflops_measured": fp64,
         }
         print(json.dumps(line))

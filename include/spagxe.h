@@ -57,7 +57,16 @@ typedef struct {
     int64_t n_snps;    /* M                                                              */
     int64_t pitch;     /* BED: bytes between consecutive SNP rows (>= ceil(N/4));
                           F64/I32: elements between consecutive columns (>= N)           */
+    /* what GRAB::GRAB.ReadGeno does between the file and the matrix (R/SPAGxECCT.R:484-487), BED only, optional: */
+    const int64_t *sample_index; /* HOST array of n_samples entries or NULL: sample_index[i] = position inside a
+                                    file row of analysis sample i (the SampleIDs subset / reorder); the gather runs
+                                    on the device, 2 bits -> 2 bits                                             */
+    int64_t n_file_samples;      /* samples per packed row of the source when sample_index is given (pitch >=
+                                    ceil(n_file_samples/4)); 0 = n_samples                                      */
+    int32_t flags;               /* SPAGXE_GENO_COUNT_A2: count the second allele (control$AlleleOrder="ref-first") */
+    int32_t reserved;
 } spagxe_geno;
+enum { SPAGXE_GENO_COUNT_A2 = 1 };
 
 /* the tuning arguments shared by SPAGxE_CCT / SPAGxEmix_CCT / SPAGxE_Plus
  * (R/SPAGxECCT.R:464-469, :926-933; R/SPAGxEPlus_functions_MYZ.R:168-173)               */

@@ -96,6 +96,32 @@ __global__ void k_pack_dense(const T *__restrict__ G, int64_t ld, int64_t n, int
     if (bad) atomicAdd(&ctr->n_nonint, 1ULL);
 }
 
+// GRAB.ReadGeno's sample subset / reorder and allele order as a device gather, 2 bits -> 2 bits (ref :484-487).
+// One thread per output 32-bit word (16 samples); idx == NULL keeps the sample order; padding samples get code 11.
+__global__ void k_bed_prepare(const uint8_t *__restrict__ src, int64_t spitch, uint32_t *__restrict__ dst, int64_t dpitch_words,
+                              int64_t n, int m, const int64_t *__restrict__ idx, int count_a2) {
+    const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (w >= dpitch_words || j >= m) return;
+    const uint8_t *row = src + (int64_t)j * spitch;
+    uint32_t word = 0xFFFFFFFFu;
+    const int64_t i0 = w * 16;
+    if (i0 < n) {
+        word = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int c = 3;
+            if (i0 + k < n) {
+                const int64_t sidx = idx ? idx[i0 + k] : i0 + k;
+                c = (row[sidx >> 2] >> (2 * (int)(sidx & 3))) & 3;
+                if (count_a2) c = (c == 0) ? 3 : (c == 3) ? 0 : c;   // hom-A1 <-> hom-A2; het and missing stay
+            }
+            word |= (uint32_t)c << (2 * k);
+        }
+    }
+    dst[(int64_t)j * dpitch_words + w] = word;
+}
+
 // per-code counts (exact integers). One warp per SNP row; pitch multiple of 4.
 __global__ void k_bed_counts(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, long long *counts) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

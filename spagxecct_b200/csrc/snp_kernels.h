@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(1024) k_vec_prep1(const double *__restrict__ R
 __global__ void __launch_bounds__(1024) k_vec_prep2(const double *__restrict__ R, const double *__restrict__ E, const double *__restrict__ Rn_in, int64_t n, int mode, double *__restrict__ Rn, double *__restrict__ V, VecConst *vc);
 // R matrix (REALSXP: f64 != 0, INTSXP: f64 == 0) -> packed PLINK rows; host launcher of the template kernel k_pack_dense
 cudaError_t launch_pack_dense(cudaStream_t s, int f64, const void *G, int64_t ld, int64_t n, int m, uint32_t *bed, int64_t pitch_words, Counters *ctr);
+__global__ void k_bed_prepare(const uint8_t *__restrict__ src, int64_t spitch, uint32_t *__restrict__ dst, int64_t dpitch_words, int64_t n, int m, const int64_t *__restrict__ idx, int count_a2);
 __global__ void k_bed_counts(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, long long *counts);
 __global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, double *__restrict__ out);
 __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n, const VecConst *__restrict__ vcp, double epsilon, double min_maf, double *__restrict__ out, SpaItem *spa_list, BItem *b_list, const uint8_t *bed, int64_t pitch, Counters *ctr);

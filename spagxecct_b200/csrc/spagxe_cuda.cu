@@ -66,6 +66,8 @@ struct spagxe_ctx {
     uint8_t *h_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;   // timing events, created once and reused by every call
+    int64_t cap_src = 0; uint8_t *d_src = nullptr;           // file-layout rows of a chunk before the sample gather
+    int64_t cap_sidx = 0; int64_t *d_sidx = nullptr;         // device copy of spagxe_geno.sample_index
     int64_t cap_util = 0; void *d_util = nullptr;            // scratch of spagxe_bed_counts / spagxe_bed_decode
     int *h_flag = nullptr;                                   // pinned word for small device -> host flags
     int64_t launches = 0;
@@ -175,7 +177,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     bb_farm_destroy(ctx->farm);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
-    cudaFree(ctx->d_util);
+    cudaFree(ctx->d_util); cudaFree(ctx->d_src); cudaFree(ctx->d_sidx);
     for (auto ev : ctx->ev_pool) cudaEventDestroy(ev);
     cudaFree(ctx->quad.x); cudaFree(ctx->quad.w); cudaFree(ctx->quad.wfix); cudaFree(ctx->quad.range); cudaFree(ctx->quad.count);
     for (int b = 0; b < 2; b++) {
@@ -415,9 +417,17 @@ static int validate_geno(spagxe_ctx *ctx, const spagxe_geno *g) {
     if (!g || !g->data) return fail(ctx, SPAGXE_ERR_ARG, "geno is NULL");
     if (g->n_samples <= 0 || g->n_snps < 0) return fail(ctx, SPAGXE_ERR_ARG, "geno: bad shape");
     if (g->n_snps > INT_MAX / 2) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "geno: too many SNPs in one call");
+    const bool prep = (g->sample_index != nullptr) || (g->flags & SPAGXE_GENO_COUNT_A2);
+    if (prep && g->kind != SPAGXE_GENO_BED) return fail(ctx, SPAGXE_ERR_ARG, "geno: sample_index / flags apply to .bed input only");
     if (g->kind == SPAGXE_GENO_BED) {
-        if (g->pitch < (g->n_samples + 3) / 4) return fail(ctx, SPAGXE_ERR_ARG, "geno: pitch < ceil(N/4)");
-        if (g->location == SPAGXE_LOC_DEVICE && ((g->pitch & 15) || ((uintptr_t)g->data & 15)))
+        const int64_t nfile = (g->sample_index && g->n_file_samples > 0) ? g->n_file_samples : g->n_samples;
+        if (g->pitch < (nfile + 3) / 4) return fail(ctx, SPAGXE_ERR_ARG, "geno: pitch < ceil(samples per file row / 4)");
+        if (g->sample_index)
+            for (int64_t i = 0; i < g->n_samples; i++)
+                if (g->sample_index[i] < 0 || g->sample_index[i] >= nfile)
+                    return fail(ctx, SPAGXE_ERR_ARG, "geno: sample_index[%lld] = %lld is outside the file row (%lld samples)",
+                                (long long)i, (long long)g->sample_index[i], (long long)nfile);
+        if (!prep && g->location == SPAGXE_LOC_DEVICE && ((g->pitch & 15) || ((uintptr_t)g->data & 15)))
             return fail(ctx, SPAGXE_ERR_ARG, "geno: device-resident .bed rows need a 16-byte aligned base and pitch");
     } else if (g->kind == SPAGXE_GENO_F64 || g->kind == SPAGXE_GENO_I32) {
         if (g->pitch < g->n_samples) return fail(ctx, SPAGXE_ERR_ARG, "geno: leading dimension < N");
@@ -426,11 +436,15 @@ static int validate_geno(spagxe_ctx *ctx, const spagxe_geno *g) {
     return SPAGXE_OK;
 }
 
+static bool geno_needs_prepare(const spagxe_geno *g) {
+    return g->kind == SPAGXE_GENO_BED && (g->sample_index != nullptr || (g->flags & SPAGXE_GENO_COUNT_A2));
+}
+
 static ChunkPlan make_plan(const spagxe_geno *g, int64_t chunk_override) {
     ChunkPlan pl;
     pl.n = g->n_samples; pl.m = g->n_snps;
     pl.row_bytes = (g->n_samples + 3) / 4;
-    if (g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) pl.dpitch = g->pitch;
+    if (g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE && !geno_needs_prepare(g)) pl.dpitch = g->pitch;
     else pl.dpitch = round_up(pl.row_bytes, 128);
     // ~1 GiB of packed rows per chunk (>> L2), dense inputs are limited by their 8 B/sample staging
     int64_t budget = (g->kind == SPAGXE_GENO_BED) ? (1ll << 30) : (1ll << 26);
@@ -445,6 +459,35 @@ static ChunkPlan make_plan(const spagxe_geno *g, int64_t chunk_override) {
 static int stage_chunk(spagxe_ctx *ctx, const spagxe_geno *g, const ChunkPlan &pl, int64_t j0, int mc, int buf,
                        const uint8_t **d_rows, int64_t *h2d_bytes) {
     cudaStream_t s = ctx->stream();
+    if (geno_needs_prepare(g)) {
+        // file-layout rows -> (device) -> gather of the analysis samples / allele order -> packed rows of N samples
+        const int64_t nfile = (g->sample_index && g->n_file_samples > 0) ? g->n_file_samples : g->n_samples;
+        const int64_t src_row = (nfile + 3) / 4;
+        const uint8_t *d_src_rows;
+        int64_t spitch;
+        if (g->location == SPAGXE_LOC_DEVICE) { d_src_rows = (const uint8_t *)g->data + j0 * g->pitch; spitch = g->pitch; }
+        else {
+            spitch = round_up(src_row, 16);
+            const int64_t need = spitch * pl.chunk_m;
+            if (need > ctx->cap_src) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_src, need)); ctx->cap_src = need; }
+            const uint8_t *src = (const uint8_t *)g->data + j0 * g->pitch;
+            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[buf], 0));
+            CU(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_done[buf ^ 1], 0));   // d_src is a single buffer
+            int rc = stage_rows(ctx, src, g->pitch, src_row, mc, ctx->d_src, spitch, host_ptr_is_pinned(src));
+            if (rc) return rc;
+            CU(cudaEventRecord(ctx->ev_copied[buf], ctx->s_copy));
+            CU(cudaStreamWaitEvent(s, ctx->ev_copied[buf], 0));
+            *h2d_bytes += src_row * mc;
+            d_src_rows = ctx->d_src;
+        }
+        const int64_t pw = pl.dpitch / 4;
+        dim3 grid((unsigned)((pw + 255) / 256), (unsigned)mc);
+        k_bed_prepare<<<grid, 256, 0, s>>>(d_src_rows, spitch, (uint32_t *)ctx->d_bed[buf], pw, pl.n, mc,
+                                           g->sample_index ? ctx->d_sidx : nullptr, (g->flags & SPAGXE_GENO_COUNT_A2) ? 1 : 0);
+        LAUNCH_CHECK();
+        *d_rows = ctx->d_bed[buf];
+        return SPAGXE_OK;
+    }
     if (g->kind == SPAGXE_GENO_BED) {
         if (g->location == SPAGXE_LOC_DEVICE) {
             *d_rows = (const uint8_t *)g->data + j0 * g->pitch;
@@ -483,6 +526,17 @@ static int stage_chunk(spagxe_ctx *ctx, const spagxe_geno *g, const ChunkPlan &p
     CU(launch_pack_dense(s, g->kind == SPAGXE_GENO_F64, dsrc, ld, pl.n, mc, (uint32_t *)ctx->d_bed[buf], pw, ctx->d_ctr));
     ctx->launches++;
     *d_rows = ctx->d_bed[buf];
+    return SPAGXE_OK;
+}
+
+// device copy of the sample gather index of this call (if any)
+static int upload_sample_index(spagxe_ctx *ctx, const spagxe_geno *g) {
+    if (!g->sample_index) return SPAGXE_OK;
+    if (g->n_samples > ctx->cap_sidx) {
+        CU(cudaStreamSynchronize(ctx->stream()));
+        CU(dev_realloc(&ctx->d_sidx, g->n_samples)); ctx->cap_sidx = g->n_samples;
+    }
+    CU(cudaMemcpyAsync(ctx->d_sidx, g->sample_index, g->n_samples * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream()));
     return SPAGXE_OK;
 }
 
@@ -602,7 +656,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     ctx->launches = 0;
     if (M == 0) { if (diag) *diag = dg; return SPAGXE_OK; }
     ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
-    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     double *d_out = nullptr;
     if (prm->out_location == SPAGXE_LOC_DEVICE) { d_out = out; rc = ensure_chunk_scratch(ctx, pl, own_bed, 0); }
     else { rc = ensure_chunk_scratch(ctx, pl, own_bed, M * ncol); d_out = ctx->d_out; }
@@ -790,7 +844,7 @@ extern "C" int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *g, int imp
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
     ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
-    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     if (ctx->vec_mode < 0 && (rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
@@ -828,7 +882,7 @@ extern "C" int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *g, int64_t 
     cudaStream_t s = ctx->stream();
     ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     ctx->launches = 0;
-    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     long long *d_counts = nullptr;
@@ -862,7 +916,7 @@ extern "C" int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *g, double *
     ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     // decode expands 32x: keep chunks small
     pl.chunk_m = (int)std::min<int64_t>(pl.chunk_m, std::max<int64_t>(1, (1ll << 28) / (pl.n * 8)));
-    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE);
+    const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
     double *d_dec = nullptr;
     {
