@@ -16,6 +16,7 @@ OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_CCT_STOP, ERR_SINGULAR = 
 TRAIT_BINARY, TRAIT_QUANTITATIVE = 1, 2
 GENO_BED, GENO_F64, GENO_I32 = 0, 1, 2
 LOC_HOST, LOC_DEVICE = 0, 1
+GENO_COUNT_A2 = 1
 
 EXPORTS = [
     "spagxe_ctx_create", "spagxe_ctx_destroy", "spagxe_last_error", "spagxe_ctx_set_stream", "spagxe_version",
@@ -31,7 +32,8 @@ OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL = 1, 2, 3, 4
 
 class Geno(C.Structure):
     _fields_ = [("kind", C.c_int32), ("location", C.c_int32), ("data", C.c_void_p), ("n_samples", C.c_int64),
-                ("n_snps", C.c_int64), ("pitch", C.c_int64)]
+                ("n_snps", C.c_int64), ("pitch", C.c_int64), ("sample_index", C.c_void_p), ("n_file_samples", C.c_int64),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Params(C.Structure):
@@ -192,8 +194,14 @@ class Context:
         return float(out3[0]), float(out3[1]), Rnew, float(out3[2])
 
     @staticmethod
-    def geno_desc(kind, data_ptr, n, m, pitch, location=LOC_HOST):
-        return Geno(kind, location, C.c_void_p(data_ptr), int(n), int(m), int(pitch))
+    def geno_desc(kind, data_ptr, n, m, pitch, location=LOC_HOST, sample_index=None, n_file_samples=0, count_a2=False):
+        """sample_index: int64 array (kept alive by the caller): position inside a file row of analysis sample i."""
+        sidx = None
+        if sample_index is not None:
+            assert sample_index.dtype == np.int64 and sample_index.flags.c_contiguous and sample_index.size == n
+            sidx = C.c_void_p(sample_index.ctypes.data)
+        return Geno(kind, location, C.c_void_p(data_ptr), int(n), int(m), int(pitch), sidx, int(n_file_samples),
+                    GENO_COUNT_A2 if count_a2 else 0, 0)
 
     def _run(self, fn, ncol, geno, params, out_ptr=None):
         prm = params if isinstance(params, Params) else make_params(**(params or {}))

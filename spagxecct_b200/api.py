@@ -19,7 +19,7 @@ import datetime
 import numpy as np
 
 from . import _lib
-from .bedio import BedFile, reorder_samples
+from .bedio import BedFile
 
 COLS_CCT = ["MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
             "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG"]
@@ -114,10 +114,55 @@ def _geno_desc_from_matrix(G):
     return G, _lib.Context.geno_desc(kind, G.ctypes.data, n, m, n)
 
 
+_CONTROL_KEYS = {"AllMarkers", "IDsToIncludeFile", "IDsToExcludeFile", "RangesToIncludeFile", "RangesToExcludeFile",
+                 "AlleleOrder", "ImputeMethod"}
+
+
+def _select_markers(bf, control):
+    """GRAB.ReadGeno's marker selection (`control`): marker ids from IDsToIncludeFile / IDsToExcludeFile (one id per
+    line) and chromosome ranges from RangesToIncludeFile / RangesToExcludeFile (CHROM START END per line).  Include
+    files are united, then exclude files are subtracted, as in GRAB; file order of the markers is kept."""
+    m = bf.m
+    has_inc = "IDsToIncludeFile" in control or "RangesToIncludeFile" in control
+    has_exc = "IDsToExcludeFile" in control or "RangesToExcludeFile" in control
+    if has_inc and has_exc:
+        raise RStop("We currently do not support both 'IncludeFile' and 'ExcludeFile' at the same time.")
+    if not (has_inc or has_exc):
+        if not control.get("AllMarkers", False):
+            raise RStop("If 'AllMarkers' is FALSE, at least one of the include / exclude files should be specified.")
+        return None
+    ids = np.asarray(bf.snp_ids)
+    chrom, pos = bf.bim_chrom_pos()
+    hit = np.zeros(m, dtype=bool)
+    for key in ("IDsToIncludeFile", "IDsToExcludeFile"):
+        if key in control:
+            want = {l.strip() for l in open(control[key]) if l.strip()}
+            hit |= np.isin(ids, list(want))
+    for key in ("RangesToIncludeFile", "RangesToExcludeFile"):
+        if key in control:
+            for l in open(control[key]):
+                f = l.split()
+                if len(f) >= 3:
+                    hit |= (chrom == f[0]) & (pos >= int(f[1])) & (pos <= int(f[2]))
+    keep = hit if has_inc else ~hit
+    return np.nonzero(keep)[0]
+
+
 def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
-    """The GRAB.ReadGeno step for PLINK input: returns (packed rows, N, M, snp ids, row ids)."""
-    if control not in (None, {"AllMarkers": True}) and dict(control) != {"AllMarkers": True}:
-        raise NotImplementedError("only control=list(AllMarkers=TRUE) is supported for GenoFile input")
+    """The GRAB.ReadGeno step for PLINK input (ref R/SPAGxECCT.R:484-487) without materialising the N x M matrix:
+    returns (geno descriptor, objects to keep alive, N, M, snp ids, row ids).  The .bed file is memory-mapped and
+    handed to the C ABI as it is (the library streams it through pinned staging buffers in ~1 GiB chunks, so a file larger
+    than RAM is fine); the SampleIDs subset / reorder is a device-side gather (spagxe_geno.sample_index); the allele
+    order is a flag; only a marker selection copies the selected rows on the host."""
+    control = dict(control) if control else {"AllMarkers": True}
+    unknown = set(control) - _CONTROL_KEYS
+    if unknown:
+        raise NotImplementedError(f"control option(s) {sorted(unknown)} are not supported")
+    if control.get("ImputeMethod", "none") != "none":
+        raise NotImplementedError('control$ImputeMethod other than "none": the Step-2 functions impute themselves (impute.method)')
+    order = control.get("AlleleOrder", "alt-first")         # GRAB's default for PLINK input: count A1
+    if order not in ("alt-first", "ref-first"):
+        raise RStop("control$AlleleOrder should be 'ref-first' or 'alt-first'.")
     if not str(GenoFile).endswith(".bed"):
         raise NotImplementedError("GenoFile must be a PLINK .bed file (BGEN input is not implemented)")
     bim = fam = None
@@ -125,7 +170,15 @@ def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
         bim, fam = GenoFileIndex[0], GenoFileIndex[1]
     bf = BedFile(GenoFile, bim, fam)
     rows = bf.rows
+    snp_ids = bf.snp_ids
+    sel = _select_markers(bf, control)
+    m = bf.m
+    if sel is not None:
+        rows = np.ascontiguousarray(np.asarray(rows).reshape(bf.m, bf.row_bytes)[sel]).ravel()
+        snp_ids = [bf.snp_ids[j] for j in sel]
+        m = len(sel)
     ids = bf.sample_ids
+    sidx = None
     if sample_ids is not None:
         want = [str(x) for x in sample_ids]
         if want != ids:
@@ -133,10 +186,12 @@ def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
             missing = [s for s in want if s not in pos]
             if missing:
                 raise RStop(f"SampleIDs not found in the .fam file: {missing[:3]}...")
-            rows = reorder_samples(rows, bf.n, bf.m, [pos[s] for s in want])
+            sidx = np.ascontiguousarray([pos[s] for s in want], dtype=np.int64)
             ids = want
-    rows = np.ascontiguousarray(rows)
-    return rows, len(ids), bf.m, bf.snp_ids, ids
+    n = len(ids)
+    geno = _lib.Context.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, bf.row_bytes, sample_index=sidx,
+                                  n_file_samples=bf.n, count_a2=(order == "ref-first"))
+    return geno, (rows, sidx, bf), n, m, snp_ids, ids
 
 
 def _now():
@@ -175,9 +230,7 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
         pIDs = _col(Phen_mtx, "ID")
         keep = None
         if Geno_mtx is None:
-            rows, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
-            keep = rows
-            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+            geno, keep, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
         else:
             G, gIDs, snp_ids = _split_geno(Geno_mtx)
             keep, geno = _geno_desc_from_matrix(G)
@@ -207,9 +260,7 @@ def _spagxe_cct_multi(traits, GenoFile, GenoFileIndex, control, Geno_mtx, R, E, 
     with _lib.MultiContext(n_gpus) as mg:
         pIDs = _col(Phen_mtx, "ID")
         if Geno_mtx is None:
-            rows, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
-            keep = rows
-            geno = _lib.Context.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+            geno, keep, n, m, snp_ids, gIDs = _read_geno_file(GenoFile, GenoFileIndex, pIDs, control)
         else:
             G, gIDs, snp_ids = _split_geno(Geno_mtx)
             keep, geno = _geno_desc_from_matrix(G)
@@ -256,9 +307,7 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
     ctx = ctx or _lib.Context(device)
     try:
         if Geno_mtx is None:
-            rows, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
-            keep = rows
-            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+            geno, keep, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
         else:
             G, _, snp_ids = _split_geno(Geno_mtx)
             keep, geno = _geno_desc_from_matrix(G)
@@ -308,9 +357,7 @@ def SPAGxE_Plus(GenoFile=None, GenoFileIndex=None, control=None, Geno_mtx=None, 
     try:
         obj = obj_SPAGxE_Plus_Nullmodel
         if Geno_mtx is None:
-            rows, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
-            keep = rows
-            geno = ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+            geno, keep, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
         else:
             G, _, snp_ids = _split_geno(Geno_mtx)
             keep, geno = _geno_desc_from_matrix(G)

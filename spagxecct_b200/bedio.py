@@ -16,6 +16,7 @@ class BedFile:
         self.fam_path = fam_path or stem + ".fam"
         self.sample_ids = [l.split()[1] for l in open(self.fam_path)]
         bim = [l.split() for l in open(self.bim_path)]
+        self._bim = bim
         self.snp_ids = [b[1] for b in bim]
         self.n = len(self.sample_ids)
         self.m = len(self.snp_ids)
@@ -27,6 +28,10 @@ class BedFile:
         if bytes(mm[:3]) != BED_MAGIC:
             raise ValueError(f"{self.bed_path}: not a variant-major PLINK .bed file")
         self.rows = mm[3:]  # M * row_bytes packed bytes, zero-copy
+
+    def bim_chrom_pos(self):
+        """(chromosome strings, base-pair positions) of the markers, for range filters."""
+        return np.asarray([b[0] for b in self._bim]), np.asarray([int(b[3]) for b in self._bim], dtype=np.int64)
 
     def rows_array(self):
         return np.ascontiguousarray(self.rows)

@@ -661,6 +661,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (prm->out_location == SPAGXE_LOC_DEVICE) { d_out = out; rc = ensure_chunk_scratch(ctx, pl, own_bed, 0); }
     else { rc = ensure_chunk_scratch(ctx, pl, own_bed, M * ncol); d_out = ctx->d_out; }
     if (rc) return rc;
+    if ((rc = upload_sample_index(ctx, g))) return rc;
     // CCT contracts with (R, R.new); plus and mix with (R, E*R); plus takes R.new from the null-model object
     const int vmode = (mode == RUN_CCT) ? 0 : (mode == RUN_PLUS ? 1 : 2);
     {
@@ -846,6 +847,7 @@ extern "C" int spagxe_score_stats(spagxe_ctx *ctx, const spagxe_geno *g, int imp
     ChunkPlan pl = make_plan(g, ctx->opt_chunk_snps);
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    if ((rc = upload_sample_index(ctx, g))) return rc;
     if (ctx->vec_mode < 0 && (rc = ensure_vec_mode(ctx, 0, nullptr))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     SnpStats st = stats_view(ctx, ctx->cap_m);
@@ -884,6 +886,7 @@ extern "C" int spagxe_bed_counts(spagxe_ctx *ctx, const spagxe_geno *g, int64_t 
     ctx->launches = 0;
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    if ((rc = upload_sample_index(ctx, g))) return rc;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     long long *d_counts = nullptr;
     {
@@ -918,6 +921,7 @@ extern "C" int spagxe_bed_decode(spagxe_ctx *ctx, const spagxe_geno *g, double *
     pl.chunk_m = (int)std::min<int64_t>(pl.chunk_m, std::max<int64_t>(1, (1ll << 28) / (pl.n * 8)));
     const bool own_bed = !(g->kind == SPAGXE_GENO_BED && g->location == SPAGXE_LOC_DEVICE) || geno_needs_prepare(g);
     if ((rc = ensure_chunk_scratch(ctx, pl, own_bed, 0))) return rc;
+    if ((rc = upload_sample_index(ctx, g))) return rc;
     double *d_dec = nullptr;
     {
         const int64_t need = (int64_t)sizeof(double) * pl.n * pl.chunk_m;

@@ -498,3 +498,56 @@ def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir):
         assert fast.diag[key] == slow.diag[key], key
     # the batched path must actually have served most SNPs: far fewer kernel launches cannot tell, the counters can
     assert fast.diag["n_branch_a"] > fast.diag["n_spa"] + fast.diag["n_branch_b"]
+
+
+def test_genofile_sample_subset_reorder_marker_filters_and_allele_order(gpu_ctx, oracle, golden_dir, tmp_path):
+    """What GRAB.ReadGeno does between the file and the loop (ref R/SPAGxECCT.R:484-487): Phen.mtx$ID is a shuffled
+    SUBSET of the .fam samples (device-side 2-bit gather), `control` selects markers (ids / ranges, include or
+    exclude) and the allele order; each variant must equal the oracle on the correspondingly decoded matrix."""
+    d = np.load(f"{golden_dir}/bed_SPAGxE.npz")
+    n_file = int(d["n"])
+    stem = str(tmp_path / "GenoMat_SPAGxE")
+    d["bed"].tofile(stem + ".bed")
+    fam_ids = [f"IID-{i + 1}" for i in range(n_file)]
+    open(stem + ".fam", "w").write("".join(f"{s} {s} 0 0 1 -9\n" for s in fam_ids))
+    snp_ids = [str(s) for s in d["snp_ids"]]
+    open(stem + ".bim", "w").write("".join(f"{1 + j // 50}\t{s}\t0\t{1000 * (j + 1)}\tA\tG\n" for j, s in enumerate(snp_ids)))
+    rng = np.random.default_rng(77)
+    keep = rng.permutation(n_file)[:7001]                       # shuffled subset, N not a multiple of 4
+    ids = [fam_ids[i] for i in keep]
+    n = len(ids)
+    ph = make_pheno(n, 78, prevalence=0.2)
+    Gfull = oracle.bed_decode(d["bed"][3:], n_file)
+    Gsub = np.ascontiguousarray(Gfull[keep])
+    phen = {"ID": ids, "Y": ph["Y"]}
+    # (a) all markers, sample gather only
+    res = SPAGxE_CCT("binary", GenoFile=stem + ".bed", R=ph["R"], E=ph["E"], Phen_mtx=phen, Cova_mtx=ph["Cova"], epsilon=0.05,
+                     ctx=gpu_ctx, quiet=True)
+    ref, *_ = oracle.cct_matrix("binary", Gsub, ph["R"], ph["E"], ph["Y"], ph["Cova"], epsilon=0.05, g_is_int=False)
+    assert_parity(res.values, ref, P_COLS, S_COLS, label="sample gather")
+    assert res.rownames == snp_ids
+    # (b) marker ids to include + ref-first allele order (counts A2: g -> 2 - g)
+    inc = tmp_path / "inc.txt"
+    inc.write_text("\n".join(snp_ids[3:40:3]) + "\n")
+    res_b = SPAGxE_CCT("binary", GenoFile=stem + ".bed", control={"IDsToIncludeFile": str(inc), "AlleleOrder": "ref-first"},
+                       R=ph["R"], E=ph["E"], Phen_mtx=phen, Cova_mtx=ph["Cova"], epsilon=0.05, ctx=gpu_ctx, quiet=True)
+    cols = list(range(3, 40, 3))
+    ref_b, *_ = oracle.cct_matrix("binary", 2 - Gsub[:, cols], ph["R"], ph["E"], ph["Y"], ph["Cova"], epsilon=0.05)
+    assert_parity(res_b.values, ref_b, P_COLS, S_COLS, label="ids include + ref-first")
+    assert res_b.rownames == [snp_ids[j] for j in cols]
+    # (c) range exclusion: chromosome 2 between positions 60,000 and 80,000 (markers 60..80 of the fixture)
+    exc = tmp_path / "exc.txt"
+    exc.write_text("2 60000 80000\n")
+    res_c = SPAGxE_CCT("binary", GenoFile=stem + ".bed", control={"RangesToExcludeFile": str(exc)}, R=ph["R"], E=ph["E"],
+                       Phen_mtx=phen, Cova_mtx=ph["Cova"], epsilon=0.05, ctx=gpu_ctx, quiet=True)
+    cols_c = [j for j in range(100) if not (59 <= j <= 79)]
+    assert res_c.rownames == [snp_ids[j] for j in cols_c]
+    assert np.array_equal(np.nan_to_num(res_c.values, nan=-1), np.nan_to_num(res.values[cols_c], nan=-1))
+    # include + exclude together is refused like GRAB does; an unknown sample id stops
+    from spagxecct_b200 import RStop
+    with pytest.raises(RStop):
+        SPAGxE_CCT("binary", GenoFile=stem + ".bed", control={"IDsToIncludeFile": str(inc), "RangesToExcludeFile": str(exc)},
+                   R=ph["R"], E=ph["E"], Phen_mtx=phen, Cova_mtx=ph["Cova"], ctx=gpu_ctx, quiet=True)
+    with pytest.raises(RStop):
+        SPAGxE_CCT("binary", GenoFile=stem + ".bed", R=ph["R"], E=ph["E"], Phen_mtx={"ID": ids[:-1] + ["nobody"], "Y": ph["Y"]},
+                   Cova_mtx=ph["Cova"], ctx=gpu_ctx, quiet=True)
