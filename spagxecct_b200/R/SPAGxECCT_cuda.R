@@ -1,9 +1,14 @@
 # SPAGxECCT_cuda.R -- drop-in replacements of the reference's exported Step-2 functions.
-# Same formals, printed lines, column names and stop() behaviour as R/SPAGxECCT.R:455-530 (SPAGxE_CCT),
-# :916-1002 (SPAGxEmix_CCT) and R/SPAGxEPlus_functions_MYZ.R:159-238 (SPAGxE_Plus); the serial
-# `for(i in 1:n.Geno)` loop is replaced by one .Call into libspagxe_cuda.so.  Step 1
-# (SPA_G_Get_Resid, SPAGxE_Plus_Nullmodel) is untouched and stays in R.
-# dyn.load("spagxe_rshim.so") once (it links libspagxe_cuda.so).
+# Same formals, printed lines, column names and stop() behaviour as R/SPAGxECCT.R:455-530 (SPAGxE_CCT), :543-683
+# (SPAGxE_CCT_one_SNP), :916-1002 (SPAGxEmix_CCT), :1013-1269 (SPAGxEmix_CCT_one_SNP) and
+# R/SPAGxEPlus_functions_MYZ.R:159-238, :248-405 (SPAGxE_Plus, SPAGxE_Plus_one_SNP); the serial `for(i in 1:n.Geno)` loop
+# is replaced by one .Call into libspagxe_cuda.so.  Step 1 (SPA_G_Get_Resid, the model fit of SPAGxE_Plus_Nullmodel) stays
+# in R.  dyn.load("spagxe_rshim.so") once (it links libspagxe_cuda.so).
+#
+# Additions to the reference's formals (all optional, defaults reproduce the reference call):
+#   n.gpus   number of GPUs of the node to spread the SNPs over (SPAGxE_CCT only; one NCCL broadcast of R/E/Y/Cova)
+#   device   CUDA ordinal for single-GPU calls
+# The result carries attr(, "diag"): routing counts and device times of the call.
 
 .spagxe_trait <- function(traits) {
   if (traits == "binary") return(1L)
@@ -11,34 +16,94 @@
   stop('the CUDA path implements traits = "binary" and "quantitative" (survival / categorical Wald tests: use the reference)')
 }
 
+.spagxe_gmodel <- function(G.model) {
+  if (G.model != "Add") stop('the CUDA path implements G.model = "Add"')
+  0L
+}
+
+.spagxe_read_lines <- function(f) { x <- trimws(readLines(f)); x[nzchar(x)] }
+
+# GRAB.ReadGeno's part of the job for PLINK input (R/SPAGxECCT.R:484-487) WITHOUT building the N x M double matrix:
+# the packed rows stay packed, the SampleIDs subset / reorder becomes a 0-based gather index that the GPU applies,
+# `control` selects marker rows and the allele order.
 .spagxe_geno <- function(GenoFile, GenoFileIndex, control, Geno.mtx, SampleIDs) {
-  if (!is.null(Geno.mtx)) return(list(g = Geno.mtx, n = nrow(Geno.mtx), m = ncol(Geno.mtx), snp = colnames(Geno.mtx), ids = rownames(Geno.mtx)))
+  if (!is.null(Geno.mtx))
+    return(list(g = Geno.mtx, n = nrow(Geno.mtx), m = ncol(Geno.mtx), snp = colnames(Geno.mtx), ids = rownames(Geno.mtx),
+                sidx = NULL, nfile = 0, a2 = 0L))
+  if (!grepl("\\.bed$", GenoFile)) stop("GenoFile must be a PLINK .bed file (BGEN input is not implemented by the CUDA path)")
   bim <- if (is.null(GenoFileIndex)) sub("\\.bed$", ".bim", GenoFile) else GenoFileIndex[1]
   fam <- if (is.null(GenoFileIndex)) sub("\\.bed$", ".fam", GenoFile) else GenoFileIndex[2]
-  ids <- read.table(fam, stringsAsFactors = FALSE)[[2]]
-  snp <- read.table(bim, stringsAsFactors = FALSE)[[2]]
-  if (!identical(as.character(SampleIDs), as.character(ids)))
-    stop("the CUDA .bed path needs Phen.mtx$ID in .fam order (or pass Geno.mtx); sample reordering is done by the Python host today")
-  raw <- readBin(GenoFile, "raw", file.size(GenoFile))
-  if (!identical(as.integer(raw[1:3]), c(0x6cL, 0x1bL, 0x01L))) stop("not a variant-major PLINK .bed file")
-  list(g = raw[-(1:3)], n = length(ids), m = length(snp), snp = snp, ids = ids)
+  fam.ids <- as.character(read.table(fam, stringsAsFactors = FALSE)[[2]])
+  bimtab <- read.table(bim, stringsAsFactors = FALSE)
+  snp <- as.character(bimtab[[2]])
+  nfile <- length(fam.ids); mfile <- length(snp); rb <- (nfile + 3) %/% 4
+  known <- c("AllMarkers", "IDsToIncludeFile", "IDsToExcludeFile", "RangesToIncludeFile", "RangesToExcludeFile",
+             "AlleleOrder", "ImputeMethod")
+  if (length(setdiff(names(control), known))) stop("unsupported control option(s): ", paste(setdiff(names(control), known), collapse = ", "))
+  if (!is.null(control$ImputeMethod) && control$ImputeMethod != "none")
+    stop('control$ImputeMethod other than "none": the Step-2 functions impute themselves (impute.method)')
+  order <- if (is.null(control$AlleleOrder)) "alt-first" else control$AlleleOrder
+  if (!order %in% c("alt-first", "ref-first")) stop("control$AlleleOrder should be 'ref-first' or 'alt-first'.")
+  inc <- intersect(names(control), c("IDsToIncludeFile", "RangesToIncludeFile"))
+  exc <- intersect(names(control), c("IDsToExcludeFile", "RangesToExcludeFile"))
+  if (length(inc) && length(exc)) stop("We currently do not support both 'IncludeFile' and 'ExcludeFile' at the same time.")
+  sel <- NULL
+  if (length(inc) || length(exc)) {
+    hit <- rep(FALSE, mfile)
+    for (k in c("IDsToIncludeFile", "IDsToExcludeFile")) if (!is.null(control[[k]])) hit <- hit | snp %in% .spagxe_read_lines(control[[k]])
+    for (k in c("RangesToIncludeFile", "RangesToExcludeFile")) if (!is.null(control[[k]])) {
+      rg <- read.table(control[[k]], stringsAsFactors = FALSE)
+      for (r in seq_len(nrow(rg))) hit <- hit | (as.character(bimtab[[1]]) == as.character(rg[r, 1]) & bimtab[[4]] >= rg[r, 2] & bimtab[[4]] <= rg[r, 3])
+    }
+    sel <- which(if (length(inc)) hit else !hit)
+  } else if (!isTRUE(control$AllMarkers)) stop("If 'AllMarkers' is FALSE, at least one of the include / exclude files should be specified.")
+  con <- file(GenoFile, "rb"); on.exit(close(con))
+  magic <- readBin(con, "raw", 3)
+  if (!identical(as.integer(magic), c(0x6cL, 0x1bL, 0x01L))) stop("not a variant-major PLINK .bed file")
+  if (is.null(sel)) raw <- readBin(con, "raw", rb * mfile)
+  else {                                      # only the selected marker rows are read
+    raw <- raw(rb * length(sel))
+    for (k in seq_along(sel)) { seek(con, 3 + (sel[k] - 1) * rb); raw[((k - 1) * rb + 1):(k * rb)] <- readBin(con, "raw", rb) }
+    snp <- snp[sel]
+  }
+  ids <- fam.ids; sidx <- NULL
+  if (!is.null(SampleIDs) && !identical(as.character(SampleIDs), fam.ids)) {
+    pos <- match(as.character(SampleIDs), fam.ids)
+    if (anyNA(pos)) stop("SampleIDs not found in the .fam file: ", paste(head(SampleIDs[is.na(pos)], 3), collapse = ", "))
+    sidx <- as.double(pos - 1)               # 0-based file positions; the gather runs on the GPU
+    ids <- as.character(SampleIDs)
+  }
+  list(g = raw, n = length(ids), m = length(snp), snp = snp, ids = ids, sidx = sidx, nfile = nfile, a2 = as.integer(order == "ref-first"))
+}
+
+.spagxe_run <- function(ctx, which, gi, prm) {
+  .Call("spagxe_r_run", ctx, which, gi$g, gi$n, gi$m, prm, gi$sidx, as.double(gi$nfile), gi$a2)
 }
 
 SPAGxE_CCT <- function(traits = "survival/binary/quantitative/categorical", GenoFile = NULL, GenoFileIndex = NULL,
                        control = list(AllMarkers = TRUE), Geno.mtx = NULL, R, E, Phen.mtx, Cova.mtx,
                        epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15,
-                       min.maf = 0.001, G.model = "Add") {
-  if (G.model != "Add") stop('the CUDA path implements G.model = "Add"')
+                       min.maf = 0.001, G.model = "Add", n.gpus = 1L, device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
   gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)
   check_input_Resid(pIDs = Phen.mtx$ID, gIDs = gi$ids, R = R)          # reference helper, unchanged (:1900-1913)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  ctx <- .Call("spagxe_r_create", 0L)
-  .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-  .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+  prm <- c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .Call("spagxe_r_run", ctx, 0L, gi$g, gi$n, gi$m, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
+  if (n.gpus > 1L) {
+    mg <- .Call("spagxe_r_mgpu_create", as.integer(n.gpus))
+    on.exit(.Call("spagxe_r_mgpu_destroy", mg), add = TRUE)
+    .Call("spagxe_r_mgpu_set_inputs", mg, as.double(R), as.double(E), .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+    output <- .Call("spagxe_r_mgpu_run_cct", mg, gi$g, gi$n, gi$m, prm, gi$sidx, as.double(gi$nfile), gi$a2)
+  } else {
+    ctx <- .Call("spagxe_r_create", as.integer(device))
+    on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)                 # GPU memory is released when the call returns
+    .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
+    .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+    output <- .spagxe_run(ctx, 0L, gi, prm)
+  }
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
                         "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG")
   rownames(output) <- gi$snp
@@ -49,28 +114,33 @@ SPAGxE_CCT <- function(traits = "survival/binary/quantitative/categorical", Geno
 
 SPAGxE_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categorical", g, R, E, Phen.mtx, Cova.mtx,
                                epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15,
-                               min.maf = 0.001, G.model = "Add") {
-  ctx <- .Call("spagxe_r_create", 0L)
+                               min.maf = 0.001, G.model = "Add", device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
   .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
-  drop(.Call("spagxe_r_run", ctx, 0L, matrix(g, ncol = 1), length(g), 1L, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1)))
+  gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
+  out <- .spagxe_run(ctx, 0L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
+  as.numeric(out)                                                       # numeric(10), attributes dropped like c(...)
 }
 
 SPAGxEmix_CCT <- function(traits = "survival/binary/quantitative/categorical", GenoFile = NULL, GenoFileIndex = NULL,
                           control = list(AllMarkers = TRUE), Geno.mtx = NULL, R, E, Phen.mtx, Cova.mtx, topPCs,
                           epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001,
-                          G.model = "Add", topPCs.pvalue.cutoff = 0.05, MAF.est.negative.ratio.cutoff = 0.1) {
-  gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)
+                          G.model = "Add", topPCs.pvalue.cutoff = 0.05, MAF.est.negative.ratio.cutoff = 0.1, device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)   # no ID check: commented out in the reference (:955)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  ctx <- .Call("spagxe_r_create", 0L)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
   .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
   .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .Call("spagxe_r_run", ctx, 1L, gi$g, gi$n, gi$m,
-                  c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff))
+  output <- .spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff))
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
                         "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG",
                         "MAF.est.negative.num", "MAC")
@@ -80,25 +150,71 @@ SPAGxEmix_CCT <- function(traits = "survival/binary/quantitative/categorical", G
   output
 }
 
+SPAGxEmix_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categorical", g, R, E, Phen.mtx, Cova.mtx, topPCs,
+                                  epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15,
+                                  min.maf = 0.001, G.model = "Add", topPCs.pvalue.cutoff = 0.05,
+                                  MAF.est.negative.ratio.cutoff = 0.1, device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
+  .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+  .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
+  gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
+  as.numeric(.spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff)))
+}
+
+.spagxe_set_plus <- function(ctx, obj, E) {
+  ids <- as.character(obj$ResidMat$SubjID)
+  .Call("spagxe_r_set_vectors", ctx, as.double(obj$R), as.double(E))
+  .Call("spagxe_r_set_grm", ctx, match(as.character(obj$sparseGRM$ID1), ids) - 1L, match(as.character(obj$sparseGRM$ID2), ids) - 1L,
+        as.double(obj$sparseGRM$Value), c(obj$R_GRM_R, obj$R_GRM_RE, obj$R.new_GRM_R.new), as.double(obj$R.new))
+}
+
 SPAGxE_Plus <- function(GenoFile = NULL, GenoFileIndex = NULL, control = list(AllMarkers = TRUE), Geno.mtx = NULL, E,
                         Phen.mtx, Cova.mtx, obj.SPAGxE_Plus_Nullmodel, epsilon = 0.001, Cutoff = 2,
-                        impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001, G.model = "Add") {
+                        impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001, G.model = "Add", device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
   obj <- obj.SPAGxE_Plus_Nullmodel
   gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  ids <- obj$ResidMat$SubjID
-  ctx <- .Call("spagxe_r_create", 0L)
-  .Call("spagxe_r_set_vectors", ctx, as.double(obj$R), as.double(E))
-  .Call("spagxe_r_set_grm", ctx, match(obj$sparseGRM$ID1, ids) - 1L, match(obj$sparseGRM$ID2, ids) - 1L,
-        as.double(obj$sparseGRM$Value), c(obj$R_GRM_R, obj$R_GRM_RE, obj$R.new_GRM_R.new), as.double(obj$R.new))
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .spagxe_set_plus(ctx, obj, E)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .Call("spagxe_r_run", ctx, 2L, gi$g, gi$n, gi$m, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
+  output <- .spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG",
                         "Stat.betaG", "Var.betaG", "z.betaG")
   rownames(output) <- gi$snp
   print("Analysis Complete.")
   print(Sys.time())
   output
+}
+
+SPAGxE_Plus_one_SNP <- function(g, E, Phen.mtx, Cova.mtx, obj.SPAGxE_Plus_Nullmodel, epsilon = 0.001, Cutoff = 2,
+                                impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001, G.model = "Add", device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .spagxe_set_plus(ctx, obj.SPAGxE_Plus_Nullmodel, E)
+  gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
+  as.numeric(.spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1)))
+}
+
+# The GRM quadratic forms of SPAGxE_Plus_Nullmodel (R/SPAGxEPlus_functions_MYZ.R:490-537) on the GPU: call this in place of
+# the dplyr match()/mutate() block after the model fit; `resid` are the residuals, SubjID their ids.
+SPAGxE_Plus_Nullmodel_GRM <- function(resid, E, SubjID, sparseGRM, device = 0L) {
+  ids <- as.character(SubjID)
+  g1 <- match(as.character(sparseGRM$ID1), ids); g2 <- match(as.character(sparseGRM$ID2), ids)
+  if (any(!ids %in% unique(c(as.character(sparseGRM$ID1), as.character(sparseGRM$ID2)))))
+    stop("At least one subject in residual matrix does not have GRM information.")
+  keep <- !is.na(g1) & !is.na(g2)                                       # filter(ID1 %in% SubjID & ID2 %in% SubjID)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  res <- .Call("spagxe_r_plus_nullmodel", ctx, as.double(resid), as.double(E), g1[keep] - 1L, g2[keep] - 1L, as.double(sparseGRM$Value[keep]))
+  list(ResidMat = data.frame(SubjID = SubjID, Resid = resid, RE = resid * E, R.new = res$R.new), R = resid,
+       R_GRM_R = res$scalars[1], R_GRM_RE = res$scalars[2], R.new = res$R.new, R.new_GRM_R.new = res$scalars[3],
+       sparseGRM = sparseGRM[keep, ])
 }

@@ -131,3 +131,29 @@ def test_bench_reference_arm_contract_on_cpu():
     assert "workload" in line["config"] and "model" not in line["config"]
     out1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=300)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_r_shim_compiles_against_the_c_abi():
+    """R is not installed here, so the .Call shim cannot be built with R CMD SHLIB; at least every call it makes into
+    include/spagxe.h and every R API use must type-check (gcc -fsyntax-only against minimal R declarations), and the
+    .Call names used by the R wrappers must all be registered by the shim with the right arity."""
+    import subprocess
+    shim = os.path.join(ROOT, "spagxecct_b200", "R", "spagxe_rshim.c")
+    cp = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "r_stub"), shim],
+                        capture_output=True, text=True)
+    assert cp.returncode == 0, cp.stderr
+    src = open(shim).read()
+    registered = dict(re.findall(r'\{"(spagxe_r_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', src))
+    rsrc = open(os.path.join(ROOT, "spagxecct_b200", "R", "SPAGxECCT_cuda.R")).read()
+    calls = re.findall(r'\.Call\("(spagxe_r_\w+)"((?:[^()]|\([^()]*(?:\([^()]*\)[^()]*)*\))*)\)', rsrc)
+    assert len(calls) >= 20
+    for name, args in calls:
+        assert name in registered, name
+        depth, nargs = 0, 0
+        for ch in args:
+            depth += ch in "(["; depth -= ch in ")]"
+            nargs += (ch == "," and depth == 0)
+        assert nargs == int(registered[name]), (name, nargs, registered[name])
+    # every exported Step-2 function of the reference's NAMESPACE has a wrapper
+    for fn in ["SPAGxE_CCT", "SPAGxE_CCT_one_SNP", "SPAGxEmix_CCT", "SPAGxEmix_CCT_one_SNP", "SPAGxE_Plus", "SPAGxE_Plus_one_SNP"]:
+        assert re.search(rf"^{fn} <- function\(", rsrc, re.M), fn
