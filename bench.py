@@ -266,6 +266,8 @@ def run_other(args, kind):
     ctx.set_vectors(x["R"], x["E"])
     if kind == "mix":
         ctx.set_wald(_lib.TRAIT_BINARY, x["Y"], x["Cova"]); ctx.set_pcs(x["PCs"])
+        if args.mix_cluster:
+            ctx.set_option(_lib.OPT_MIX_CLUSTER, args.mix_cluster)
         run, ncol, prm_kw = ctx.run_mix, 12, dict(min_maf=1e-5)
         metric = "SNPs/sec at N=200k, 10 PCs (SPAGxEmix_CCT Step-2 loop, device-timed)"
     else:
@@ -368,6 +370,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-affinity", action="store_true")
+    ap.add_argument("--mix-cluster", type=int, default=0)           # tuning probe for --workload mix
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

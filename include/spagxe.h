@@ -128,6 +128,7 @@ enum {
     SPAGXE_OPT_CHUNK_SNPS = 1,  /* SNPs per pipeline chunk (0 = automatic, ~1 GiB of packed rows)             */
     SPAGXE_OPT_EXACT_SPA = 2,   /* 1: per-sample CGF sums instead of the SNP-invariant quadrature (K4 vs K4c) */
     SPAGXE_OPT_MIX_PER_SNP = 3, /* 1: every SPAGxEmix SNP through the per-SNP kernel (K6b) instead of K6a      */
+    SPAGXE_OPT_MIX_CLUSTER = 5, /* CTAs per SNP in the per-SNP SPAGxEmix kernel (1..8; tuning, results agree to rounding) */
     SPAGXE_OPT_SCORE_IMPL = 4,  /* 0: tcgen05 score kernel (default), 1: fp64 CUDA-core cross-check kernel    */
     SPAGXE_OPT_PROBE_CFG = 100  /* builds with -DSPAGXE_PROBES only (tools/): score-kernel timing probes       */
 };

@@ -27,7 +27,7 @@ EXPORTS = [
     "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
-OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL = 1, 2, 3, 4
+OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL, OPT_MIX_CLUSTER = 1, 2, 3, 4, 5
 
 
 class Geno(C.Structure):

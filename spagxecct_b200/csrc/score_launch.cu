@@ -10,6 +10,7 @@
 #include "score.cuh"
 #include "score_tc.cuh"
 #include "score_tc3.cuh"
+#include "score_tc4.cuh"
 
 namespace spagxe {
 
@@ -41,6 +42,7 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN(k_score_tc3_probe<9>);
     SMEM_OPT_IN(k_score_tc3_probe<10>);
     SMEM_OPT_IN(k_score_tc3_probe<12>);
+    SMEM_OPT_IN(k_score_tc3_probe<11>);
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -110,13 +112,15 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
     const int n_row_tiles = m_pad / kTcRows;
     int want_splits = std::max(1, (4 * num_sms + n_row_tiles - 1) / n_row_tiles);
     want_splits = std::min(want_splits, std::max(1, n_tiles / 16));
-    // int32 TMEM accumulators are exact while samples per split * 2 * 128 < 2^31: at most 16,383 tiles of 512 samples
-    want_splits = std::max(want_splits, (n_tiles + 16382) / 16383);
+    // int32 TMEM accumulators are exact while samples per split * 128 * 128 < 2^31 (unsigned view of the missing code 0x80
+    // against a digit of -128): at most 255 tiles of 512 samples per split
+    want_splits = std::max(want_splits, (n_tiles + kT4MaxTilesPerSplit - 1) / kT4MaxTilesPerSplit);
     const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
     const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_items = n_row_tiles * n_splits;
     const int grid = std::min(n_items, num_sms);
 #define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
+    const uint32_t lut = 0x00018002u;   // A1-dosage byte per PLINK code: 00 -> 2, 01 (missing) -> 0x80, 10 -> 1, 11 -> 0
 #ifdef SPAGXE_PROBES
     if (tc_cfg == 99) {   // one-off diagnostic of the access pattern
         const double gb = (double)mc * g.row_bytes / 1e9;
@@ -140,11 +144,14 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 18: k_score_tc3_probe<5><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // only group 0 expands
         case 17: k_score_tc3_probe<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // B tiles not loaded
         case 16: k_score_tc3_probe<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over timing trace
-        default: k_score_unpack_mma<<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;
+        case 10: k_score_tc3_probe<11><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // round 1's product kernel
+        default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
+    const bool tc3 = (tc_cfg != 0);
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
-    k_score_unpack_mma<<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS);
+    k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);
+    const bool tc3 = false;
 #endif
 #undef TC_ARGS
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_unpack_mma launch"; return e; }
@@ -171,7 +178,8 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         }
     }
 #endif
-    k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
+    if (tc3) k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
+    else k_score_tc4_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
     *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc_reduce launch"; return e; }
     return cudaSuccess;

@@ -11,6 +11,7 @@
 // accumulate (integer adds commute); the epilogue warps zero the accumulators after reading them.
 #pragma once
 #include "score_tc.cuh"
+#ifdef SPAGXE_PROBES
 
 namespace spagxe {
 
@@ -31,8 +32,8 @@ __device__ unsigned long long g_tc_trace[kT3Warps * kT3TraceRounds * kT3TraceEv]
 #endif
 
 // The kernel body is a template over the schedule variant.  The library ships exactly one instantiation
-// (kT3Product, as the plain kernel k_score_unpack_mma below); every other value is a timing probe or an A/B
-// variant and only exists in builds with -DSPAGXE_PROBES (tools/, never the product .so).
+// kT3Product was round 1's product kernel; round 2's is score_tc4.cuh (one A matrix read as signed and unsigned bytes).
+// Everything in this file only exists in builds with -DSPAGXE_PROBES (tools/, never the product .so).
 constexpr int kT3Product = 11;   // half-round hand-over + packed bytes read before the A-buffer wait
 
 template <int kProbe>
@@ -299,13 +300,6 @@ score_tc3_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
     }
 }
 
-// K1+K2 product kernel: 2-bit unpack + exact int8 contraction on tcgen05 (the only score kernel in the product .so
-// besides the fp64 cross-check kernel k_score_v1)
-__global__ void __launch_bounds__(kT3Threads, 1)
-k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
-                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc) {
-    score_tc3_body<kT3Product>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc);
-}
 #ifdef SPAGXE_PROBES
 template <int kProbe>
 __global__ void __launch_bounds__(kT3Threads, 1)
@@ -316,3 +310,4 @@ k_score_tc3_probe(const __grid_constant__ CUtensorMap bedmap, const int8_t *__re
 #endif
 
 }  // namespace spagxe
+#endif  // SPAGXE_PROBES

@@ -1,0 +1,253 @@
+// score_tc4.cuh -- K1+K2, round-2 kernel: ONE expanded A matrix, read twice by the tensor cores.
+//
+// The round-1 kernel (score_tc3.cuh, now a probe build) expands every packed row into two int8 matrices (-dosage and
+// missing) and is paced by that expansion (LDS + 8 PRMT + 2 STTM.x16 per 16 samples and row; profiles/
+// r01_score_tc_analysis.md).  Here a row is expanded ONCE, with the byte code
+//        00 (hom A1) -> 0x02     10 (het) -> 0x01     11 (hom A2) -> 0x00     01 (missing) -> 0x80
+// and the tensor cores read that matrix twice per K chunk: once as SIGNED bytes and once as UNSIGNED bytes (the
+// a-format field of the tcgen05 instruction descriptor).  With class sums T_c of a digit column,
+//        signed view    E1 = 2 T00 + T10 - 128 T01
+//        unsigned view  E2 = 2 T00 + T10 + 128 T01          =>  T01 = (E2 - E1) / 256,   2 T00 + T10 = E1 + 128 T01
+// both exact in integers.  So: half the PRMT / STTM work and half the TMEM per sample, the same number of UTCIMMA.
+// The freed TMEM gives every expander group TWO A buffers (ping-pong), so a group expands round k+1 while the tensor
+// cores still read round k -- the serial "expand, then wait for the MMA round trip" chain of the round-1 kernel is gone.
+//
+// A full 4-entry byte LUT needs the selector nibble's mode bit (bit 3) cleared: the packed word is masked with
+// 0x77777777 (even samples) / shifted by 2 and masked (odd samples), then PRMT picks LUT[code] with the code in the low
+// two bits of each nibble; bit 2 (the neighbour's low bit) selects between two identical LUT registers.
+// The B matrix (digits of R and V, a column of ones), its tiling and the sample order inside a 64-sample chunk are
+// those of score_tc.cuh; int32 accumulation is exact while samples per split * 128 * 128 < 2^31 (<= 255 tiles of 512).
+#pragma once
+#include "score_tc.cuh"
+
+namespace spagxe {
+
+constexpr int kT4Groups = 3;
+constexpr int kT4ExpWarps = 4 * kT4Groups;                 // 12
+constexpr int kT4Warps = kT4ExpWarps + 2 + kT4Groups;      // + genotype producer, B producer, 3 MMA warps = 17
+constexpr int kT4Threads = kT4Warps * 32;
+constexpr uint32_t kT4ACols = 64;                          // TMEM columns of one A buffer: 256 samples x int8
+constexpr uint32_t kT4ColAcc = kT4Groups * 2 * kT4ACols;   // 384: accumulators (2 x 16 columns) behind the six A buffers
+constexpr int kT4MaxTilesPerSplit = 255;                   // int32 exactness of the unsigned view
+constexpr uint32_t kT4IdescS = kTcIdesc;                                   // A = s8, B = s8
+constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A = u8, B = s8
+
+__global__ void __launch_bounds__(kT4Threads, 1)
+k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bbase = sbase + kTcGStages * kTcGStageBytes;
+    const uint32_t bars = bbase + kTcBStages * kTcBTileBytes;
+    auto bar_gfull = [&](int s) { return bars + 8u * s; };
+    auto bar_gempty = [&](int s) { return bars + 8u * (kTcGStages + s); };
+    auto bar_bfull = [&](int s) { return bars + 8u * (2 * kTcGStages + s); };
+    auto bar_bempty = [&](int s) { return bars + 8u * (2 * kTcGStages + kTcBStages + s); };
+    constexpr int kB0 = 2 * kTcGStages + 2 * kTcBStages;
+    auto bar_afull = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + q * 2u + pp); };
+    auto bar_aempty = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + 2 * kT4Groups + q * 2u + pp); };
+    const uint32_t bar_accfull = bars + 8u * (kB0 + 4 * kT4Groups), bar_accempty = bars + 8u * (kB0 + 4 * kT4Groups + 1);
+    const uint32_t tmem_slot = bars + 8u * (kB0 + 4 * kT4Groups + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcGStages; s++) { mbar_init(bar_gfull(s), 1); mbar_init(bar_gempty(s), 8); }   // 2 rounds x 4 warps
+        for (int s = 0; s < kTcBStages; s++) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 2); }   // 1 commit per round
+        for (uint32_t q = 0; q < (uint32_t)kT4Groups; q++)
+            for (uint32_t pp = 0; pp < 2; pp++) { mbar_init(bar_afull(q, pp), 4); mbar_init(bar_aempty(q, pp), 1); }
+        mbar_init(bar_accfull, kT4Groups); mbar_init(bar_accempty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kT4ExpWarps) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (warp < 4) {  // zero the accumulators once; afterwards the epilogue re-zeroes them
+        const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t la = tmem_base + ((uint32_t)(warp * 32) << 16);
+        tmem_st16(la + kT4ColAcc, z); tmem_st16(la + kT4ColAcc + 16, z);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int n_items = n_row_tiles * n_splits;
+    if (warp == kT4ExpWarps) {
+        if (lane == 0) {   // ---- TMA producer: packed genotype tiles (HBM)
+            uint32_t f = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int rt = item / n_splits, ks = item % n_splits;
+                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+                for (int t = t0; t < t1; t++, f++) {
+                    const int s = f % kTcGStages;
+                    mbar_wait(bar_gempty(s), ((f / kTcGStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_gfull(s), kTcGStageBytes);
+                    tma_load_2d(sbase + s * kTcGStageBytes, &bedmap, t * kTcTileBytes, rt * kTcRows, bar_gfull(s));
+                }
+            }
+        }
+    } else if (warp == kT4ExpWarps + 1) {
+        if (lane == 0) {   // ---- bulk-copy producer: B tiles (L2)
+            uint32_t f = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int ks = item % n_splits;
+                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+                for (int t = t0; t < t1; t++, f++) {
+                    const int s = f % kTcBStages;
+                    mbar_wait(bar_bempty(s), ((f / kTcBStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_bfull(s), kTcBTileBytes);
+                    bulk_load_1d(bbase + s * kTcBTileBytes, Bmat + (int64_t)t * kTcBTileBytes, kTcBTileBytes, bar_bfull(s));
+                }
+            }
+        }
+    } else if (warp > kT4ExpWarps + 1) {
+        // ---- MMA issuer of group q: 8 K-chunks of a round, each read as signed and as unsigned bytes
+        const uint32_t q = (uint32_t)(warp - (kT4ExpWarps + 2));
+        const uint32_t ds = tmem_base + kT4ColAcc, du = tmem_base + kT4ColAcc + 16;
+        uint32_t gbase = 0, use = 0, itc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int ks = item % n_splits;
+            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
+            if (nr == 0) continue;
+            bool waited = false;
+            for (uint32_t G = gbase + ((q + 3u - gbase % 3u) % 3u); G < gbase + nr; G += 3u, use++) {
+                if (!waited) { mbar_wait(bar_accempty, (itc & 1) ^ 1); tc_fence_after(); waited = true; }
+                const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages, pp = use & 1u;
+                mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
+                mbar_wait(bar_afull(q, pp), (use >> 1) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t abase = tmem_base + (q * 2u + pp) * kT4ACols;
+                    const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const uint64_t bd = bd0 + (uint64_t)(((c4 * 4 + 2 * j) * 256) >> 4);
+                            const uint32_t acol = (uint32_t)(c4 * 16 + j * 8);
+                            tc_mma_i8_ts(ds, abase + acol, bd, kT4IdescS, 1u);
+                            tc_mma_i8_ts(du, abase + acol, bd, kT4IdescU, 1u);
+                        }
+                    }
+                    tc_commit(bar_aempty(q, pp));
+                    tc_commit(bar_bempty(sb));
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(bar_accfull);
+            __syncwarp();
+            gbase += nr; itc++;
+        }
+    } else {
+        // ---- expander warps: group q = warp / 4 fills its two A buffers in turn; thread = SNP row = TMEM lane
+        const uint32_t q = (uint32_t)(warp >> 2), quarter = (uint32_t)(warp & 3);
+        const int row = (int)quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((quarter * 32u) << 16);
+        const uint32_t swz = (uint32_t)(row & 7);
+        uint32_t gbase = 0, use = 0, itc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int rt = item / n_splits, ks = item % n_splits;
+            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
+            if (nr == 0) continue;
+            for (uint32_t G = gbase + ((q + 3u - gbase % 3u) % 3u); G < gbase + nr; G += 3u, use++) {
+                const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, pp = use & 1u;
+                mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
+                const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
+                uint4 xv[4];   // the four 16-byte chunks of this row's half stage (loads in flight together)
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const uint32_t chunk = hs * 4u + (uint32_t)c4;
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(xv[c4].x), "=r"(xv[c4].y), "=r"(xv[c4].z), "=r"(xv[c4].w)
+                                 : "r"(rowaddr + ((chunk ^ swz) << 4)));
+                }
+                mbar_wait(bar_aempty(q, pp), ((use >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t abuf = lane_addr + (q * 2u + pp) * kT4ACols;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const uint32_t x[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
+                    uint32_t d[16];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        // right shifts through IMAD.HI (FMA pipe): the ALU pipe is left to LOP3 / PRMT
+                        const uint32_t xe = x[k] & 0x77777777u;                          // even samples: code in nibble bits 0-1
+                        const uint32_t xo = __umulhi(x[k], 1u << 30) & 0x77777777u;      // odd samples (x >> 2)
+                        d[4 * k + 0] = prmt(lut, lut, xo);
+                        d[4 * k + 1] = prmt(lut, lut, xe);
+                        d[4 * k + 2] = prmt(lut, lut, __umulhi(xo, 1u << 16));
+                        d[4 * k + 3] = prmt(lut, lut, __umulhi(xe, 1u << 16));
+                    }
+                    tmem_st16(abuf + (uint32_t)(c4 * 16), d);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_afull(q, pp)); mbar_arrive(bar_gempty(s)); }
+            }
+            gbase += nr;
+            if (q == 0) {
+                // epilogue: read the two accumulator blocks (2 x 16 int32 per row), re-zero them, add to the int64 totals
+                mbar_wait(bar_accfull, itc & 1);
+                tc_fence_after();
+                uint32_t es[16], eu[16];
+                tmem_ld16(lane_addr + kT4ColAcc, es);
+                tmem_ld16(lane_addr + kT4ColAcc + 16, eu);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                tmem_st16(lane_addr + kT4ColAcc, z); tmem_st16(lane_addr + kT4ColAcc + 16, z);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty);
+                const int grow = rt * kTcRows + row;
+                if (grow < m_chunk) {
+                    unsigned long long *dst = (unsigned long long *)(acc + (int64_t)grow * 32);
+#pragma unroll
+                    for (int k = 0; k < 15; k++) {
+                        atomicAdd(dst + k, (unsigned long long)(long long)(int)es[k]);
+                        atomicAdd(dst + 16 + k, (unsigned long long)(long long)(int)eu[k]);
+                    }
+                }
+            }
+            itc++;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kT4ExpWarps) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// digit recombination for the signed / unsigned pair: per digit column k, missing sum M_k = (E2_k - E1_k) / 256 and
+// dosage sum D_k = E1_k + 128 M_k, both exact; then value = sum_k 256^k (.)_k as in tc_combine
+__global__ void k_score_tc4_reduce(const long long *__restrict__ acc, int m_chunk, const BmatInfo *__restrict__ info, SnpStats st) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_chunk) return;
+    const long long *a = acc + (int64_t)j * 32;
+    long long d[16], m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const long long e1 = a[k], e2 = a[16 + k];
+        m[k] = (e2 - e1) >> 8;            // exact: the difference is 256 * T01
+        d[k] = e1 + 128 * m[k];
+    }
+    st.D0[j] = tc_combine(d, info->sR);
+    st.D1[j] = tc_combine(d + 8, info->sV);
+    st.asum[j] = (int)d[7];
+    st.T0[j] = tc_combine(m, info->sR);
+    st.T1[j] = tc_combine(m + 8, info->sV);
+    st.nmiss[j] = (int)m[7];
+}
+
+}  // namespace spagxe

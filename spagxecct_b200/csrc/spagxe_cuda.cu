@@ -56,7 +56,7 @@ struct spagxe_ctx {
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
     bool use_tc = true; int tc_cfg = 0;
     // test / tuning hooks (spagxe_ctx_set_option); no environment variable is ever read by this library
-    int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false;
+    int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false; int opt_mix_cluster = 8;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     BbFarm *farm = nullptr;                                // SPAGxE_CCT branch-B solver farm (K5)
@@ -207,6 +207,7 @@ extern "C" int spagxe_ctx_set_option(spagxe_ctx *ctx, int option, int64_t value)
         case SPAGXE_OPT_CHUNK_SNPS: if (value < 0) break; ctx->opt_chunk_snps = value; return SPAGXE_OK;
         case SPAGXE_OPT_EXACT_SPA: ctx->opt_exact_spa = value != 0; ctx->vec_mode = -1; return SPAGXE_OK;
         case SPAGXE_OPT_MIX_PER_SNP: ctx->opt_mix_per_snp = value != 0; return SPAGXE_OK;
+        case SPAGXE_OPT_MIX_CLUSTER: if (value < 1 || value > 8) break; ctx->opt_mix_cluster = (int)value; return SPAGXE_OK;
         case SPAGXE_OPT_SCORE_IMPL: if (value != 0 && value != 1) break; ctx->use_tc = (value == 0); return SPAGXE_OK;
 #ifdef SPAGXE_PROBES
         case SPAGXE_OPT_PROBE_CFG: ctx->tc_cfg = (int)value; return SPAGXE_OK;
@@ -605,14 +606,15 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
                          ctx->d_xtx_inv, ctx->n_pcs, bp, d_out, ctx->d_b_list, ctx->d_ctr, &ctx->launches));
     }
     cudaLaunchConfig_t cfg = {};
-    const int n_clusters = std::max(1, ctx->num_sms / kBCluster);
-    cfg.gridDim = dim3((unsigned)(n_clusters * kBCluster));
+    const int mcs = ctx->opt_mix_cluster;      // CTAs cooperating on one SNP of the per-SNP route
+    const int n_clusters = std::max(1, ctx->num_sms / mcs);
+    cfg.gridDim = dim3((unsigned)(n_clusters * mcs));
     cfg.blockDim = dim3(kBThreads);
     cfg.dynamicSmemBytes = branch_b_smem(kMaxQ);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kBCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = (unsigned)mcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int *list = ctx->d_b_list;
     Counters *ctr = ctx->d_ctr;
