@@ -371,6 +371,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-affinity", action="store_true")
     ap.add_argument("--mix-cluster", type=int, default=0)           # tuning probe for --workload mix
+    ap.add_argument("--probe-cfg", type=int, default=0)             # tools only: score-kernel variant of libspagxe_cuda_probes.so
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -380,6 +381,8 @@ def main():
     import torch
     import torch.distributed as dist
     from spagxecct_b200 import Context, _lib
+    if args.probe_cfg:      # tuning runs against the probe build (make -C spagxecct_b200/csrc probes); never a reported number
+        _lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libspagxe_cuda_probes.so")
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -406,6 +409,8 @@ def main():
         vec, ycov = broadcast_inputs(dist, [vec, ycov])           # the ONE collective of the run (NCCL)
         vec = vec.contiguous(); ycov = ycov.contiguous()
     ctx = Context(local)
+    if args.probe_cfg:
+        ctx.set_option(100, args.probe_cfg)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_vectors_device(n, vec[0].data_ptr(), vec[1].data_ptr())
     ctx.set_wald_device(_lib.TRAIT_BINARY, ycov[0].data_ptr(), ycov[1].data_ptr(), 2)

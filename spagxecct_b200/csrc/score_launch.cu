@@ -43,6 +43,11 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN(k_score_tc3_probe<10>);
     SMEM_OPT_IN(k_score_tc3_probe<12>);
     SMEM_OPT_IN(k_score_tc3_probe<11>);
+    SMEM_OPT_IN((k_score_tc4_probe<4, 1>));
+    SMEM_OPT_IN((k_score_tc4_probe<6, 1>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 1>));
+    SMEM_OPT_IN((k_score_tc4_probe<2, 2>));
+    SMEM_OPT_IN((k_score_tc4_probe<2, 3>));
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -145,9 +150,14 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 17: k_score_tc3_probe<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // B tiles not loaded
         case 16: k_score_tc3_probe<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over timing trace
         case 10: k_score_tc3_probe<11><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // round 1's product kernel
+        case 41: k_score_tc4_probe<4, 1><<<grid, t4_threads(4), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 4 groups, single buffers
+        case 61: k_score_tc4_probe<6, 1><<<grid, t4_threads(6), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 6 groups, single buffers
+        case 31: k_score_tc4_probe<3, 1><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 3 groups, single buffers
+        case 22: k_score_tc4_probe<2, 2><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, ping-pong
+        case 23: k_score_tc4_probe<2, 3><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, 3 buffers
         default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
-    const bool tc3 = (tc_cfg != 0);
+    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23);
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
     k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);

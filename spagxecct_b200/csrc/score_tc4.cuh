@@ -22,19 +22,24 @@
 
 namespace spagxe {
 
-constexpr int kT4Groups = 3;
-constexpr int kT4ExpWarps = 4 * kT4Groups;                 // 12
-constexpr int kT4Warps = kT4ExpWarps + 2 + kT4Groups;      // + genotype producer, B producer, 3 MMA warps = 17
-constexpr int kT4Threads = kT4Warps * 32;
+constexpr int kT4Groups = 3;                               // product geometry: 3 groups x 2 A buffers
+constexpr int kT4Bufs = 2;
 constexpr uint32_t kT4ACols = 64;                          // TMEM columns of one A buffer: 256 samples x int8
-constexpr uint32_t kT4ColAcc = kT4Groups * 2 * kT4ACols;   // 384: accumulators (2 x 16 columns) behind the six A buffers
 constexpr int kT4MaxTilesPerSplit = 255;                   // int32 exactness of the unsigned view
+constexpr int t4_threads(int groups) { return (4 * groups + 2 + groups) * 32; }   // expanders + 2 producers + MMA warps
+constexpr int kT4Threads = t4_threads(kT4Groups);          // 17 warps
 constexpr uint32_t kT4IdescS = kTcIdesc;                                   // A = s8, B = s8
 constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A = u8, B = s8
 
-__global__ void __launch_bounds__(kT4Threads, 1)
-k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
-                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
+// NG expander groups (4 warps + 1 MMA warp each), NB A buffers per group; the product instantiation is <3, 2>
+template <int NG, int NB>
+__device__ __forceinline__ void
+score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+               int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
+    constexpr int kT4Groups = NG;
+    constexpr int kT4ExpWarps = 4 * NG;
+    constexpr uint32_t kT4ColAcc = NG * NB * kT4ACols;
+    static_assert(NG * NB * kT4ACols + 32 <= 512, "TMEM columns");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bbase = sbase + kTcGStages * kTcGStageBytes;
@@ -44,17 +49,17 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
     auto bar_bfull = [&](int s) { return bars + 8u * (2 * kTcGStages + s); };
     auto bar_bempty = [&](int s) { return bars + 8u * (2 * kTcGStages + kTcBStages + s); };
     constexpr int kB0 = 2 * kTcGStages + 2 * kTcBStages;
-    auto bar_afull = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + q * 2u + pp); };
-    auto bar_aempty = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + 2 * kT4Groups + q * 2u + pp); };
-    const uint32_t bar_accfull = bars + 8u * (kB0 + 4 * kT4Groups), bar_accempty = bars + 8u * (kB0 + 4 * kT4Groups + 1);
-    const uint32_t tmem_slot = bars + 8u * (kB0 + 4 * kT4Groups + 2);
+    auto bar_afull = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + q * NB + pp); };
+    auto bar_aempty = [&](uint32_t q, uint32_t pp) { return bars + 8u * (kB0 + NB * kT4Groups + q * NB + pp); };
+    const uint32_t bar_accfull = bars + 8u * (kB0 + 2 * NB * kT4Groups), bar_accempty = bars + 8u * (kB0 + 2 * NB * kT4Groups + 1);
+    const uint32_t tmem_slot = bars + 8u * (kB0 + 2 * NB * kT4Groups + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcGStages; s++) { mbar_init(bar_gfull(s), 1); mbar_init(bar_gempty(s), 8); }   // 2 rounds x 4 warps
         for (int s = 0; s < kTcBStages; s++) { mbar_init(bar_bfull(s), 1); mbar_init(bar_bempty(s), 2); }   // 1 commit per round
         for (uint32_t q = 0; q < (uint32_t)kT4Groups; q++)
-            for (uint32_t pp = 0; pp < 2; pp++) { mbar_init(bar_afull(q, pp), 4); mbar_init(bar_aempty(q, pp), 1); }
+            for (uint32_t pp = 0; pp < (uint32_t)NB; pp++) { mbar_init(bar_afull(q, pp), 4); mbar_init(bar_aempty(q, pp), 1); }
         mbar_init(bar_accfull, kT4Groups); mbar_init(bar_accempty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -118,14 +123,14 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
             const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
             if (nr == 0) continue;
             bool waited = false;
-            for (uint32_t G = gbase + ((q + 3u - gbase % 3u) % 3u); G < gbase + nr; G += 3u, use++) {
+            for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
                 if (!waited) { mbar_wait(bar_accempty, (itc & 1) ^ 1); tc_fence_after(); waited = true; }
-                const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages, pp = use & 1u;
+                const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages, pp = use % (uint32_t)NB;
                 mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
-                mbar_wait(bar_afull(q, pp), (use >> 1) & 1);
+                mbar_wait(bar_afull(q, pp), (use / (uint32_t)NB) & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t abase = tmem_base + (q * 2u + pp) * kT4ACols;
+                    const uint32_t abase = tmem_base + (q * (uint32_t)NB + pp) * kT4ACols;
                     const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) {
@@ -158,8 +163,8 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
             const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
             const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
             if (nr == 0) continue;
-            for (uint32_t G = gbase + ((q + 3u - gbase % 3u) % 3u); G < gbase + nr; G += 3u, use++) {
-                const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, pp = use & 1u;
+            for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
+                const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, pp = use % (uint32_t)NB;
                 mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
                 const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 uint4 xv[4];   // the four 16-byte chunks of this row's half stage (loads in flight together)
@@ -170,9 +175,9 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
                                  : "=r"(xv[c4].x), "=r"(xv[c4].y), "=r"(xv[c4].z), "=r"(xv[c4].w)
                                  : "r"(rowaddr + ((chunk ^ swz) << 4)));
                 }
-                mbar_wait(bar_aempty(q, pp), ((use >> 1) & 1) ^ 1);
+                mbar_wait(bar_aempty(q, pp), ((use / (uint32_t)NB) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t abuf = lane_addr + (q * 2u + pp) * kT4ACols;
+                const uint32_t abuf = lane_addr + (q * (uint32_t)NB + pp) * kT4ACols;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
                     const uint32_t x[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
@@ -228,6 +233,21 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
+
+// K1+K2 product kernel (the only tensor-core score kernel in the product .so)
+__global__ void __launch_bounds__(kT4Threads, 1)
+k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
+    score_tc4_body<kT4Groups, kT4Bufs>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc, lut);
+}
+#ifdef SPAGXE_PROBES
+template <int NG, int NB>
+__global__ void __launch_bounds__(t4_threads(NG), 1)
+k_score_tc4_probe(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
+                  int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
+    score_tc4_body<NG, NB>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc, lut);
+}
+#endif
 
 // digit recombination for the signed / unsigned pair: per digit column k, missing sum M_k = (E2_k - E1_k) / 256 and
 // dosage sum D_k = E1_k + 128 M_k, both exact; then value = sum_k 256^k (.)_k as in tc_combine
