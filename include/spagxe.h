@@ -33,7 +33,7 @@ enum {
     SPAGXE_ERR_CUDA = 1,        /* CUDA runtime failure (message has the detail)          */
     SPAGXE_ERR_ARG = 2,         /* bad argument (NULL, size mismatch, unknown enum)       */
     SPAGXE_ERR_STATE = 3,       /* a required spagxe_set_* call is missing                */
-    SPAGXE_ERR_UNSUPPORTED = 4, /* e.g. non-integer dosages, G.model != "Add", survival   */
+    SPAGXE_ERR_UNSUPPORTED = 4, /* e.g. non-integer dosages, categorical traits              */
     SPAGXE_ERR_CCT_STOP = 5,    /* CCT() would stop(): NA / out-of-range p (ref :2072-2087)*/
     SPAGXE_ERR_SINGULAR = 6     /* solve(t(W)%*%W) singular (ref :609)                    */
 };
@@ -77,7 +77,7 @@ typedef struct {
     double missing_cutoff;   /* 0.15; accepted and ignored like the reference (never applied)  */
     double pc_pvalue_cutoff; /* topPCs.pvalue.cutoff = 0.05 (mix only)                  */
     double neg_ratio_cutoff; /* MAF.est.negative.ratio.cutoff = 0.1 (mix only)          */
-    int32_t g_model;         /* 0 = "Add" (only model implemented on device)            */
+    int32_t g_model;         /* 0 = "Add", 1 = "Dom", 2 = "Rec" (R/SPAGxECCT.R:572-574)  */
     int32_t impute_method;   /* 0 = "fixed"                                             */
     int32_t out_location;    /* SPAGXE_LOC_HOST (default) or SPAGXE_LOC_DEVICE for `out` */
     int32_t reserved;

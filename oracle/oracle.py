@@ -61,6 +61,11 @@ def set_mean_mode(mode):
     lib().orc_set_mean_mode(C.c_int(mode))
 
 
+def set_gmodel(mode):
+    """G.model of the outer *_one_SNP functions: 0 Add, 1 Dom, 2 Rec (process-wide, like set_mean_mode)."""
+    lib().orc_set_gmodel(C.c_int(mode))
+
+
 def pnorm(x, lower=True):
     return lib().orc_pnorm(float(x), 1 if lower else 0)
 

@@ -54,6 +54,11 @@ double orc_na(void) { return orc_na_real(); }
  *            1 = R-faithful long-double mean (with 2nd pass for doubles)   */
 static int g_mean_mode = 0;
 void orc_set_mean_mode(int m) { g_mean_mode = m; }
+/* G.model of the OUTER *_one_SNP functions: 0 "Add", 1 "Dom", 2 "Rec" (R/SPAGxECCT.R:572-574, :1045-1047,
+ * R/SPAGxEPlus_functions_MYZ.R:285-287).  The inner SPA_G_one_SNP_homo_new call of SPAGxE_CCT never receives
+ * G.model (:598, :616), so orc_spa_homo always runs its prologue with "Add". */
+static int g_gmodel = 0;
+void orc_set_gmodel(int m) { g_gmodel = m; }
 
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -305,8 +310,8 @@ double orc_getprob_spa(const double *R, const double *mafvec, double maf, long n
 /* ------------------------------------------------------------------ */
 /* genotype prologue: R/SPAGxECCT.R:557-577 (dup :1030-1051, :2000-2020,
  * R/SPAGxEPlus_functions_MYZ.R:270-290).  g is modified in place.
- * returns 1 if MAF < min.maf (early NA row).  G.model "Add" only.       */
-static int prologue(double *g, long n, int g_is_int, double min_maf, double *maf_out, double *miss_out, int *touched) {
+ * returns 1 if MAF < min.maf (early NA row).  gm: G.model 0 Add, 1 Dom, 2 Rec. */
+static int prologue(double *g, long n, int g_is_int, double min_maf, double *maf_out, double *miss_out, int *touched, int gm) {
     int tch = 0;
     long n_obs;
     double MAF = r_mean_narm(g, n, g_is_int, &n_obs) / 2;
@@ -321,6 +326,8 @@ static int prologue(double *g, long n, int g_is_int, double min_maf, double *maf
         for (long i = 0; i < n; i++) g[i] = 2 - g[i];
         tch = 1;
     }
+    if (gm == 1) { for (long i = 0; i < n; i++) g[i] = (g[i] >= 1) ? 1.0 : 0.0; tch = 1; }   /* ifelse(g>=1,1,0) */
+    if (gm == 2) { for (long i = 0; i < n; i++) g[i] = (g[i] <= 1) ? 0.0 : 1.0; tch = 1; }   /* ifelse(g<=1,0,1) */
     *maf_out = MAF; *miss_out = missing_rate;
     if (touched) *touched = tch;
     return (MAF < min_maf);
@@ -336,7 +343,7 @@ void orc_spa_homo(const double *g_in, int g_is_int, const double *R, long n, dou
     double MAF, miss; int touched = 0;
     if (info) *info = 0;
     if (iters) iters[0] = iters[1] = 0;
-    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched)) {
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, 0)) {
         out[0] = MAF; out[1] = miss;
         for (int k = 2; k < 7; k++) out[k] = ORC_NA;
         if (info) *info |= 1;
@@ -609,7 +616,7 @@ int orc_cct_one_snp(int trait, const double *g_in, int g_is_int, const double *R
     memcpy(g, g_in, sizeof(double) * n);
     double MAF, miss; int rt = 0, rc = 0, touched = 0;
     if (iters) iters[0] = iters[1] = 0;
-    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched)) {
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
         out[0] = MAF; out[1] = miss; for (int k = 2; k < 10; k++) out[k] = ORC_NA;
         if (route) *route = 1; free(g); return 0;
     }
@@ -732,7 +739,7 @@ int orc_mix_one_snp(int trait, const double *g_in, int g_is_int, const double *R
     memcpy(g, g_in, sizeof(double) * n);
     double MAF, miss; int rt = 0, rc = 0, touched = 0;
     if (iters) iters[0] = iters[1] = 0;
-    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched)) {
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
         out[0] = MAF; out[1] = miss; for (int j = 2; j < 12; j++) out[j] = ORC_NA;
         if (route) *route = 1; free(g); return 0;
     }
@@ -920,7 +927,7 @@ int orc_plus_one_snp(const double *g_in, int g_is_int, const double *R, const do
     memcpy(g, g_in, sizeof(double) * n);
     double MAF, miss; int rt = 0, touched = 0;
     if (iters) iters[0] = iters[1] = 0;
-    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched)) {
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
         out[0] = MAF; out[1] = miss; for (int j = 2; j < 8; j++) out[j] = ORC_NA;
         if (route) *route = 1; free(g); return 0;
     }

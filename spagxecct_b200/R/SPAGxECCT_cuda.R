@@ -16,8 +16,10 @@
   stop('the CUDA path implements traits = "binary" and "quantitative" (survival / categorical Wald tests: use the reference)')
 }
 
+# R/SPAGxECCT.R:572-574: "Dom" / "Rec" recode g after imputation and the flip; any other string acts like "Add"
 .spagxe_gmodel <- function(G.model) {
-  if (G.model != "Add") stop('the CUDA path implements G.model = "Add"')
+  if (G.model == "Dom") return(1L)
+  if (G.model == "Rec") return(2L)
   0L
 }
 

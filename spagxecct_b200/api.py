@@ -208,9 +208,10 @@ def _prep_common(ctx, R, E):
 def _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model, **kw):
     if impute_method != "fixed":
         raise NotImplementedError('only impute.method = "fixed" exists in the reference')
-    if G_model != "Add":
-        raise NotImplementedError('only G.model = "Add" is implemented on the device')
-    return _lib.make_params(epsilon=epsilon, cutoff=Cutoff, min_maf=min_maf, missing_cutoff=missing_cutoff, **kw)
+    # ref R/SPAGxECCT.R:572-574: any other string leaves g untouched, i.e. behaves like "Add"
+    g_model = {"Dom": 1, "Rec": 2}.get(G_model, 0)
+    return _lib.make_params(epsilon=epsilon, cutoff=Cutoff, min_maf=min_maf, missing_cutoff=missing_cutoff,
+                            g_model=g_model, **kw)
 
 
 def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None, GenoFileIndex=None,

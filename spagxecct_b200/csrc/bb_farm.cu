@@ -42,6 +42,7 @@ struct FItem {   // per-item state in shared memory (identical in every CTA)
     double mafi, S, Smean, z, pnorm_, pspa;
     double tail_s[2], tail_t[2], tail_H1[2], tail_diff[2], tail_p[2];
     double D0, T0, sum_g, u;             // u: imputed dosage 2 * MAF_raw before the flip
+    double H0;                           // sum of R over hom-A1 samples (G.model Dom / Rec only)
     int tail_iter[2], tail_phase[2];     // phase: 0 Newton, 1 final evaluation, 2 done
     int w_it, w_status;                  // Wald: 0 active, 1 done, 2 rank deficient, 3 invalid
     int spa_kind;                        // homo_scalar: 0 normal, 1 SPA, 2 inner min.maf NA, 3 singular W'W
@@ -695,8 +696,9 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
             const BItem bi = A.items[b0 + threadIdx.x];
             const Prologue pr = make_prologue(bi.asum, bi.nmiss, gm.n);
             it.row = bi.row; it.snp = bi.snp; it.asum = bi.asum; it.nmiss = bi.nmiss; it.D0 = bi.D0; it.T0 = bi.T0;
-            it.gval[0] = 2.0; it.gval[1] = pr.u; it.gval[2] = 1.0; it.gval[3] = 0.0;
-            if (pr.flip) for (int c = 0; c < 4; c++) it.gval[c] = 2 - it.gval[c];
+            const GClass gc = make_gclass(pr, A.g_model);
+            for (int c = 0; c < 4; c++) it.gval[c] = gc.val[c];
+            it.H0 = bi.H0;
             for (int c = 0; c < 4; c++) it.fit[c] = 0;
             it.flip = pr.flip; it.sum_g = pr.sum_g; it.u = pr.u;
             for (int c = 0; c < kMaxQ; c++) it.beta[c] = 0;
@@ -811,6 +813,11 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
                                                 n10 * (it.gval[2] * it.gval[2])) + n11 * (it.gval[3] * it.gval[3]);
                             double S1 = it.D0 + ((it.nmiss > 0) ? it.u * it.T0 : 0.0);   // sum(g R) from the score pass (ref :582)
                             if (it.flip) S1 = 2 * vc.sumR - S1;
+                            if (A.g_model != 0) {   // recoded genotypes: class values times class sums / counts
+                                GClass gc; for (int c = 0; c < 4; c++) gc.val[c] = it.gval[c];
+                                S1 = class_dot(gc, it.D0, it.T0, it.H0, vc.sumR);
+                                it.sum_g = ((n00 * it.gval[0] + n01 * it.gval[1]) + n10 * it.gval[2]) + n11 * it.gval[3];
+                            }
                             const double a_ = (double)gm.n, b_ = it.sum_g, d_ = sg2;
                             const double det = a_ * d_ - b_ * b_;
                             if (det == 0 || !isfinite(det)) { it.spa_kind = 3; it.prep = 2; }   // solve() would stop (ref :609)

@@ -25,6 +25,7 @@ struct BbFarmArgs {
     const double *Y, *cova;    // Wald data: Phen.mtx$Y and Cova.mtx (n x p column-major)
     int p, trait;              // trait: 1 binary (glm.fit), 2 quantitative (lm)
     double min_maf;            // forwarded to the inner SPA call (ref :616)
+    int g_model;               // 0 Add, 1 Dom, 2 Rec (ref :572-574): the item's H0 separates het and hom sums
     double *out;               // M x 10 column-major result matrix (device)
     Counters *ctr;
 };

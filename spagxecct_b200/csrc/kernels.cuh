@@ -162,7 +162,7 @@ __global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int
 __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                const VecConst *__restrict__ vcp, double epsilon, double min_maf,
                                double *__restrict__ out, SpaItem *spa_list, BItem *b_list, const uint8_t *bed,
-                               int64_t pitch, Counters *ctr) {
+                               int64_t pitch, Counters *ctr, int g_model) {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = jl < m_chunk;
     const VecConst vc = *vcp;
@@ -186,6 +186,13 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
             double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
             double SV = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
             if (pr.flip) { S1 = 2 * vc.sumR - S1; SV = 2 * vc.sumV - SV; }
+            double sum_g = pr.sum_g;
+            if (g_model != 0) {   // Dom / Rec (ref :573-574): g takes one value per genotype class, MAF stays additive
+                const GClass gc = make_gclass(pr, g_model);
+                S1 = class_dot(gc, st.D0[jl], st.T0[jl], st.H0[jl], vc.sumR);
+                SV = class_dot(gc, st.D1[jl], st.T1[jl], st.H1[jl], vc.sumV);
+                sum_g = class_sum(gc, make_gcounts(asum, nmiss, st.nhom[jl], n), 1);
+            }
             const double VarG = 2 * pr.maf * (1 - pr.maf);
             const double VarS1 = vc.sumR2 * VarG;
             const double Z1 = S1 / sqrt(VarS1);
@@ -195,7 +202,7 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
                 atomicAdd(&ctr->n_branch_a, 1ULL);
                 double mafi, S, Smean, z;
                 // Cutoff is not forwarded by the reference (:598): always 2, inner min.maf 1e-5
-                int r = homo_scalar(pr.sum_g, n, SV, vc.sumV, vc.sumV2, 0.00001, 2.0, &mafi, &S, &Smean, &z);
+                int r = homo_scalar(sum_g, n, SV, vc.sumV, vc.sumV2, 0.00001, 2.0, &mafi, &S, &Smean, &z);
                 if (r == 2) {
                     o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
                 } else if (r == 0) {
@@ -216,7 +223,8 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
     int pos = list_reserve(&ctr->spa_count, want_spa);
     if (want_spa) spa_list[pos] = item;
     pos = list_reserve(&ctr->b_count, want_b);
-    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl]};
+    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl],
+                                    g_model ? st.H0[jl] : 0.0, g_model ? st.nhom[jl] : 0, 0};
 }
 
 // Reduction policies: every thread of every participating CTA gets the same fixed-order total.
@@ -917,7 +925,7 @@ __global__ void __launch_bounds__(1024) k_plus_nullmodel(const double *__restric
 __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                 const VecConst *__restrict__ vcp, PlusConst pc, double epsilon, double cutoff,
                                 double min_maf, double *__restrict__ out, SpaItem *spa_list, BItem *b_list,
-                                const uint8_t *bed, int64_t pitch, Counters *ctr) {
+                                const uint8_t *bed, int64_t pitch, Counters *ctr, int g_model) {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = jl < m_chunk;
     const VecConst vc = *vcp;
@@ -941,6 +949,11 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
             double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
             double S2 = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
             if (pr.flip) { S1 = 2 * vc.sumR - S1; S2 = 2 * vc.sumV - S2; }
+            if (g_model != 0) {   // Dom / Rec (ref R/SPAGxEPlus_functions_MYZ.R:286-287)
+                const GClass gc = make_gclass(pr, g_model);
+                S1 = class_dot(gc, st.D0[jl], st.T0[jl], st.H0[jl], vc.sumR);
+                S2 = class_dot(gc, st.D1[jl], st.T1[jl], st.H1[jl], vc.sumV);
+            }
             const double gvar = 2 * pr.maf * (1 - pr.maf);
             const double VarS1 = gvar * pc.R_GRM_R;             // ref :300
             const double Z1 = (S1 - 0) / sqrt(VarS1);
@@ -972,7 +985,8 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
     int pos = list_reserve(&ctr->spa_count, want_spa);
     if (want_spa) spa_list[pos] = item;
     pos = list_reserve(&ctr->b_count, want_b);
-    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl]};
+    if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl],
+                                    g_model ? st.H0[jl] : 0.0, g_model ? st.nhom[jl] : 0, 0};
 }
 
 // branch B of SPAGxE_Plus (ref :342-400): cluster per SNP; K7 = sparse-GRM quadratic form of R.new0
@@ -980,7 +994,7 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__rest
                                                               int64_t m_total, int64_t n,
                                                               const double *__restrict__ R, const double *__restrict__ E,
                                                               const VecConst *__restrict__ vcp, GrmCoo grm, double cutoff,
-                                                              double *__restrict__ out) {
+                                                              double *__restrict__ out, int g_model) {
     namespace cg = cooperative_groups;
     __shared__ BShared sh;
     cg::cluster_group cl = cg::this_cluster();
@@ -1001,14 +1015,19 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__rest
         const Prologue pr = make_prologue(asum, nmiss, n);
         GFromRow gf;
         gf.row = row;
-        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
-        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
+        const GClass gc = make_gclass(pr, g_model);
+        for (int c = 0; c < 4; c++) gf.gval[c] = gc.val[c];
         double S1 = bi.D0 + ((nmiss > 0) ? pr.u * bi.T0 : 0.0);
         if (pr.flip) S1 = 2 * vc.sumR - S1;
+        double sum_g = pr.sum_g;
+        if (g_model != 0) {
+            S1 = class_dot(gc, bi.D0, bi.T0, bi.H0, vc.sumR);
+            sum_g = class_sum(gc, make_gcounts(asum, nmiss, bi.nhom, n), 1);
+        }
         double v3[3] = {0, 0, 0};
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
         red.sum<3>(v3);
-        const double a = (double)n, b = pr.sum_g, d = v3[0];
+        const double a = (double)n, b = sum_g, d = v3[0];
         const double det = a * d - b * b;
         const double NA = d_na_real();
         double *o = out + j;
@@ -1157,11 +1176,18 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         const Prologue pr = make_prologue(asum, nmiss, n);
         GFromRow gf;
         gf.row = row;
-        gf.gval[0] = 2.0; gf.gval[1] = pr.u; gf.gval[2] = 1.0; gf.gval[3] = 0.0;
-        if (pr.flip) for (int c = 0; c < 4; c++) gf.gval[c] = 2 - gf.gval[c];
+        const int g_model = md.g_model;
+        const GClass gc = make_gclass(pr, g_model);
+        for (int c = 0; c < 4; c++) gf.gval[c] = gc.val[c];
         double S1 = st.D0[jl] + ((nmiss > 0) ? pr.u * st.T0[jl] : 0.0);
         double S2 = st.D1[jl] + ((nmiss > 0) ? pr.u * st.T1[jl] : 0.0);
         if (pr.flip) { S1 = 2 * vc.sumR - S1; S2 = 2 * vc.sumV - S2; }
+        double sum_g = pr.sum_g;
+        if (g_model != 0) {   // Dom / Rec (ref :1046-1047)
+            S1 = class_dot(gc, st.D0[jl], st.T0[jl], st.H0[jl], vc.sumR);
+            S2 = class_dot(gc, st.D1[jl], st.T1[jl], st.H1[jl], vc.sumV);
+            sum_g = class_sum(gc, make_gcounts(asum, nmiss, st.nhom[jl], n), 1);
+        }
         const double MAC = pr.maf * 2 * (double)n;                                   // ref :1058
         double negnum = 0;
         __syncthreads();
@@ -1288,7 +1314,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
             double v3[3] = {0, 0, 0};
             for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
             red.sum<3>(v3);
-            const double a = (double)n, b = pr.sum_g, d = v3[0];
+            const double a = (double)n, b = sum_g, d = v3[0];
             const double det = a * d - b * b;
             if (det == 0 || !isfinite(det)) {
                 if (writer) {

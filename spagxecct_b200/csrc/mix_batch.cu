@@ -39,7 +39,7 @@ template <int KPAD, int MODE>
 __global__ void __launch_bounds__(kMbThreads)
 k_mix_tile(const uint8_t *__restrict__ bed, int64_t pitch, int mc, int64_t n, int k, const double *__restrict__ pcs,
            const double *__restrict__ R, const double *__restrict__ E, const double *__restrict__ beta,
-           const int *__restrict__ asum, const int *__restrict__ nmiss, double *__restrict__ partial, int64_t per_split) {
+           const int *__restrict__ asum, const int *__restrict__ nmiss, double *__restrict__ partial, int64_t per_split, int g_model) {
     constexpr int ROW = (MODE == 0) ? KPAD : KPAD + 6;    // doubles per staged sample row (even)
     constexpr int NP = (MODE == 0) ? KPAD : kMbStats;
     __shared__ __align__(16) double xs[kMbTile * ROW];
@@ -55,8 +55,9 @@ k_mix_tile(const uint8_t *__restrict__ bed, int64_t pitch, int mc, int64_t n, in
     for (int c = 0; c < KPAD; c++) b[c] = 0;
     if (MODE == 0 && valid) {
         const Prologue pr = make_prologue(asum[j], nmiss[j], n);
-        gval[0] = 2.0; gval[1] = pr.u; gval[2] = 1.0; gval[3] = 0.0;
-        if (pr.flip) for (int c = 0; c < 4; c++) gval[c] = 2 - gval[c];
+        const GClass gc = make_gclass(pr, g_model);   // ref :1030-1047
+#pragma unroll
+        for (int c = 0; c < 4; c++) gval[c] = gc.val[c];
     }
     if (MODE == 1 && valid) {
 #pragma unroll
@@ -183,6 +184,11 @@ __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, i
             double S1 = st.D0[j] + ((nmiss > 0) ? pr.u * st.T0[j] : 0.0);
             double S2 = st.D1[j] + ((nmiss > 0) ? pr.u * st.T1[j] : 0.0);
             if (pr.flip) { S1 = 2 * vc.sumR - S1; S2 = 2 * vc.sumV - S2; }
+            if (prm.g_model != 0) {
+                const GClass gc = make_gclass(pr, prm.g_model);
+                S1 = class_dot(gc, st.D0[j], st.T0[j], st.H0[j], vc.sumR);
+                S2 = class_dot(gc, st.D1[j], st.T1[j], st.H1[j], vc.sumV);
+            }
             const double meanS1 = 2 * a[1], VarS1 = a[2];                              // ref :1105-1106
             const double Z1 = (S1 - meanS1) / sqrt(VarS1);
             const double pG = d_pnorm(-fabs(Z1), true) * 2;
@@ -244,9 +250,9 @@ static cudaError_t run_k(cudaStream_t s, int num_sms, MixScratch &ms, const uint
     if ((e = grow(&ms.part, &ms.cap_part, (int64_t)n_splits * mc * np)) != cudaSuccess) return e;
     if ((e = grow(&ms.beta, &ms.cap_beta, (int64_t)mc * KPAD)) != cudaSuccess) return e;
     dim3 grid((unsigned)blocks, (unsigned)n_splits);
-    k_mix_tile<KPAD, 0><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, nullptr, st.asum, st.nmiss, ms.part, per_split);
+    k_mix_tile<KPAD, 0><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, nullptr, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
     k_mix_beta<KPAD><<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, k, xtx_inv, ms.beta);
-    k_mix_tile<KPAD, 1><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, ms.beta, st.asum, st.nmiss, ms.part, per_split);
+    k_mix_tile<KPAD, 1><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, ms.beta, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
     k_mix_finish<<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, j0, M, n, st, vc, ms.want, prm, d_out, b_list, ctr);
     *launches += 4;
     return cudaGetLastError();

@@ -6,7 +6,7 @@
 
 namespace spagxe {
 
-struct MixBatchParams { double epsilon, cutoff, neg_ratio_cut; };
+struct MixBatchParams { double epsilon, cutoff, neg_ratio_cut; int g_model; };
 
 // device scratch of the batched path (per-SNP flags, partial sums, coefficients); owned by the calling context
 struct MixScratch;

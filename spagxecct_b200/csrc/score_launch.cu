@@ -48,6 +48,10 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN((k_score_tc4_probe<3, 1>));
     SMEM_OPT_IN((k_score_tc4_probe<2, 2>));
     SMEM_OPT_IN((k_score_tc4_probe<2, 3>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 1>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 2>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 3>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 4>));
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -94,7 +98,7 @@ static float run_probe(cudaStream_t s, int num_sms, const CUtensorMap &map, int 
 #endif
 
 cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8_t *d_rows, const ScoreGeom &g, const int8_t *d_bmat,
-                            const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err) {
+                            const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err, bool hom_pass) {
     const int mc = g.mc;
     const int m_pad = score_acc_rows(mc);
     cudaError_t e = cudaMemsetAsync(d_acc, 0, sizeof(long long) * (size_t)m_pad * 32, s);
@@ -125,7 +129,9 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
     const int n_items = n_row_tiles * n_splits;
     const int grid = std::min(n_items, num_sms);
 #define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
-    const uint32_t lut = 0x00018002u;   // A1-dosage byte per PLINK code: 00 -> 2, 01 (missing) -> 0x80, 10 -> 1, 11 -> 0
+    // A1-dosage byte per PLINK code: 00 -> 2, 01 (missing) -> 0x80, 10 -> 1, 11 -> 0.  The second pass of G.model Dom / Rec
+    // counts hom-A1 samples only (00 -> 1), which separates the dosage sums into their het and hom parts
+    const uint32_t lut = hom_pass ? 0x00008001u : 0x00018002u;
 #ifdef SPAGXE_PROBES
     if (tc_cfg == 99) {   // one-off diagnostic of the access pattern
         const double gb = (double)mc * g.row_bytes / 1e9;
@@ -155,9 +161,13 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 31: k_score_tc4_probe<3, 1><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 3 groups, single buffers
         case 22: k_score_tc4_probe<2, 2><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, ping-pong
         case 23: k_score_tc4_probe<2, 3><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, 3 buffers
+        case 51: k_score_tc4_probe<3, 2, 1><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no UTCIMMA (wrong sums)
+        case 52: k_score_tc4_probe<3, 2, 2><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // signed view only (wrong sums)
+        case 53: k_score_tc4_probe<3, 2, 3><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no expansion ALU (wrong sums)
+        case 54: k_score_tc4_probe<3, 2, 4><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no tcgen05.st (wrong sums)
         default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
-    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23);
+    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 54));
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
     k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);
@@ -188,7 +198,8 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         }
     }
 #endif
-    if (tc3) k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
+    if (hom_pass) k_score_tc4_reduce_hom<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
+    else if (tc3) k_score_tc_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
     else k_score_tc4_reduce<<<(mc + 127) / 128, 128, 0, s>>>(d_acc, mc, d_info, st);
     *launches += 2;
     if ((e = cudaGetLastError()) != cudaSuccess) { *err = "k_score_tc_reduce launch"; return e; }

@@ -24,7 +24,7 @@ int score_acc_rows(int mc);   // rows of the int64 accumulator block (32 x int64
 cudaError_t score_build_b(cudaStream_t s, const double *R, const double *V, int64_t n, BmatInfo *d_info, int8_t *d_bmat, int64_t *launches);
 // tensor-core score pass (+ digit recombination) into `st`; returns cudaSuccess or sets *err
 cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8_t *d_rows, const ScoreGeom &g, const int8_t *d_bmat,
-                            const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err);
+                            const BmatInfo *d_info, long long *d_acc, SnpStats st, int64_t *launches, std::string *err, bool hom_pass = false);
 // fp64 CUDA-core cross-check kernel (SPAGXE_SCORE=v1)
 int64_t score_v1_partial_elems(const ScoreGeom &g, int chunk_m);
 cudaError_t score_launch_v1(cudaStream_t s, const uint8_t *d_rows, const ScoreGeom &g, const double *R, const double *V,

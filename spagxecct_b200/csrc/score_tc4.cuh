@@ -32,7 +32,9 @@ constexpr uint32_t kT4IdescS = kTcIdesc;                                   // A 
 constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A = u8, B = s8
 
 // NG expander groups (4 warps + 1 MMA warp each), NB A buffers per group; the product instantiation is <3, 2>
-template <int NG, int NB>
+// PROBE (probe build only, timing experiments that give WRONG sums): 1 no UTCIMMA, 2 no unsigned-view UTCIMMA,
+// 3 no expansion ALU work (raw words stored), 4 no tcgen05.st, 5 MMA warps of a CTA issue through one elected warp order
+template <int NG, int NB, int PROBE = 0>
 __device__ __forceinline__ void
 score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
                int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
@@ -138,8 +140,8 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                         for (int j = 0; j < 2; j++) {
                             const uint64_t bd = bd0 + (uint64_t)(((c4 * 4 + 2 * j) * 256) >> 4);
                             const uint32_t acol = (uint32_t)(c4 * 16 + j * 8);
-                            tc_mma_i8_ts(ds, abase + acol, bd, kT4IdescS, 1u);
-                            tc_mma_i8_ts(du, abase + acol, bd, kT4IdescU, 1u);
+                            if (PROBE != 1) tc_mma_i8_ts(ds, abase + acol, bd, kT4IdescS, 1u);
+                            if (PROBE != 1 && PROBE != 2) tc_mma_i8_ts(du, abase + acol, bd, kT4IdescU, 1u);
                         }
                     }
                     tc_commit(bar_aempty(q, pp));
@@ -184,6 +186,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                     uint32_t d[16];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
+                        if (PROBE == 3) { d[4 * k + 0] = x[k]; d[4 * k + 1] = x[k] + 1u; d[4 * k + 2] = x[k] + 2u; d[4 * k + 3] = x[k] + 3u; continue; }
                         // right shifts through IMAD.HI (FMA pipe): the ALU pipe is left to LOP3 / PRMT
                         const uint32_t xe = x[k] & 0x77777777u;                          // even samples: code in nibble bits 0-1
                         const uint32_t xo = __umulhi(x[k], 1u << 30) & 0x77777777u;      // odd samples (x >> 2)
@@ -192,7 +195,13 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                         d[4 * k + 2] = prmt(lut, lut, __umulhi(xo, 1u << 16));
                         d[4 * k + 3] = prmt(lut, lut, __umulhi(xe, 1u << 16));
                     }
-                    tmem_st16(abuf + (uint32_t)(c4 * 16), d);
+                    if (PROBE != 4) tmem_st16(abuf + (uint32_t)(c4 * 16), d);
+                    else {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) v ^= d[k];
+                        if (v == 0x12345679u) tmem_st16(abuf + (uint32_t)(c4 * 16), d);   // keeps the expansion alive
+                    }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
@@ -241,11 +250,11 @@ k_score_unpack_mma(const __grid_constant__ CUtensorMap bedmap, const int8_t *__r
     score_tc4_body<kT4Groups, kT4Bufs>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc, lut);
 }
 #ifdef SPAGXE_PROBES
-template <int NG, int NB>
+template <int NG, int NB, int PROBE = 0>
 __global__ void __launch_bounds__(t4_threads(NG), 1)
 k_score_tc4_probe(const __grid_constant__ CUtensorMap bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
                   int n_splits, int n_row_tiles, int m_chunk, long long *__restrict__ acc, uint32_t lut) {
-    score_tc4_body<NG, NB>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc, lut);
+    score_tc4_body<NG, NB, PROBE>(bedmap, Bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, m_chunk, acc, lut);
 }
 #endif
 
@@ -268,6 +277,22 @@ __global__ void k_score_tc4_reduce(const long long *__restrict__ acc, int m_chun
     st.T0[j] = tc_combine(m, info->sR);
     st.T1[j] = tc_combine(m + 8, info->sV);
     st.nmiss[j] = (int)m[7];
+}
+
+// second pass of G.model Dom / Rec (LUT 00 -> 1, missing -> 0x80, others 0): the dosage part is the hom-A1 class sum
+__global__ void k_score_tc4_reduce_hom(const long long *__restrict__ acc, int m_chunk, const BmatInfo *__restrict__ info, SnpStats st) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m_chunk) return;
+    const long long *a = acc + (int64_t)j * 32;
+    long long d[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const long long e1 = a[k], e2 = a[16 + k];
+        d[k] = e1 + 128 * ((e2 - e1) >> 8);
+    }
+    st.H0[j] = tc_combine(d, info->sR);
+    st.H1[j] = tc_combine(d + 8, info->sV);
+    st.nhom[j] = (int)d[7];
 }
 
 }  // namespace spagxe

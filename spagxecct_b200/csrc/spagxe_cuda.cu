@@ -326,13 +326,13 @@ static int launch_spa(spagxe_ctx *ctx, const double *rv, int64_t N, int64_t M, d
 // Deferred branch B: work items accumulate on the device; a flush launches the kernel that drains them.  The item count
 // is read ON THE DEVICE (persistent grids), so the host never synchronises here and the next chunk's copies keep flowing.
 static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldData wd, double min_maf, double cutoff,
-                          double *d_out) {
+                          double *d_out, int g_model) {
     cudaStream_t s = ctx->stream();
     if (mode == 0) {   // SPAGxE_CCT: the solver farm (cooperative persistent kernel, one CTA per SM)
         BbFarmArgs a;
         a.items = ctx->d_bitems; a.count = &ctx->d_ctr->b_count; a.m_total = M; a.n = N;
         a.R = ctx->d_R; a.E = ctx->d_E; a.vc = ctx->d_vc; a.Y = wd.Y; a.cova = wd.cova; a.p = wd.p; a.trait = wd.trait;
-        a.min_maf = min_maf; a.out = d_out; a.ctr = ctx->d_ctr;
+        a.min_maf = min_maf; a.g_model = g_model; a.out = d_out; a.ctr = ctx->d_ctr;
         const char *what = "bb_farm_launch";
         cudaError_t e = bb_farm_launch(ctx->farm, s, a, &ctx->launches, &what);
         if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -354,7 +354,7 @@ static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldD
         const double *R = ctx->d_R, *E = ctx->d_E;
         const VecConst *vc = ctx->d_vc;
         GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
-        CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, items, count, ctr, M, N, R, E, vc, grm, cutoff, d_out));
+        CU(cudaLaunchKernelEx(&cfg, k_branch_b_plus, items, count, ctr, M, N, R, E, vc, grm, cutoff, d_out, g_model));
         ctx->launches++;
     }
     CU(cudaMemsetAsync(&ctx->d_ctr->b_count, 0, sizeof(int), s));
@@ -373,7 +373,7 @@ static int ensure_chunk_scratch(spagxe_ctx *ctx, const ChunkPlan &pl, bool need_
         ctx->cap_chunk_bytes = bytes;
     }
     if (pl.chunk_m > ctx->cap_m) {
-        CU(dev_realloc(&ctx->d_stats, (size_t)4 * pl.chunk_m)); CU(dev_realloc(&ctx->d_istats, (size_t)2 * pl.chunk_m));
+        CU(dev_realloc(&ctx->d_stats, (size_t)6 * pl.chunk_m)); CU(dev_realloc(&ctx->d_istats, (size_t)3 * pl.chunk_m));
         CU(dev_realloc(&ctx->d_spa_list, pl.chunk_m)); CU(dev_realloc(&ctx->d_b_list, pl.chunk_m));
         CU(dev_realloc(&ctx->d_spax_list, pl.chunk_m));
         ctx->cap_m = pl.chunk_m;
@@ -545,10 +545,11 @@ static SnpStats stats_view(spagxe_ctx *ctx, int cap) {
     SnpStats st;
     st.D0 = ctx->d_stats; st.D1 = ctx->d_stats + cap; st.T0 = ctx->d_stats + 2 * (size_t)cap; st.T1 = ctx->d_stats + 3 * (size_t)cap;
     st.asum = ctx->d_istats; st.nmiss = ctx->d_istats + cap;
+    st.H0 = ctx->d_stats + 4 * (size_t)cap; st.H1 = ctx->d_stats + 5 * (size_t)cap; st.nhom = ctx->d_istats + 2 * (size_t)cap;
     return st;
 }
 
-static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st) {
+static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan &pl, int mc, SnpStats st, int g_model = 0) {
     cudaStream_t s = ctx->stream();
     const ScoreGeom sg{pl.n, pl.row_bytes, pl.dpitch, mc};
     if (!ctx->use_tc) {   // fp64 cross-check kernel: its partial-sum scratch is only allocated when it is used
@@ -558,6 +559,7 @@ static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan 
             CU(dev_realloc(&ctx->d_partial, need)); CU(dev_realloc(&ctx->d_ipartial, need / 2));
             ctx->cap_partial = need;
         }
+        if (g_model != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "G.model Dom / Rec needs the tcgen05 score kernel (SPAGXE_OPT_SCORE_IMPL = 0)");
         CU(score_launch_v1(s, d_rows, sg, ctx->d_R, ctx->d_V, ctx->d_partial, ctx->d_ipartial, st, &ctx->launches));
         return SPAGXE_OK;
     }
@@ -570,6 +572,10 @@ static int launch_score(spagxe_ctx *ctx, const uint8_t *d_rows, const ChunkPlan 
     std::string serr;
     cudaError_t e = score_launch_tc(s, ctx->num_sms, ctx->tc_cfg, d_rows, sg, ctx->d_bmat, ctx->d_binfo, ctx->d_acc, st, &ctx->launches, &serr);
     if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", serr.c_str(), cudaGetErrorString(e));
+    if (g_model != 0) {   // hom-A1 class sums: the same kernel with a 0/1 LUT
+        e = score_launch_tc(s, ctx->num_sms, 0, d_rows, sg, ctx->d_bmat, ctx->d_binfo, ctx->d_acc, st, &ctx->launches, &serr, true);
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s (hom pass): %s", serr.c_str(), cudaGetErrorString(e));
+    }
     return SPAGXE_OK;
 }
 
@@ -600,7 +606,7 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     k_finalize_mix<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, prm->min_maf, d_out, ctx->d_b_list, ctx->d_ctr);
     LAUNCH_CHECK();
     if (!ctx->opt_mix_per_snp) {   // test hook: every SNP through the cluster kernel
-        const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff};
+        const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff, prm->g_model};
         if (!ctx->mix_scratch) ctx->mix_scratch = mix_scratch_create();
         CU(mix_batch_run(s, ctx->mix_scratch, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
                          ctx->d_xtx_inv, ctx->n_pcs, bp, d_out, ctx->d_b_list, ctx->d_ctr, &ctx->launches));
@@ -620,7 +626,7 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     Counters *ctr = ctx->d_ctr;
     const double *R = ctx->d_R, *E = ctx->d_E;
     const VecConst *vc = ctx->d_vc;
-    MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff};
+    MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff, prm->g_model};
     {   // per-cluster cache of the individual allele frequencies m_i (N doubles each)
         const int64_t need = (int64_t)n_clusters * N;
         if (need > ctx->cap_mcache) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_mcache, need)); ctx->cap_mcache = need; }
@@ -647,7 +653,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_wald first (Wald test data)", name);
     if (mode == RUN_PLUS && !ctx->have_grm) return fail(ctx, SPAGXE_ERR_STATE, "run_plus: call spagxe_set_grm first");
     if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
-    if (prm->g_model != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only G.model=\"Add\" is implemented");
+    if (prm->g_model < 0 || prm->g_model > 2) return fail(ctx, SPAGXE_ERR_ARG, "g_model must be 0 (Add), 1 (Dom) or 2 (Rec)");
     if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
     if (prm->out_ld != 0 && (prm->out_ld < g->n_snps || prm->out_location == SPAGXE_LOC_DEVICE))
         return fail(ctx, SPAGXE_ERR_ARG, "out_ld must be 0 or >= M, and only applies to a host result matrix");
@@ -686,18 +692,18 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         // reset per-chunk work-list cursors (counters keep accumulating)
         CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, (mode == RUN_MIX ? 4 : 2) * sizeof(int), s));  // branch-B items persist until flushed
         cudaEvent_t a = evp.rec(s);
-        if ((rc = launch_score(ctx, d_rows, pl, mc, st))) return rc;
+        if ((rc = launch_score(ctx, d_rows, pl, mc, st, prm->g_model))) return rc;
         cudaEvent_t b = evp.rec(s);
         score_ev.push_back({a, b});
         if (mode == RUN_CCT) {
             k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
-                                                            ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch, ctx->d_ctr);
+                                                            ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch, ctx->d_ctr, prm->g_model);
             LAUNCH_CHECK();
             if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
         } else if (mode == RUN_PLUS) {
             k_finalize_plus<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, pc, prm->epsilon, prm->cutoff,
                                                              prm->min_maf, d_out, ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch,
-                                                             ctx->d_ctr);
+                                                             ctx->d_ctr, prm->g_model);
             LAUNCH_CHECK();
             if ((rc = launch_spa(ctx, ctx->d_Rn, N, M, d_out))) return rc;
         } else {
@@ -710,7 +716,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         cudaEvent_t c = evp.rec(s);
         spa_ev.push_back({b, c});
         if (mode != RUN_MIX && (last || (own_bed && buf == 1))) {
-            if ((rc = flush_branch_b(ctx, mode == RUN_CCT ? 0 : 1, M, N, wd, prm->min_maf, prm->cutoff, d_out))) return rc;
+            if ((rc = flush_branch_b(ctx, mode == RUN_CCT ? 0 : 1, M, N, wd, prm->min_maf, prm->cutoff, d_out, prm->g_model))) return rc;
             flushed = true;
         }
         cudaEvent_t d = evp.rec(s);

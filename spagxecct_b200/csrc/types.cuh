@@ -22,11 +22,14 @@ struct SnpStats {  // per-SNP outputs of the score pass (chunk-local index)
     double *T0, *T1;  // sum over missing samples of R, V
     int *asum;        // allele sum over non-missing = n_het + 2 n_homA1
     int *nmiss;       // number of missing calls
+    // G.model Dom / Rec only (second score pass with a 0/1 LUT): sums over hom-A1 samples of R, V and their number
+    double *H0, *H1;
+    int *nhom;
 };
 
 struct SpaItem { int snp; int flags; double maf; double S; double Smean; double aux; };
 // deferred branch-B work item: everything the cluster kernel needs, valid until the next flush
-struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0; };
+struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0; double H0; int nhom, pad_; };   // H0, nhom: G.model Dom / Rec
 
 struct Counters {  // device-side diagnostics / work-list cursors
     unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
@@ -78,6 +81,7 @@ struct MixData {
     const double *xtx_inv;  // (k+1) x (k+1) inverse of [1,PCs]'[1,PCs] (SNP-invariant)
     int k;
     double pc_pcut, neg_ratio_cut;
+    int g_model;            // 0 Add, 1 Dom, 2 Rec
 };
 
 }  // namespace spagxe
