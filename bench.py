@@ -371,6 +371,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-affinity", action="store_true")
     ap.add_argument("--mix-cluster", type=int, default=0)           # tuning probe for --workload mix
+    ap.add_argument("--trait", default="binary", choices=["binary", "survival"])   # survival: a variant run (Cox Wald test in branch B), single GPU
     ap.add_argument("--probe-cfg", type=int, default=0)             # tools only: score-kernel variant of libspagxe_cuda_probes.so
     args = ap.parse_args()
     if args.impl == "reference":
@@ -414,6 +415,10 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_vectors_device(n, vec[0].data_ptr(), vec[1].data_ptr())
     ctx.set_wald_device(_lib.TRAIT_BINARY, ycov[0].data_ptr(), ycov[1].data_ptr(), 2)
+    if args.trait == "survival":   # same cohort read as time-to-event: the cases are the events (1 %), exponential times
+        assert world == 1, "--trait survival is a single-GPU variant run"
+        rs = np.random.default_rng(777)
+        ctx.set_wald_survival(rs.exponential(1.0, n) * np.where(ph["Y"] > 0, 0.5, 1.0), ph["Y"], ph["Cova"])
 
     rb = (n + 3) // 4
     pitch = (rb + 127) // 128 * 128
@@ -534,7 +539,7 @@ def main():
             "metric": "SNPs/sec at N=500k (SPAGxE_CCT Step-2 loop, device-timed)", "value": value, "unit": "SNPs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(n, m),
+            "config": dict(workload_config(n, m), **({"variant": "traits=survival: branch-B Wald test = Cox model (k_cox_wald), cpu_baseline skipped"} if args.trait == "survival" else {})),
             "e2e": e2e, "gpu_launches": int(sum(d["kernel_launches"] for d in diags)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_score_unpack_mma (2-bit unpack + score pass, tcgen05 kind::i8)",

@@ -39,7 +39,7 @@ enum {
 };
 
 /* traits: the reference's `traits=` argument (R/SPAGxECCT.R:455, :622-677) */
-enum { SPAGXE_TRAIT_BINARY = 1, SPAGXE_TRAIT_QUANTITATIVE = 2 };
+enum { SPAGXE_TRAIT_BINARY = 1, SPAGXE_TRAIT_QUANTITATIVE = 2, SPAGXE_TRAIT_SURVIVAL = 3 };
 
 /* genotype sources (R/SPAGxECCT.R:483-488: Geno.mtx or GenoFile) */
 enum {
@@ -147,6 +147,11 @@ int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *c
 
 /* same with device pointers (the multi-GPU driver hands over what arrived by the NCCL broadcast) */
 int spagxe_set_wald_device(spagxe_ctx *ctx, int trait, const double *dY, const double *dcova, int p);
+
+/* traits = "survival" (R/SPAGxECCT.R:622-634): the Wald model is coxph(Surv(Phen.mtx$surv.time, Phen.mtx$event) ~
+ * as.matrix(Cova.mtx) + E + g + g*E, iter.max = 1000) with Efron ties; host pointers, event in {0, 1}, p <= 2.
+ * SPAGxE_CCT only (spagxe_run_cct); sets the trait to SPAGXE_TRAIT_SURVIVAL.                                    */
+int spagxe_set_wald_survival(spagxe_ctx *ctx, const double *surv_time, const double *event, const double *cova, int p);
 
 /* topPCs of SPAGxEmix_CCT (R/SPAGxECCT.R:925, :1066): N x k column-major, k <= 15         */
 int spagxe_set_pcs(spagxe_ctx *ctx, const double *pcs, int k);

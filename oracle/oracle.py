@@ -139,7 +139,17 @@ def spa_homo(g, R, cutoff=2.0, min_maf=1e-5, g_is_int=False):
     return out, info.value, (its[0], its[1])
 
 
-TRAIT = {"binary": 1, "quantitative": 2}
+TRAIT = {"binary": 1, "quantitative": 2, "survival": 3}   # survival: Y = np.r_[surv.time, event] (2 n doubles)
+
+
+def coxph(X, time, event, maxiter=20):
+    """coxph(Surv(time, event) ~ X, ties = "efron") restated from coxph.fit / coxfit6.c: (coef, se, iterations, rc)."""
+    X, Xp = _f(np.asarray(X, dtype=np.float64)); time, tp = _d(time); event, ep = _d(event)
+    n, q = X.shape
+    coef = np.empty(q); se = np.empty(q); it = C.c_int()
+    rc = lib().orc_coxph(Xp, tp, ep, C.c_long(n), C.c_int(q), C.c_int(maxiter), coef.ctypes.data_as(c_dp),
+                         se.ctypes.data_as(c_dp), C.byref(it))
+    return coef, se, it.value, rc
 
 
 def _threads(nthreads):

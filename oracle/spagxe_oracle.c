@@ -560,10 +560,181 @@ int orc_lm(const double *X, const double *y, long n, int q, double *coef, double
     return 0;
 }
 
+/* ------------------------------------------------------------------ */
+/* survival::coxph(Surv(time, status) ~ X, ties = "efron", iter.max)  (call site R/SPAGxECCT.R:624).
+ * `survival` is a third-party package absent from the reference tree (DESCRIPTION Imports, no version pin); this is a
+ * restatement of its published fitter coxph.fit -> coxfit6.c: subjects ordered by time, covariates centred and scaled
+ * (columns whose values all lie in {-1, 0, 1} are left alone: coxph.control(nocenter)), accumulation from the largest
+ * time down, Efron approximation for tied deaths, beta0 = 0, Newton-Raphson with
+ * |1 - loglik_old / loglik_new| <= eps (1e-9) as the stop and step halving when the likelihood decreases, LDL'
+ * (cholesky2, toler.chol = eps^0.75), variance = inverse information at the last iterate.
+ * X is n x q column-major.  coef[q], se[q]; returns 0, or 1 when the information matrix is rank deficient.  */
+static double coxsafe(double x) { return x < -200 ? -200 : (x > 22 ? 22 : x); }
+static int cholesky2(double *m, int n, double toler) {   /* m[i*n + j], lower triangle holds L, diagonal D */
+    double eps = 0;
+    for (int i = 0; i < n; i++) { if (m[i * n + i] > eps) eps = m[i * n + i]; for (int j = i + 1; j < n; j++) m[j * n + i] = m[i * n + j]; }
+    eps = (eps == 0) ? toler : eps * toler;
+    int rank = 0;
+    for (int i = 0; i < n; i++) {
+        double pivot = m[i * n + i];
+        if (!isfinite(pivot) || pivot < eps) { m[i * n + i] = 0; continue; }
+        rank++;
+        for (int j = i + 1; j < n; j++) {
+            double temp = m[j * n + i] / pivot;
+            m[j * n + i] = temp;
+            m[j * n + j] -= temp * temp * pivot;
+            for (int k = j + 1; k < n; k++) m[k * n + j] -= temp * m[k * n + i];
+        }
+    }
+    return rank;
+}
+static void chsolve2(const double *m, int n, double *y) {
+    for (int i = 0; i < n; i++) { double t = y[i]; for (int j = 0; j < i; j++) t -= y[j] * m[i * n + j]; y[i] = t; }
+    for (int i = n - 1; i >= 0; i--) {
+        if (m[i * n + i] == 0) { y[i] = 0; continue; }
+        double t = y[i] / m[i * n + i];
+        for (int j = i + 1; j < n; j++) t -= y[j] * m[j * n + i];
+        y[i] = t;
+    }
+}
+typedef struct { double t; long i; } cox_key;
+static int cox_key_cmp(const void *a, const void *b) {
+    const cox_key *x = (const cox_key *)a, *y = (const cox_key *)b;
+    if (x->t < y->t) return -1;
+    if (x->t > y->t) return 1;
+    return (x->i > y->i) - (x->i < y->i);   /* stable, like R's order() */
+}
+/* one pass of coxfit6's accumulation loop at `beta`: loglik, u[q], imat[q*q] (upper triangle filled like imat[j][i]) */
+static double cox_pass(const double *cov, const double *stime, const int *status, long n, int q, const double *beta,
+                       double *u, double *imat) {
+    double a[16], a2[16], cmat[256], cmat2[256];
+    double loglik = 0, denom = 0;
+    for (int i = 0; i < q; i++) { u[i] = 0; a[i] = 0; a2[i] = 0; for (int j = 0; j < q; j++) { imat[i * q + j] = 0; cmat[i * q + j] = 0; cmat2[i * q + j] = 0; } }
+    for (long person = n - 1; person >= 0;) {
+        double dtime = stime[person];
+        int ndead = 0; double denom2 = 0;
+        while (person >= 0 && stime[person] == dtime) {
+            double zbeta = 0;
+            for (int i = 0; i < q; i++) zbeta += beta[i] * cov[(long)i * n + person];
+            zbeta = coxsafe(zbeta);
+            double risk = exp(zbeta);
+            if (status[person] == 0) {
+                denom += risk;
+                for (int i = 0; i < q; i++) {
+                    a[i] += risk * cov[(long)i * n + person];
+                    for (int j = 0; j <= i; j++) cmat[i * q + j] += risk * cov[(long)i * n + person] * cov[(long)j * n + person];
+                }
+            } else {
+                ndead++;
+                denom2 += risk;
+                loglik += zbeta;
+                for (int i = 0; i < q; i++) {
+                    u[i] += cov[(long)i * n + person];
+                    a2[i] += risk * cov[(long)i * n + person];
+                    for (int j = 0; j <= i; j++) cmat2[i * q + j] += risk * cov[(long)i * n + person] * cov[(long)j * n + person];
+                }
+            }
+            person--;
+        }
+        if (ndead > 0) {   /* Efron: the deaths enter the sums in ndead equal steps */
+            for (int k = 0; k < ndead; k++) {
+                denom += denom2 / ndead;
+                loglik -= log(denom);
+                for (int i = 0; i < q; i++) {
+                    a[i] += a2[i] / ndead;
+                    double temp2 = a[i] / denom;
+                    u[i] -= temp2;
+                    for (int j = 0; j <= i; j++) {
+                        cmat[i * q + j] += cmat2[i * q + j] / ndead;
+                        imat[j * q + i] += (cmat[i * q + j] - temp2 * a[j]) / denom;
+                    }
+                }
+            }
+            for (int i = 0; i < q; i++) { a2[i] = 0; for (int j = 0; j < q; j++) cmat2[i * q + j] = 0; }
+        }
+    }
+    return loglik;
+}
+int orc_coxph(const double *X, const double *time, const double *event, long n, int q, int maxiter,
+              double *coef, double *se, int *iters_out) {
+    if (q > 16) return 2;
+    cox_key *key = (cox_key *)malloc(sizeof(cox_key) * n);
+    for (long i = 0; i < n; i++) { key[i].t = time[i]; key[i].i = i; }
+    qsort(key, n, sizeof(cox_key), cox_key_cmp);
+    double *cov = (double *)malloc(sizeof(double) * n * q), *stime = (double *)malloc(sizeof(double) * n);
+    int *status = (int *)malloc(sizeof(int) * n);
+    for (long k = 0; k < n; k++) { stime[k] = key[k].t; status[k] = event[key[k].i] != 0; }
+    double scale[16];
+    for (int c = 0; c < q; c++) {
+        int zero_one = 1;
+        for (long k = 0; k < n; k++) { double v = X[(long)c * n + key[k].i]; cov[(long)c * n + k] = v; if (v != -1 && v != 0 && v != 1) zero_one = 0; }
+        scale[c] = 1.0;
+        if (!zero_one) {
+            double temp = 0;
+            for (long k = 0; k < n; k++) temp += cov[(long)c * n + k];
+            temp /= (double)n;
+            for (long k = 0; k < n; k++) cov[(long)c * n + k] -= temp;
+            temp = 0;
+            for (long k = 0; k < n; k++) temp += fabs(cov[(long)c * n + k]);
+            temp = (temp > 0) ? (double)n / temp : 1.0;
+            scale[c] = temp;
+            for (long k = 0; k < n; k++) cov[(long)c * n + k] *= temp;
+        }
+    }
+    const double eps = 1e-9, toler = pow(DBL_EPSILON, 0.75);
+    double beta[16], newbeta[16], u[16], a[16], imat[256];
+    for (int i = 0; i < q; i++) beta[i] = 0;
+    double loglik = cox_pass(cov, stime, status, n, q, beta, u, imat);
+    for (int i = 0; i < q; i++) a[i] = u[i];
+    int rank = cholesky2(imat, q, toler);
+    chsolve2(imat, q, a);
+    for (int i = 0; i < q; i++) newbeta[i] = beta[i] + a[i];
+    int halving = 0, iter, rc = (rank < q);
+    for (iter = 1; iter <= maxiter && !rc; iter++) {
+        double newlk = cox_pass(cov, stime, status, n, q, newbeta, u, imat);
+        rank = cholesky2(imat, q, toler);
+        if (rank < q) { rc = 1; break; }
+        if ((fabs(1 - (loglik / newlk)) <= eps && halving == 0) || iter == maxiter) break;
+        if (!(newlk >= loglik)) {
+            halving = 1;
+            for (int i = 0; i < q; i++) newbeta[i] = (newbeta[i] + beta[i]) / 2;
+        } else {
+            halving = 0;
+            loglik = newlk;
+            chsolve2(imat, q, u);
+            for (int i = 0; i < q; i++) { beta[i] = newbeta[i]; newbeta[i] = newbeta[i] + u[i]; }
+        }
+    }
+    if (iters_out) *iters_out = iter;
+    if (!rc) {   /* chinv2: diagonal of the inverse, column by column through the factorisation; undo the scaling */
+        for (int k = 0; k < q; k++) {
+            double e[16];
+            for (int i = 0; i < q; i++) e[i] = (i == k);
+            chsolve2(imat, q, e);
+            coef[k] = newbeta[k] * scale[k];
+            se[k] = sqrt(e[k] * scale[k] * scale[k]);
+        }
+    }
+    free(key); free(cov); free(stime); free(status);
+    return rc;
+}
+
 /* Wald p-value of the E:g term for Y ~ Cova + E + g + E:g
- * (R/SPAGxECCT.R:622-677).  trait: 1 binary (glm binomial), 2 quantitative (lm).
+ * (R/SPAGxECCT.R:622-677).  trait: 1 binary (glm binomial), 2 quantitative (lm), 3 survival (coxph: no intercept
+ * column; Y then holds 2n doubles, surv.time followed by event).
  * returns 0 ok, else error code; *pw = NA on failure.                    */
 static int wald_eg(int trait, const double *g, const double *E, const double *Y, const double *Cova, int p, long n, double *pw) {
+    if (trait == 3) {   /* coxph(Surv(surv.time, event) ~ as.matrix(Cova.mtx) + E + g + g*E, iter.max = 1000): ref :624 */
+        int qc = p + 3;
+        double *Xc = (double *)malloc(sizeof(double) * n * qc), cf[16], sc[16];
+        for (int j = 0; j < p; j++) memcpy(Xc + (long)j * n, Cova + (long)j * n, sizeof(double) * n);
+        for (long i = 0; i < n; i++) { Xc[i + (long)p * n] = E[i]; Xc[i + (long)(p + 1) * n] = g[i]; Xc[i + (long)(p + 2) * n] = E[i] * g[i]; }
+        int itc, rcx = orc_coxph(Xc, Y, Y + n, n, qc, 1000, cf, sc, &itc);
+        *pw = ORC_NA;
+        if (rcx == 0) *pw = 2 * orc_pnorm(-fabs(cf[qc - 1] / sc[qc - 1]), 1);   /* pchisq(z^2, 1, lower.tail = FALSE) */
+        free(Xc);
+        return rcx;
+    }
     int q = p + 4;
     double *X = (double *)malloc(sizeof(double) * n * q);
     for (long i = 0; i < n; i++) X[i] = 1.0;

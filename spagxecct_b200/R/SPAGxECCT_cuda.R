@@ -13,7 +13,16 @@
 .spagxe_trait <- function(traits) {
   if (traits == "binary") return(1L)
   if (traits == "quantitative") return(2L)
-  stop('the CUDA path implements traits = "binary" and "quantitative" (survival / categorical Wald tests: use the reference)')
+  if (traits == "survival") return(3L)
+  stop('the CUDA path implements traits = "binary", "quantitative" and "survival" (categorical needs ordinal::clm: use the reference)')
+}
+
+# Wald data of branch B (R/SPAGxECCT.R:622-677): Phen.mtx$Y, or Phen.mtx$surv.time / $event for a survival trait (:624)
+.spagxe_set_wald <- function(ctx, traits, Phen.mtx, Cova.mtx) {
+  if (.spagxe_trait(traits) == 3L)
+    .Call("spagxe_r_set_wald_survival", ctx, as.double(Phen.mtx$surv.time), as.double(Phen.mtx$event), as.matrix(Cova.mtx) + 0)
+  else
+    .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
 }
 
 # R/SPAGxECCT.R:572-574: "Dom" / "Rec" recode g after imputation and the flip; any other string acts like "Add"
@@ -91,10 +100,11 @@ SPAGxE_CCT <- function(traits = "survival/binary/quantitative/categorical", Geno
   check_input_Resid(pIDs = Phen.mtx$ID, gIDs = gi$ids, R = R)          # reference helper, unchanged (:1900-1913)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  prm <- c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1)
+  prm <- c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm)
   print("Start Analyzing...")
   print(Sys.time())
   if (n.gpus > 1L) {
+    if (.spagxe_trait(traits) == 3L) stop('traits = "survival" runs on one GPU')
     mg <- .Call("spagxe_r_mgpu_create", as.integer(n.gpus))
     on.exit(.Call("spagxe_r_mgpu_destroy", mg), add = TRUE)
     .Call("spagxe_r_mgpu_set_inputs", mg, as.double(R), as.double(E), .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
@@ -103,7 +113,7 @@ SPAGxE_CCT <- function(traits = "survival/binary/quantitative/categorical", Geno
     ctx <- .Call("spagxe_r_create", as.integer(device))
     on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)                 # GPU memory is released when the call returns
     .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-    .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+    .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
     output <- .spagxe_run(ctx, 0L, gi, prm)
   }
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
@@ -121,9 +131,9 @@ SPAGxE_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categorica
   ctx <- .Call("spagxe_r_create", as.integer(device))
   on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-  .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
   gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
-  out <- .spagxe_run(ctx, 0L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
+  out <- .spagxe_run(ctx, 0L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm))
   as.numeric(out)                                                       # numeric(10), attributes dropped like c(...)
 }
 
@@ -142,7 +152,7 @@ SPAGxEmix_CCT <- function(traits = "survival/binary/quantitative/categorical", G
   .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff))
+  output <- .spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm))
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
                         "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG",
                         "MAF.est.negative.num", "MAC")
@@ -163,7 +173,7 @@ SPAGxEmix_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categor
   .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
   .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
   gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
-  as.numeric(.spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff)))
+  as.numeric(.spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm)))
 }
 
 .spagxe_set_plus <- function(ctx, obj, E) {
@@ -186,7 +196,7 @@ SPAGxE_Plus <- function(GenoFile = NULL, GenoFileIndex = NULL, control = list(Al
   .spagxe_set_plus(ctx, obj, E)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1))
+  output <- .spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm))
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG",
                         "Stat.betaG", "Var.betaG", "z.betaG")
   rownames(output) <- gi$snp
@@ -202,7 +212,7 @@ SPAGxE_Plus_one_SNP <- function(g, E, Phen.mtx, Cova.mtx, obj.SPAGxE_Plus_Nullmo
   on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .spagxe_set_plus(ctx, obj.SPAGxE_Plus_Nullmodel, E)
   gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
-  as.numeric(.spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1)))
+  as.numeric(.spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm)))
 }
 
 # The GRM quadratic forms of SPAGxE_Plus_Nullmodel (R/SPAGxEPlus_functions_MYZ.R:490-537) on the GPU: call this in place of

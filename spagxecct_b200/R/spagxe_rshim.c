@@ -50,6 +50,12 @@ SEXP spagxe_r_set_wald(SEXP ptr, SEXP trait, SEXP Y, SEXP cova) {
     CHECK(ctx, spagxe_set_wald(ctx, asInteger(trait), REAL(Y), REAL(cova), ncols(cova)));
     return R_NilValue;
 }
+/* traits = "survival": Phen.mtx$surv.time, Phen.mtx$event (R/SPAGxECCT.R:624) */
+SEXP spagxe_r_set_wald_survival(SEXP ptr, SEXP time, SEXP event, SEXP cova) {
+    spagxe_ctx *ctx = get_ctx(ptr);
+    CHECK(ctx, spagxe_set_wald_survival(ctx, REAL(time), REAL(event), REAL(cova), ncols(cova)));
+    return R_NilValue;
+}
 SEXP spagxe_r_set_pcs(SEXP ptr, SEXP pcs) {
     spagxe_ctx *ctx = get_ctx(ptr);
     CHECK(ctx, spagxe_set_pcs(ctx, REAL(pcs), ncols(pcs)));
@@ -106,6 +112,7 @@ static void params_from_sexp(SEXP prm, spagxe_params *sp) {
     memset(sp, 0, sizeof *sp);
     sp->epsilon = p[0]; sp->cutoff = p[1]; sp->min_maf = p[2]; sp->missing_cutoff = p[3];
     sp->pc_pvalue_cutoff = p[4]; sp->neg_ratio_cutoff = p[5]; sp->out_location = SPAGXE_LOC_HOST;
+    if (XLENGTH(prm) > 6) sp->g_model = (int)p[6];   /* 0 "Add", 1 "Dom", 2 "Rec" (R/SPAGxECCT.R:572-574) */
 }
 
 /* attr(out, "diag") <- named numeric vector of the routing counts and device times */
@@ -183,6 +190,7 @@ static const R_CallMethodDef call_methods[] = {
     {"spagxe_r_destroy", (DL_FUNC)&spagxe_r_destroy, 1},
     {"spagxe_r_set_vectors", (DL_FUNC)&spagxe_r_set_vectors, 3},
     {"spagxe_r_set_wald", (DL_FUNC)&spagxe_r_set_wald, 4},
+    {"spagxe_r_set_wald_survival", (DL_FUNC)&spagxe_r_set_wald_survival, 4},
     {"spagxe_r_set_pcs", (DL_FUNC)&spagxe_r_set_pcs, 2},
     {"spagxe_r_set_grm", (DL_FUNC)&spagxe_r_set_grm, 6},
     {"spagxe_r_plus_nullmodel", (DL_FUNC)&spagxe_r_plus_nullmodel, 6},

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspagxe_cuda.so")
 
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_CCT_STOP, ERR_SINGULAR = range(7)
-TRAIT_BINARY, TRAIT_QUANTITATIVE = 1, 2
+TRAIT_BINARY, TRAIT_QUANTITATIVE, TRAIT_SURVIVAL = 1, 2, 3
 GENO_BED, GENO_F64, GENO_I32 = 0, 1, 2
 LOC_HOST, LOC_DEVICE = 0, 1
 GENO_COUNT_A2 = 1
@@ -23,7 +23,7 @@ EXPORTS = [
     "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
     "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
     "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
-    "spagxe_set_wald_device", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
+    "spagxe_set_wald_device", "spagxe_set_wald_survival", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
     "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
@@ -87,6 +87,7 @@ def load():
     L.spagxe_set_vectors_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.spagxe_set_wald.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_set_wald_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_set_wald_survival.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_mgpu_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     L.spagxe_mgpu_destroy.argtypes = [C.c_void_p]
     L.spagxe_mgpu_destroy.restype = None
@@ -170,6 +171,12 @@ class Context:
         Y = _f64(Y)
         cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(Y.size, -1))
         self._chk(self.L.spagxe_set_wald(self.h, int(trait), Y.ctypes.data, cova.ctypes.data, cova.shape[1]))
+
+    def set_wald_survival(self, surv_time, event, cova):
+        """traits = "survival": Phen.mtx$surv.time, Phen.mtx$event, as.matrix(Cova.mtx) (ref R/SPAGxECCT.R:624)."""
+        t = _f64(surv_time); ev = _f64(event)
+        cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(t.size, -1))
+        self._chk(self.L.spagxe_set_wald_survival(self.h, t.ctypes.data, ev.ctypes.data, cova.ctypes.data, cova.shape[1]))
 
     def set_wald_device(self, trait, dY_ptr, dcova_ptr, p):
         self._chk(self.L.spagxe_set_wald_device(self.h, int(trait), C.c_void_p(dY_ptr), C.c_void_p(dcova_ptr), int(p)))

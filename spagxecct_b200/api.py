@@ -27,14 +27,23 @@ COLS_MIX = COLS_CCT + ["MAF.est.negative.num", "MAC"]
 COLS_PLUS = ["MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG", "Stat.betaG",
              "Var.betaG", "z.betaG"]
 
-_TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE}
+_TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE, "survival": _lib.TRAIT_SURVIVAL}
 
 
 def _trait_code(traits):
     if traits not in _TRAITS:
-        raise NotImplementedError(f'traits="{traits}": only "binary" and "quantitative" Wald tests are implemented '
-                                  '(survival / categorical are listed as next in DESIGN.md)')
+        raise NotImplementedError(f'traits="{traits}": the "binary", "quantitative" and "survival" Wald tests are implemented '
+                                  '(categorical needs ordinal::clm, which the reference does not even import)')
     return _TRAITS[traits]
+
+
+def _set_wald(ctx, traits, Phen_mtx, Cova_mtx):
+    """Wald data of branch B (ref R/SPAGxECCT.R:622-677): Phen.mtx$Y, or $surv.time / $event for a survival trait."""
+    cova = np.asarray(Cova_mtx, dtype=np.float64)
+    if _trait_code(traits) == _lib.TRAIT_SURVIVAL:
+        ctx.set_wald_survival(_col(Phen_mtx, "surv.time"), _col(Phen_mtx, "event"), cova)
+    else:
+        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), cova)
 
 
 class RStop(Exception):
@@ -221,7 +230,8 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
     """Drop-in for SPAGxE_CCT (R/SPAGxECCT.R:455-530): returns an M x 10 named matrix.
     n_gpus > 1 (an addition to the reference's formals, like `n.gpus` of the R wrapper): the SNPs are cut into contiguous
     ranges over that many GPUs of the node (spagxe_mgpu_*: one NCCL broadcast of R/E/Y/Cova, no other collective)."""
-    _trait_code(traits)
+    if _trait_code(traits) == _lib.TRAIT_SURVIVAL and n_gpus > 1:
+        raise NotImplementedError('traits="survival" runs on one GPU (spagxe_mgpu_set_inputs carries a single Y vector)')
     if n_gpus > 1 and ctx is None:
         return _spagxe_cct_multi(traits, GenoFile, GenoFileIndex, control, Geno_mtx, R, E, Phen_mtx, Cova_mtx, epsilon, Cutoff,
                                  impute_method, missing_cutoff, min_maf, G_model, quiet, n_gpus)
@@ -241,7 +251,7 @@ def SPAGxE_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None,
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
-        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        _set_wald(ctx, traits, Phen_mtx, Cova_mtx)
         if not quiet:
             print('[1] "Start Analyzing..."')
             print(_now())
@@ -290,7 +300,7 @@ def SPAGxE_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, epsilon=0.001, Cutof
         g = np.asarray(g)
         G, geno = _geno_desc_from_matrix(g.reshape(-1, 1))
         _prep_common(ctx, R, E)
-        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        _set_wald(ctx, traits, Phen_mtx, Cova_mtx)
         out, _ = ctx.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
         return out[0].copy()
     finally:
@@ -317,6 +327,8 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
+        if _trait_code(traits) == _lib.TRAIT_SURVIVAL:
+            raise NotImplementedError('SPAGxEmix_CCT: the survival Wald test is implemented for SPAGxE_CCT only')
         ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
         ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
         if not quiet:

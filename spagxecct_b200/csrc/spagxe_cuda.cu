@@ -20,6 +20,7 @@
 #include "score_launch.h"
 #include "mix_batch.h"
 #include "bb_farm.h"
+#include "cox_wald.h"
 
 using namespace spagxe;
 
@@ -60,6 +61,8 @@ struct spagxe_ctx {
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     BbFarm *farm = nullptr;                                // SPAGxE_CCT branch-B solver farm (K5)
+    CoxData *cox = nullptr;                                // traits = "survival": time order, tie groups, gathered columns
+    std::vector<double> h_time, h_event;                   // Phen.mtx$surv.time / $event (host copies for the sort)
     MixScratch *mix_scratch = nullptr;                    // SPAGxEmix: scratch of the batched common path
     int64_t cap_mcache = 0; double *d_mcache = nullptr;   // SPAGxEmix: cached allele frequencies, one vector per cluster
     // pinned staging
@@ -175,6 +178,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
     mix_scratch_destroy(ctx->mix_scratch);
     bb_farm_destroy(ctx->farm);
+    cox_destroy(ctx->cox);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_util); cudaFree(ctx->d_src); cudaFree(ctx->d_sidx);
@@ -236,6 +240,7 @@ static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const
     k_vec_prep1<<<1, 1024, 0, s>>>(ctx->d_R, ctx->d_E, n, ctx->d_vc);
     LAUNCH_CHECK();
     ctx->vec_mode = -1;
+    cox_invalidate(ctx->cox);   // E is one of the Cox design columns
     // R and E must be finite: the fixed-point digits of the score pass and the SPA sums are undefined otherwise
     // (R would carry the NaN through sum() and stop in the first `if`)
     CU(cudaMemcpyAsync(ctx->h_flag, &ctx->d_vc->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -263,9 +268,11 @@ extern "C" int spagxe_set_wald_device(spagxe_ctx *ctx, int trait, const double *
 static int set_wald_common(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p, cudaMemcpyKind kind) {
     if (!ctx) return SPAGXE_ERR_ARG;
     if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_wald: call spagxe_set_vectors first");
+    if (trait == SPAGXE_TRAIT_SURVIVAL)
+        return fail(ctx, SPAGXE_ERR_ARG, "traits = survival takes two vectors: use spagxe_set_wald_survival(time, event, cova, p)");
     if (trait != SPAGXE_TRAIT_BINARY && trait != SPAGXE_TRAIT_QUANTITATIVE)
         return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
-                    "traits must be binary(1) or quantitative(2); survival/categorical Wald tests are not implemented");
+                    "traits must be binary(1), quantitative(2) or survival(3); the categorical (ordinal::clm) Wald test is not implemented");
     if (!Y || p < 0 || (p > 0 && !cova)) return fail(ctx, SPAGXE_ERR_ARG, "set_wald: bad arguments");
     if (p + 4 > kMaxQ) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "set_wald: at most %d covariates", kMaxQ - 4);
     CU(cudaSetDevice(ctx->device));
@@ -275,6 +282,34 @@ static int set_wald_common(spagxe_ctx *ctx, int trait, const double *Y, const do
     if (p > 0) CU(cudaMemcpyAsync(ctx->d_cova, cova, (size_t)ctx->n * p * sizeof(double), kind, ctx->stream()));
     CU(cudaStreamSynchronize(ctx->stream()));
     ctx->wald_p = p; ctx->wald_trait = trait;
+    return SPAGXE_OK;
+}
+
+// traits = "survival" (ref R/SPAGxECCT.R:622-634): Phen.mtx$surv.time, Phen.mtx$event and as.matrix(Cova.mtx); host pointers.
+// The time order and the gathered design columns are built at the next run (they also depend on E).
+extern "C" int spagxe_set_wald_survival(spagxe_ctx *ctx, const double *surv_time, const double *event, const double *cova, int p) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_wald_survival: call spagxe_set_vectors first");
+    if (!surv_time || !event || p < 0 || (p > 0 && !cova)) return fail(ctx, SPAGXE_ERR_ARG, "set_wald_survival: bad arguments");
+    if (p > kCoxMaxCov) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "set_wald_survival: at most %d covariate columns", kCoxMaxCov);
+    int64_t n_events = 0;
+    for (int64_t i = 0; i < ctx->n; i++) {
+        if (!std::isfinite(surv_time[i])) return fail(ctx, SPAGXE_ERR_ARG, "set_wald_survival: surv.time[%lld] is not finite", (long long)i);
+        if (event[i] != 0.0 && event[i] != 1.0) return fail(ctx, SPAGXE_ERR_ARG, "set_wald_survival: event must be 0 / 1");
+        n_events += event[i] != 0.0;
+    }
+    if (n_events == 0) return fail(ctx, SPAGXE_ERR_ARG, "set_wald_survival: no events");
+    CU(cudaSetDevice(ctx->device));
+    ctx->h_time.assign(surv_time, surv_time + ctx->n);
+    ctx->h_event.assign(event, event + ctx->n);
+    CU(dev_realloc(&ctx->d_Y, ctx->n));     // the solver farm stages a Y column; it is not used for this trait
+    CU(dev_realloc(&ctx->d_cova, (size_t)ctx->n * std::max(p, 1)));
+    CU(cudaMemcpyAsync(ctx->d_Y, event, ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream()));
+    if (p > 0) CU(cudaMemcpyAsync(ctx->d_cova, cova, (size_t)ctx->n * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream()));
+    CU(cudaStreamSynchronize(ctx->stream()));
+    ctx->wald_p = p; ctx->wald_trait = SPAGXE_TRAIT_SURVIVAL;
+    if (!ctx->cox) ctx->cox = cox_create();
+    cox_invalidate(ctx->cox);
     return SPAGXE_OK;
 }
 
@@ -336,6 +371,10 @@ static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldD
         const char *what = "bb_farm_launch";
         cudaError_t e = bb_farm_launch(ctx->farm, s, a, &ctx->launches, &what);
         if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        if (wd.trait == SPAGXE_TRAIT_SURVIVAL) {   // the farm left the Wald / CCT columns to the Cox kernel
+            e = cox_launch(ctx->cox, s, ctx->num_sms, ctx->d_bitems, &ctx->d_ctr->b_count, M, g_model, d_out, ctx->d_ctr, &ctx->launches);
+            if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "cox_launch: %s", cudaGetErrorString(e));
+        }
     } else {           // SPAGxE_Plus: one 4-CTA cluster per item, persistent over the device-side list
         constexpr int cs = 4;
         cudaLaunchConfig_t cfg = {};
@@ -653,6 +692,15 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_wald first (Wald test data)", name);
     if (mode == RUN_PLUS && !ctx->have_grm) return fail(ctx, SPAGXE_ERR_STATE, "run_plus: call spagxe_set_grm first");
     if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
+    if (mode == RUN_MIX && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL)
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the survival Wald test is implemented for SPAGxE_CCT only");
+    if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL && !cox_ready(ctx->cox)) {
+        CU(cudaSetDevice(ctx->device));
+        const char *what = "cox_setup";
+        cudaError_t ce = cox_setup(ctx->cox, ctx->stream(), ctx->n, ctx->h_time.data(), ctx->h_event.data(), ctx->d_E, ctx->d_cova,
+                                   ctx->wald_p, &what);
+        if (ce != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+    }
     if (prm->g_model < 0 || prm->g_model > 2) return fail(ctx, SPAGXE_ERR_ARG, "g_model must be 0 (Add), 1 (Dom) or 2 (Rec)");
     if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
     if (prm->out_ld != 0 && (prm->out_ld < g->n_snps || prm->out_location == SPAGXE_LOC_DEVICE))
