@@ -556,7 +556,7 @@ def main():
             "stages_ms": {"score": ms_score, "tests(finalize+SPA+branchB)": float(np.mean([d["ms_tests"] for d in diags])),
                           "spa(finalize+quadrature SPA)": ms_spa, "branch_b(solver farm)": ms_bb,
                           "total_device": float(np.mean([d["ms_total"] for d in diags]))},
-            "farm_work": {k: int(dg[k]) for k in ["bb_irls_sample_passes", "bb_tail_sample_passes", "bb_prep_sample_passes",
+            "farm_work": {k: int(dg[k]) for k in ["cox_evals", "bb_irls_sample_passes", "bb_tail_sample_passes", "bb_prep_sample_passes",
                                                   "bb_iterations", "spa_nodes"]},
             "routing": {k: int(dg[k]) for k in ["n_filtered", "n_branch_a", "n_branch_b", "n_spa", "newton_iters"]},
             "per_rank_ms": ms_all,

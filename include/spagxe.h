@@ -111,6 +111,7 @@ typedef struct {
     int64_t bb_tail_sample_passes; /* samples x CGF evaluations of branch-B SPA tails    */
     int64_t bb_prep_sample_passes; /* samples x preparation passes (counts, R.new0 sums) */
     int64_t bb_iterations;  /* lock-step iterations (grid barriers) of the farm          */
+    int64_t cox_evals;      /* traits = survival: partial-likelihood evaluations, all items */
 } spagxe_diag;
 
 /* ---- lifetime ------------------------------------------------------------- */

@@ -50,7 +50,7 @@ class Diag(C.Structure):
                [("ms_total", C.c_double), ("ms_score", C.c_double), ("ms_tests", C.c_double),
                 ("score_bytes", C.c_int64), ("ms_spa", C.c_double), ("ms_branch_b", C.c_double),
                 ("spa_nodes", C.c_int64), ("bb_irls_sample_passes", C.c_int64), ("bb_tail_sample_passes", C.c_int64),
-                ("bb_prep_sample_passes", C.c_int64), ("bb_iterations", C.c_int64)]
+                ("bb_prep_sample_passes", C.c_int64), ("bb_iterations", C.c_int64), ("cox_evals", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

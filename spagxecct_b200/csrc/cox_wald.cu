@@ -15,12 +15,13 @@
 // are in no risk set and are dropped.
 //
 // Kernel: one thread-block cluster (8 CTAs x 8 warps) per work item, persistent over the device-side item list.
-// A warp owns a contiguous run of sorted samples.  Per likelihood evaluation: pass A = per-warp totals of
-// v = (w, w x_a, w x_a x_b), w = exp(x'beta), and of the deaths behind the warp's last group end; the totals meet
-// through distributed shared memory and every warp forms its carry-in in a fixed order; pass B = the same sweep with
-// warp scans in the chunks that hold a death or a group end, the Efron terms of every death group evaluated by the lane
-// that owns its last sample.  All sums have a fixed order, so results are reproducible; every CTA redoes the scalar
-// Newton logic on identical totals.
+// Every LANE owns a contiguous run of sorted samples (the arrays are stored lane-interleaved so that the loads of a warp
+// stay coalesced).  Per likelihood evaluation: pass A = per-lane totals of v = (w, w x_a, w x_a x_b), w = exp(x'beta),
+// and of the deaths behind the lane's last group end; one warp scan, then the warp / CTA totals meet through
+// distributed shared memory and every lane forms its carry-in in a fixed order; pass B = the same walk with a running
+// prefix in registers, the Efron terms of a death group evaluated by the lane that reaches its last sample.  No
+// shuffles inside the walks, all sums have a fixed order (reproducible results); every CTA redoes the scalar Newton
+// logic on identical totals.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -54,6 +55,7 @@ struct CoxArgs {
     const int *info;        // bit 0 death, bits 1..: deaths of the tie group ending here
     int p, g_model, unit_len;
     double *out; Counters *ctr;
+    uint8_t *codes;         // per cluster: the item's 2-bit codes gathered into time order (n_eff bytes each)
 };
 
 __device__ __forceinline__ constexpr int cx_pair(int a, int b) { return 1 + kCxQ + a * (a + 1) / 2 + b; }   // b <= a
@@ -106,11 +108,23 @@ __device__ double cx_inv_diag(double (*m)[kCxQ], int q, int k) {
     return e[k];
 }
 
-// one sample of the sorted order: design row, linear predictor, the 21 values
+// one sample of the sorted order: raw operands (loaded one chunk ahead: every sweep is a dependent chain of loads
+// otherwise), then the design row, the linear predictor and the 21 values
+struct CxIn { int info, code; double e, c0, c1; };
+__device__ __forceinline__ CxIn cx_load(const CoxArgs &A, const uint8_t *__restrict__ codes, int64_t s, int64_t s_hi) {
+    CxIn in; in.info = 0; in.code = 3; in.e = 0; in.c0 = 0; in.c1 = 0;
+    if (s < s_hi) {
+        in.info = A.info[s];                      // bit 30: a valid sample (clear in the padding of the storage order)
+        in.code = __ldcg(codes + s);              // written by other SMs for this item: not through L1
+        in.e = A.x[s];
+        if (A.p > 0) in.c0 = A.x[A.n_eff + s];
+        if (A.p > 1) in.c1 = A.x[2 * A.n_eff + s];
+    }
+    return in;
+}
 struct CxSample { double x[kCxQ]; double zb; double v[kCxNV]; };
-__device__ __forceinline__ void cx_eval(const CoxArgs &A, const uint8_t *__restrict__ row, const double (&gval)[4],
-                                        const double (&b)[kCxQ], int64_t s, bool valid, CxSample &o) {
-    if (!valid) {
+__device__ __forceinline__ void cx_eval(const CxIn &in, const double (&gval)[4], const double (&b)[kCxQ], CxSample &o) {
+    if (!(in.info >> 30)) {
 #pragma unroll
         for (int k = 0; k < kCxNV; k++) o.v[k] = 0;
 #pragma unroll
@@ -118,13 +132,12 @@ __device__ __forceinline__ void cx_eval(const CoxArgs &A, const uint8_t *__restr
         o.zb = 0;
         return;
     }
-    const int i = A.perm[s];
-    const int code = (row[i >> 2] >> (2 * (i & 3))) & 3;
+    const int code = in.code;
     const double g = (code & 1) ? ((code & 2) ? gval[3] : gval[1]) : ((code & 2) ? gval[2] : gval[0]);
-    const double e = A.x[s];
+    const double e = in.e;
     o.x[0] = e; o.x[1] = g; o.x[2] = e * g;
-    o.x[3] = (A.p > 0) ? A.x[A.n_eff + s] : 0.0;
-    o.x[4] = (A.p > 1) ? A.x[2 * A.n_eff + s] : 0.0;
+    o.x[3] = in.c0;
+    o.x[4] = in.c1;
     double eta = 0;
 #pragma unroll
     for (int k = 0; k < kCxQ; k++) eta += b[k] * o.x[k];
@@ -148,7 +161,9 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
     const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int unit = rank * kCxWarps + warp;
-    const int64_t s_lo = min(A.n_eff, (int64_t)unit * A.unit_len), s_hi = min(A.n_eff, s_lo + A.unit_len);
+    // storage order: unit u, step t, lane l at index u * unit_len + 32 t + l holds sorted position u * unit_len + l * (unit_len / 32) + t,
+    // i.e. a lane walks a contiguous run of the time order while the warp's loads stay coalesced
+    const int64_t j_lo = (int64_t)unit * A.unit_len, j_hi = j_lo + A.unit_len;
     const int q = 3 + A.p;
     const int count = *A.count;
     const double NA = d_na_real();
@@ -160,7 +175,15 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
         double gval[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) gval[c] = gc.val[c];
-        __syncthreads();
+        // the item's genotype codes in time order, gathered once (every sweep then streams them)
+        uint8_t *codes = A.codes + (size_t)cluster_id * (size_t)A.n_eff;
+        cl.sync();   // the previous item's sweeps are over in every CTA of the cluster
+        for (int64_t s = (int64_t)rank * kCxThreads + threadIdx.x; s < A.n_eff; s += (int64_t)cs * kCxThreads) {
+            const int i = A.perm[s];   // -1: padding of the storage order
+            codes[s] = (i < 0) ? (uint8_t)3 : (uint8_t)((row[i >> 2] >> (2 * (i & 3))) & 3);
+        }
+        __threadfence();
+        cl.sync();
         if (threadIdx.x == 0) {
             for (int k = 0; k < kCxQ; k++) { sh.beta[k] = 0; sh.newbeta[k] = 0; }
             sh.loglik_old = 0; sh.iter = 0; sh.halving = 0; sh.status = 0; sh.pw = NA;
@@ -170,42 +193,54 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
             double b[kCxQ];
 #pragma unroll
             for (int k = 0; k < kCxQ; k++) b[k] = sh.newbeta[k];
-            // ---------------- pass A: totals of the run, deaths behind its last group end ----------------
+            // ---------------- pass A: totals of every lane's sub-run, deaths behind its last group end ----------------
+            double P[kCxNV], G[kCxNV];      // become the running prefix / open-death sums of pass B
+            bool open_lane;                 // no group end in this warp before this lane
             {
-                double accP[kCxNV], accD[kCxNV];
 #pragma unroll
-                for (int k = 0; k < kCxNV; k++) { accP[k] = 0; accD[k] = 0; }
+                for (int k = 0; k < kCxNV; k++) { P[k] = 0; G[k] = 0; }
                 int hasb = 0;
-                for (int64_t s0 = s_lo; s0 < s_hi; s0 += 32) {
-                    const int64_t s = s0 + lane;
-                    const bool valid = s < s_hi;
-                    const int info = valid ? A.info[s] : 0;
+                CxIn nxt = cx_load(A, codes, j_lo + lane, j_hi);
+                for (int64_t j = j_lo; j < j_hi; j += 32) {
+                    const CxIn cur = nxt;
+                    nxt = cx_load(A, codes, j + 32 + lane, j_hi);
+                    const int info = cur.info & 0x3fffffff;
                     CxSample sm;
-                    cx_eval(A, row, gval, b, s, valid, sm);
+                    cx_eval(cur, gval, b, sm);
                     const bool death = info & 1;
-                    const unsigned bm = __ballot_sync(0xffffffffu, (info >> 1) > 0);
 #pragma unroll
-                    for (int k = 0; k < kCxNV; k++) { accP[k] += sm.v[k]; if (death) accD[k] += sm.v[k]; }
-                    if (bm) {   // every death up to the last group end of this chunk is closed
-                        const int lb = 31 - __clz(bm);
+                    for (int k = 0; k < kCxNV; k++) { P[k] += sm.v[k]; if (death) G[k] += sm.v[k]; }
+                    if (info >> 1) {   // a death group ends here: every death so far is closed
 #pragma unroll
-                        for (int k = 0; k < kCxNV; k++) accD[k] = (lane > lb && death) ? sm.v[k] : 0.0;
+                        for (int k = 0; k < kCxNV; k++) G[k] = 0;
                         hasb = 1;
                     }
                 }
+                // lanes in order: exclusive prefix of the totals, segmented (reset at a group end) sum of the open deaths
+                int f = hasb;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int tf = __shfl_up_sync(0xffffffffu, f, o);
+#pragma unroll
+                    for (int k = 0; k < kCxNV; k++) {
+                        const double tp = __shfl_up_sync(0xffffffffu, P[k], o), tg = __shfl_up_sync(0xffffffffu, G[k], o);
+                        if (lane >= o) { P[k] += tp; if (!f) G[k] += tg; }
+                    }
+                    if (lane >= o) f |= tf;
+                }
+                if (lane == 31) {
+#pragma unroll
+                    for (int k = 0; k < kCxNV; k++) { sh.totP[warp][k] = P[k]; sh.tailD[warp][k] = G[k]; }
+                    sh.hasb[warp] = f;
+                }
+                // shift to exclusive: what the lanes before this one hold
+                const int fprev = __shfl_up_sync(0xffffffffu, f, 1);
 #pragma unroll
                 for (int k = 0; k < kCxNV; k++) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        accP[k] += __shfl_xor_sync(0xffffffffu, accP[k], o);
-                        accD[k] += __shfl_xor_sync(0xffffffffu, accD[k], o);
-                    }
+                    const double tp = __shfl_up_sync(0xffffffffu, P[k], 1), tg = __shfl_up_sync(0xffffffffu, G[k], 1);
+                    P[k] = lane ? tp : 0.0; G[k] = lane ? tg : 0.0;
                 }
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < kCxNV; k++) { sh.totP[warp][k] = accP[k]; sh.tailD[warp][k] = accD[k]; sh.contrib[warp][k] = 0; }
-                    sh.hasb[warp] = hasb;
-                }
+                open_lane = lane ? !fprev : true;
             }
             __syncthreads();
             if (warp == 0 && lane < kCxNV) {
@@ -232,109 +267,58 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
                 sh.carryG[warp][lane] = cgv;
             }
             __syncwarp();
-            // ---------------- pass B: Efron terms at the group ends ----------------
+#pragma unroll
+            for (int k = 0; k < kCxNV; k++) { P[k] += sh.carryP[warp][k]; if (open_lane) G[k] += sh.carryG[warp][k]; }
+            // ---------------- pass B: running prefix per lane, Efron terms where a death group ends ----------------
             {
-                double runP[kCxNV];
+                double ct[kCxNV];           // loglik, u[5], information (lower triangle): this lane's share
 #pragma unroll
-                for (int k = 0; k < kCxNV; k++) runP[k] = 0;
-                for (int64_t s0 = s_lo; s0 < s_hi; s0 += 32) {
-                    const int64_t s = s0 + lane;
-                    const bool valid = s < s_hi;
-                    const int info = valid ? A.info[s] : 0;
+                for (int k = 0; k < kCxNV; k++) ct[k] = 0;
+                CxIn nxt = cx_load(A, codes, j_lo + lane, j_hi);
+                for (int64_t j = j_lo; j < j_hi; j += 32) {
+                    const CxIn cur = nxt;
+                    nxt = cx_load(A, codes, j + 32 + lane, j_hi);
+                    const int info = cur.info & 0x3fffffff;
                     CxSample sm;
-                    cx_eval(A, row, gval, b, s, valid, sm);
-                    const bool death = info & 1;
+                    cx_eval(cur, gval, b, sm);
                     const int nd = info >> 1;
-                    const unsigned bm = __ballot_sync(0xffffffffu, nd > 0);
-                    const unsigned dm = __ballot_sync(0xffffffffu, death);
-                    if (!(bm | dm)) {
 #pragma unroll
-                        for (int k = 0; k < kCxNV; k++) runP[k] += sm.v[k];
-                        continue;
+                    for (int k = 0; k < kCxNV; k++) P[k] += sm.v[k];
+                    if (info & 1) {   // a death: direct terms, and it joins the open group
+                        ct[0] += sm.zb;
+#pragma unroll
+                        for (int a = 0; a < kCxQ; a++) ct[1 + a] += sm.x[a];
+#pragma unroll
+                        for (int k = 0; k < kCxNV; k++) G[k] += sm.v[k];
                     }
-                    // fold the lanes' private sums of the quiet chunks into the carry
+                    if (nd > 0) {     // the group ends here: nd Efron terms, then the group is closed
+                        for (int jd = 1; jd <= nd; jd++) {
+                            const double f = (double)(nd - jd) / (double)nd;   // share of the death sums left out
+                            const double denom = P[0] - f * G[0];
+                            const double rden = 1.0 / denom;
+                            ct[0] -= log(denom);
+                            double mean[kCxQ];
 #pragma unroll
-                    for (int k = 0; k < kCxNV; k++) {
+                            for (int a = 0; a < kCxQ; a++) { mean[a] = (P[1 + a] - f * G[1 + a]) * rden; ct[1 + a] -= mean[a]; }
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) runP[k] += __shfl_xor_sync(0xffffffffu, runP[k], o);
-                    }
-                    if (lane == 0) {
+                            for (int a = 0; a < kCxQ; a++) {
 #pragma unroll
-                        for (int k = 0; k < kCxNV; k++) sh.carryP[warp][k] += runP[k];
-                    }
-#pragma unroll
-                    for (int k = 0; k < kCxNV; k++) runP[k] = 0;
-                    // inclusive scans over the lanes: all samples (sv, in place) and deaths only (sd)
-                    double sd[kCxNV];
-#pragma unroll
-                    for (int k = 0; k < kCxNV; k++) {
-                        double a = sm.v[k], d = death ? sm.v[k] : 0.0;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const double ta = __shfl_up_sync(0xffffffffu, a, o), td = __shfl_up_sync(0xffffffffu, d, o);
-                            if (lane >= o) { a += ta; d += td; }
-                        }
-                        sm.v[k] = a; sd[k] = d;
-                    }
-                    __syncwarp();
-                    // deaths since the previous group end: inside the chunk a difference of scans, else carry + scan
-                    const unsigned below = bm & ((1u << lane) - 1u);
-                    const int pbl = below ? 31 - __clz(below) : -1;
-                    const int lb = bm ? 31 - __clz(bm) : -1;
-                    double gsum[kCxNV];
-#pragma unroll
-                    for (int k = 0; k < kCxNV; k++) {
-                        const double t = __shfl_sync(0xffffffffu, sd[k], pbl < 0 ? 0 : pbl);
-                        gsum[k] = (pbl >= 0) ? sd[k] - t : sh.carryG[warp][k] + sd[k];
-                    }
-                    // direct terms of the deaths: loglik += zbeta, u += x (lane order)
-                    for (unsigned m = dm; m; m &= m - 1) {
-                        if (lane == __ffs(m) - 1) {
-                            sh.contrib[warp][0] += sm.zb;
-#pragma unroll
-                            for (int a = 0; a < kCxQ; a++) sh.contrib[warp][1 + a] += sm.x[a];
-                        }
-                        __syncwarp();
-                    }
-                    // Efron terms of the groups that end in this chunk (lane order)
-                    for (unsigned m = bm; m; m &= m - 1) {
-                        if (lane == __ffs(m) - 1) {
-                            double P[kCxNV];
-#pragma unroll
-                            for (int k = 0; k < kCxNV; k++) P[k] = sh.carryP[warp][k] + sm.v[k];
-                            for (int jd = 1; jd <= nd; jd++) {
-                                const double f = (double)(nd - jd) / (double)nd;   // share of the death sums left out
-                                const double denom = P[0] - f * gsum[0];
-                                sh.contrib[warp][0] -= log(denom);
-                                double av[kCxQ];
-#pragma unroll
-                                for (int a = 0; a < kCxQ; a++) av[a] = P[1 + a] - f * gsum[1 + a];
-#pragma unroll
-                                for (int a = 0; a < kCxQ; a++) {
-                                    const double mean = av[a] / denom;
-                                    sh.contrib[warp][1 + a] -= mean;
-#pragma unroll
-                                    for (int c = 0; c <= a; c++) {
-                                        const double cm = P[cx_pair(a, c)] - f * gsum[cx_pair(a, c)];
-                                        sh.contrib[warp][cx_pair(a, c)] += (cm - mean * av[c]) / denom;
-                                    }
-                                }
+                                for (int c = 0; c <= a; c++)
+                                    ct[cx_pair(a, c)] += (P[cx_pair(a, c)] - f * G[cx_pair(a, c)]) * rden - mean[a] * mean[c];
                             }
                         }
-                        __syncwarp();
-                    }
-                    // carries behind this chunk
 #pragma unroll
-                    for (int k = 0; k < kCxNV; k++) {
-                        const double t31 = __shfl_sync(0xffffffffu, sm.v[k], 31);
-                        const double e31 = __shfl_sync(0xffffffffu, sd[k], 31);
-                        const double elb = __shfl_sync(0xffffffffu, sd[k], lb < 0 ? 0 : lb);
-                        if (lane == 0) {
-                            sh.carryP[warp][k] += t31;
-                            sh.carryG[warp][k] = (lb >= 0) ? e31 - elb : sh.carryG[warp][k] + e31;
-                        }
+                        for (int k = 0; k < kCxNV; k++) G[k] = 0;
                     }
-                    __syncwarp();
+                }
+#pragma unroll
+                for (int k = 0; k < kCxNV; k++) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ct[k] += __shfl_xor_sync(0xffffffffu, ct[k], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < kCxNV; k++) sh.contrib[warp][k] = ct[k];
                 }
             }
             __syncthreads();
@@ -392,6 +376,7 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
             double *o = A.out + bi.snp;
             const int64_t M = A.m_total;
             double pw = sh.pw;
+            atomicAdd(&A.ctr->cox_evals, (unsigned long long)(sh.iter + 1));   // likelihood evaluations of this item
             if (sh.status == 2 || isnan(pw)) { pw = NA; atomicAdd(&A.ctr->n_wald_fail, 1ULL); }
             double pc = NA;
             const int crc = d_cct2(o[2 * M], pw, &pc);   // p.spa of this item was written by the solver farm
@@ -419,18 +404,20 @@ __global__ void k_cox_gather(const double *__restrict__ E, const double *__restr
     if (s >= n_eff) return;
     const int c = blockIdx.y;
     const double *col = (c == 0) ? E : cova + (int64_t)(c - 1) * n;
-    x[(int64_t)c * n_eff + s] = col[perm[s]] - means[c];
+    const int i = perm[s];
+    x[(int64_t)c * n_eff + s] = (i < 0) ? 0.0 : col[i] - means[c];
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
 struct CoxData {
-    int64_t n = 0, n_eff = 0; int p = 0; bool ready = false;
+    int64_t n = 0, n_eff = 0; int p = 0, unit_len = 0; bool ready = false;   // n_eff: length of the (padded) storage order
     int *d_perm = nullptr, *d_info = nullptr; double *d_x = nullptr, *d_means = nullptr;
+    uint8_t *d_codes = nullptr; size_t cap_codes = 0;
 };
 CoxData *cox_create() { return new CoxData(); }
 void cox_destroy(CoxData *c) {
     if (!c) return;
-    cudaFree(c->d_perm); cudaFree(c->d_info); cudaFree(c->d_x); cudaFree(c->d_means);
+    cudaFree(c->d_perm); cudaFree(c->d_info); cudaFree(c->d_x); cudaFree(c->d_means); cudaFree(c->d_codes);
     delete c;
 }
 void cox_invalidate(CoxData *c) { if (c) c->ready = false; }
@@ -458,6 +445,19 @@ cudaError_t cox_setup(CoxData *c, cudaStream_t s, int64_t n, const double *h_tim
         a = e;
     }
     if (n_eff == 0) { *what = "survival Wald: no events"; return cudaErrorInvalidValue; }
+    // storage order (see k_cox_wald): unit u, step t, lane l  <-  sorted position u * unit_len + l * (unit_len / 32) + t
+    {
+        const int units = kCxCluster * kCxWarps;
+        const int64_t unit_len = ((n_eff + units - 1) / units + 31) / 32 * 32, run = unit_len / 32, n_pad = unit_len * units;
+        std::vector<int> perm_st((size_t)n_pad, -1), info_st((size_t)n_pad, 0);
+        for (int64_t j = 0; j < n_pad; j++) {
+            const int64_t u = j / unit_len, r = j % unit_len, t = r / 32, l = r % 32;
+            const int64_t sp = u * unit_len + l * run + t;
+            if (sp < n_eff) { perm_st[(size_t)j] = perm[(size_t)sp]; info_st[(size_t)j] = info[(size_t)sp] | (1 << 30); }
+        }
+        perm.swap(perm_st); info.swap(info_st);
+        n_eff = n_pad; c->unit_len = (int)unit_len;
+    }
     cudaError_t err;
     cudaFree(c->d_perm); cudaFree(c->d_info); cudaFree(c->d_x); cudaFree(c->d_means);
     c->d_perm = c->d_info = nullptr; c->d_x = c->d_means = nullptr;
@@ -481,11 +481,19 @@ cudaError_t cox_launch(CoxData *c, cudaStream_t s, int num_sms, const BItem *ite
     CoxArgs a;
     a.items = items; a.count = count; a.m_total = m_total; a.n = c->n; a.n_eff = c->n_eff;
     a.perm = c->d_perm; a.x = c->d_x; a.info = c->d_info; a.p = c->p; a.g_model = g_model;
-    const int units = kCxCluster * kCxWarps;
-    a.unit_len = (int)(((c->n_eff + units - 1) / units + 31) / 32 * 32);
+    a.unit_len = c->unit_len;
     a.out = out; a.ctr = ctr;
     cudaLaunchConfig_t cfg = {};
     const int n_clusters = std::max(1, num_sms / kCxCluster);
+    const size_t need = (size_t)n_clusters * (size_t)c->n_eff;
+    if (need > c->cap_codes) {
+        cudaError_t e0 = cudaStreamSynchronize(s);
+        if (e0 != cudaSuccess) return e0;
+        cudaFree(c->d_codes); c->d_codes = nullptr; c->cap_codes = 0;
+        if ((e0 = cudaMalloc((void **)&c->d_codes, need)) != cudaSuccess) return e0;
+        c->cap_codes = need;
+    }
+    a.codes = c->d_codes;
     cfg.gridDim = dim3((unsigned)(n_clusters * kCxCluster));
     cfg.blockDim = dim3(kCxThreads);
     cfg.dynamicSmemBytes = 0;

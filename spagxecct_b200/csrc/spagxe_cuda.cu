@@ -803,6 +803,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
         dg.bb_prep_sample_passes = (int64_t)w.prep_sample_passes; dg.bb_iterations = (int64_t)w.iterations;
     }
     fill_diag(&dg, hc, M);
+    dg.cox_evals = (int64_t)hc.cox_evals;
     dg.kernel_launches = ctx->launches;
     dg.score_bytes = M * pl.row_bytes;
     if (diag) *diag = dg;
