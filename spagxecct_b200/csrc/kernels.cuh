@@ -239,26 +239,31 @@ struct BlockRed {
 // shared memory and added in rank order by everyone.
 struct ClusterRed {
     double *scratch;  // block scratch (>= 4*32 doubles)
-    double *slot;     // this CTA's exchange slot in shared memory (>= 4 doubles)
+    double *slot;     // this CTA's exchange slots in shared memory: two alternating buffers of 4 doubles
+    mutable int par = 0;
+    // ONE cluster barrier per call: a buffer is rewritten two calls later, and every CTA has passed the barrier of the
+    // call in between after it finished reading, so no reader can still be on it
     template <int NV>
     __device__ __forceinline__ void sum(double (&v)[NV]) const {
+        static_assert(NV <= 4, "exchange slot holds 4 doubles");
         namespace cg = cooperative_groups;
         cg::cluster_group cl = cg::this_cluster();
         block_sum<NV>(v, scratch);
+        double *mine = slot + 4 * par;
+        par ^= 1;
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < NV; k++) slot[k] = v[k];
+            for (int k = 0; k < NV; k++) mine[k] = v[k];
         }
         cl.sync();
         const unsigned cs = cl.num_blocks();
 #pragma unroll
         for (int k = 0; k < NV; k++) v[k] = 0;
         for (unsigned r = 0; r < cs; r++) {
-            const double *rs = cl.map_shared_rank(slot, r);
+            const double *rs = cl.map_shared_rank(mine, r);
 #pragma unroll
             for (int k = 0; k < NV; k++) v[k] += rs[k];
         }
-        cl.sync();
     }
     __device__ __forceinline__ int rank() const { return (int)cooperative_groups::this_cluster().block_rank(); }
     __device__ __forceinline__ int size() const { return (int)cooperative_groups::this_cluster().num_blocks(); }
@@ -334,6 +339,77 @@ __device__ double spa_two_tail(const Src &src, const Red &red, int64_t i_lo, int
     if (isnan(pval2)) pval2 = pval1;
     *iters = i1 + i2;
     return pval1 + pval2;
+}
+
+// The same two tails advanced in lock step: one pass over the samples serves both Newton iterations (and both final
+// evaluations), so a SNP needs max(iterations) + 1 passes instead of their sum + 2.  Every tail sees exactly the
+// sequence of iterates and the summation order of spa_tail, so the result is bit-identical to spa_two_tail.
+template <class Src, class Red>
+__device__ double spa_two_tail_fused(const Src &src, const Red &red, int64_t i_lo, int64_t i_hi, double s_hi, double s_lo,
+                                     int *iters) {
+    const double tol = 0x1p-13;
+    const double sv[2] = {s_hi, s_lo};
+    double t[2] = {0, 0}, H1[2] = {0, 0}, diff[2] = {CUDART_INF, CUDART_INF}, pv[2] = {0, 0};
+    int it[2] = {0, 0}, phase[2] = {0, 0};   // 0 Newton, 1 final evaluation pending, 2 done
+    for (;;) {
+        if (phase[0] == 2 && phase[1] == 2) break;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (phase[h] == 0 && ++it[h] > 100) { it[h] = 100; pv[h] = 0.0; phase[h] = 2; }   // maxiter: t = NA -> p = 0 (ref :1846, :1873)
+        }
+        if (phase[0] == 2 && phase[1] == 2) break;
+        double v[4] = {0, 0, 0, 0};
+#pragma unroll 2
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, maf, w, k1, k2;
+            src.get(i, r, maf, w);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (phase[h] == 2) continue;
+                cgf_k12(t[h] * r, maf, k1, k2);
+                v[2 * h] += w * ((phase[h] == 0) ? (r * k1) : cgf_k0(t[h] * r, maf));
+                v[2 * h + 1] += w * ((r * r) * k2);
+            }
+        }
+        red.template sum<4>(v);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (phase[h] == 1) {
+                const double temp1 = t[h] * sv[h] - v[2 * h];
+                const double w = d_sign(t[h]) * sqrt(2 * temp1);
+                const double vv = t[h] * sqrt(v[2 * h + 1]);
+                double pval = d_pnorm(w + 1 / w * log(vv / w), h == 1);
+                if (isnan(pval)) pval = 0;
+                pv[h] = pval; phase[h] = 2;
+            } else if (phase[h] == 0) {
+                const double old_t = t[h], old_diff = diff[h], old_H1 = H1[h];
+                H1[h] = v[2 * h] - sv[h];
+                double d = -1 * H1[h] / v[2 * h + 1];
+                if (isnan(d)) d = 5;
+                bool brk = false;
+                if (isnan(H1[h]) || isinf(H1[h])) { t[h] = d_sign(sv[h]) * CUDART_INF; brk = true; }
+                else {
+                    if (d_sign(H1[h]) != d_sign(old_H1)) {
+                        int guard = 0;
+                        while (fabs(d) > fabs(old_diff) - tol && guard++ < 1200) d = d / 2;
+                    }
+                    if (isnan(d)) d = 5;
+                    if (fabs(d) < tol) brk = true;
+                    else t[h] = old_t + d;
+                }
+                diff[h] = d;
+                if (brk) {
+                    if (it[h] == 100) t[h] = CUDART_NAN;
+                    if (!isfinite(t[h])) { pv[h] = 0.0; phase[h] = 2; }   // every non-finite root yields NA -> 0 (ref :1873)
+                    else phase[h] = 1;
+                }
+            }
+        }
+    }
+    double p2 = pv[1];
+    if (isnan(p2)) p2 = pv[0];
+    *iters = it[0] + it[1];
+    return pv[0] + p2;
 }
 
 struct SrcHomo {  // SNP-invariant vector, scalar MAF (SPAGxE_CCT branch A, SPAGxE_Plus)
@@ -522,7 +598,7 @@ struct BShared {  // static shared state of the branch-B kernel
     double rhs[kMaxQ], beta[kMaxQ];
     double ne_part[kBMaxEnt];
     double scratch[4 * 32];
-    double slot[4];
+    double slot[8];
     double se2; int ok;
 };
 
@@ -1153,7 +1229,8 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                                                         const double *__restrict__ R, const double *__restrict__ E,
                                                         const VecConst *__restrict__ vcp, WaldData wd, MixData md,
                                                         double epsilon, double cutoff, double *__restrict__ out,
-                                                        double *__restrict__ mcache_all) {
+                                                        double *__restrict__ mcache_all, const double *__restrict__ hbeta,
+                                                        int hbeta_ld, const MixHand *__restrict__ hand) {
     namespace cg = cooperative_groups;
     extern __shared__ double tile[];
     __shared__ BShared sh;
@@ -1169,11 +1246,40 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
     const int k = md.k, k1 = md.k + 1;
     const double NA = d_na_real();
     for (int idx = cluster_id; idx < count; idx += n_clusters) {
-        const int jl = list[idx];
+        const int entry = list[idx];
+        const int jl = entry & (kMixHandFlag - 1);
         const int64_t j = snp0 + jl;
         const uint8_t *row = bed + (int64_t)jl * pitch;
         const int asum = st.asum[jl], nmiss = st.nmiss[jl];
         const Prologue pr = make_prologue(asum, nmiss, n);
+        if (hand && (entry & kMixHandFlag)) {
+            // ---- the batched path finished everything but the saddlepoint tails (ref :1127-1140) ----
+            const MixHand h = hand[jl];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                ms.af.kind = 1; ms.af.maf = pr.maf; ms.af.k = k; ms.af.nsel = 0;
+                for (int a = 0; a < k1; a++) ms.af.beta[a] = hbeta[(int64_t)jl * hbeta_ld + a];
+            }
+            __syncthreads();
+            double *mc = mcache_all ? mcache_all + (int64_t)cluster_id * n : nullptr;
+            if (mc) for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) mc[i] = af_eval(ms.af, md.pcs, n, i);
+            SrcMix src;
+            src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row; src.mcache = mc;
+            src.lambda = h.lambda; src.adj = 0;
+            int iters = 0;
+            const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(h.S_GxE, 2 * h.Smean - h.S_GxE),
+                                                 fmin(h.S_GxE, 2 * h.Smean - h.S_GxE), &iters);
+            if (rank == 0 && threadIdx.x == 0) {
+                double *o = out + j;
+                o[2 * m_total] = ps; o[3 * m_total] = ps; o[4 * m_total] = ps;
+                o[5 * m_total] = d_pnorm(fabs(h.z), false) + d_pnorm(-fabs(h.z), true);
+                o[6 * m_total] = h.pG; o[7 * m_total] = h.S1; o[8 * m_total] = h.VarS1; o[9 * m_total] = h.Z1;
+                o[10 * m_total] = h.negnum; o[11 * m_total] = h.MAC;
+                atomicAdd(&ctr->n_branch_a, 1ULL); atomicAdd(&ctr->n_spa, 1ULL);
+                atomicAdd(&ctr->newton_iters, (unsigned long long)iters);
+            }
+            continue;
+        }
         GFromRow gf;
         gf.row = row;
         const int g_model = md.g_model;
@@ -1303,8 +1409,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                 po[0] = po[1] = po[2] = po[3] = pn;
             } else {
                 spa = true;
-                const double ps = spa_two_tail(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE),
-                                               CUDART_INF, &iters);
+                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE), &iters);
                 po[0] = po[1] = po[2] = ps;
                 po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             }
@@ -1343,7 +1448,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
             if (fabs(z) < cutoff) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
             else {
                 spa = true;
-                pspa = spa_two_tail(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), CUDART_INF, &iters);
+                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), &iters);
                 pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             }
             int wfail;

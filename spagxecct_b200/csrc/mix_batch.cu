@@ -164,9 +164,9 @@ __global__ void k_mix_beta(const double *__restrict__ partial, int n_splits, int
 
 __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, int mc, int64_t snp0, int64_t m_total, int64_t n,
                              SnpStats st, const VecConst *__restrict__ vcp, const uint8_t *__restrict__ want, MixBatchParams prm,
-                             double *__restrict__ out, int *__restrict__ slow_list, Counters *ctr) {
+                             double *__restrict__ out, int *__restrict__ slow_list, Counters *ctr, MixHand *__restrict__ hand) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    bool slow = false;
+    bool slow = false, spa_only = false;
     if (j < mc && want[j]) {
         const VecConst vc = *vcp;
         double a[kMbStats] = {0, 0, 0, 0, 0, 0};
@@ -201,6 +201,10 @@ __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, i
                 const double Svar = a[5] - 2 * lambda * a[3] + (lambda * lambda) * a[2];
                 const double z = (S_GxE - Smean) / sqrt(Svar);
                 slow = !(fabs(z) < prm.cutoff);                                       // SPA (ref :1127)
+                if (slow) {   // everything but the two tail probabilities is final: hand the statistics over
+                    spa_only = true;
+                    hand[j] = MixHand{S1, VarS1, Z1, pG, lambda, S_GxE, Smean, Svar, z, negnum, MAC};
+                }
                 if (!slow) {
                     const double pn = d_pnorm(fabs(z), false) * 2;
                     double *o = out + snp0 + j;
@@ -213,15 +217,20 @@ __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, i
         }
     }
     const int pos = list_reserve(&ctr->b_count, slow);
-    if (slow) slow_list[pos] = j;
+    if (slow) slow_list[pos] = spa_only ? (j | kMixHandFlag) : j;
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-struct MixScratch { uint8_t *want = nullptr; double *part = nullptr, *beta = nullptr; int64_t cap_want = 0, cap_part = 0, cap_beta = 0; };
+struct MixScratch {
+    uint8_t *want = nullptr; double *part = nullptr, *beta = nullptr; MixHand *hand = nullptr;
+    int64_t cap_want = 0, cap_part = 0, cap_beta = 0, cap_hand = 0; int beta_ld = 0;
+};
+const double *mix_scratch_beta(const MixScratch *ms, int *ld) { *ld = ms->beta_ld; return ms->beta; }
+const MixHand *mix_scratch_hand(const MixScratch *ms) { return ms->hand; }
 MixScratch *mix_scratch_create() { return new MixScratch(); }
 void mix_scratch_destroy(MixScratch *ms) {
     if (!ms) return;
-    cudaFree(ms->want); cudaFree(ms->part); cudaFree(ms->beta);
+    cudaFree(ms->want); cudaFree(ms->part); cudaFree(ms->beta); cudaFree(ms->hand);
     delete ms;
 }
 
@@ -249,11 +258,13 @@ static cudaError_t run_k(cudaStream_t s, int num_sms, MixScratch &ms, const uint
     const int64_t np = std::max<int64_t>(KPAD, kMbStats);
     if ((e = grow(&ms.part, &ms.cap_part, (int64_t)n_splits * mc * np)) != cudaSuccess) return e;
     if ((e = grow(&ms.beta, &ms.cap_beta, (int64_t)mc * KPAD)) != cudaSuccess) return e;
+    if ((e = grow(&ms.hand, &ms.cap_hand, (int64_t)mc)) != cudaSuccess) return e;
+    ms.beta_ld = KPAD;
     dim3 grid((unsigned)blocks, (unsigned)n_splits);
     k_mix_tile<KPAD, 0><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, nullptr, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
     k_mix_beta<KPAD><<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, k, xtx_inv, ms.beta);
     k_mix_tile<KPAD, 1><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, ms.beta, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
-    k_mix_finish<<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, j0, M, n, st, vc, ms.want, prm, d_out, b_list, ctr);
+    k_mix_finish<<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, j0, M, n, st, vc, ms.want, prm, d_out, b_list, ctr, ms.hand);
     *launches += 4;
     return cudaGetLastError();
 }

@@ -12,6 +12,10 @@ struct MixBatchParams { double epsilon, cutoff, neg_ratio_cut; int g_model; };
 struct MixScratch;
 MixScratch *mix_scratch_create();
 void mix_scratch_destroy(MixScratch *ms);
+// what the last mix_batch_run left for the per-SNP kernel: OLS coefficients (row j, leading dimension *ld) and the
+// statistics of the SNPs whose work-list entry carries kMixHandFlag
+const double *mix_scratch_beta(const MixScratch *ms, int *ld);
+const MixHand *mix_scratch_hand(const MixScratch *ms);
 
 // Consumes the candidate list k_finalize_mix left in (b_list, ctr->b_count): writes the output rows of the SNPs that
 // take the common route and leaves the others in (b_list, ctr->b_count) for k_mix_snp.  All work is queued on `s`.

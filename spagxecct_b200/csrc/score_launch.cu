@@ -52,6 +52,7 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 2>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 3>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 4>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 6>));
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -165,9 +166,10 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 52: k_score_tc4_probe<3, 2, 2><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // signed view only (wrong sums)
         case 53: k_score_tc4_probe<3, 2, 3><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no expansion ALU (wrong sums)
         case 54: k_score_tc4_probe<3, 2, 4><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no tcgen05.st (wrong sums)
+        case 56: k_score_tc4_probe<3, 2, 6><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // packed words read one round ahead (exact)
         default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
-    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 54));
+    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 56));
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
     k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);

@@ -33,7 +33,7 @@ constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A 
 
 // NG expander groups (4 warps + 1 MMA warp each), NB A buffers per group; the product instantiation is <3, 2>
 // PROBE (probe build only, timing experiments that give WRONG sums): 1 no UTCIMMA, 2 no unsigned-view UTCIMMA,
-// 3 no expansion ALU work (raw words stored), 4 no tcgen05.st, 5 MMA warps of a CTA issue through one elected warp order
+// 3 no expansion ALU work (raw words stored), 4 no tcgen05.st; 6 (exact sums) next round's packed words read one round ahead
 template <int NG, int NB, int PROBE = 0>
 __device__ __forceinline__ void
 score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n_tiles, int tiles_per_split,
@@ -160,6 +160,8 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
         const uint32_t lane_addr = tmem_base + ((quarter * 32u) << 16);
         const uint32_t swz = (uint32_t)(row & 7);
         uint32_t gbase = 0, use = 0, itc = 0;
+        bool have_next = false;
+        uint4 xn[4];
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int rt = item / n_splits, ks = item % n_splits;
             const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
@@ -167,15 +169,20 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
             if (nr == 0) continue;
             for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
                 const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, pp = use % (uint32_t)NB;
-                mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
-                const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
                 uint4 xv[4];   // the four 16-byte chunks of this row's half stage (loads in flight together)
+                if (PROBE == 6 && have_next) {
 #pragma unroll
-                for (int c4 = 0; c4 < 4; c4++) {
-                    const uint32_t chunk = hs * 4u + (uint32_t)c4;
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(xv[c4].x), "=r"(xv[c4].y), "=r"(xv[c4].z), "=r"(xv[c4].w)
-                                 : "r"(rowaddr + ((chunk ^ swz) << 4)));
+                    for (int c4 = 0; c4 < 4; c4++) xv[c4] = xn[c4];
+                } else {
+                    mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
+                    const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) {
+                        const uint32_t chunk = hs * 4u + (uint32_t)c4;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(xv[c4].x), "=r"(xv[c4].y), "=r"(xv[c4].z), "=r"(xv[c4].w)
+                                     : "r"(rowaddr + ((chunk ^ swz) << 4)));
+                    }
                 }
                 mbar_wait(bar_aempty(q, pp), ((use / (uint32_t)NB) & 1) ^ 1);
                 tc_fence_after();
@@ -201,6 +208,21 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
 #pragma unroll
                         for (int k = 0; k < 16; k++) v ^= d[k];
                         if (v == 0x12345679u) tmem_st16(abuf + (uint32_t)(c4 * 16), d);   // keeps the expansion alive
+                    }
+                }
+                if (PROBE == 6) {   // the next round's packed words: their latency hides behind the store wait and the hand-over
+                    have_next = (G + (uint32_t)NG < gbase + nr);
+                    if (have_next) {
+                        const uint32_t Gn = G + (uint32_t)NG, Fn = Gn >> 1, hn = Gn & 1u, sn = Fn % kTcGStages;
+                        mbar_wait(bar_gfull(sn), (Fn / kTcGStages) & 1);
+                        const uint32_t rowaddr = sbase + sn * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const uint32_t chunk = hn * 4u + (uint32_t)c4;
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(xn[c4].x), "=r"(xn[c4].y), "=r"(xn[c4].z), "=r"(xn[c4].w)
+                                         : "r"(rowaddr + ((chunk ^ swz) << 4)));
+                        }
                     }
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -671,7 +671,10 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
         if (need > ctx->cap_mcache) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_mcache, need)); ctx->cap_mcache = need; }
     }
     double *mcache = ctx->d_mcache;
-    CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out, mcache));
+    const double *hbeta = nullptr; int hbeta_ld = 0; const MixHand *hand = nullptr;
+    if (!ctx->opt_mix_per_snp) { hbeta = mix_scratch_beta(ctx->mix_scratch, &hbeta_ld); hand = mix_scratch_hand(ctx->mix_scratch); }
+    CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out, mcache,
+                          hbeta, hbeta_ld, hand));
     ctx->launches++;
     return SPAGXE_OK;
 }

@@ -76,6 +76,11 @@ inline __host__ __device__ size_t branch_b_smem(int q) { return sizeof(double) *
 struct PlusConst { double R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew; };
 struct GrmCoo { const int *gi, *gj; const double *gv; long long nnz; };
 
+// hand-over of the batched SPAGxEmix path (mix_batch.cu) to the per-SNP kernel for a SNP whose only open item is the
+// saddlepoint approximation: its statistics are final, k_mix_snp starts from the batch's OLS coefficients
+struct MixHand { double S1, VarS1, Z1, pG, lambda, S_GxE, Smean, Svar, z, negnum, MAC; };
+constexpr int kMixHandFlag = 1 << 28;   // set in a work-list entry whose MixHand record is valid
+
 struct MixData {
     const double *pcs;      // n x k column-major (topPCs)
     const double *xtx_inv;  // (k+1) x (k+1) inverse of [1,PCs]'[1,PCs] (SNP-invariant)

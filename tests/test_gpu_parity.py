@@ -156,8 +156,8 @@ def test_one_snp_entry_point_and_errors(gpu_ctx, oracle):
     with pytest.raises(_lib.SpagxeError) as ei:
         gpu_ctx.run_cct(gpu_ctx.geno_desc(_lib.GENO_F64, G.ctypes.data, n - 1, 1, n - 1))
     assert ei.value.code == _lib.ERR_ARG
-    with pytest.raises(NotImplementedError):
-        SPAGxE_CCT_one_SNP("survival", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+    with pytest.raises(NotImplementedError):    # ordinal::clm is not restated (the reference does not import `ordinal` either)
+        SPAGxE_CCT_one_SNP("categorical", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
 
 
 def test_extreme_pvalues_down_to_1e300(gpu_ctx, oracle):
