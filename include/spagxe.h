@@ -206,6 +206,18 @@ int spagxe_mgpu_set_inputs(spagxe_mgpu *mg, int64_t n, const double *R, const do
  * out: HOST matrix (sum of the shards' SNPs) x 10, column-major, rows in shard order.  diag: totals (times: maximum). */
 int spagxe_mgpu_run_cct(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
                         spagxe_diag *diag);
+/* the other two loops and the survival trait on several GPUs (SPAGxEmix_CCT R/SPAGxECCT.R:975-997, SPAGxE_Plus
+ * R/SPAGxEPlus_functions_MYZ.R:214-233): spagxe_mgpu_set_inputs first (trait 0 = no Wald data: SPAGxE_Plus, or survival
+ * whose data follow here), then the per-analysis extras, which every GPU receives from the host arrays; out is
+ * M x 12 (mix) / M x 8 (plus).  Same sharding, still no collective on the data path.                                */
+int spagxe_mgpu_set_wald_survival(spagxe_mgpu *mg, const double *surv_time, const double *event, const double *cova, int p);
+int spagxe_mgpu_set_pcs(spagxe_mgpu *mg, const double *pcs, int k);
+int spagxe_mgpu_set_grm(spagxe_mgpu *mg, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,
+                        double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew);
+int spagxe_mgpu_run_mix(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                        spagxe_diag *diag);
+int spagxe_mgpu_run_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                         spagxe_diag *diag);
 
 /* ---- genotype unpack (K1) exposed for the bit-exact decode checks ----------- */
 /* per-SNP code counts of packed rows: counts[4*j + c], c = 00,01,10,11 (GRAB decode: 2,NA,1,0);

@@ -24,7 +24,8 @@ EXPORTS = [
     "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
     "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
     "spagxe_set_wald_device", "spagxe_set_wald_survival", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
-    "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct",
+    "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus", "spagxe_mgpu_set_wald_survival",
+    "spagxe_mgpu_set_pcs", "spagxe_mgpu_set_grm",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
 OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL, OPT_MIX_CLUSTER = 1, 2, 3, 4, 5
@@ -95,7 +96,12 @@ def load():
     L.spagxe_mgpu_last_error.restype = C.c_char_p
     L.spagxe_mgpu_n_gpus.argtypes = [C.c_void_p]
     L.spagxe_mgpu_set_inputs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    L.spagxe_mgpu_run_cct.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
+    for f in ("spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus"):
+        getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
+    L.spagxe_mgpu_set_wald_survival.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_mgpu_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.spagxe_mgpu_set_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                      C.c_double, C.c_void_p]
     L.spagxe_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_set_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                  C.c_double, C.c_void_p]
@@ -294,13 +300,40 @@ class MultiContext:
         if rc != OK:
             raise SpagxeError(rc, self.L.spagxe_mgpu_last_error(self.h).decode())
 
-    def set_inputs(self, R, E, trait, Y, cova):
-        R = _f64(R); E = _f64(E); Y = _f64(Y)
+    def set_inputs(self, R, E, trait=0, Y=None, cova=None):
+        """trait 0: no Wald data (SPAGxE_Plus, or a survival trait followed by set_wald_survival)."""
+        R = _f64(R); E = _f64(E)
+        self.n = R.size
+        if not trait:
+            self._chk(self.L.spagxe_mgpu_set_inputs(self.h, R.size, R.ctypes.data, E.ctypes.data, 0, None, None, 0))
+            return
+        Y = _f64(Y)
         cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(Y.size, -1))
         self._chk(self.L.spagxe_mgpu_set_inputs(self.h, R.size, R.ctypes.data, E.ctypes.data, int(trait), Y.ctypes.data,
                                                 cova.ctypes.data, cova.shape[1]))
 
-    def run_cct(self, geno, params=None, out_ptr=None):
+    def set_wald_survival(self, surv_time, event, cova):
+        t = _f64(surv_time); ev = _f64(event)
+        cova = np.asfortranarray(np.asarray(cova, dtype=np.float64).reshape(t.size, -1))
+        self._chk(self.L.spagxe_mgpu_set_wald_survival(self.h, t.ctypes.data, ev.ctypes.data, cova.ctypes.data, cova.shape[1]))
+
+    def set_pcs(self, pcs):
+        pcs = np.asfortranarray(np.asarray(pcs, dtype=np.float64).reshape(self.n, -1))
+        self._chk(self.L.spagxe_mgpu_set_pcs(self.h, pcs.ctypes.data, pcs.shape[1]))
+
+    def set_grm(self, gi, gj, gv, R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew, Rnew):
+        gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
+        gv = _f64(gv); Rnew = _f64(Rnew)
+        self._chk(self.L.spagxe_mgpu_set_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data,
+                                             float(R_GRM_R), float(R_GRM_RE), float(Rnew_GRM_Rnew), Rnew.ctypes.data))
+
+    def run_mix(self, geno, params=None, out_ptr=None):
+        return self.run_cct(geno, params, out_ptr, _fn="spagxe_mgpu_run_mix", _ncol=12)
+
+    def run_plus(self, geno, params=None, out_ptr=None):
+        return self.run_cct(geno, params, out_ptr, _fn="spagxe_mgpu_run_plus", _ncol=8)
+
+    def run_cct(self, geno, params=None, out_ptr=None, _fn="spagxe_mgpu_run_cct", _ncol=10):
         """geno: one host Geno (cut into SNP ranges) or a list of n_gpus Geno shards (host or that GPU's memory)."""
         prm = params if isinstance(params, Params) else make_params(**(params or {}))
         diag = Diag()
@@ -313,9 +346,9 @@ class MultiContext:
             gp = C.byref(geno)
         out = None
         if out_ptr is None:
-            out = np.empty((m, 10), dtype=np.float64, order="F")
+            out = np.empty((m, _ncol), dtype=np.float64, order="F")
             out_ptr = out.ctypes.data
-        rc = self.L.spagxe_mgpu_run_cct(self.h, gp, n_sh, C.byref(prm), C.c_void_p(out_ptr), C.byref(diag))
+        rc = getattr(self.L, _fn)(self.h, gp, n_sh, C.byref(prm), C.c_void_p(out_ptr), C.byref(diag))
         self.last_diag = diag.asdict()
         self._chk(rc)
         return out, self.last_diag

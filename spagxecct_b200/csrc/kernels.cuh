@@ -1300,7 +1300,15 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         if (threadIdx.x == 0) { ms.af.kind = 0; ms.af.maf = pr.maf; ms.af.k = k; ms.af.nsel = 0; }
         __syncthreads();
         if (!(MAC <= 20)) {
-            // ---- lm(g ~ topPCs): X'g, beta = (X'X)^-1 X'g (ref :1066) ----
+            // ---- lm(g ~ topPCs): X'g, beta = (X'X)^-1 X'g (ref :1066); the batched path has them already ----
+            if (hbeta) {
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (int a = 0; a < k1; a++) ms.af.beta[a] = hbeta[(int64_t)jl * hbeta_ld + a];
+                    ms.af.kind = 1;
+                }
+                __syncthreads();
+            } else {
             for (int c0 = 0; c0 < k1; c0 += 4) {
                 double v4[4] = {0, 0, 0, 0};
                 for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
@@ -1322,6 +1330,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                 ms.af.kind = 1;
             }
             __syncthreads();
+            }
             // fitted values: negative count and residual sum of squares
             double v2[2] = {0, 0};
             for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {

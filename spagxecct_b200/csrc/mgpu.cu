@@ -136,7 +136,9 @@ extern "C" int spagxe_mgpu_create(int n_gpus, const int *devices, spagxe_mgpu **
 extern "C" int spagxe_mgpu_set_inputs(spagxe_mgpu *mg, int64_t n, const double *R, const double *E, int trait, const double *Y,
                                       const double *cova, int p) {
     if (!mg) return SPAGXE_ERR_ARG;
-    if (n <= 0 || !R || !E || !Y || p < 0 || (p > 0 && !cova)) return mfail(mg, SPAGXE_ERR_ARG, "set_inputs: bad arguments");
+    // trait == 0: no Wald data (SPAGxE_Plus, or a survival trait whose data follow through spagxe_mgpu_set_wald_survival)
+    if (trait == 0) { Y = nullptr; cova = nullptr; p = 0; }
+    if (n <= 0 || !R || !E || (trait != 0 && !Y) || p < 0 || (p > 0 && !cova)) return mfail(mg, SPAGXE_ERR_ARG, "set_inputs: bad arguments");
     const int64_t total = n * (3 + (int64_t)p);
     if (total > mg->cap_in) {
         for (int k = 0; k < mg->n; k++) {
@@ -153,7 +155,8 @@ extern "C" int spagxe_mgpu_set_inputs(spagxe_mgpu *mg, int64_t n, const double *
     double *b0 = mg->d_in[0];
     MCU(cudaMemcpyAsync(b0, R, n * sizeof(double), cudaMemcpyHostToDevice, s0));
     MCU(cudaMemcpyAsync(b0 + n, E, n * sizeof(double), cudaMemcpyHostToDevice, s0));
-    MCU(cudaMemcpyAsync(b0 + 2 * n, Y, n * sizeof(double), cudaMemcpyHostToDevice, s0));
+    if (Y) MCU(cudaMemcpyAsync(b0 + 2 * n, Y, n * sizeof(double), cudaMemcpyHostToDevice, s0));
+    else MCU(cudaMemsetAsync(b0 + 2 * n, 0, n * sizeof(double), s0));
     if (p > 0) MCU(cudaMemcpyAsync(b0 + 3 * n, cova, n * (int64_t)p * sizeof(double), cudaMemcpyHostToDevice, s0));
     // ... and ONE broadcast to the others (the only collective of the whole analysis)
     if (mg->n > 1) {
@@ -170,15 +173,46 @@ extern "C" int spagxe_mgpu_set_inputs(spagxe_mgpu *mg, int64_t n, const double *
     for (int k = 0; k < mg->n; k++) {
         const double *b = mg->d_in[k];
         int rc = spagxe_set_vectors_device(mg->ctx[k], n, b, b + n);
-        if (!rc) rc = spagxe_set_wald_device(mg->ctx[k], trait, b + 2 * n, b + 3 * n, p);
+        if (!rc && trait != 0) rc = spagxe_set_wald_device(mg->ctx[k], trait, b + 2 * n, b + 3 * n, p);
         if (rc) return mfail(mg, rc, "GPU %d: %s", mg->devices[k], spagxe_last_error(mg->ctx[k]));
     }
     mg->n_samples = n;
     return SPAGXE_OK;
 }
 
+// per-analysis data beyond [R | E | Y | Cova]: every GPU receives its copy from the host arrays (tens of MB at most)
+#define MG_EACH(expr)                                                                                  \
+    do {                                                                                               \
+        if (!mg) return SPAGXE_ERR_ARG;                                                                \
+        if (mg->n_samples <= 0) return mfail(mg, SPAGXE_ERR_STATE, "call spagxe_mgpu_set_inputs first"); \
+        for (int k = 0; k < mg->n; k++) {                                                              \
+            cudaSetDevice(mg->devices[k]);                                                             \
+            spagxe_ctx *c = mg->ctx[k];                                                                \
+            const int rc = (expr);                                                                     \
+            if (rc) return mfail(mg, rc, "GPU %d: %s", mg->devices[k], spagxe_last_error(c));          \
+        }                                                                                              \
+        return SPAGXE_OK;                                                                              \
+    } while (0)
+extern "C" int spagxe_mgpu_set_wald_survival(spagxe_mgpu *mg, const double *surv_time, const double *event, const double *cova, int p) {
+    MG_EACH(spagxe_set_wald_survival(c, surv_time, event, cova, p));
+}
+extern "C" int spagxe_mgpu_set_pcs(spagxe_mgpu *mg, const double *pcs, int k_pcs) { MG_EACH(spagxe_set_pcs(c, pcs, k_pcs)); }
+extern "C" int spagxe_mgpu_set_grm(spagxe_mgpu *mg, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,
+                                   double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew) {
+    MG_EACH(spagxe_set_grm(c, nnz, gi, gj, gv, R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew, Rnew));
+}
+
+static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                    spagxe_diag *diag, int which);
 extern "C" int spagxe_mgpu_run_cct(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
-                                   spagxe_diag *diag) {
+                                   spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 0); }
+extern "C" int spagxe_mgpu_run_mix(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                                   spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 1); }
+extern "C" int spagxe_mgpu_run_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                                    spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 2); }
+
+static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                    spagxe_diag *diag, int which) {
     if (!mg) return SPAGXE_ERR_ARG;
     if (!geno || !out) return mfail(mg, SPAGXE_ERR_ARG, "run_cct: geno / out is NULL");
     if (n_shards != 1 && n_shards != mg->n) return mfail(mg, SPAGXE_ERR_ARG, "run_cct: n_shards must be 1 or n_gpus (%d)", mg->n);
@@ -216,7 +250,9 @@ extern "C" int spagxe_mgpu_run_cct(spagxe_mgpu *mg, const spagxe_geno *geno, int
             memset(&dgs[k], 0, sizeof(spagxe_diag));
             if (sh[k].n_snps == 0) return;
             cudaSetDevice(mg->devices[k]);
-            rcs[k] = spagxe_run_cct(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k]);
+            rcs[k] = which == 0 ? spagxe_run_cct(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k])
+                   : which == 1 ? spagxe_run_mix(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k])
+                                : spagxe_run_plus(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k]);
         });
     }
     for (auto &t : th) t.join();
@@ -228,7 +264,7 @@ extern "C" int spagxe_mgpu_run_cct(spagxe_mgpu *mg, const spagxe_geno *geno, int
         tot.n_mix_logistic += d.n_mix_logistic; tot.newton_iters += d.newton_iters; tot.kernel_launches += d.kernel_launches;
         tot.h2d_bytes += d.h2d_bytes; tot.d2h_bytes += d.d2h_bytes; tot.score_bytes += d.score_bytes;
         tot.bb_irls_sample_passes += d.bb_irls_sample_passes; tot.bb_tail_sample_passes += d.bb_tail_sample_passes;
-        tot.bb_prep_sample_passes += d.bb_prep_sample_passes; tot.bb_iterations += d.bb_iterations;
+        tot.bb_prep_sample_passes += d.bb_prep_sample_passes; tot.bb_iterations += d.bb_iterations; tot.cox_evals += d.cox_evals;
         if (d.ms_total > tot.ms_total) tot.ms_total = d.ms_total;
         if (d.ms_score > tot.ms_score) tot.ms_score = d.ms_score;
         if (d.ms_tests > tot.ms_tests) tot.ms_tests = d.ms_tests;

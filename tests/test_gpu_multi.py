@@ -79,3 +79,44 @@ def test_single_gpu_multicontext_is_the_plain_path(gpu_ctx):
         mg.set_inputs(ph["R"], ph["E"], _lib.TRAIT_BINARY, ph["Y"], ph["Cova"])
         many, _ = mg.run_cct(g)
     assert np.array_equal(np.nan_to_num(many, nan=-1), np.nan_to_num(one, nan=-1))
+
+
+@needs2
+def test_mix_plus_and_survival_shard_like_cct(gpu_ctx, golden_dir):
+    """spagxe_mgpu_run_mix / _plus and the survival trait: the 2-GPU matrices equal the single-GPU ones bit for bit."""
+    from tests.test_gpu_parity import _mix_inputs
+    from tests.test_survival import _surv_pheno
+    # SPAGxEmix_CCT
+    x = _mix_inputs(golden_dir, "binary")
+    rows = to_bed_rows(x["G"]); n = x["n"]; m = x["G"].shape[1]
+    gpu_ctx.set_vectors(x["R"], x["E"]); gpu_ctx.set_wald(_lib.TRAIT_BINARY, x["Y"], x["Cova"]); gpu_ctx.set_pcs(x["PCs"])
+    g = gpu_ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, (n + 3) // 4)
+    one, d1 = gpu_ctx.run_mix(g, dict(epsilon=0.2, min_maf=0.0002))
+    with _lib.MultiContext(2) as mg:
+        mg.set_inputs(x["R"], x["E"], _lib.TRAIT_BINARY, x["Y"], x["Cova"]); mg.set_pcs(x["PCs"])
+        two, d2 = mg.run_mix(g, dict(epsilon=0.2, min_maf=0.0002))
+    assert np.array_equal(np.nan_to_num(two, nan=-1), np.nan_to_num(one, nan=-1))
+    assert d2["n_mix_logistic"] == d1["n_mix_logistic"] and d2["newton_iters"] == d1["newton_iters"]
+    # SPAGxE_Plus (sib pairs) and SPAGxE_CCT with a survival trait on the same cohort
+    n_fam = 2001; n = 2 * n_fam + 1001
+    ph = _surv_pheno(n, 41, 25)
+    rng = np.random.default_rng(42)
+    G = make_geno(n, rng.uniform(0.02, 0.5, 61), 43, miss_rates=np.where(rng.random(61) < 0.5, 0, 0.03))
+    rows = to_bed_rows(G)
+    gi = np.r_[np.arange(n), np.arange(1, 2 * n_fam, 2)].astype(np.int32)
+    gj = np.r_[np.arange(n), np.arange(0, 2 * n_fam, 2)].astype(np.int32)
+    gv = np.r_[np.ones(n), np.full(n_fam, 0.5)]
+    a, b, Rnew, c = gpu_ctx.plus_nullmodel(gi, gj, gv, ph["R"], ph["E"])
+    g = gpu_ctx.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, 61, (n + 3) // 4)
+    gpu_ctx.set_vectors(ph["R"], ph["E"]); gpu_ctx.set_grm(gi, gj, gv, a, b, c, Rnew)
+    one_p, _ = gpu_ctx.run_plus(g, dict(epsilon=0.3, cutoff=1.0))
+    gpu_ctx.set_wald_survival(ph["time"], ph["event"], ph["Cova"])
+    one_s, ds = gpu_ctx.run_cct(g, dict(epsilon=0.3))
+    assert ds["n_branch_b"] >= 5
+    with _lib.MultiContext(2) as mg:
+        mg.set_inputs(ph["R"], ph["E"]); mg.set_grm(gi, gj, gv, a, b, c, Rnew)
+        two_p, _ = mg.run_plus(g, dict(epsilon=0.3, cutoff=1.0))
+        mg.set_wald_survival(ph["time"], ph["event"], ph["Cova"])
+        two_s, _ = mg.run_cct(g, dict(epsilon=0.3))
+    assert np.array_equal(np.nan_to_num(two_p, nan=-1), np.nan_to_num(one_p, nan=-1))
+    assert np.array_equal(np.nan_to_num(two_s, nan=-1), np.nan_to_num(one_s, nan=-1))

@@ -467,7 +467,7 @@ def test_edge_cases_empty_tiny_and_fatal_inputs(gpu_ctx, oracle):
             c2.run_plus(_bed_desc(c2, rows, n))
         assert ei.value.code == _lib.ERR_STATE and "set_grm" in str(ei.value)
         with pytest.raises(_lib.SpagxeError) as ei:
-            c2.set_wald(3, Y, cova)
+            c2.set_wald(4, Y, cova)            # categorical: ordinal::clm is not restated
         assert ei.value.code == _lib.ERR_UNSUPPORTED
 
 
