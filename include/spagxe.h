@@ -39,7 +39,7 @@ enum {
 };
 
 /* traits: the reference's `traits=` argument (R/SPAGxECCT.R:455, :622-677) */
-enum { SPAGXE_TRAIT_BINARY = 1, SPAGXE_TRAIT_QUANTITATIVE = 2, SPAGXE_TRAIT_SURVIVAL = 3 };
+enum { SPAGXE_TRAIT_BINARY = 1, SPAGXE_TRAIT_QUANTITATIVE = 2, SPAGXE_TRAIT_SURVIVAL = 3, SPAGXE_TRAIT_CATEGORICAL = 4 };
 
 /* genotype sources (R/SPAGxECCT.R:483-488: Geno.mtx or GenoFile) */
 enum {
@@ -112,6 +112,7 @@ typedef struct {
     int64_t bb_prep_sample_passes; /* samples x preparation passes (counts, R.new0 sums) */
     int64_t bb_iterations;  /* lock-step iterations (grid barriers) of the farm          */
     int64_t cox_evals;      /* traits = survival: partial-likelihood evaluations, all items */
+    int64_t clm_evals;      /* traits = categorical: likelihood evaluations, all items   */
 } spagxe_diag;
 
 /* ---- lifetime ------------------------------------------------------------- */
@@ -143,7 +144,10 @@ int spagxe_set_vectors(spagxe_ctx *ctx, int64_t n, const double *R, const double
 int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const double *dR, const double *dE);
 
 /* data of the Wald model Y ~ Cova + E + g + E:g (R/SPAGxECCT.R:622-677): Phen.mtx$Y and
- * as.matrix(Cova.mtx) (N x p column-major, p <= 12).  trait = SPAGXE_TRAIT_*.            */
+ * as.matrix(Cova.mtx) (N x p column-major, p <= 12).  trait = SPAGXE_TRAIT_*.
+ * SPAGXE_TRAIT_CATEGORICAL (R/SPAGxECCT.R:664-677: ordinal::clm(as.factor(Phen.mtx$Y) ~ ..., logit link, flexible
+ * thresholds): Y holds the index of every sample's level in sort(unique(Y)), 0 .. J-1 with J <= 8 and every level
+ * present; p <= 2; SPAGxE_CCT only.  Survival data go through spagxe_set_wald_survival.   */
 int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p);
 
 /* same with device pointers (the multi-GPU driver hands over what arrived by the NCCL broadcast) */

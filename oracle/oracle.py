@@ -139,7 +139,19 @@ def spa_homo(g, R, cutoff=2.0, min_maf=1e-5, g_is_int=False):
     return out, info.value, (its[0], its[1])
 
 
-TRAIT = {"binary": 1, "quantitative": 2, "survival": 3}   # survival: Y = np.r_[surv.time, event] (2 n doubles)
+TRAIT = {"binary": 1, "quantitative": 2, "survival": 3, "categorical": 4}
+# survival: Y = np.r_[surv.time, event] (2 n doubles); categorical: Y = index of the level in sort(unique(Y)), 0 .. J-1
+
+
+def clm(X, ycat, J):
+    """ordinal::clm(as.factor(y) ~ X), logit link, flexible thresholds: (coef, se, iterations, rc); thresholds first."""
+    X, Xp = _f(np.asarray(X, dtype=np.float64))
+    yc = np.ascontiguousarray(ycat, dtype=np.int32)
+    n, q = X.shape
+    coef = np.empty(J - 1 + q); se = np.empty(J - 1 + q); it = C.c_int()
+    rc = lib().orc_clm(Xp, yc.ctypes.data_as(C.c_void_p), C.c_long(n), C.c_int(q), C.c_int(J), coef.ctypes.data_as(c_dp),
+                       se.ctypes.data_as(c_dp), C.byref(it))
+    return coef, se, it.value, rc
 
 
 def coxph(X, time, event, maxiter=20):

@@ -719,9 +719,88 @@ int orc_coxph(const double *X, const double *time, const double *event, long n, 
     return rc;
 }
 
+/* ------------------------------------------------------------------ */
+/* ordinal::clm(as.factor(Y) ~ X) with the defaults of the call site R/SPAGxECCT.R:666 (logit link, flexible
+ * thresholds): the proportional-odds model P(Y <= j) = F(alpha_j - x'beta), j = 1 .. J-1.  `ordinal` is a third-party
+ * package that the reference does not even import; what is restated is the model, not clm's iteration path: clm runs
+ * Newton-Raphson to max|gradient| < 1e-6 on a strictly concave likelihood, i.e. to the maximum-likelihood estimate
+ * within ~1e-11, and reports z = estimate / sqrt(diag(solve(-Hessian))), p = 2 pnorm(-|z|).  Here: Newton-Raphson from
+ * alpha_j = qlogis(j / J), beta = 0, step halving while the likelihood drops, stop when the Newton step is below
+ * 1e-10 (1 + max|theta|); the Hessian of that last evaluation gives the standard errors.
+ * X is n x q column-major (no intercept), ycat[i] in 0 .. J-1.  coef / se: J-1 thresholds, then q slopes.
+ * returns 0, 1 singular Hessian, 2 no convergence in 100 iterations.                                              */
+int orc_clm(const double *X, const int *ycat, long n, int q, int J, double *coef, double *se, int *iters_out) {
+    const int nth = J - 1, np = nth + q;
+    if (J < 2 || np > 24) return 3;
+    double th[24], prev[24], g[24], H[24 * 24], step[24];
+    for (int j = 0; j < nth; j++) { double pr = (double)(j + 1) / (double)J; th[j] = log(pr / (1 - pr)); }
+    for (int a = 0; a < q; a++) th[nth + a] = 0;
+    double ll_old = -INFINITY; int halv = 0, iter, rc = 2;
+    memcpy(prev, th, sizeof th);
+    for (iter = 0; iter < 100; iter++) {
+        ld ll = 0;
+        for (int a = 0; a < np; a++) { g[a] = 0; for (int b = 0; b < np; b++) H[a * np + b] = 0; }
+        for (long i = 0; i < n; i++) {
+            double eta = 0;
+            for (int a = 0; a < q; a++) eta += th[nth + a] * X[(long)a * n + i];
+            const int y = ycat[i], u = (y < nth) ? y : -1, l = (y > 0) ? y - 1 : -1;
+            double Fu = 1, fu = 0, su = 0, Fl = 0, fl = 0, sl = 0;   /* F, F' = F(1-F), F'' = F'(1-2F) */
+            if (u >= 0) { Fu = 1 / (1 + exp(-(th[u] - eta))); fu = Fu * (1 - Fu); su = fu * (1 - 2 * Fu); }
+            if (l >= 0) { Fl = 1 / (1 + exp(-(th[l] - eta))); fl = Fl * (1 - Fl); sl = fl * (1 - 2 * Fl); }
+            const double pi = Fu - Fl, rp = 1 / pi, d = (fu - fl) * rp;
+            ll += log(pi);
+            const double cu = fu * rp, cl = -fl * rp;
+            if (u >= 0) { g[u] += cu; H[u * np + u] += su * rp - cu * cu; }
+            if (l >= 0) { g[l] += cl; H[l * np + l] += -sl * rp - cl * cl; }
+            if (u >= 0 && l >= 0) { H[u * np + l] += fu * fl * rp * rp; H[l * np + u] += fu * fl * rp * rp; }
+            const double hub = -su * rp + cu * d, hlb = sl * rp + cl * d, hbb = (su - sl) * rp - d * d;
+            for (int a = 0; a < q; a++) {
+                const double xa = X[(long)a * n + i];
+                g[nth + a] -= d * xa;
+                if (u >= 0) { H[u * np + nth + a] += hub * xa; H[(nth + a) * np + u] += hub * xa; }
+                if (l >= 0) { H[l * np + nth + a] += hlb * xa; H[(nth + a) * np + l] += hlb * xa; }
+                for (int b = 0; b <= a; b++) {
+                    const double v = hbb * xa * X[(long)b * n + i];
+                    H[(nth + a) * np + nth + b] += v;
+                    if (b != a) H[(nth + b) * np + nth + a] += v;
+                }
+            }
+        }
+        const double llv = (double)ll;
+        if (iter > 0 && !(llv >= ll_old) && halv < 30) {   /* the step overshot: halve it */
+            for (int a = 0; a < np; a++) th[a] = (th[a] + prev[a]) / 2;
+            halv++; iter--;
+            continue;
+        }
+        halv = 0;
+        /* Newton step: solve (-H) step = g */
+        double A[24 * 24];
+        for (int a = 0; a < np * np; a++) A[a] = -H[a];
+        for (int a = 0; a < np; a++) step[a] = g[a];
+        if (cholesky2(A, np, pow(DBL_EPSILON, 0.75)) < np) { rc = 1; break; }
+        chsolve2(A, np, step);
+        double ms = 0, mt = 0;
+        for (int a = 0; a < np; a++) { if (fabs(step[a]) > ms) ms = fabs(step[a]); if (fabs(th[a]) > mt) mt = fabs(th[a]); }
+        if (ms < 1e-10 * (1 + mt)) {
+            for (int k = 0; k < np; k++) {
+                double e[24];
+                for (int a = 0; a < np; a++) e[a] = (a == k);
+                chsolve2(A, np, e);
+                coef[k] = th[k]; se[k] = sqrt(e[k]);
+            }
+            rc = 0; break;
+        }
+        memcpy(prev, th, sizeof th);
+        ll_old = llv;
+        for (int a = 0; a < np; a++) th[a] += step[a];
+    }
+    if (iters_out) *iters_out = iter;
+    return rc;
+}
+
 /* Wald p-value of the E:g term for Y ~ Cova + E + g + E:g
  * (R/SPAGxECCT.R:622-677).  trait: 1 binary (glm binomial), 2 quantitative (lm), 3 survival (coxph: no intercept
- * column; Y then holds 2n doubles, surv.time followed by event).
+ * column; Y then holds 2n doubles, surv.time followed by event), 4 categorical (clm; Y = category index 0 .. J-1).
  * returns 0 ok, else error code; *pw = NA on failure.                    */
 static int wald_eg(int trait, const double *g, const double *E, const double *Y, const double *Cova, int p, long n, double *pw) {
     if (trait == 3) {   /* coxph(Surv(surv.time, event) ~ as.matrix(Cova.mtx) + E + g + g*E, iter.max = 1000): ref :624 */
@@ -733,6 +812,19 @@ static int wald_eg(int trait, const double *g, const double *E, const double *Y,
         *pw = ORC_NA;
         if (rcx == 0) *pw = 2 * orc_pnorm(-fabs(cf[qc - 1] / sc[qc - 1]), 1);   /* pchisq(z^2, 1, lower.tail = FALSE) */
         free(Xc);
+        return rcx;
+    }
+    if (trait == 4) {   /* clm(as.factor(Phen.mtx$Y) ~ as.matrix(Cova.mtx) + E + g + g*E): ref :666; Y holds the category indices 0 .. J-1 */
+        int qc = p + 3, J = 0;
+        int *yc = (int *)malloc(sizeof(int) * n);
+        for (long i = 0; i < n; i++) { yc[i] = (int)Y[i]; if (yc[i] + 1 > J) J = yc[i] + 1; }
+        double *Xc = (double *)malloc(sizeof(double) * n * qc), cf[24], sc[24];
+        for (int j = 0; j < p; j++) memcpy(Xc + (long)j * n, Cova + (long)j * n, sizeof(double) * n);
+        for (long i = 0; i < n; i++) { Xc[i + (long)p * n] = E[i]; Xc[i + (long)(p + 1) * n] = g[i]; Xc[i + (long)(p + 2) * n] = E[i] * g[i]; }
+        int itc, rcx = orc_clm(Xc, yc, n, qc, J, cf, sc, &itc);
+        *pw = ORC_NA;
+        if (rcx == 0) *pw = 2 * orc_pnorm(-fabs(cf[J - 1 + qc - 1] / sc[J - 1 + qc - 1]), 1);
+        free(Xc); free(yc);
         return rcx;
     }
     int q = p + 4;

@@ -14,7 +14,14 @@
   if (traits == "binary") return(1L)
   if (traits == "quantitative") return(2L)
   if (traits == "survival") return(3L)
-  stop('the CUDA path implements traits = "binary", "quantitative" and "survival" (categorical needs ordinal::clm: use the reference)')
+  if (traits == "categorical") return(4L)
+  stop('traits must be "survival", "binary", "quantitative" or "categorical"')
+}
+
+# Phen.mtx$Y as the C ABI takes it; categorical (R/SPAGxECCT.R:666): the level index of as.factor(Y), 0 .. J-1
+.spagxe_wald_y <- function(traits, Phen.mtx) {
+  if (.spagxe_trait(traits) == 4L) return(as.double(as.integer(as.factor(Phen.mtx$Y)) - 1L))
+  as.double(Phen.mtx$Y)
 }
 
 # Wald data of branch B (R/SPAGxECCT.R:622-677): Phen.mtx$Y, or Phen.mtx$surv.time / $event for a survival trait (:624)
@@ -22,7 +29,7 @@
   if (.spagxe_trait(traits) == 3L)
     .Call("spagxe_r_set_wald_survival", ctx, as.double(Phen.mtx$surv.time), as.double(Phen.mtx$event), as.matrix(Cova.mtx) + 0)
   else
-    .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+    .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), .spagxe_wald_y(traits, Phen.mtx), as.matrix(Cova.mtx) + 0)
 }
 
 # R/SPAGxECCT.R:572-574: "Dom" / "Rec" recode g after imputation and the flip; any other string acts like "Add"
@@ -107,7 +114,7 @@ SPAGxE_CCT <- function(traits = "survival/binary/quantitative/categorical", Geno
     if (.spagxe_trait(traits) == 3L) stop('traits = "survival" runs on one GPU')
     mg <- .Call("spagxe_r_mgpu_create", as.integer(n.gpus))
     on.exit(.Call("spagxe_r_mgpu_destroy", mg), add = TRUE)
-    .Call("spagxe_r_mgpu_set_inputs", mg, as.double(R), as.double(E), .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+    .Call("spagxe_r_mgpu_set_inputs", mg, as.double(R), as.double(E), .spagxe_trait(traits), .spagxe_wald_y(traits, Phen.mtx), as.matrix(Cova.mtx) + 0)
     output <- .Call("spagxe_r_mgpu_run_cct", mg, gi$g, gi$n, gi$m, prm, gi$sidx, as.double(gi$nfile), gi$a2)
   } else {
     ctx <- .Call("spagxe_r_create", as.integer(device))

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspagxe_cuda.so")
 
 OK, ERR_CUDA, ERR_ARG, ERR_STATE, ERR_UNSUPPORTED, ERR_CCT_STOP, ERR_SINGULAR = range(7)
-TRAIT_BINARY, TRAIT_QUANTITATIVE, TRAIT_SURVIVAL = 1, 2, 3
+TRAIT_BINARY, TRAIT_QUANTITATIVE, TRAIT_SURVIVAL, TRAIT_CATEGORICAL = 1, 2, 3, 4
 GENO_BED, GENO_F64, GENO_I32 = 0, 1, 2
 LOC_HOST, LOC_DEVICE = 0, 1
 GENO_COUNT_A2 = 1
@@ -51,7 +51,7 @@ class Diag(C.Structure):
                [("ms_total", C.c_double), ("ms_score", C.c_double), ("ms_tests", C.c_double),
                 ("score_bytes", C.c_int64), ("ms_spa", C.c_double), ("ms_branch_b", C.c_double),
                 ("spa_nodes", C.c_int64), ("bb_irls_sample_passes", C.c_int64), ("bb_tail_sample_passes", C.c_int64),
-                ("bb_prep_sample_passes", C.c_int64), ("bb_iterations", C.c_int64), ("cox_evals", C.c_int64)]
+                ("bb_prep_sample_passes", C.c_int64), ("bb_iterations", C.c_int64), ("cox_evals", C.c_int64), ("clm_evals", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -27,14 +27,22 @@ COLS_MIX = COLS_CCT + ["MAF.est.negative.num", "MAC"]
 COLS_PLUS = ["MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG", "Stat.betaG",
              "Var.betaG", "z.betaG"]
 
-_TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE, "survival": _lib.TRAIT_SURVIVAL}
+_TRAITS = {"binary": _lib.TRAIT_BINARY, "quantitative": _lib.TRAIT_QUANTITATIVE, "survival": _lib.TRAIT_SURVIVAL,
+           "categorical": _lib.TRAIT_CATEGORICAL}
 
 
 def _trait_code(traits):
     if traits not in _TRAITS:
-        raise NotImplementedError(f'traits="{traits}": the "binary", "quantitative" and "survival" Wald tests are implemented '
-                                  '(categorical needs ordinal::clm, which the reference does not even import)')
+        raise RStop(f'traits="{traits}": expected "survival", "binary", "quantitative" or "categorical"')
     return _TRAITS[traits]
+
+
+def _wald_y(traits, Phen_mtx):
+    """Phen.mtx$Y as the C ABI takes it; categorical: as.factor(Y) (ref R/SPAGxECCT.R:666) = index into sort(unique(Y))."""
+    y = _col(Phen_mtx, "Y")
+    if _trait_code(traits) == _lib.TRAIT_CATEGORICAL:
+        return np.unique(np.asarray(y), return_inverse=True)[1].astype(np.float64)
+    return y
 
 
 def _set_wald(ctx, traits, Phen_mtx, Cova_mtx):
@@ -43,7 +51,7 @@ def _set_wald(ctx, traits, Phen_mtx, Cova_mtx):
     if _trait_code(traits) == _lib.TRAIT_SURVIVAL:
         ctx.set_wald_survival(_col(Phen_mtx, "surv.time"), _col(Phen_mtx, "event"), cova)
     else:
-        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), cova)
+        ctx.set_wald(_trait_code(traits), _wald_y(traits, Phen_mtx), cova)
 
 
 class RStop(Exception):
@@ -282,7 +290,7 @@ def _spagxe_cct_multi(traits, GenoFile, GenoFileIndex, control, Geno_mtx, R, E, 
             print(f'[1] "Number of variants is {m}."')
             print('[1] "Start Analyzing..."')
             print(_now())
-        mg.set_inputs(R, E, _trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        mg.set_inputs(R, E, _trait_code(traits), _wald_y(traits, Phen_mtx), np.asarray(Cova_mtx, dtype=np.float64))
         out, diag = mg.run_cct(geno, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
         del keep
         if not quiet:
@@ -327,8 +335,8 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
-        if _trait_code(traits) == _lib.TRAIT_SURVIVAL:
-            raise NotImplementedError('SPAGxEmix_CCT: the survival Wald test is implemented for SPAGxE_CCT only')
+        if _trait_code(traits) in (_lib.TRAIT_SURVIVAL, _lib.TRAIT_CATEGORICAL):
+            raise NotImplementedError('SPAGxEmix_CCT: the survival and categorical Wald tests are implemented for SPAGxE_CCT only')
         ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
         ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
         if not quiet:

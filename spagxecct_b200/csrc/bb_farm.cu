@@ -703,7 +703,7 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
             it.flip = pr.flip; it.sum_g = pr.sum_g; it.u = pr.u;
             for (int c = 0; c < kMaxQ; c++) it.beta[c] = 0;
             it.devold = 0; it.se2 = 0; it.bl = 0; it.pw = d_na_real();
-            it.w_it = 0; it.w_status = (gm.trait == 3) ? 1 : 0; it.spa_kind = 0; it.prep = 0; it.pad_ = 0;   // survival: the Wald test is cox_wald.cu's
+            it.w_it = 0; it.w_status = (gm.trait >= 3) ? 1 : 0; it.spa_kind = 0; it.prep = 0; it.pad_ = 0;   // survival / categorical: the Wald test is cox_wald.cu's / clm_wald.cu's
             it.mafi = 0; it.S = 0; it.Smean = 0; it.z = 0;
             it.pspa = d_na_real(); it.pnorm_ = d_na_real();
             for (int h = 0; h < 2; h++) { it.tail_phase[h] = 2; it.tail_iter[h] = 0; it.tail_p[h] = 0; it.tail_t[h] = 0; it.tail_H1[h] = 0; it.tail_diff[h] = CUDART_INF; it.tail_s[h] = 0; }
@@ -880,7 +880,7 @@ k_bb_farm(BbFarmArgs A, FGeom gm, double *__restrict__ part /*2 x batch x rows x
                     atomicAdd(&A.ctr->n_spa, 1ULL);
                     atomicAdd(&A.ctr->newton_iters, (unsigned long long)(it.tail_iter[0] + it.tail_iter[1]));
                 }
-                if (gm.trait == 3) {   // survival: k_cox_wald fills the Wald and CCT columns from p.spa
+                if (gm.trait >= 3) {   // survival / categorical: k_cox_wald / k_clm_wald fill the Wald and CCT columns from p.spa
                     o[2 * M] = pspa; o[3 * M] = NA; o[4 * M] = NA; o[5 * M] = it.pnorm_;
                 } else {
                 double pw = it.pw;

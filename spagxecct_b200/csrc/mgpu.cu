@@ -264,7 +264,7 @@ static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, cons
         tot.n_mix_logistic += d.n_mix_logistic; tot.newton_iters += d.newton_iters; tot.kernel_launches += d.kernel_launches;
         tot.h2d_bytes += d.h2d_bytes; tot.d2h_bytes += d.d2h_bytes; tot.score_bytes += d.score_bytes;
         tot.bb_irls_sample_passes += d.bb_irls_sample_passes; tot.bb_tail_sample_passes += d.bb_tail_sample_passes;
-        tot.bb_prep_sample_passes += d.bb_prep_sample_passes; tot.bb_iterations += d.bb_iterations; tot.cox_evals += d.cox_evals;
+        tot.bb_prep_sample_passes += d.bb_prep_sample_passes; tot.bb_iterations += d.bb_iterations; tot.cox_evals += d.cox_evals; tot.clm_evals += d.clm_evals;
         if (d.ms_total > tot.ms_total) tot.ms_total = d.ms_total;
         if (d.ms_score > tot.ms_score) tot.ms_score = d.ms_score;
         if (d.ms_tests > tot.ms_tests) tot.ms_tests = d.ms_tests;

@@ -21,6 +21,7 @@
 #include "mix_batch.h"
 #include "bb_farm.h"
 #include "cox_wald.h"
+#include "clm_wald.h"
 
 using namespace spagxe;
 
@@ -63,6 +64,8 @@ struct spagxe_ctx {
     BbFarm *farm = nullptr;                                // SPAGxE_CCT branch-B solver farm (K5)
     CoxData *cox = nullptr;                                // traits = "survival": time order, tie groups, gathered columns
     std::vector<double> h_time, h_event;                   // Phen.mtx$surv.time / $event (host copies for the sort)
+    ClmData *clm = nullptr;                                // traits = "categorical": category order, gathered columns
+    std::vector<double> h_ycat;                            // level index of Phen.mtx$Y (host copy for the ordering)
     MixScratch *mix_scratch = nullptr;                    // SPAGxEmix: scratch of the batched common path
     int64_t cap_mcache = 0; double *d_mcache = nullptr;   // SPAGxEmix: cached allele frequencies, one vector per cluster
     // pinned staging
@@ -179,6 +182,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     mix_scratch_destroy(ctx->mix_scratch);
     bb_farm_destroy(ctx->farm);
     cox_destroy(ctx->cox);
+    clm_destroy(ctx->clm);
     cudaFree(ctx->d_bmat); cudaFree(ctx->d_binfo); cudaFree(ctx->d_acc); cudaFree(ctx->d_bitems);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     cudaFree(ctx->d_util); cudaFree(ctx->d_src); cudaFree(ctx->d_sidx);
@@ -241,6 +245,7 @@ static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const
     LAUNCH_CHECK();
     ctx->vec_mode = -1;
     cox_invalidate(ctx->cox);   // E is one of the Cox design columns
+    clm_invalidate(ctx->clm);   // and of the cumulative-link design
     // R and E must be finite: the fixed-point digits of the score pass and the SPA sums are undefined otherwise
     // (R would carry the NaN through sum() and stop in the first `if`)
     CU(cudaMemcpyAsync(ctx->h_flag, &ctx->d_vc->nonfinite, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -270,11 +275,30 @@ static int set_wald_common(spagxe_ctx *ctx, int trait, const double *Y, const do
     if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_wald: call spagxe_set_vectors first");
     if (trait == SPAGXE_TRAIT_SURVIVAL)
         return fail(ctx, SPAGXE_ERR_ARG, "traits = survival takes two vectors: use spagxe_set_wald_survival(time, event, cova, p)");
-    if (trait != SPAGXE_TRAIT_BINARY && trait != SPAGXE_TRAIT_QUANTITATIVE)
-        return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
-                    "traits must be binary(1), quantitative(2) or survival(3); the categorical (ordinal::clm) Wald test is not implemented");
+    if (trait != SPAGXE_TRAIT_BINARY && trait != SPAGXE_TRAIT_QUANTITATIVE && trait != SPAGXE_TRAIT_CATEGORICAL)
+        return fail(ctx, SPAGXE_ERR_ARG, "traits must be binary(1), quantitative(2), survival(3) or categorical(4)");
     if (!Y || p < 0 || (p > 0 && !cova)) return fail(ctx, SPAGXE_ERR_ARG, "set_wald: bad arguments");
     if (p + 4 > kMaxQ) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "set_wald: at most %d covariates", kMaxQ - 4);
+    if (trait == SPAGXE_TRAIT_CATEGORICAL) {
+        // ref R/SPAGxECCT.R:666: clm(as.factor(Phen.mtx$Y) ~ ...); Y holds the index of each sample's level, 0 .. J-1
+        if (p > kClmMaxCov) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "set_wald: the categorical Wald test takes at most %d covariate columns", kClmMaxCov);
+        CU(cudaSetDevice(ctx->device));
+        ctx->h_ycat.resize((size_t)ctx->n);
+        if (kind == cudaMemcpyHostToDevice) std::copy(Y, Y + ctx->n, ctx->h_ycat.begin());
+        else CU(cudaMemcpy(ctx->h_ycat.data(), Y, ctx->n * sizeof(double), cudaMemcpyDeviceToHost));
+        bool seen[kClmMaxJ] = {false}; int J = 0;
+        for (int64_t i = 0; i < ctx->n; i++) {
+            const double y = ctx->h_ycat[(size_t)i];
+            if (!(y >= 0 && y < kClmMaxJ) || y != std::floor(y))
+                return fail(ctx, SPAGXE_ERR_ARG, "set_wald: categorical Y[%lld] = %g is not a level index 0 .. %d", (long long)i, y, kClmMaxJ - 1);
+            seen[(int)y] = true; J = std::max(J, (int)y + 1);
+        }
+        if (J < 2) return fail(ctx, SPAGXE_ERR_ARG, "set_wald: a categorical trait needs at least two levels");
+        for (int k = 0; k < J; k++)
+            if (!seen[k]) return fail(ctx, SPAGXE_ERR_ARG, "set_wald: level index %d has no samples (as.factor() has no empty levels)", k);
+        if (!ctx->clm) ctx->clm = clm_create();
+        clm_invalidate(ctx->clm);
+    }
     CU(cudaSetDevice(ctx->device));
     CU(dev_realloc(&ctx->d_Y, ctx->n));
     CU(dev_realloc(&ctx->d_cova, (size_t)ctx->n * std::max(p, 1)));
@@ -374,6 +398,10 @@ static int flush_branch_b(spagxe_ctx *ctx, int mode, int64_t M, int64_t N, WaldD
         if (wd.trait == SPAGXE_TRAIT_SURVIVAL) {   // the farm left the Wald / CCT columns to the Cox kernel
             e = cox_launch(ctx->cox, s, ctx->num_sms, ctx->d_bitems, &ctx->d_ctr->b_count, M, g_model, d_out, ctx->d_ctr, &ctx->launches);
             if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "cox_launch: %s", cudaGetErrorString(e));
+        }
+        if (wd.trait == SPAGXE_TRAIT_CATEGORICAL) {   // ... or to the cumulative-link kernel
+            e = clm_launch(ctx->clm, s, ctx->num_sms, ctx->d_bitems, &ctx->d_ctr->b_count, M, g_model, d_out, ctx->d_ctr, &ctx->launches);
+            if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "clm_launch: %s", cudaGetErrorString(e));
         }
     } else {           // SPAGxE_Plus: one 4-CTA cluster per item, persistent over the device-side list
         constexpr int cs = 4;
@@ -697,6 +725,14 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
     if (mode == RUN_MIX && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL)
         return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the survival Wald test is implemented for SPAGxE_CCT only");
+    if (mode == RUN_MIX && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL)
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the categorical Wald test is implemented for SPAGxE_CCT only");
+    if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL && !clm_ready(ctx->clm)) {
+        CU(cudaSetDevice(ctx->device));
+        const char *what = "clm_setup";
+        cudaError_t ce = clm_setup(ctx->clm, ctx->stream(), ctx->n, ctx->h_ycat.data(), ctx->d_E, ctx->d_cova, ctx->wald_p, &what);
+        if (ce != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
+    }
     if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL && !cox_ready(ctx->cox)) {
         CU(cudaSetDevice(ctx->device));
         const char *what = "cox_setup";
@@ -807,6 +843,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     }
     fill_diag(&dg, hc, M);
     dg.cox_evals = (int64_t)hc.cox_evals;
+    dg.clm_evals = (int64_t)hc.clm_evals;
     dg.kernel_launches = ctx->launches;
     dg.score_bytes = M * pl.row_bytes;
     if (diag) *diag = dg;
