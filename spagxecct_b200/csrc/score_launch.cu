@@ -53,6 +53,7 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 3>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 4>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 6>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 7>));
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -166,10 +167,11 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 52: k_score_tc4_probe<3, 2, 2><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // signed view only (wrong sums)
         case 53: k_score_tc4_probe<3, 2, 3><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no expansion ALU (wrong sums)
         case 54: k_score_tc4_probe<3, 2, 4><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no tcgen05.st (wrong sums)
+        case 57: k_score_tc4_probe<3, 2, 7><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // timing trace (exact)
         case 56: k_score_tc4_probe<3, 2, 6><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // packed words read one round ahead (exact)
         default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
-    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 56));
+    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 59));
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
     k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);
@@ -192,6 +194,31 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
                     fprintf(stderr, "[trace] warp %2d round %2d:", w, r);
                     for (int k = 0; k < 6; k++) {
                         unsigned long long v = h[((size_t)w * kT3TraceRounds + r) * kT3TraceEv + k];
+                        fprintf(stderr, " %8lld", v ? (long long)(v - t0) : -1ll);
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+    }
+#endif
+#ifdef SPAGXE_PROBES
+    if (tc_cfg == 57) {   // dump the tc4 timing trace of CTA 0 (fourth call)
+        static int dumped4 = 0;
+        cudaStreamSynchronize(s);
+        if (dumped4++ == 3) {
+            static unsigned long long h[kT4TraceWarps * kT4TraceRounds * kT4TraceEv];
+            cudaMemcpyFromSymbol(h, g_t4_trace, sizeof h);
+            unsigned long long t0 = ~0ull;
+            for (size_t i = 0; i < sizeof h / sizeof h[0]; i++) if (h[i] && h[i] < t0) t0 = h[i];
+            for (int w = 0; w < t4_threads(3) / 32; w++) {
+                for (int r = 0; r < kT4TraceRounds; r++) {
+                    bool any = false;
+                    for (int k = 0; k < kT4TraceEv; k++) any |= h[((size_t)w * kT4TraceRounds + r) * kT4TraceEv + k] != 0;
+                    if (!any) continue;
+                    fprintf(stderr, "[trace4] warp %2d use %2d:", w, r + 16);
+                    for (int k = 0; k < 6; k++) {
+                        unsigned long long v = h[((size_t)w * kT4TraceRounds + r) * kT4TraceEv + k];
                         fprintf(stderr, " %8lld", v ? (long long)(v - t0) : -1ll);
                     }
                     fprintf(stderr, "\n");

@@ -31,6 +31,17 @@ constexpr int kT4Threads = t4_threads(kT4Groups);          // 17 warps
 constexpr uint32_t kT4IdescS = kTcIdesc;                                   // A = s8, B = s8
 constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A = u8, B = s8
 
+#ifdef SPAGXE_PROBES
+// PROBE 7: CTA 0 records clock64() at the hand-over points of uses [16, 48) of every warp (timing trace; exact sums)
+constexpr int kT4TraceRounds = 32, kT4TraceEv = 8, kT4TraceWarps = 32;
+__device__ unsigned long long g_t4_trace[kT4TraceWarps * kT4TraceRounds * kT4TraceEv];
+#define T4_TRACE(k)                                                                                        \
+    if (PROBE == 7 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT4TraceRounds)              \
+        g_t4_trace[((size_t)warp * kT4TraceRounds + (use - 16)) * kT4TraceEv + (k)] = (unsigned long long)clock64();
+#else
+#define T4_TRACE(k)
+#endif
+
 // NG expander groups (4 warps + 1 MMA warp each), NB A buffers per group; the product instantiation is <3, 2>
 // PROBE (probe build only, timing experiments that give WRONG sums): 1 no UTCIMMA, 2 no unsigned-view UTCIMMA,
 // 3 no expansion ALU work (raw words stored), 4 no tcgen05.st; 6 (exact sums) next round's packed words read one round ahead
@@ -128,9 +139,12 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
             for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
                 if (!waited) { mbar_wait(bar_accempty, (itc & 1) ^ 1); tc_fence_after(); waited = true; }
                 const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages, pp = use % (uint32_t)NB;
+                T4_TRACE(0)
                 mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
+                T4_TRACE(1)
                 mbar_wait(bar_afull(q, pp), (use / (uint32_t)NB) & 1);
                 tc_fence_after();
+                T4_TRACE(2)
                 if (elect_one()) {
                     const uint32_t abase = tmem_base + (q * (uint32_t)NB + pp) * kT4ACols;
                     const uint64_t bd0 = tc_bdesc(bbase + sb * kTcBTileBytes + hs * (kTcBTileBytes / 2));
@@ -148,6 +162,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                     tc_commit(bar_bempty(sb));
                 }
                 __syncwarp();
+                T4_TRACE(3)
             }
             if (elect_one()) tc_commit(bar_accfull);
             __syncwarp();
@@ -170,11 +185,13 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
             for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
                 const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, pp = use % (uint32_t)NB;
                 uint4 xv[4];   // the four 16-byte chunks of this row's half stage (loads in flight together)
+                T4_TRACE(0)
                 if (PROBE == 6 && have_next) {
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) xv[c4] = xn[c4];
                 } else {
                     mbar_wait(bar_gfull(s), (F / kTcGStages) & 1);
+                    T4_TRACE(1)
                     const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
 #pragma unroll
                     for (int c4 = 0; c4 < 4; c4++) {
@@ -186,6 +203,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                 }
                 mbar_wait(bar_aempty(q, pp), ((use / (uint32_t)NB) & 1) ^ 1);
                 tc_fence_after();
+                T4_TRACE(2)
                 const uint32_t abuf = lane_addr + (q * (uint32_t)NB + pp) * kT4ACols;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
@@ -225,10 +243,13 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                         }
                     }
                 }
+                T4_TRACE(3)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                T4_TRACE(4)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_afull(q, pp)); mbar_arrive(bar_gempty(s)); }
+                T4_TRACE(5)
             }
             gbase += nr;
             if (q == 0) {

@@ -4,7 +4,7 @@ properties at larger sizes."""
 import numpy as np
 import pytest
 
-from spagxecct_b200 import SPAGxE_CCT, SPAGxE_CCT_one_SNP, _lib
+from spagxecct_b200 import RStop, SPAGxE_CCT, SPAGxE_CCT_one_SNP, _lib
 from spagxecct_b200.harness import get_resid
 from tests._data import assert_parity, make_geno, make_pheno, routes_from_cct_output, to_bed_rows
 
@@ -156,8 +156,8 @@ def test_one_snp_entry_point_and_errors(gpu_ctx, oracle):
     with pytest.raises(_lib.SpagxeError) as ei:
         gpu_ctx.run_cct(gpu_ctx.geno_desc(_lib.GENO_F64, G.ctypes.data, n - 1, 1, n - 1))
     assert ei.value.code == _lib.ERR_ARG
-    with pytest.raises(NotImplementedError):    # ordinal::clm is not restated (the reference does not import `ordinal` either)
-        SPAGxE_CCT_one_SNP("categorical", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+    with pytest.raises(RStop):                   # a trait the reference does not know
+        SPAGxE_CCT_one_SNP("ordinal", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
 
 
 def test_extreme_pvalues_down_to_1e300(gpu_ctx, oracle):
@@ -467,8 +467,8 @@ def test_edge_cases_empty_tiny_and_fatal_inputs(gpu_ctx, oracle):
             c2.run_plus(_bed_desc(c2, rows, n))
         assert ei.value.code == _lib.ERR_STATE and "set_grm" in str(ei.value)
         with pytest.raises(_lib.SpagxeError) as ei:
-            c2.set_wald(4, Y, cova)            # categorical: ordinal::clm is not restated
-        assert ei.value.code == _lib.ERR_UNSUPPORTED
+            c2.set_wald(5, Y, cova)            # no such trait
+        assert ei.value.code == _lib.ERR_ARG
 
 
 def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir):
