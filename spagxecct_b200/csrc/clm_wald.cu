@@ -7,8 +7,8 @@
 // the model of that call -- logit link, flexible thresholds: P(Y <= j) = F(alpha_j - x'beta), j = 1 .. J-1 -- and its
 // summary: z = estimate / sqrt(diag(solve(-Hessian))) at the maximum-likelihood estimate, p = 2 pnorm(-|z|).  The
 // likelihood is strictly concave, so clm's Newton iteration (stop: max |gradient| < 1e-6) and the one below (stop: Newton
-// step < 1e-10 (1 + max |theta|)) meet at the same estimate to ~1e-11; the iteration path itself is the oracle's
-// (oracle/spagxe_oracle.c: orc_clm): alpha_j = qlogis(j / J), beta = 0, step halving while the likelihood drops.
+// step < 1e-10 (1 + max |theta|)) meet at the same estimate to ~1e-11.  Iteration: alpha_j = qlogis(j / J), beta = 0, step halving while the
+// likelihood drops (the CPU test checker in tests/ walks the same path).
 //
 // Data layout (SNP-invariant, built once per analysis by clm_setup): samples ordered by category, every category's
 // run padded to a multiple of 32, so that a warp-wide chunk of 32 samples has ONE category: which thresholds a
@@ -66,7 +66,7 @@ struct ClShared {
     int iter, halv, status, evals;            // status: 0 running, 1 done, 2 failed (singular Hessian / no convergence)
 };
 
-// LDL' in place (cholesky2 of the oracle): returns the rank, zeroes deficient pivots
+// LDL' in place (as cholesky2 of the survival package, cox_wald.cu): returns the rank, zeroes deficient pivots
 __device__ int cl_cholesky(double (*m)[kClMaxP], int n, double toler) {
     double eps = 0;
     for (int i = 0; i < n; i++) { if (m[i][i] > eps) eps = m[i][i]; for (int j = i + 1; j < n; j++) m[j][i] = m[i][j]; }

@@ -54,6 +54,10 @@ cudaError_t score_init(std::string *err) {
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 4>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 6>));
     SMEM_OPT_IN((k_score_tc4_probe<3, 2, 7>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 8>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 9>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 10>));
+    SMEM_OPT_IN((k_score_tc4_probe<3, 2, 11>));
 #endif
 #undef SMEM_OPT_IN
     if (!g_encode_tiled) {
@@ -129,7 +133,11 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
     const int tiles_per_split = (n_tiles + want_splits - 1) / want_splits;
     const int n_splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_items = n_row_tiles * n_splits;
-    const int grid = std::min(n_items, num_sms);
+    const int grid = std::min(n_items, num_sms);   // round-1 kernels of the probe build: whole items, round-robin
+    (void)grid;
+    // k_score_unpack_mma: one CTA per SM, each takes an equal contiguous range of the (row tile, sample tile) units
+    const long long n_units = (long long)n_row_tiles * n_tiles;
+    const int grid4 = (int)std::min<long long>(num_sms, std::max<long long>(1, n_units / 8));
 #define TC_ARGS map, d_bmat, n_tiles, tiles_per_split, n_splits, n_row_tiles, mc, d_acc
     // A1-dosage byte per PLINK code: 00 -> 2, 01 (missing) -> 0x80, 10 -> 1, 11 -> 0.  The second pass of G.model Dom / Rec
     // counts hom-A1 samples only (00 -> 1), which separates the dosage sums into their het and hom parts
@@ -158,23 +166,27 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
         case 17: k_score_tc3_probe<4><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // B tiles not loaded
         case 16: k_score_tc3_probe<3><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // hand-over timing trace
         case 10: k_score_tc3_probe<11><<<grid, kT3Threads, kTcSmemBytes, s>>>(TC_ARGS); break;   // round 1's product kernel
-        case 41: k_score_tc4_probe<4, 1><<<grid, t4_threads(4), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 4 groups, single buffers
-        case 61: k_score_tc4_probe<6, 1><<<grid, t4_threads(6), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 6 groups, single buffers
-        case 31: k_score_tc4_probe<3, 1><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 3 groups, single buffers
-        case 22: k_score_tc4_probe<2, 2><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, ping-pong
-        case 23: k_score_tc4_probe<2, 3><<<grid, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, 3 buffers
-        case 51: k_score_tc4_probe<3, 2, 1><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no UTCIMMA (wrong sums)
-        case 52: k_score_tc4_probe<3, 2, 2><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // signed view only (wrong sums)
-        case 53: k_score_tc4_probe<3, 2, 3><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no expansion ALU (wrong sums)
-        case 54: k_score_tc4_probe<3, 2, 4><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no tcgen05.st (wrong sums)
-        case 57: k_score_tc4_probe<3, 2, 7><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // timing trace (exact)
-        case 56: k_score_tc4_probe<3, 2, 6><<<grid, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // packed words read one round ahead (exact)
-        default: k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
+        case 41: k_score_tc4_probe<4, 1><<<grid4, t4_threads(4), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 4 groups, single buffers
+        case 61: k_score_tc4_probe<6, 1><<<grid4, t4_threads(6), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 6 groups, single buffers
+        case 31: k_score_tc4_probe<3, 1><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 3 groups, single buffers
+        case 22: k_score_tc4_probe<2, 2><<<grid4, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, ping-pong
+        case 23: k_score_tc4_probe<2, 3><<<grid4, t4_threads(2), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 2 groups, 3 buffers
+        case 51: k_score_tc4_probe<3, 2, 1><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no UTCIMMA (wrong sums)
+        case 52: k_score_tc4_probe<3, 2, 2><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // signed view only (wrong sums)
+        case 53: k_score_tc4_probe<3, 2, 3><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no expansion ALU (wrong sums)
+        case 54: k_score_tc4_probe<3, 2, 4><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // no tcgen05.st (wrong sums)
+        case 58: k_score_tc4_probe<3, 2, 8><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // software-pipelined barrier probes (exact)
+        case 59: k_score_tc4_probe<3, 2, 9><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // 58 with the timing trace
+        case 60: k_score_tc4_probe<3, 2, 10><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // in-body timing trace (exact)
+        case 62: k_score_tc4_probe<3, 2, 11><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // incremental loop state (exact)
+        case 57: k_score_tc4_probe<3, 2, 7><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // timing trace (exact)
+        case 56: k_score_tc4_probe<3, 2, 6><<<grid4, t4_threads(3), kTcSmemBytes, s>>>(TC_ARGS, lut); break;   // packed words read one round ahead (exact)
+        default: k_score_unpack_mma<<<grid4, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut); break;
     }
-    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 59));
+    const bool tc3 = (tc_cfg != 0 && tc_cfg != 41 && tc_cfg != 61 && tc_cfg != 31 && tc_cfg != 22 && tc_cfg != 23 && (tc_cfg < 51 || tc_cfg > 62));
 #else
     (void)tc_cfg;   // the product library has exactly one tensor-core score kernel
-    k_score_unpack_mma<<<grid, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);
+    k_score_unpack_mma<<<grid4, kT4Threads, kTcSmemBytes, s>>>(TC_ARGS, lut);
     const bool tc3 = false;
 #endif
 #undef TC_ARGS
@@ -203,23 +215,23 @@ cudaError_t score_launch_tc(cudaStream_t s, int num_sms, int tc_cfg, const uint8
     }
 #endif
 #ifdef SPAGXE_PROBES
-    if (tc_cfg == 57) {   // dump the tc4 timing trace of CTA 0 (fourth call)
+    if (tc_cfg == 57 || tc_cfg == 59 || tc_cfg == 60) {   // dump the tc4 timing trace of CTA 0 (fourth call)
         static int dumped4 = 0;
         cudaStreamSynchronize(s);
         if (dumped4++ == 3) {
             static unsigned long long h[kT4TraceWarps * kT4TraceRounds * kT4TraceEv];
             cudaMemcpyFromSymbol(h, g_t4_trace, sizeof h);
             unsigned long long t0 = ~0ull;
-            for (size_t i = 0; i < sizeof h / sizeof h[0]; i++) if (h[i] && h[i] < t0) t0 = h[i];
+            for (size_t i = 0; i < sizeof h / sizeof h[0]; i++) if (i % kT4TraceEv < 6 && h[i] && h[i] < t0) t0 = h[i];
             for (int w = 0; w < t4_threads(3) / 32; w++) {
                 for (int r = 0; r < kT4TraceRounds; r++) {
                     bool any = false;
                     for (int k = 0; k < kT4TraceEv; k++) any |= h[((size_t)w * kT4TraceRounds + r) * kT4TraceEv + k] != 0;
                     if (!any) continue;
                     fprintf(stderr, "[trace4] warp %2d use %2d:", w, r + 16);
-                    for (int k = 0; k < 6; k++) {
+                    for (int k = 0; k < 7; k++) {
                         unsigned long long v = h[((size_t)w * kT4TraceRounds + r) * kT4TraceEv + k];
-                        fprintf(stderr, " %8lld", v ? (long long)(v - t0) : -1ll);
+                        fprintf(stderr, " %8lld", v ? (k < 6 ? (long long)(v - t0) : (long long)v) : -1ll);
                     }
                     fprintf(stderr, "\n");
                 }

@@ -36,10 +36,14 @@ constexpr uint32_t kT4IdescU = kTcIdesc & ~(7u << 7);                      // A 
 constexpr int kT4TraceRounds = 32, kT4TraceEv = 8, kT4TraceWarps = 32;
 __device__ unsigned long long g_t4_trace[kT4TraceWarps * kT4TraceRounds * kT4TraceEv];
 #define T4_TRACE(k)                                                                                        \
-    if (PROBE == 7 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT4TraceRounds)              \
+    if ((PROBE == 7 || PROBE == 9) && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT4TraceRounds)              \
+        g_t4_trace[((size_t)warp * kT4TraceRounds + (use - 16)) * kT4TraceEv + (k)] = (unsigned long long)clock64();
+#define T4_TRACEB(k)                                                                                       \
+    if (PROBE == 10 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT4TraceRounds)             \
         g_t4_trace[((size_t)warp * kT4TraceRounds + (use - 16)) * kT4TraceEv + (k)] = (unsigned long long)clock64();
 #else
 #define T4_TRACE(k)
+#define T4_TRACEB(k)
 #endif
 
 // NG expander groups (4 warps + 1 MMA warp each), NB A buffers per group; the product instantiation is <3, 2>
@@ -96,13 +100,24 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
     __syncthreads();
     tc_fence_after();
 
-    const int n_items = n_row_tiles * n_splits;
+    // Work partition: the (row tile, sample tile) units of the launch form one linear sequence, CTA c takes the c-th of
+    // gridDim.x equal contiguous ranges (they differ by at most one unit) and walks it as items (row tile, [t0, t1)) cut at
+    // row-tile boundaries and at the int32 exactness limit.  Any partition gives the same bits (int64 atomics), so
+    // the split only has to balance the SMs: with whole (row tile x sample split) items dealt round-robin, 640 items on
+    // 148 SMs left 100 SMs idle for the last fifth of the kernel.
+    const long long n_units = (long long)n_row_tiles * n_tiles;
+    const long long u_begin = n_units * blockIdx.x / gridDim.x, u_end = n_units * (blockIdx.x + 1) / gridDim.x;
+    (void)tiles_per_split; (void)n_splits;
+#define T4_FOR_ITEMS                                                                                             \
+    for (long long u_ = u_begin; u_ < u_end;) {                                                                  \
+        const int rt = (int)(u_ / n_tiles), t0 = (int)(u_ % n_tiles);                                            \
+        const int t1 = (int)min((long long)min(n_tiles, t0 + kT4MaxTilesPerSplit), (long long)t0 + (u_end - u_)); \
+        u_ += t1 - t0;                                                                                           \
+        (void)rt;
     if (warp == kT4ExpWarps) {
         if (lane == 0) {   // ---- TMA producer: packed genotype tiles (HBM)
             uint32_t f = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int rt = item / n_splits, ks = item % n_splits;
-                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            T4_FOR_ITEMS
                 for (int t = t0; t < t1; t++, f++) {
                     const int s = f % kTcGStages;
                     mbar_wait(bar_gempty(s), ((f / kTcGStages) & 1) ^ 1);
@@ -114,9 +129,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
     } else if (warp == kT4ExpWarps + 1) {
         if (lane == 0) {   // ---- bulk-copy producer: B tiles (L2)
             uint32_t f = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int ks = item % n_splits;
-                const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+            T4_FOR_ITEMS
                 for (int t = t0; t < t1; t++, f++) {
                     const int s = f % kTcBStages;
                     mbar_wait(bar_bempty(s), ((f / kTcBStages) & 1) ^ 1);
@@ -130,9 +143,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
         const uint32_t q = (uint32_t)(warp - (kT4ExpWarps + 2));
         const uint32_t ds = tmem_base + kT4ColAcc, du = tmem_base + kT4ColAcc + 16;
         uint32_t gbase = 0, use = 0, itc = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int ks = item % n_splits;
-            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+        T4_FOR_ITEMS
             const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
             if (nr == 0) continue;
             bool waited = false;
@@ -140,9 +151,12 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                 if (!waited) { mbar_wait(bar_accempty, (itc & 1) ^ 1); tc_fence_after(); waited = true; }
                 const uint32_t F = G >> 1, hs = G & 1u, sb = F % kTcBStages, pp = use % (uint32_t)NB;
                 T4_TRACE(0)
-                mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
+                uint32_t b_ready = 0;
+                if (PROBE == 8 || PROBE == 9) b_ready = mbar_test(bar_bfull(sb), (F / kTcBStages) & 1);   // answered while the A buffer is awaited
+                else mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
                 T4_TRACE(1)
                 mbar_wait(bar_afull(q, pp), (use / (uint32_t)NB) & 1);
+                if ((PROBE == 8 || PROBE == 9) && !b_ready) mbar_wait(bar_bfull(sb), (F / kTcBStages) & 1);
                 tc_fence_after();
                 T4_TRACE(2)
                 if (elect_one()) {
@@ -174,12 +188,199 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
         const int row = (int)quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((quarter * 32u) << 16);
         const uint32_t swz = (uint32_t)(row & 7);
+        if constexpr (PROBE == 0 || PROBE == 11) {
+        // ---- same protocol as the product path, loop state kept incrementally (stage / phase / addresses advance by
+        // additions; no division by the ring depth per round)
+        static_assert(NB == 2, "streamlined path: ping-pong buffers");
+        uint32_t gbase = 0, use = 0, itc = 0;
+        uint32_t o0[4];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) o0[c4] = (((uint32_t)c4 ^ swz) << 4) + (uint32_t)row * kTcTileBytes;
+        const uint32_t a_bar0 = bar_afull(q, 0), abuf0 = lane_addr + (q * (uint32_t)NB) * kT4ACols;
+        constexpr uint32_t kAEmptyOff = 8u * NB * NG;
+        T4_FOR_ITEMS
+            const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
+            if (nr == 0) continue;
+            uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG);
+            const uint32_t Gend = gbase + nr;
+            // ring state of this group's first round of the item
+            uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages, gph = (F / kTcGStages) & 1;
+            uint32_t sdata = sbase + s * kTcGStageBytes, gbar = bar_gfull(0) + 8u * s;
+            uint32_t pp = use & 1u, aph = ((use >> 1) & 1u) ^ 1u;
+            for (; G < Gend; G += (uint32_t)NG) {
+                uint4 xv[4];
+                mbar_wait(gbar, gph);
+                const uint32_t hx = hs << 6;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++)
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(xv[c4].x), "=r"(xv[c4].y), "=r"(xv[c4].z), "=r"(xv[c4].w)
+                                 : "r"(sdata + (o0[c4] ^ hx)));
+                const uint32_t abar = a_bar0 + 8u * pp;
+                mbar_wait(abar + kAEmptyOff, aph);
+                tc_fence_after();
+                const uint32_t abuf = abuf0 + pp * kT4ACols;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; c4++) {
+                    const uint32_t x[4] = {xv[c4].x, xv[c4].y, xv[c4].z, xv[c4].w};
+                    uint32_t d[16];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t xe = x[k] & 0x77777777u;
+                        const uint32_t xo = __umulhi(x[k], 1u << 30) & 0x77777777u;
+                        d[4 * k + 0] = prmt(lut, lut, xo);
+                        d[4 * k + 1] = prmt(lut, lut, xe);
+                        d[4 * k + 2] = prmt(lut, lut, __umulhi(xo, 1u << 16));
+                        d[4 * k + 3] = prmt(lut, lut, __umulhi(xe, 1u << 16));
+                    }
+                    tmem_st16(abuf + (uint32_t)(c4 * 16), d);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(abar); mbar_arrive(gbar + 8u * kTcGStages); }
+                // advance by NG = 3 rounds: one or two stages
+                use++;
+                aph ^= pp; pp ^= 1u;                       // the phase flips when the ping-pong wraps
+                const uint32_t dF = 1u + hs;
+                hs ^= 1u;
+                s += dF; sdata += dF * kTcGStageBytes; gbar += 8u * dF;
+                if (s >= (uint32_t)kTcGStages) { s -= kTcGStages; sdata -= kTcGStages * kTcGStageBytes; gbar -= 8u * kTcGStages; gph ^= 1u; }
+            }
+            gbase += nr;
+            if (q == 0) {
+                mbar_wait(bar_accfull, itc & 1);
+                tc_fence_after();
+                uint32_t es[16], eu[16];
+                tmem_ld16(lane_addr + kT4ColAcc, es);
+                tmem_ld16(lane_addr + kT4ColAcc + 16, eu);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                tmem_st16(lane_addr + kT4ColAcc, z); tmem_st16(lane_addr + kT4ColAcc + 16, z);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty);
+                const int grow = rt * kTcRows + row;
+                if (grow < m_chunk) {
+                    unsigned long long *dst = (unsigned long long *)(acc + (int64_t)grow * 32);
+#pragma unroll
+                    for (int k = 0; k < 15; k++) {
+                        atomicAdd(dst + k, (unsigned long long)(long long)(int)es[k]);
+                        atomicAdd(dst + 16 + k, (unsigned long long)(long long)(int)eu[k]);
+                    }
+                }
+            }
+            itc++;
+        }
+        } else if constexpr (PROBE == 8 || PROBE == 9) {
+        // ---- software-pipelined rounds: a completed mbarrier still costs ~200 clk to query (the predicate comes back
+        // through the MIO queue, behind the tcgen05.st traffic), so the state of the NEXT round's barriers is probed
+        // with non-blocking test_wait while this round expands, and the next round's packed words are read while the
+        // last tcgen05.st of this round drains.  The blocking wait is only the fallback.
+        uint32_t gbase = 0, use = 0, itc = 0;
+        auto expand_chunk = [&](const uint4 &xq, uint32_t taddr) {
+            const uint32_t x[4] = {xq.x, xq.y, xq.z, xq.w};
+            uint32_t d[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t xe = x[k] & 0x77777777u;                          // even samples: code in nibble bits 0-1
+                const uint32_t xo = __umulhi(x[k], 1u << 30) & 0x77777777u;      // odd samples (x >> 2)
+                d[4 * k + 0] = prmt(lut, lut, xo);
+                d[4 * k + 1] = prmt(lut, lut, xe);
+                d[4 * k + 2] = prmt(lut, lut, __umulhi(xo, 1u << 16));
+                d[4 * k + 3] = prmt(lut, lut, __umulhi(xe, 1u << 16));
+            }
+            tmem_st16(taddr, d);
+        };
+        auto read_round = [&](uint32_t G, uint4 (&xr)[4]) {
+            const uint32_t F = G >> 1, hs = G & 1u, s = F % kTcGStages;
+            const uint32_t rowaddr = sbase + s * kTcGStageBytes + (uint32_t)row * kTcTileBytes;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) {
+                const uint32_t chunk = hs * 4u + (uint32_t)c4;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(xr[c4].x), "=r"(xr[c4].y), "=r"(xr[c4].z), "=r"(xr[c4].w)
+                             : "r"(rowaddr + ((chunk ^ swz) << 4)));
+            }
+        };
+        T4_FOR_ITEMS
+            const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
+            if (nr == 0) continue;
+            uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG);
+            const uint32_t Gend = gbase + nr;
+            if (G < Gend) {
+                uint4 xv[4];
+                mbar_wait(bar_gfull((G >> 1) % kTcGStages), ((G >> 1) / kTcGStages) & 1);
+                read_round(G, xv);
+                uint32_t a_ready = 0;
+                for (;;) {
+                    const uint32_t s = (G >> 1) % kTcGStages, pp = use % (uint32_t)NB;
+                    const uint32_t Gn = G + (uint32_t)NG, Fn = Gn >> 1, sn = Fn % kTcGStages, phn = (Fn / kTcGStages) & 1;
+                    const uint32_t ppn = (use + 1) % (uint32_t)NB, aphn = (((use + 1) / (uint32_t)NB) & 1) ^ 1;
+                    const bool have_next = Gn < Gend;
+                    T4_TRACE(0)
+                    if (!a_ready) mbar_wait(bar_aempty(q, pp), ((use / (uint32_t)NB) & 1) ^ 1);
+                    tc_fence_after();
+                    T4_TRACE(1)
+                    const uint32_t g_ready = have_next ? mbar_test(bar_gfull(sn), phn) : 0u;   // consumed after the expansion
+                    const uint32_t abuf = lane_addr + (q * (uint32_t)NB + pp) * kT4ACols;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++) expand_chunk(xv[c4], abuf + (uint32_t)(c4 * 16));
+                    T4_TRACE(2)
+                    uint32_t a_next = 0;
+                    if (have_next) {
+                        a_next = mbar_test(bar_aempty(q, ppn), aphn);
+                        if (!g_ready) mbar_wait(bar_gfull(sn), phn);
+                        read_round(Gn, xv);                 // xv is dead: its words went through the expansion
+                    }
+                    T4_TRACE(3)
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    T4_TRACE(4)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(bar_afull(q, pp)); mbar_arrive(bar_gempty(s)); }
+                    T4_TRACE(5)
+#ifdef SPAGXE_PROBES
+                    if (PROBE == 9 && blockIdx.x == 0 && lane == 0 && use >= 16 && use < 16 + kT4TraceRounds)
+                        g_t4_trace[((size_t)warp * kT4TraceRounds + (use - 16)) * kT4TraceEv + 6] = 1000ull + a_ready * 2 + (g_ready ? 1 : 0);
+#endif
+                    use++;
+                    if (!have_next) break;
+                    G = Gn; a_ready = a_next;
+                }
+            }
+            gbase += nr;
+            if (q == 0) {
+                mbar_wait(bar_accfull, itc & 1);
+                tc_fence_after();
+                uint32_t es[16], eu[16];
+                tmem_ld16(lane_addr + kT4ColAcc, es);
+                tmem_ld16(lane_addr + kT4ColAcc + 16, eu);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                tmem_st16(lane_addr + kT4ColAcc, z); tmem_st16(lane_addr + kT4ColAcc + 16, z);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_accempty);
+                const int grow = rt * kTcRows + row;
+                if (grow < m_chunk) {
+                    unsigned long long *dst = (unsigned long long *)(acc + (int64_t)grow * 32);
+#pragma unroll
+                    for (int k = 0; k < 15; k++) {
+                        atomicAdd(dst + k, (unsigned long long)(long long)(int)es[k]);
+                        atomicAdd(dst + 16 + k, (unsigned long long)(long long)(int)eu[k]);
+                    }
+                }
+            }
+            itc++;
+        }
+        } else {
         uint32_t gbase = 0, use = 0, itc = 0;
         bool have_next = false;
         uint4 xn[4];
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const int rt = item / n_splits, ks = item % n_splits;
-            const int t0 = ks * tiles_per_split, t1 = min(n_tiles, t0 + tiles_per_split);
+        T4_FOR_ITEMS
             const uint32_t nr = 2u * (uint32_t)max(t1 - t0, 0);
             if (nr == 0) continue;
             for (uint32_t G = gbase + ((q + (uint32_t)NG - gbase % (uint32_t)NG) % (uint32_t)NG); G < gbase + nr; G += (uint32_t)NG, use++) {
@@ -204,6 +405,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                 mbar_wait(bar_aempty(q, pp), ((use / (uint32_t)NB) & 1) ^ 1);
                 tc_fence_after();
                 T4_TRACE(2)
+                T4_TRACEB(0)
                 const uint32_t abuf = lane_addr + (q * (uint32_t)NB + pp) * kT4ACols;
 #pragma unroll
                 for (int c4 = 0; c4 < 4; c4++) {
@@ -220,7 +422,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                         d[4 * k + 2] = prmt(lut, lut, __umulhi(xo, 1u << 16));
                         d[4 * k + 3] = prmt(lut, lut, __umulhi(xe, 1u << 16));
                     }
-                    if (PROBE != 4) tmem_st16(abuf + (uint32_t)(c4 * 16), d);
+                    if (PROBE != 4) { tmem_st16(abuf + (uint32_t)(c4 * 16), d); T4_TRACEB(1 + c4) }
                     else {
                         uint32_t v = 0;
 #pragma unroll
@@ -246,6 +448,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
                 T4_TRACE(3)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 T4_TRACE(4)
+                T4_TRACEB(5)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(bar_afull(q, pp)); mbar_arrive(bar_gempty(s)); }
@@ -278,6 +481,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
             }
             itc++;
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -285,6 +489,8 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
+
+#undef T4_FOR_ITEMS
 
 // K1+K2 product kernel (the only tensor-core score kernel in the product .so)
 __global__ void __launch_bounds__(kT4Threads, 1)
