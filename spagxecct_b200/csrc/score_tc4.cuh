@@ -188,7 +188,7 @@ score_tc4_body(const CUtensorMap &bedmap, const int8_t *__restrict__ Bmat, int n
         const int row = (int)quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((quarter * 32u) << 16);
         const uint32_t swz = (uint32_t)(row & 7);
-        if constexpr (PROBE == 0 || PROBE == 11) {
+        if constexpr ((PROBE == 0 && NB == 2) || PROBE == 11) {
         // ---- same protocol as the product path, loop state kept incrementally (stage / phase / addresses advance by
         // additions; no division by the ring depth per round)
         static_assert(NB == 2, "streamlined path: ping-pong buffers");
