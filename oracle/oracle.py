@@ -272,6 +272,22 @@ def mix_one_snp(trait, g, R, E, Y, Cova, PCs, epsilon=0.001, cutoff=2.0, min_maf
     return out, route.value, (its[0], its[1]), mafest, rc
 
 
+def localance_matrix(trait, G, H, R, E, Y, Cova, cova_haplo, epsilon=0.001, min_maf=0.0001):
+    """SPAGxEmixCCT_localance loop (ref R/SPAGxECCT.R:1443-1476) over (N, M) matrices: G ancestry-specific genotypes,
+    H local ancestry counts, cova_haplo a list of (N, M) matrices (Cova.haplo.mtx.list).  OpenMP over SNPs."""
+    G, Gp = _f(G); H, Hp = _f(H)
+    n, m = G.shape
+    R, Rp = _d(R); E, Ep = _d(E); Y, Yp = _d(Y)
+    Cova, Cp = _f(np.asarray(Cova, dtype=np.float64).reshape(n, -1))
+    chs = [_f(c)[0] for c in cova_haplo]
+    arr = (C.c_void_p * max(len(chs), 1))(*[c.ctypes.data for c in chs])
+    out = np.empty((m, 10), order="F"); route = np.zeros(m, dtype=np.int32); iters = np.zeros((m, 2), dtype=np.int32)
+    rc = lib().orc_localance_matrix(C.c_int(TRAIT[trait]), Gp, Hp, C.c_long(n), C.c_long(m), Rp, Ep, Yp, Cp,
+                                    C.c_int(Cova.shape[1]), arr, C.c_int(len(chs)), C.c_double(epsilon), C.c_double(min_maf),
+                                    out.ctypes.data_as(c_dp), C.c_void_p(route.ctypes.data), C.c_void_p(iters.ctypes.data))
+    return out, route, iters, rc
+
+
 def plus_nullmodel_scalars(grm_i, grm_j, grm_v, R, E):
     gi = np.ascontiguousarray(grm_i, dtype=np.int32); gj = np.ascontiguousarray(grm_j, dtype=np.int32)
     gv, gvp = _d(grm_v); R, Rp = _d(R); E, Ep = _d(E)

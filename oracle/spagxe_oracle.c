@@ -1156,6 +1156,249 @@ int orc_mix_bed(int trait, const uint8_t *bed, long pitch, long n, long mm, cons
 }
 
 /* ------------------------------------------------------------------ */
+/* SPAGxEmixCCT_localance (R/SPAGxECCT.R:1401-1647): ancestry-specific G x E test with local ancestry.
+ * g = ancestry-specific genotype (0/1/2, never NA: the reference stops on `if (MAF > 0.5)` with an NA), h = number of
+ * haplotypes of that ancestry (0/1/2); G ~ Binomial(h_i, MAF).                                                      */
+static inline double r_pow_small(double x, double y) {   /* R_pow for the exponents that occur here (-2 .. 2) */
+    if (y == 2.0) return x * x;
+    if (y == 1.0) return x;
+    if (y == 0.0) return 1.0;
+    return pow(x, y);
+}
+/* M_G0_local :2132, M_G1_local :2138, M_G2_local :2144, K_G*_local :2152-2168 */
+static inline double MGl0(double t, double maf, double h) { return r_pow_small(1 - maf + maf * exp(t), h); }
+static inline double MGl1(double t, double maf, double h) { return h * (maf * exp(t)) * r_pow_small(1 - maf + maf * exp(t), h - 1); }
+static inline double MGl2(double t, double maf, double h) {
+    double me = maf * exp(t), u = 1 - maf + maf * exp(t);
+    return h * (h - 1) * (me * me) * r_pow_small(u, h - 2) + h * me * r_pow_small(u, h - 1);
+}
+static double Hl_org(double t, const double *R, double maf, const double *h, long n) {
+    ld s = 0; for (long i = 0; i < n; i++) s += log(MGl0(t * R[i], maf, h[i])); return (double)s;
+}
+static double Hl1_adj(double t, const double *R, double sstat, double maf, const double *h, long n) {
+    ld s = 0; for (long i = 0; i < n; i++) s += R[i] * (MGl1(t * R[i], maf, h[i]) / MGl0(t * R[i], maf, h[i])); return (double)s - sstat;
+}
+static double Hl2(double t, const double *R, double maf, const double *h, long n) {
+    ld s = 0;
+    for (long i = 0; i < n; i++) {
+        double m0 = MGl0(t * R[i], maf, h[i]), m1 = MGl1(t * R[i], maf, h[i]), m2 = MGl2(t * R[i], maf, h[i]);
+        s += (R[i] * R[i]) * ((m0 * m2 - m1 * m1) / (m0 * m0));
+    }
+    return (double)s;
+}
+/* GetProb_SPA_G_new_local :2287-2311 with fastgetroot_H1_new_local :2223-2281 */
+static double getprob_spa_local(const double *R, double maf, const double *h, long n, double sstat, int lower_tail, int *iter_out) {
+    const double tol = 0x1p-13; const int maxiter = 100;
+    double t = 0, H1 = 0, diff_t = INFINITY;
+    int iter;
+    for (iter = 1; iter <= maxiter; iter++) {
+        double old_t = t, old_diff = diff_t, old_H1 = H1;
+        H1 = Hl1_adj(t, R, sstat, maf, h, n);
+        double H2e = Hl2(t, R, maf, h, n);
+        diff_t = -1 * H1 / H2e;
+        if (isnan(diff_t)) diff_t = 5;
+        if (isnan(H1) || isinf(H1)) { t = r_sign(sstat) * INFINITY; break; }
+        if (r_sign(H1) != r_sign(old_H1)) {
+            int guard = 0;
+            while (fabs(diff_t) > fabs(old_diff) - tol && guard++ < 1200) diff_t = diff_t / 2;
+        }
+        if (isnan(diff_t)) diff_t = 5;
+        if (fabs(diff_t) < tol) break;
+        t = old_t + diff_t;
+    }
+    if (iter > maxiter) iter = maxiter;
+    if (iter == maxiter) t = NAN;
+    if (iter_out) *iter_out = iter;
+    double k1 = Hl_org(t, R, maf, h, n), k2 = Hl2(t, R, maf, h, n);
+    double temp1 = t * sstat - k1;
+    double w = r_sign(t) * sqrt(2 * temp1), v = t * sqrt(k2);
+    double pval = orc_pnorm(w + 1 / w * log(v / w), lower_tail);
+    if (isnan(pval)) pval = 0;
+    return pval;
+}
+/* SPAmix_localance_one_SNP :2324-2395 (Cutoff = 2, G.model = "Add": the caller does not forward them).
+ * g is modified in place.  res[0] = p.spa (res[3] of the reference), res[1] = p.norm; info bit0 filtered, bit1 SPA  */
+static void spa_localance(double *g, const double *R, const double *h, long n, double min_maf, double res[2], int *info, int iters[2]) {
+    ld sg = 0, sh = 0;
+    for (long i = 0; i < n; i++) { sg += g[i]; sh += h[i]; }
+    double MAF = (double)sg / (double)sh;
+    *info = 0; if (iters) iters[0] = iters[1] = 0;
+    if (MAF > 0.5) { MAF = 1 - MAF; for (long i = 0; i < n; i++) g[i] = 2 - g[i]; }
+    if (MAF < min_maf) { res[0] = res[1] = ORC_NA; *info = 1; return; }
+    ld a = 0, b = 0, c = 0;
+    for (long i = 0; i < n; i++) {
+        a += g[i] * R[i];
+        b += (MAF * h[i]) * R[i];
+        c += (R[i] * R[i]) * ((h[i] * MAF) * (1 - MAF));
+    }
+    double S = (double)a, Smean = (double)b, Svar = (double)c;
+    double z = (S - Smean) / sqrt(Svar);
+    if (fabs(z) < 2.0) { res[0] = res[1] = orc_pnorm(fabs(z), 0) * 2; return; }
+    *info = 2;
+    int i1 = 0, i2 = 0;
+    double p1 = getprob_spa_local(R, MAF, h, n, fmax(S, 2 * Smean - S), 0, &i1);
+    double p2 = getprob_spa_local(R, MAF, h, n, fmin(S, 2 * Smean - S), 1, &i2);
+    if (iters) { iters[0] = i1; iters[1] = i2; }
+    res[0] = p1 + p2;
+    res[1] = orc_pnorm(fabs(z), 0) + orc_pnorm(-fabs(z), 1);
+}
+/* columns of X (n x q column-major) that lm() / glm() would report as aliased (dqrdc2's limited pivoting moves a column
+ * whose remaining norm falls below tol x its norm to the end; the fit then ignores it): keep[j] = 0 for those.
+ * returns the rank                                                                                                  */
+static int drop_aliased(const double *X, long n, int q, double tol, int *keep) {
+    double *Q = (double *)malloc(sizeof(double) * n * q);
+    int rank = 0;
+    for (int j = 0; j < q; j++) {
+        double *v = Q + (long)rank * n;
+        ld n0 = 0;
+        for (long i = 0; i < n; i++) { v[i] = X[i + (long)j * n]; n0 += (ld)v[i] * v[i]; }
+        for (int pass = 0; pass < 2; pass++)
+            for (int k = 0; k < rank; k++) {
+                const double *u = Q + (long)k * n;
+                ld d = 0; for (long i = 0; i < n; i++) d += (ld)u[i] * v[i];
+                for (long i = 0; i < n; i++) v[i] = (double)(v[i] - d * u[i]);
+            }
+        ld n1 = 0; for (long i = 0; i < n; i++) n1 += (ld)v[i] * v[i];
+        if (n0 == 0 || sqrtl(n1) <= tol * sqrtl(n0)) { keep[j] = 0; continue; }
+        ld inv = 1 / sqrtl(n1);
+        for (long i = 0; i < n; i++) v[i] = (double)(v[i] * inv);
+        keep[j] = 1; rank++;
+    }
+    free(Q);
+    return rank;
+}
+/* Wald model of the local-ancestry test (ref :1593, :1607, :1621): binary glm(Y ~ Cova.haplo + Cova + E + g + g*E),
+ * quantitative lm(Y ~ Cova.haplo + Cova + haplo_numVec + E + g + g*E); aliased columns (two-way admixture with both
+ * ancestries' counts in Cova.haplo.mtx.list: h1 + h2 = 2) are dropped as lm / glm do.  returns 0, 1 ("E:g" itself
+ * aliased or rank failure), 2 (IRLS invalid)                                                                        */
+static int wald_localance(int trait, const double *g, const double *h, const double *E, const double *Y, const double *Cova, int p,
+                          const double *CH, int L, long n, double *pw) {
+    const int q0 = 1 + L + p + (trait == 2 ? 1 : 0) + 3;
+    double *X = (double *)malloc(sizeof(double) * n * q0);
+    int c = 0;
+    for (long i = 0; i < n; i++) X[i] = 1.0;
+    c = 1;
+    for (int j = 0; j < L; j++, c++) memcpy(X + (long)c * n, CH + (long)j * n, sizeof(double) * n);
+    for (int j = 0; j < p; j++, c++) memcpy(X + (long)c * n, Cova + (long)j * n, sizeof(double) * n);
+    if (trait == 2) { memcpy(X + (long)c * n, h, sizeof(double) * n); c++; }
+    for (long i = 0; i < n; i++) { X[i + (long)c * n] = E[i]; X[i + (long)(c + 1) * n] = g[i]; X[i + (long)(c + 2) * n] = E[i] * g[i]; }
+    int keep[64];
+    *pw = ORC_NA;
+    drop_aliased(X, n, q0, 1e-7, keep);
+    if (!keep[q0 - 1]) { free(X); return 1; }
+    int q = 0;
+    for (int j = 0; j < q0; j++) if (keep[j]) { if (q != j) memmove(X + (long)q * n, X + (long)j * n, sizeof(double) * n); q++; }
+    double *coef = (double *)malloc(sizeof(double) * q), *se = (double *)malloc(sizeof(double) * q);
+    int rc;
+    if (trait == 1) {
+        int it, cv;
+        rc = orc_glm_binomial(X, Y, n, q, coef, se, &it, &cv, NULL);
+        if (rc == 0) *pw = 2 * orc_pnorm(-fabs(coef[q - 1] / se[q - 1]), 1);
+    } else {
+        double *pv = (double *)malloc(sizeof(double) * q);
+        rc = orc_lm(X, Y, n, q, coef, se, pv, NULL);
+        if (rc == 0) *pw = pv[q - 1];
+        free(pv);
+    }
+    free(X); free(coef); free(se);
+    return rc;
+}
+/* SPAGxEmixCCT_localance_one_SNP :1496-1647.  CH: the L columns of Cova.haplo.mtx.list for this SNP (n x L).
+ * trait 1 binary, 2 quantitative.  route bits as orc_cct_one_snp; rc 40: g holds NA (the reference stops).          */
+int orc_localance_one_snp(int trait, const double *g_in, const double *h, const double *R, const double *E, const double *Y,
+                          const double *Cova, int p, const double *CH, int L, long n, double epsilon, double min_maf,
+                          double out[10], int *route, int iters[2]) {
+    double *g = (double *)malloc(sizeof(double) * n);
+    memcpy(g, g_in, sizeof(double) * n);
+    int rt = 0, rc = 0;
+    if (iters) iters[0] = iters[1] = 0;
+    ld sg = 0, sh = 0;
+    for (long i = 0; i < n; i++) {
+        if (isnan(g[i])) { for (int k = 0; k < 10; k++) out[k] = ORC_NA; if (route) *route = 1; free(g); return 40; }
+        sg += g[i]; sh += h[i];
+    }
+    double MAF = (double)sg / (double)sh, miss = 0.0;
+    if (MAF > 0.5) { MAF = 1 - MAF; for (long i = 0; i < n; i++) g[i] = 2 - g[i]; }
+    if (g_gmodel == 1) for (long i = 0; i < n; i++) g[i] = (g[i] >= 1) ? 1.0 : 0.0;
+    if (g_gmodel == 2) for (long i = 0; i < n; i++) g[i] = (g[i] <= 1) ? 0.0 : 1.0;
+    if (MAF < min_maf || isnan(MAF)) {
+        out[0] = MAF; out[1] = miss; for (int k = 2; k < 10; k++) out[k] = ORC_NA;
+        if (route) *route = 1; free(g); return 0;
+    }
+    ld a = 0, b = 0, c = 0;
+    for (long i = 0; i < n; i++) {
+        a += g[i] * R[i];
+        b += (MAF * h[i]) * R[i];
+        c += (R[i] * R[i]) * ((h[i] * MAF) * (1 - MAF));
+    }
+    double S1 = (double)a, S1mean = (double)b, VarS1 = (double)c;
+    double Z1 = (S1 - S1mean) / sqrt(VarS1);
+    double pnorm1 = orc_pnorm(-fabs(Z1), 1) * 2;
+    double po[5];
+    double *Rn = (double *)malloc(sizeof(double) * n);
+    if (pnorm1 > epsilon) {
+        ld u = 0, v = 0;
+        for (long i = 0; i < n; i++) { u += (h[i] * E[i]) * (R[i] * R[i]); v += h[i] * (R[i] * R[i]); }
+        double lambda = (double)u / (double)v;
+        for (long i = 0; i < n; i++) Rn[i] = (E[i] - lambda) * R[i];
+        double res[2]; int info;
+        spa_localance(g, Rn, h, n, min_maf, res, &info, iters);
+        if (info & 2) rt |= 4;
+        po[0] = res[0]; po[1] = res[0]; po[2] = res[0]; po[3] = res[1]; po[4] = pnorm1;
+    } else {
+        rt |= 2;
+        if (adjust_for_g(g, R, n, Rn)) {
+            rt |= 32; for (int k = 0; k < 4; k++) po[k] = ORC_NA; po[4] = pnorm1;
+        } else {
+            for (long i = 0; i < n; i++) Rn[i] = E[i] * Rn[i];
+            double *g2 = (double *)malloc(sizeof(double) * n);   /* the inner function may flip its own copy of g */
+            memcpy(g2, g, sizeof(double) * n);
+            double res[2]; int info;
+            spa_localance(g2, Rn, h, n, min_maf, res, &info, iters);
+            free(g2);
+            if (info & 2) rt |= 4;
+            double pw; int wrc = wald_localance(trait, g, h, E, Y, Cova, p, CH, L, n, &pw);
+            if (wrc) rt |= 8;
+            double pc = ORC_NA; int warn;
+            int crc = wrc ? 1 : orc_cct2(res[0], pw, &pc, &warn);
+            if (crc) { rt |= 16; rc = crc; pc = ORC_NA; }
+            po[0] = res[0]; po[1] = pw; po[2] = pc; po[3] = res[1]; po[4] = pnorm1;
+        }
+    }
+    free(Rn);
+    out[0] = MAF; out[1] = miss; for (int k = 0; k < 5; k++) out[2 + k] = po[k];
+    out[7] = S1; out[8] = VarS1; out[9] = Z1;
+    if (route) *route = rt;
+    free(g);
+    return rc;
+}
+/* loop of SPAGxEmixCCT_localance :1443-1476 over N x M column-major matrices; CHs: L matrices, each N x M */
+int orc_localance_matrix(int trait, const double *G, const double *H, long n, long m, const double *R, const double *E,
+                         const double *Y, const double *Cova, int p, const double *const *CHs, int L, double epsilon, double min_maf,
+                         double *out, int *route, int *iters) {
+    int rc_all = 0;
+#pragma omp parallel
+    {
+        double *ch = (double *)malloc(sizeof(double) * n * (L > 0 ? L : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (long j = 0; j < m; j++) {
+            double o[10]; int rt, it[2];
+            for (int l = 0; l < L; l++) memcpy(ch + (long)l * n, CHs[l] + j * n, sizeof(double) * n);
+            int rc = orc_localance_one_snp(trait, G + j * n, H + j * n, R, E, Y, Cova, p, ch, L, n, epsilon, min_maf, o, &rt, it);
+            for (int c = 0; c < 10; c++) out[j + c * m] = o[c];
+            if (route) route[j] = rt;
+            if (iters) { iters[2 * j] = it[0]; iters[2 * j + 1] = it[1]; }
+            if (rc) {
+#pragma omp critical
+                rc_all = rc;
+            }
+        }
+        free(ch);
+    }
+    return rc_all;
+}
+
+/* ------------------------------------------------------------------ */
 /* sparse-GRM quadratic form 2*sum_{nnz} v x_i x_j - sum x^2
  * (R/SPAGxEPlus_functions_MYZ.R:352-361, :509); i,j 0-based indices.    */
 double orc_grm_quad(long nnz, const int32_t *gi, const int32_t *gj, const double *gv, const double *x, long n) {

@@ -1481,4 +1481,243 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
     cl.sync();
 }
 
+// ===========================================================================
+// SPAGxEmixCCT_localance (R/SPAGxECCT.R:1401-1647): ancestry-specific G x E test with local ancestry.  One cluster per
+// SNP; g (ancestry-specific genotype), haplo_numVec and the Cova.haplo.mtx.list columns are per-SNP 2-bit rows.
+// G_i ~ Binomial(h_i, MAF): the CGF of a sample is h_i / 2 times the CGF of the two-allele case, so the saddlepoint
+// code above runs with the weight w = h_i / 2 (exact for h in {0, 1, 2}).
+__device__ __forceinline__ int code_at(const uint8_t *row, int64_t i) { return (row[i >> 2] >> (2 * (i & 3))) & 3; }
+__device__ __forceinline__ double hap_of_code(int c) { return (c == 0) ? 2.0 : ((c == 2) ? 1.0 : 0.0); }
+
+struct SrcLocal {  // residual vector (E - lambda) R or E * (R - fit[class]); scalar allele frequency; weight h_i / 2
+    const double *R, *E; const uint8_t *row_g, *row_h; double fit[4]; double lambda, maf; int adj;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
+        if (adj) r = E[i] * (R[i] - fit[code_at(row_g, i)]);
+        else r = (E[i] - lambda) * R[i];
+        m = maf; w = 0.5 * hap_of_code(code_at(row_h, i));
+    }
+};
+
+// Wald design of the local-ancestry test (ref :1593, :1607): [1, Cova.haplo (L), Cova (p), haplo_numVec (quantitative only),
+// E, g, E:g] restricted to the columns lm() / glm() keep (map[c] = column of the full design)
+struct DesignLocal {
+    WaldData wd; const double *E; GFromRow gf; int64_t n;
+    const uint8_t *row_h; const uint8_t *ch[kMaxLocalCov]; int L, has_h, nq; const int *map;
+    __device__ __forceinline__ int q() const { return nq; }
+    __device__ __forceinline__ int q_full() const { return 1 + L + wd.p + has_h + 3; }
+    __device__ __forceinline__ int trait() const { return wd.trait; }
+    __device__ __forceinline__ double y(int64_t i) const { return wd.Y[i]; }
+    __device__ __forceinline__ double col(int id, int64_t i) const {
+        if (id == 0) return 1.0;
+        id -= 1;
+        if (id < L) return hap_of_code(code_at(ch[id], i));
+        id -= L;
+        if (id < wd.p) return wd.cova[i + (int64_t)id * n];
+        id -= wd.p;
+        if (has_h) { if (id == 0) return hap_of_code(code_at(row_h, i)); id -= 1; }
+        if (id == 0) return E[i];
+        if (id == 1) return gf(i);
+        return E[i] * gf(i);
+    }
+    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
+        for (int c = 0; c < q; c++) x[c] = col(map ? map[c] : c, i);
+    }
+    template <int Q>
+    __device__ __forceinline__ void fill(int64_t i, double *x) const {
+#pragma unroll
+        for (int c = 0; c < Q; c++) x[c] = col(map ? map[c] : c, i);
+    }
+};
+
+struct LocalShared { int map[kMaxQ]; int nq; int last_kept; };
+
+// which columns of the design survive lm()'s / glm()'s rank check: Cholesky of the equilibrated Gram matrix, a pivot
+// below 1e-13 (remaining norm < 3e-7 of the column norm; dqrdc2 uses 1e-7) marks the column as aliased
+__device__ void local_alias_map(const double (*NE)[kMaxQ], int q0, LocalShared &ls) {
+    double A[kMaxQ][kMaxQ], sc[kMaxQ];
+    int kept[kMaxQ], nk = 0;
+    for (int i = 0; i < q0; i++) sc[i] = (NE[i][i] > 0) ? 1.0 / sqrt(NE[i][i]) : 0.0;
+    for (int j = 0; j < q0; j++) {
+        // row of L for candidate column j against the kept columns
+        double lrow[kMaxQ];
+        double d = (sc[j] > 0) ? 1.0 : 0.0;
+        for (int a = 0; a < nk; a++) {
+            const int ca = kept[a];
+            double sacc = NE[j][ca] * sc[j] * sc[ca];
+            for (int b = 0; b < a; b++) sacc -= lrow[b] * A[a][b];
+            lrow[a] = sacc / A[a][a];
+            d -= lrow[a] * lrow[a];
+        }
+        if (!(d > 1e-13)) continue;
+        for (int a = 0; a < nk; a++) A[nk][a] = lrow[a];
+        A[nk][nk] = sqrt(d);
+        kept[nk++] = j;
+    }
+    for (int a = 0; a < nk; a++) ls.map[a] = kept[a];
+    ls.nq = nk;
+    ls.last_kept = (nk > 0 && kept[nk - 1] == q0 - 1) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A) {
+    namespace cg = cooperative_groups;
+    extern __shared__ double tile[];
+    __shared__ BShared sh;
+    __shared__ LocalShared ls;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const VecConst vc = *A.vc;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t n = A.n, m_total = A.m_total;
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const double NA = d_na_real();
+    const bool writer = (rank == 0 && threadIdx.x == 0);
+    for (int jl = cluster_id; jl < A.m; jl += n_clusters) {
+        const uint8_t *row_g = A.g_rows + (int64_t)jl * A.pitch, *row_h = A.h_rows + (int64_t)jl * A.pitch;
+        double *o = A.out + A.snp0 + jl;
+        // ---- class counts and the SNP-specific sums with h (ref :1514-1543) ----
+        double c4[4] = {0, 0, 0, 0}, t4[4] = {0, 0, 0, 0}, u2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const int cg_ = code_at(row_g, i), ch_ = code_at(row_h, i);
+            const double r = A.R[i], h = hap_of_code(ch_), r2 = r * r;
+            c4[0] += (cg_ == 0); c4[1] += (cg_ == 2); c4[2] += (cg_ == 1) + (ch_ == 1); c4[3] += h;
+            t4[0] += (cg_ == 0) ? r : 0.0; t4[1] += (cg_ == 2) ? r : 0.0; t4[2] += h * r; t4[3] += h * r2;
+            u2[0] += (h * A.E[i]) * r2;
+        }
+        red.sum<4>(c4); red.sum<4>(t4); red.sum<2>(u2);
+        const double n_hom = c4[0], n_het = c4[1], n_hz = (double)n - n_hom - n_het, sum_h = c4[3];
+        if (c4[2] > 0) {   // an NA in g or haplo_numVec: `if (MAF > 0.5)` stops the reference
+            if (writer) { for (int c = 0; c < 10; c++) o[c * m_total] = NA; atomicAdd(&A.ctr->n_allmissing, 1ULL); }
+            continue;
+        }
+        double MAF = (n_het + 2 * n_hom) / sum_h;
+        double gv[4] = {2.0, 0.0, 1.0, 0.0};                           // by PLINK code: 00 -> 2, 10 -> 1, 11 -> 0
+        if (MAF > 0.5) { MAF = 1 - MAF; for (int c = 0; c < 4; c++) gv[c] = 2 - gv[c]; }
+        if (A.g_model == 1) for (int c = 0; c < 4; c++) gv[c] = (gv[c] >= 1) ? 1.0 : 0.0;
+        if (A.g_model == 2) for (int c = 0; c < 4; c++) gv[c] = (gv[c] <= 1) ? 0.0 : 1.0;
+        if (!(MAF >= A.min_maf)) {
+            if (writer) { o[0] = MAF; o[m_total] = 0.0; for (int c = 2; c < 10; c++) o[c * m_total] = NA; atomicAdd(&A.ctr->n_filtered, 1ULL); }
+            continue;
+        }
+        const double T_hz = vc.sumR - t4[0] - t4[1];
+        const double S1 = gv[0] * t4[0] + gv[2] * t4[1] + gv[3] * T_hz;
+        const double S1mean = MAF * t4[2], VarS1 = (MAF * (1 - MAF)) * t4[3];
+        const double Z1 = (S1 - S1mean) / sqrt(VarS1);
+        const double pG = d_pnorm(-fabs(Z1), true) * 2;
+        // the inner SPAmix_localance_one_SNP re-derives the frequency from the processed g and may flip again (ref :2334-2350)
+        const double sum_g = gv[0] * n_hom + gv[2] * n_het + gv[3] * n_hz;
+        double MAFin = sum_g / sum_h, gin[4];
+        for (int c = 0; c < 4; c++) gin[c] = gv[c];
+        if (MAFin > 0.5) { MAFin = 1 - MAFin; for (int c = 0; c < 4; c++) gin[c] = 2 - gin[c]; }
+        const bool inner_filtered = !(MAFin >= A.min_maf);
+        SrcLocal src;
+        src.R = A.R; src.E = A.E; src.row_g = row_g; src.row_h = row_h; src.maf = MAFin;
+        GFromRow gf; gf.row = row_g;
+        for (int c = 0; c < 4; c++) gf.gval[c] = gv[c];
+        double po[4];
+        int iters = 0; bool spa = false;
+        const bool branch_a = pG > A.epsilon;
+        bool singular = false;
+        if (branch_a) {
+            src.lambda = u2[0] / t4[3]; src.adj = 0;                              // ref :1551
+        } else {
+            const double a = (double)n, b = sum_g, d = gv[0] * gv[0] * n_hom + gv[2] * gv[2] * n_het + gv[3] * gv[3] * n_hz;
+            const double det = a * d - b * b;
+            if (det == 0 || !isfinite(det)) singular = true;
+            else {
+                const double i00 = d / det, i01 = -b / det, i11 = a / det;
+                for (int c = 0; c < 4; c++) {
+                    const double wi0 = i00 + gv[c] * i01, wi1 = i01 + gv[c] * i11;
+                    src.fit[c] = wi0 * vc.sumR + wi1 * S1;
+                }
+                src.adj = 1; src.lambda = 0;
+            }
+        }
+        if (singular) {
+            if (writer) {
+                o[0] = MAF; o[m_total] = 0.0;
+                o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+                atomicAdd(&A.ctr->n_branch_b, 1ULL); atomicAdd(&A.ctr->n_singular, 1ULL);
+            }
+            continue;
+        }
+        double pspa = NA, pn = NA;
+        if (!inner_filtered) {
+            double v3[3] = {0, 0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                double r, mm, w; src.get(i, r, mm, w);
+                const double h = 2 * w;
+                v3[0] += gin[code_at(row_g, i)] * r; v3[1] += h * r; v3[2] += h * (r * r);
+            }
+            red.sum<3>(v3);
+            const double S = v3[0], Smean = MAFin * v3[1], Svar = (MAFin * (1 - MAFin)) * v3[2];
+            const double z = (S - Smean) / sqrt(Svar);
+            if (fabs(z) < 2.0) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }   // Cutoff is not forwarded (ref :1559, :1579)
+            else {
+                spa = true;
+                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), &iters);
+                pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            }
+        }
+        if (branch_a) {
+            po[0] = po[1] = po[2] = pspa; po[3] = pn;
+            if (writer) atomicAdd(&A.ctr->n_branch_a, 1ULL);
+        } else {
+            if (writer) atomicAdd(&A.ctr->n_branch_b, 1ULL);
+            // ---- Wald test: which columns does the fit keep, then glm.fit / lm on them ----
+            DesignLocal ds;
+            ds.wd = A.wd; ds.E = A.E; ds.gf = gf; ds.n = n; ds.row_h = row_h; ds.L = A.n_ch; ds.has_h = (A.wd.trait == 2) ? 1 : 0;
+            for (int l = 0; l < kMaxLocalCov; l++) ds.ch[l] = (l < A.n_ch) ? A.ch_rows[l] + (int64_t)jl * A.pitch : nullptr;
+            ds.map = nullptr; ds.nq = ds.q_full();
+            const int q0 = ds.nq;
+            int invalid;
+            {   // X'X of the full design: the lm-type first pass (unit weights)
+                DesignLocal dl = ds; dl.wd.trait = 2;
+                wald_pass_any(dl, i_lo, i_hi, q0, true, tile, sh, red, &invalid);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) local_alias_map(sh.NE, q0, ls);
+            __syncthreads();
+            double pw = NA; int wfail = 0;
+            if (!ls.last_kept) wfail = 1;                                         // "E:g" itself aliased: the reference stops
+            else {
+                ds.map = ls.map; ds.nq = ls.nq;
+                const int q = ds.nq;
+                if (A.wd.trait == 1) {
+                    double se2 = 0;
+                    const int rc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
+                    if (rc) wfail = rc;
+                    else pw = 2 * d_pnorm(-fabs(sh.beta[q - 1] / sqrt(se2)), true);
+                } else {
+                    wald_pass_any(ds, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+                    wald_solve(sh, q);
+                    if (!sh.ok) wfail = 1;
+                    else {
+                        const double il = sh.se2, bl = sh.beta[q - 1];
+                        const double rss = wald_pass_any(ds, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+                        const double rdf = (double)(n - q);
+                        pw = d_pt2(bl / sqrt(il * (rss / rdf)), rdf);
+                    }
+                }
+            }
+            double pc = NA;
+            const int crc = d_cct2(pspa, pw, &pc);
+            if (writer) {
+                if (wfail) atomicAdd(&A.ctr->n_wald_fail, 1ULL);
+                if (crc) atomicAdd(&A.ctr->n_cct_stop, 1ULL);
+            }
+            po[0] = pspa; po[1] = pw; po[2] = crc ? NA : pc; po[3] = pn;
+        }
+        if (writer) {
+            o[0] = MAF; o[m_total] = 0.0;
+            o[2 * m_total] = po[0]; o[3 * m_total] = po[1]; o[4 * m_total] = po[2]; o[5 * m_total] = po[3];
+            o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+            if (spa) { atomicAdd(&A.ctr->n_spa, 1ULL); atomicAdd(&A.ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+    cl.sync();
+}
+
 }  // namespace spagxe

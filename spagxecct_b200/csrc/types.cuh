@@ -89,4 +89,15 @@ struct MixData {
     int g_model;            // 0 Add, 1 Dom, 2 Rec
 };
 
+// SPAGxEmixCCT_localance (ref R/SPAGxECCT.R:1401-1647): packed 2-bit rows (code -> value: 00 2, 10 1, 11 0; 01 = NA is refused)
+// of the ancestry-specific genotypes, of the local ancestry counts and of the Cova.haplo.mtx.list columns of every SNP
+constexpr int kMaxLocalCov = 4;
+struct LocalArgs {
+    const uint8_t *g_rows, *h_rows; const uint8_t *ch_rows[kMaxLocalCov]; int n_ch; int64_t pitch;
+    int m; int64_t snp0, m_total, n;
+    const double *R, *E; const VecConst *vc; WaldData wd;
+    double epsilon, min_maf; int g_model;
+    double *out; Counters *ctr;
+};
+
 }  // namespace spagxe

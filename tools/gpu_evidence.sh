@@ -20,4 +20,9 @@ $short > $out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_bb_farm|k_spa_quad|k_finalize_cct|k_score_unpack_mma' -s 8 -c 8 \
     -o $out/${tag}_prof_cct $short > $out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+shortmix="python bench.py --workload mix --steps 1 --warmup 2 --no-e2e --cpu-sample-snps 0"
+$shortmix > $out/${tag}_plain_mix.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|spagxe' -c 400 --csv \
+    --log-file $out/${tag}_launches_bench_mix.csv $shortmix > $out/${tag}_ncu_launches_mix.log 2>&1
+echo "mix launch list rc=$?"
 for f in default reference mix plus; do tail -c 400 $out/${tag}_bench_$f.json | head -c 400; echo; done
