@@ -190,6 +190,20 @@ int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params
 int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
                     spagxe_diag *diag);
 
+/* SPAGxEmixCCT_localance loop body, R/SPAGxECCT.R:1443-1476 -> SPAGxEmixCCT_localance_one_SNP :1496-1647 (with
+ * SPAmix_localance_one_SNP :2324-2395 and the binomial(h_i, MAF) saddlepoint functions :2132-2311): ancestry-specific
+ * G x E test with local ancestry.  The reference takes R matrices only: G (Geno.mtx, ancestry-specific genotypes), H
+ * (haplo.mtx, local ancestry counts) and the n_cov_haplo matrices of Cova.haplo.mtx.list, all HOST, double,
+ * column-major n x m with leading dimension ld, values in {0, 1, 2} (an NA stops the reference at `if (MAF > 0.5)`).
+ * spagxe_set_vectors and spagxe_set_wald (binary or quantitative) first.  Wald designs: binary glm(Y ~ Cova.haplo +
+ * Cova + E + g + g*E), quantitative lm(Y ~ Cova.haplo + Cova + haplo_numVec + E + g + g*E); columns that lm / glm would
+ * report as aliased (both ancestries' counts of a two-way admixture: h1 + h2 = 2) are dropped as there.  out: HOST
+ * m x 10, column-major: MAF, missing.rate, p.value.spaGxE.index.ance, p.value.spaGxE.Wald.index.ance,
+ * p.value.spaGxE.CCT.Wald.index.ance, p.value.normGxE.index.ance, p.value.betaG.index.ance, Stat / Var / z.betaG.      */
+int spagxe_run_localance(spagxe_ctx *ctx, int64_t n, int64_t m, const double *G, const double *H, int n_cov_haplo,
+                         const double *const *cov_haplo, int64_t ld, const spagxe_params *prm, double *out,
+                         spagxe_diag *diag);
+
 /* ---- the same loop on several GPUs of one node ----------------------------------
  * One process, one host thread + stream per GPU.  SNPs are independent, so the M SNPs of a call are cut into contiguous
  * ranges (a .bed file is variant-major: a range of SNPs is a range of bytes); the per-analysis vectors are uploaded to

@@ -237,3 +237,46 @@ SPAGxE_Plus_Nullmodel_GRM <- function(resid, E, SubjID, sparseGRM, device = 0L) 
        R_GRM_R = res$scalars[1], R_GRM_RE = res$scalars[2], R.new = res$R.new, R.new_GRM_R.new = res$scalars[3],
        sparseGRM = sparseGRM[keep, ])
 }
+
+# R/SPAGxECCT.R:1401-1481: ancestry-specific G x E test with local ancestry (binary and quantitative traits on the GPU)
+SPAGxEmixCCT_localance <- function(traits = "survival/binary/quantitative/categorical", Geno.mtx, haplo.mtx, R, Cutoff = 2, E,
+                                   Phen.mtx, Cova.mtx, Cova.haplo.mtx.list, epsilon = 0.001, impute.method = "fixed",
+                                   missing.cutoff = 0.15, min.maf = 0.0001, G.model = "Add", device = 0L) {
+  if (!(.spagxe_trait(traits) %in% c(1L, 2L))) stop('SPAGxEmixCCT_localance on the GPU: traits = "binary" or "quantitative"')
+  gm <- .spagxe_gmodel(G.model)
+  print(paste0("Sample size is ", nrow(Geno.mtx), "."))
+  print(paste0("Number of variants is ", ncol(Geno.mtx), "."))
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
+  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
+  print("Start Analyzing...")
+  print(Sys.time())
+  output <- .Call("spagxe_r_run_localance", ctx, as.matrix(Geno.mtx) + 0, as.matrix(haplo.mtx) + 0,
+                  lapply(unname(Cova.haplo.mtx.list), function(x) as.matrix(x) + 0),
+                  c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm))
+  colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE.index.ance", "p.value.spaGxE.Wald.index.ance",
+                        "p.value.spaGxE.CCT.Wald.index.ance", "p.value.normGxE.index.ance", "p.value.betaG.index.ance",
+                        "Stat.betaG.index.ance", "Var.betaG.index.ance", "z.betaG.index.ance")
+  rownames(output) <- colnames(Geno.mtx)
+  output <- as.data.frame(cbind(rsID = colnames(Geno.mtx), output))   # as the reference returns it (:1478)
+  print("Analysis Complete.")
+  print(Sys.time())
+  output
+}
+
+SPAGxEmixCCT_localance_one_SNP <- function(traits = "survival/binary/quantitative/categorical", g, haplo_numVec, R, E, Phen.mtx,
+                                           Cova.mtx, Cova.haplo.mtx, epsilon = 0.001, Cutoff = 2, impute.method = "fixed",
+                                           missing.cutoff = 0.15, min.maf = 0.0001, G.model = "Add", device = 0L) {
+  if (!(.spagxe_trait(traits) %in% c(1L, 2L))) stop('SPAGxEmixCCT_localance on the GPU: traits = "binary" or "quantitative"')
+  gm <- .spagxe_gmodel(G.model)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
+  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
+  ch <- as.matrix(Cova.haplo.mtx) + 0
+  output <- .Call("spagxe_r_run_localance", ctx, matrix(as.double(g), ncol = 1), matrix(as.double(haplo_numVec), ncol = 1),
+                  lapply(seq_len(ncol(ch)), function(l) ch[, l, drop = FALSE]),
+                  c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm))
+  as.numeric(output[1, ])
+}

@@ -149,6 +149,29 @@ SEXP spagxe_r_run(SEXP ptr, SEXP which, SEXP geno, SEXP n_, SEXP m_, SEXP prm, S
     return out;
 }
 
+/* SPAGxEmixCCT_localance (R/SPAGxECCT.R:1443-1476): Geno.mtx, haplo.mtx (REALSXP n x m) and the list of the
+ * Cova.haplo.mtx.list matrices (each REALSXP n x m) */
+SEXP spagxe_r_run_localance(SEXP ptr, SEXP G, SEXP H, SEXP chl, SEXP prm) {
+    spagxe_ctx *ctx = get_ctx(ptr);
+    const int n = nrows(G), m = ncols(G), L = (int)XLENGTH(chl);
+    if (nrows(H) != n || ncols(H) != m) Rf_error("haplo.mtx must have the shape of Geno.mtx");
+    if (L > 4) Rf_error("at most 4 matrices in Cova.haplo.mtx.list");
+    const double *ch[4] = {NULL, NULL, NULL, NULL};
+    for (int l = 0; l < L; l++) {
+        SEXP c = VECTOR_ELT(chl, l);
+        if (!isReal(c) || nrows(c) != n || ncols(c) != m) Rf_error("Cova.haplo.mtx.list[[%d]] must be a numeric matrix of the shape of Geno.mtx", l + 1);
+        ch[l] = REAL(c);
+    }
+    spagxe_params sp; params_from_sexp(prm, &sp);
+    SEXP out = PROTECT(allocMatrix(REALSXP, m, 10));
+    spagxe_diag diag; memset(&diag, 0, sizeof diag);
+    int rc = spagxe_run_localance(ctx, n, m, REAL(G), REAL(H), L, ch, n, &sp, REAL(out), &diag);
+    if (rc != SPAGXE_OK) { UNPROTECT(1); Rf_error("%s", spagxe_last_error(ctx)); }
+    attach_diag(out, &diag);
+    UNPROTECT(1);
+    return out;
+}
+
 /* ---- several GPUs of the node (SPAGxE_CCT's n.gpus argument) ---- */
 SEXP spagxe_r_mgpu_create(SEXP n_gpus) {
     spagxe_mgpu *mg = NULL;
@@ -195,6 +218,7 @@ static const R_CallMethodDef call_methods[] = {
     {"spagxe_r_set_grm", (DL_FUNC)&spagxe_r_set_grm, 6},
     {"spagxe_r_plus_nullmodel", (DL_FUNC)&spagxe_r_plus_nullmodel, 6},
     {"spagxe_r_run", (DL_FUNC)&spagxe_r_run, 9},
+    {"spagxe_r_run_localance", (DL_FUNC)&spagxe_r_run_localance, 5},
     {"spagxe_r_mgpu_create", (DL_FUNC)&spagxe_r_mgpu_create, 1},
     {"spagxe_r_mgpu_destroy", (DL_FUNC)&spagxe_r_mgpu_destroy, 1},
     {"spagxe_r_mgpu_set_inputs", (DL_FUNC)&spagxe_r_mgpu_set_inputs, 6},

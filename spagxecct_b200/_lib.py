@@ -21,7 +21,7 @@ GENO_COUNT_A2 = 1
 EXPORTS = [
     "spagxe_ctx_create", "spagxe_ctx_destroy", "spagxe_last_error", "spagxe_ctx_set_stream", "spagxe_version",
     "spagxe_set_vectors", "spagxe_set_vectors_device", "spagxe_set_wald", "spagxe_set_pcs", "spagxe_set_grm",
-    "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_bed_counts", "spagxe_bed_decode",
+    "spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_run_localance", "spagxe_bed_counts", "spagxe_bed_decode",
     "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
     "spagxe_set_wald_device", "spagxe_set_wald_survival", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
     "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus", "spagxe_mgpu_set_wald_survival",
@@ -109,6 +109,8 @@ def load():
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     for f in ("spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
+    L.spagxe_run_localance.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                                       C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
     L.spagxe_bed_counts.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
     L.spagxe_bed_decode.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
     L.spagxe_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -238,6 +240,22 @@ class Context:
 
     def run_plus(self, geno, params=None, out_ptr=None):
         return self._run(self.L.spagxe_run_plus, 8, geno, params, out_ptr)
+
+    def run_localance(self, G, H, cova_haplo=(), params=None):
+        """SPAGxEmixCCT_localance loop (ref R/SPAGxECCT.R:1443-1476): G, H and every matrix of cova_haplo are (N, M)."""
+        G = np.asfortranarray(G, dtype=np.float64); H = np.asfortranarray(H, dtype=np.float64)
+        chs = [np.asfortranarray(c, dtype=np.float64) for c in cova_haplo]
+        n, m = G.shape
+        assert H.shape == (n, m) and all(c.shape == (n, m) for c in chs)
+        arr = (C.c_void_p * max(len(chs), 1))(*[c.ctypes.data for c in chs])
+        prm = params if isinstance(params, Params) else make_params(**(params or {}))
+        diag = Diag()
+        out = np.empty((m, 10), dtype=np.float64, order="F")
+        rc = self.L.spagxe_run_localance(self.h, n, m, G.ctypes.data, H.ctypes.data, len(chs), arr, n, C.byref(prm),
+                                         out.ctypes.data, C.byref(diag))
+        self.last_diag = diag.asdict()
+        self._chk(rc)
+        return out, self.last_diag
 
     def bed_counts(self, geno):
         counts = np.zeros((geno.n_snps, 4), dtype=np.int64)

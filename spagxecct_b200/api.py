@@ -413,6 +413,62 @@ def SPAGxE_Plus_one_SNP(g, E, Phen_mtx, Cova_mtx, obj_SPAGxE_Plus_Nullmodel, eps
     return res.values[0].copy()
 
 
+COLS_LOCAL = ["MAF", "missing.rate", "p.value.spaGxE.index.ance", "p.value.spaGxE.Wald.index.ance",
+              "p.value.spaGxE.CCT.Wald.index.ance", "p.value.normGxE.index.ance", "p.value.betaG.index.ance",
+              "Stat.betaG.index.ance", "Var.betaG.index.ance", "z.betaG.index.ance"]
+
+
+def SPAGxEmixCCT_localance(traits="survival/binary/quantitative/categorical", Geno_mtx=None, haplo_mtx=None, R=None, Cutoff=2,
+                           E=None, Phen_mtx=None, Cova_mtx=None, Cova_haplo_mtx_list=None, epsilon=0.001,
+                           impute_method="fixed", missing_cutoff=0.15, min_maf=0.0001, G_model="Add", ctx=None, device=0,
+                           quiet=False):
+    """Drop-in for SPAGxEmixCCT_localance (R/SPAGxECCT.R:1401-1481): M x 10 (the reference returns them as a data
+    frame behind an rsID column: Result.rownames holds the marker names).  Cova_haplo_mtx_list: mapping or sequence
+    of (N, M) matrices.  Binary and quantitative traits; Cutoff is accepted and not used, like the reference."""
+    if _trait_code(traits) not in (_lib.TRAIT_BINARY, _lib.TRAIT_QUANTITATIVE):
+        raise NotImplementedError('SPAGxEmixCCT_localance: the survival and categorical Wald tests are implemented for SPAGxE_CCT only')
+    if impute_method != "fixed":
+        raise NotImplementedError('only impute.method = "fixed" exists in the reference')
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        G, _, snp_ids = _split_geno(Geno_mtx)
+        H, _, _ = _split_geno(haplo_mtx)
+        chl = Cova_haplo_mtx_list or []
+        chs = [_split_geno(c)[0] for c in (chl.values() if hasattr(chl, "values") else chl)]
+        n, m = np.shape(G)
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+        _prep_common(ctx, R, E)
+        ctx.set_wald(_trait_code(traits), _wald_y(traits, Phen_mtx), np.asarray(Cova_mtx, dtype=np.float64))
+        if not quiet:
+            print('[1] "Start Analyzing..."')
+            print(_now())
+        out, diag = ctx.run_localance(G, H, chs, _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model))
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_LOCAL, diag)
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxEmixCCT_localance_one_SNP(traits, g, haplo_numVec, R, E, Phen_mtx, Cova_mtx, Cova_haplo_mtx=None, epsilon=0.001,
+                                   Cutoff=2, impute_method="fixed", missing_cutoff=0.15, min_maf=0.0001, G_model="Add",
+                                   ctx=None, device=0):
+    """Drop-in for SPAGxEmixCCT_localance_one_SNP (R/SPAGxECCT.R:1496-1647): numeric(10).  Cova_haplo_mtx: (N, L)."""
+    ch = [] if Cova_haplo_mtx is None else [np.asarray(Cova_haplo_mtx, dtype=np.float64).reshape(len(g), -1)[:, [l]]
+                                            for l in range(np.asarray(Cova_haplo_mtx).reshape(len(g), -1).shape[1])]
+    res = SPAGxEmixCCT_localance(traits, Geno_mtx=np.asarray(g, dtype=np.float64).reshape(-1, 1),
+                                 haplo_mtx=np.asarray(haplo_numVec, dtype=np.float64).reshape(-1, 1), R=R, Cutoff=Cutoff, E=E,
+                                 Phen_mtx=Phen_mtx, Cova_mtx=Cova_mtx, Cova_haplo_mtx_list=ch, epsilon=epsilon,
+                                 impute_method=impute_method, missing_cutoff=missing_cutoff, min_maf=min_maf, G_model=G_model,
+                                 ctx=ctx, device=device, quiet=True)
+    return res.values[0].copy()
+
+
 def _grm_triplets(obj):
     grm = obj["sparseGRM"]
     if "i" in grm:

@@ -61,6 +61,7 @@ struct spagxe_ctx {
     int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false; int opt_mix_cluster = 8;
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
+    int64_t cap_local = 0; uint8_t *d_local = nullptr;     // SPAGxEmixCCT_localance: packed rows of g, haplo and the haplotype covariates
     BbFarm *farm = nullptr;                                // SPAGxE_CCT branch-B solver farm (K5)
     CoxData *cox = nullptr;                                // traits = "survival": time order, tie groups, gathered columns
     std::vector<double> h_time, h_event;                   // Phen.mtx$surv.time / $event (host copies for the sort)
@@ -154,6 +155,8 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     // opt in to the large dynamic shared memory of the per-SNP SPAGxEmix kernel
     e = cudaFuncSetAttribute(k_mix_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
+    e = cudaFuncSetAttribute(k_localance_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_localance_snp)", e);
     if ((e = cudaMalloc((void **)&ctx->quad.x, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.w, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void **)&ctx->quad.wfix, sizeof(long long) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -178,7 +181,7 @@ extern "C" void spagxe_ctx_destroy(spagxe_ctx *ctx) {
     cudaFree(ctx->d_gi); cudaFree(ctx->d_gj); cudaFree(ctx->d_gv); cudaFree(ctx->d_Rn_user);
     cudaFree(ctx->d_bed[0]); cudaFree(ctx->d_bed[1]); cudaFree(ctx->d_stats); cudaFree(ctx->d_istats);
     cudaFree(ctx->d_partial); cudaFree(ctx->d_ipartial); cudaFree(ctx->d_spa_list); cudaFree(ctx->d_b_list);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_dense); cudaFree(ctx->d_local); cudaFree(ctx->d_spax_list); cudaFree(ctx->d_mcache);
     mix_scratch_destroy(ctx->mix_scratch);
     bb_farm_destroy(ctx->farm);
     cox_destroy(ctx->cox);
@@ -865,6 +868,101 @@ extern "C" int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *g, const spag
 }
 extern "C" int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
     return run_generic(ctx, g, prm, out, diag, RUN_MIX);
+}
+
+// ---------------------------------------------------------------------------
+// SPAGxEmixCCT_localance (ref R/SPAGxECCT.R:1401-1647).  The reference takes R matrices only (Geno.mtx, haplo.mtx and
+// the matrices of Cova.haplo.mtx.list, all N x M): they are copied in column blocks, packed to 2 bits on the device
+// (values outside {0, 1, 2} are refused) and tested by one cluster per SNP (k_localance_snp).
+extern "C" int spagxe_run_localance(spagxe_ctx *ctx, int64_t n, int64_t m, const double *G, const double *H, int n_cov_haplo,
+                                    const double *const *cov_haplo, int64_t ld, const spagxe_params *prm, double *out,
+                                    spagxe_diag *diag) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (!prm) prm = &kDefaultParams;
+    if (!G || !H || !out || m < 0 || n <= 0) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: bad arguments");
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_localance: call spagxe_set_vectors first");
+    if (n != ctx->n) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: matrices have %lld rows but R has %lld", (long long)n, (long long)ctx->n);
+    if (ld < n) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: leading dimension < N");
+    if (n_cov_haplo < 0 || n_cov_haplo > kMaxLocalCov || (n_cov_haplo > 0 && !cov_haplo))
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_localance: at most %d matrices in Cova.haplo.mtx.list", kMaxLocalCov);
+    if (ctx->wald_trait != SPAGXE_TRAIT_BINARY && ctx->wald_trait != SPAGXE_TRAIT_QUANTITATIVE)
+        return fail(ctx, ctx->wald_trait == 0 ? SPAGXE_ERR_STATE : SPAGXE_ERR_UNSUPPORTED,
+                    "run_localance: call spagxe_set_wald first (binary or quantitative trait; the survival / categorical Wald tests "
+                    "are implemented for SPAGxE_CCT only)");
+    const int q_full = 1 + n_cov_haplo + ctx->wald_p + (ctx->wald_trait == SPAGXE_TRAIT_QUANTITATIVE ? 1 : 0) + 3;
+    if (q_full > kMaxQ) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_localance: the Wald design has %d columns (at most %d)", q_full, kMaxQ);
+    if (prm->g_model < 0 || prm->g_model > 2) return fail(ctx, SPAGXE_ERR_ARG, "g_model must be 0 (Add), 1 (Dom) or 2 (Rec)");
+    if (prm->impute_method != 0) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "only impute.method=\"fixed\" exists");
+    if (prm->out_location == SPAGXE_LOC_DEVICE) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: the result matrix lives on the host");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    int rc = ensure_vec_mode(ctx, 1, nullptr);   // R, E and the constants of R on the device (V = E R is not used here)
+    if (rc) return rc;
+    spagxe_diag dg; memset(&dg, 0, sizeof dg);
+    cudaEvent_t ev0, ev1;
+    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    CU(cudaEventRecord(ev0, s));
+    const int nmat = 2 + n_cov_haplo;
+    const int64_t row_bytes = (n + 3) / 4, pitch = round_up(row_bytes, 16);
+    // column blocks: the dense staging buffer holds `mc` columns of one matrix (<= 256 MB), the packed rows of all matrices follow
+    const int64_t mc_max = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(m, 1), (256ll << 20) / (n * 8)));
+    const int64_t need_dense = mc_max * n * 8, need_rows = (int64_t)nmat * mc_max * pitch, need_out = std::max<int64_t>(m, 1) * 10;
+    if (need_dense > ctx->cap_dense) { CU(cudaStreamSynchronize(s)); cudaFree(ctx->d_dense); ctx->d_dense = nullptr; CU(cudaMalloc(&ctx->d_dense, need_dense)); ctx->cap_dense = need_dense; }
+    if (need_rows > ctx->cap_local) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_local, need_rows)); ctx->cap_local = need_rows; }
+    if (need_out > ctx->cap_out) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_out, need_out)); ctx->cap_out = need_out; }
+    const double *mats[2 + kMaxLocalCov] = {G, H};
+    for (int l = 0; l < n_cov_haplo; l++) {
+        if (!cov_haplo[l]) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: Cova.haplo.mtx.list[%d] is NULL", l);
+        mats[2 + l] = cov_haplo[l];
+    }
+    cudaLaunchConfig_t cfg = {};
+    const int mcs = 8;
+    const int n_clusters = std::max(1, ctx->num_sms / mcs);
+    cfg.gridDim = dim3((unsigned)(n_clusters * mcs));
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = branch_b_smem(kMaxQ);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)mcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    for (int64_t j0 = 0; j0 < m; j0 += mc_max) {
+        const int mc = (int)std::min<int64_t>(mc_max, m - j0);
+        for (int k = 0; k < nmat; k++) {
+            CU(cudaMemcpy2DAsync(ctx->d_dense, n * 8, mats[k] + j0 * ld, ld * 8, n * 8, mc, cudaMemcpyHostToDevice, s));
+            dg.h2d_bytes += n * 8 * mc;
+            CU(launch_pack_dense(s, 1, ctx->d_dense, n, n, mc, (uint32_t *)(ctx->d_local + (int64_t)k * mc_max * pitch), pitch / 4, ctx->d_ctr));
+            ctx->launches++;
+        }
+        LocalArgs a;
+        a.g_rows = ctx->d_local; a.h_rows = ctx->d_local + mc_max * pitch; a.n_ch = n_cov_haplo; a.pitch = pitch;
+        for (int l = 0; l < kMaxLocalCov; l++) a.ch_rows[l] = (l < n_cov_haplo) ? ctx->d_local + (int64_t)(2 + l) * mc_max * pitch : nullptr;
+        a.m = mc; a.snp0 = j0; a.m_total = m; a.n = n;
+        a.R = ctx->d_R; a.E = ctx->d_E; a.vc = ctx->d_vc; a.wd = WaldData{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
+        a.epsilon = prm->epsilon; a.min_maf = prm->min_maf; a.g_model = prm->g_model;
+        a.out = ctx->d_out; a.ctr = ctx->d_ctr;
+        CU(cudaLaunchKernelEx(&cfg, k_localance_snp, a));
+        ctx->launches++;
+    }
+    CU(cudaEventRecord(ev1, s));
+    Counters hc;
+    CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
+    if (m > 0) CU(cudaMemcpyAsync(out, ctx->d_out, sizeof(double) * m * 10, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    dg.ms_total = ms; dg.ms_tests = ms; dg.d2h_bytes = m * 10 * 8;
+    fill_diag(&dg, hc, m);
+    dg.kernel_launches = ctx->launches;
+    if (diag) *diag = dg;
+    if (hc.n_nonint) return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
+                                 "run_localance: Geno.mtx / haplo.mtx / Cova.haplo.mtx.list hold values outside {0, 1, 2}");
+    if (hc.n_allmissing) return fail(ctx, SPAGXE_ERR_ARG, "run_localance: %llu SNP(s) hold NA in g or haplo_numVec (the reference stops at `if (MAF > 0.5)`)",
+                                     hc.n_allmissing);
+    if (hc.n_singular) return fail(ctx, SPAGXE_ERR_SINGULAR, "solve(t(W)%%*%%W) is singular for %llu SNP(s)", hc.n_singular);
+    if (hc.n_cct_stop) return fail(ctx, SPAGXE_ERR_CCT_STOP, "CCT() would stop() for %llu SNP(s) (NA or out-of-range p-value)",
+                                   hc.n_cct_stop);
+    return SPAGXE_OK;
 }
 
 extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv,

@@ -11,4 +11,5 @@ void Rf_error(const char *, ...); int asInteger(SEXP); double asReal(SEXP); R_xl
 double *REAL(SEXP); int *INTEGER(SEXP); unsigned char *RAW(SEXP); int TYPEOF(SEXP); int nrows(SEXP); int ncols(SEXP);
 SEXP allocVector(int, R_xlen_t); SEXP allocMatrix(int, int, int); SEXP PROTECT(SEXP); void UNPROTECT(int);
 void SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); void SET_STRING_ELT(SEXP, R_xlen_t, SEXP); SEXP mkChar(const char *);
+SEXP VECTOR_ELT(SEXP, R_xlen_t); int isReal(SEXP);
 SEXP setAttrib(SEXP, SEXP, SEXP); SEXP install(const char *);
