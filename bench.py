@@ -28,8 +28,9 @@ N_SAMPLES = 500_000
 PREVALENCE = 0.01
 SEED_PHENO = 12345
 SEED_GENO = 20251019
-# DRAM bytes per algorithmic byte of the score kernel: 1.070415 GB read + 7.95 MB written per 1.024 GB launch (ncu --set full)
-SCORE_TRAFFIC_PER_ALGORITHMIC_BYTE = (1.070415e9 + 7.950592e6) / 1.024e9
+# DRAM bytes per algorithmic byte of the score kernel: mean of the two 1.024 GB launches of the committed ncu --set full
+# capture (profiles/r02_ncu_k_score_unpack_mma.txt): 1.008 / 1.106 GB read, 8.0 / 8.8 MB written
+SCORE_TRAFFIC_PER_ALGORITHMIC_BYTE = ((1.008232e9 + 1.105881e9) / 2 + (8.013056e6 + 8.835072e6) / 2) / 1.024e9
 
 
 def make_pheno(n=N_SAMPLES):
