@@ -1245,8 +1245,20 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
     const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
     const int k = md.k, k1 = md.k + 1;
     const double NA = d_na_real();
-    for (int idx = cluster_id; idx < count; idx += n_clusters) {
+    // Dynamic queue over the item list, heavy items first: the first sweep takes the SNPs that still need their allele-frequency
+    // model or branch B (several times the cost of the others), the second the saddlepoint-only SNPs the batched path
+    // handed over; a static round-robin left the clusters up to a third apart at the end of the kernel.
+    __shared__ int s_next;
+    (void)n_clusters;
+    for (;;) {
+        cl.sync();   // every CTA of the cluster is done with the previous item (and has read s_next)
+        if (rank == 0 && threadIdx.x == 0) s_next = atomicAdd(&ctr->work_cursor, 1);
+        cl.sync();
+        const int v = *cl.map_shared_rank(&s_next, 0);
+        if (v >= 2 * count) break;
+        const int idx = (v < count) ? v : v - count;
         const int entry = list[idx];
+        if ((v < count) == (hand != nullptr && (entry & kMixHandFlag) != 0)) continue;
         const int jl = entry & (kMixHandFlag - 1);
         const int64_t j = snp0 + jl;
         const uint8_t *row = bed + (int64_t)jl * pitch;

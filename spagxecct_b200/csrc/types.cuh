@@ -34,7 +34,7 @@ struct BItem { const uint8_t *row; long long snp; int asum, nmiss; double D0, T0
 struct Counters {  // device-side diagnostics / work-list cursors
     unsigned long long n_filtered, n_branch_a, n_branch_b, n_spa, n_wald_fail, n_cct_stop, n_singular,
         n_mix_logistic, newton_iters, n_allmissing, n_nonint, cox_evals, clm_evals;
-    int spa_count, spax_count, b_count, pad_;
+    int spa_count, spax_count, b_count, work_cursor;   // work_cursor: dynamic item queue of k_mix_snp (reset with the lists)
 };
 
 struct BmatInfo { int sR, sV; double maxR, maxV; };   // fixed-point scales of the tensor-core B matrix
