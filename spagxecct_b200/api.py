@@ -15,6 +15,7 @@ with the columns the reference reads (`ID`, `Y`).  Geno_mtx is an (N, M) array (
 NA) or a pandas DataFrame whose index/columns play the role of dimnames.
 """
 import datetime
+import os
 
 import numpy as np
 
@@ -177,11 +178,14 @@ def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
         raise NotImplementedError(f"control option(s) {sorted(unknown)} are not supported")
     if control.get("ImputeMethod", "none") != "none":
         raise NotImplementedError('control$ImputeMethod other than "none": the Step-2 functions impute themselves (impute.method)')
-    order = control.get("AlleleOrder", "alt-first")         # GRAB's default for PLINK input: count A1
+    is_bgen = str(GenoFile).endswith(".bgen")
+    order = control.get("AlleleOrder", "ref-first" if is_bgen else "alt-first")   # GRAB's defaults: PLINK counts A1, BGEN the second allele
     if order not in ("alt-first", "ref-first"):
         raise RStop("control$AlleleOrder should be 'ref-first' or 'alt-first'.")
+    if is_bgen:
+        return _read_bgen_file(GenoFile, GenoFileIndex, sample_ids, control, order)
     if not str(GenoFile).endswith(".bed"):
-        raise NotImplementedError("GenoFile must be a PLINK .bed file (BGEN input is not implemented)")
+        raise NotImplementedError("GenoFile must be a PLINK .bed or a .bgen file")
     bim = fam = None
     if GenoFileIndex is not None:
         bim, fam = GenoFileIndex[0], GenoFileIndex[1]
@@ -209,6 +213,35 @@ def _read_geno_file(GenoFile, GenoFileIndex, sample_ids, control):
     geno = _lib.Context.geno_desc(_lib.GENO_BED, rows.ctypes.data, n, m, bf.row_bytes, sample_index=sidx,
                                   n_file_samples=bf.n, count_a2=(order == "ref-first"))
     return geno, (rows, sidx, bf), n, m, snp_ids, ids
+
+
+def _read_bgen_file(GenoFile, GenoFileIndex, sample_ids, control, order):
+    """GRAB.ReadGeno for BGEN input (GenoFileIndex = c(bgiFile, sampleFile); the .bgi index is not needed here): the
+    probabilities are decoded on the host into the N x M dosage matrix (spagxecct_b200/bgenio.py); hard-call-valued
+    dosages then take the 2-bit pipeline, imputed ones the dense dosage kernel of SPAGxE_CCT."""
+    from .bgenio import BgenFile
+    sample_path = None
+    if GenoFileIndex is not None and len(GenoFileIndex) > 1:
+        sample_path = GenoFileIndex[1]
+    elif os.path.exists(str(GenoFile)[:-5] + ".sample"):
+        sample_path = str(GenoFile)[:-5] + ".sample"
+    bf = BgenFile(GenoFile, sample_path)
+    sel = _select_markers(bf, control)
+    D = bf.read_dosages(sel, allele_order=order)
+    snp_ids = bf.snp_ids if sel is None else [bf.snp_ids[j] for j in sel]
+    ids = bf.sample_ids
+    if sample_ids is not None:
+        want = [str(x) for x in sample_ids]
+        if want != ids:
+            pos = {s_: i for i, s_ in enumerate(ids)}
+            missing = [s_ for s_ in want if s_ not in pos]
+            if missing:
+                raise RStop(f"SampleIDs not found in the BGEN sample list: {missing[:3]}...")
+            D = np.asfortranarray(D[[pos[s_] for s_ in want], :])
+            ids = want
+    n, m = D.shape
+    geno = _lib.Context.geno_desc(_lib.GENO_F64, D.ctypes.data, n, m, n)
+    return geno, (D, bf), n, m, snp_ids, ids
 
 
 def _now():

@@ -1732,4 +1732,172 @@ __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A) {
     cl.sync();
 }
 
+// ===========================================================================
+// SPAGxE_CCT_one_SNP (R/SPAGxECCT.R:543-683) on a real-valued genotype vector (imputed dosages): the 2-bit path above
+// needs g in {0, 1, 2, NA}; a matrix with other values goes through this kernel -- one cluster per SNP, g read as
+// doubles (8 bytes per sample instead of 0.25: a compatibility path, HBM / PCIe bound by its input).
+struct GDense {   // processed genotype: NA -> 2 MAF, flip, Dom / Rec (ref :562-574)
+    const double *col; double imp; int flip, g_model;
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        double g = col[i];
+        if (isnan(g)) g = imp;
+        if (flip) g = 2 - g;
+        if (g_model == 1) g = (g >= 1) ? 1.0 : 0.0;
+        if (g_model == 2) g = (g <= 1) ? 0.0 : 1.0;
+        return g;
+    }
+};
+struct SrcDenseAdj {  // R.new0_i = E_i (R_i - a - b g_i) (ref :609-612)
+    const double *R, *E; GDense gf; double a, b, maf;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
+        r = E[i] * (R[i] - (a + b * gf(i))); m = maf; w = 1.0;
+    }
+};
+struct DesignWaldDense {
+    WaldData wd; const double *E; GDense gf; int64_t n;
+    __device__ __forceinline__ int q() const { return wd.p + 4; }
+    __device__ __forceinline__ int trait() const { return wd.trait; }
+    __device__ __forceinline__ double y(int64_t i) const { return wd.Y[i]; }
+    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
+        const int p = q - 4;
+        const double g = gf(i), ev = E[i];
+        x[0] = 1.0;
+        for (int c = 0; c < p; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
+        x[p + 1] = ev; x[p + 2] = g; x[p + 3] = ev * g;
+    }
+    template <int Q>
+    __device__ __forceinline__ void fill(int64_t i, double *x) const { fill_rt(i, x, Q); }
+};
+
+__global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A) {
+    namespace cg = cooperative_groups;
+    extern __shared__ double tile[];
+    __shared__ BShared sh;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const VecConst vc = *A.vc;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t n = A.n, m_total = A.m_total;
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const double NA = d_na_real();
+    const bool writer = (rank == 0 && threadIdx.x == 0);
+    for (int jl = cluster_id; jl < A.m; jl += n_clusters) {
+        const double *col = A.G + (int64_t)jl * A.ld;
+        double *o = A.out + A.snp0 + jl;
+        // ---- mean(g, na.rm = T), missing rate (ref :557-560) ----
+        double a2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = col[i];
+            if (!isnan(g)) { a2[0] += g; a2[1] += 1.0; }
+        }
+        red.sum<2>(a2);
+        const double n_obs = a2[1], n_miss = (double)n - n_obs;
+        if (n_obs == 0) {
+            if (writer) { for (int c = 0; c < 10; c++) o[c * m_total] = NA; o[m_total] = 1.0; atomicAdd(&A.ctr->n_allmissing, 1ULL); }
+            continue;
+        }
+        double MAF = (a2[0] / n_obs) / 2;
+        const double miss_rate = n_miss / (double)n;
+        GDense gf; gf.col = col; gf.imp = 2 * MAF; gf.flip = 0; gf.g_model = A.g_model;
+        if (MAF > 0.5) { MAF = 1 - MAF; gf.flip = 1; }
+        if (MAF < A.min_maf) {
+            if (writer) { o[0] = MAF; o[m_total] = miss_rate; for (int c = 2; c < 10; c++) o[c * m_total] = NA; atomicAdd(&A.ctr->n_filtered, 1ULL); }
+            continue;
+        }
+        // ---- sums of the processed vector: S1 = sum(g R), sum(g R.new), sum(g), sum(g^2) ----
+        double s4[4] = {0, 0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = gf(i);
+            s4[0] += g * A.R[i]; s4[1] += g * A.Rn[i]; s4[2] += g; s4[3] += g * g;
+        }
+        red.sum<4>(s4);
+        const double S1 = s4[0], sum_g = s4[2];
+        const double VarS1 = vc.sumR2 * (2 * MAF * (1 - MAF));
+        const double Z1 = S1 / sqrt(VarS1);
+        const double pG = d_pnorm(-fabs(Z1), true) * 2;
+        double po[4];
+        int iters = 0; bool spa = false;
+        if (pG > A.epsilon) {
+            if (writer) atomicAdd(&A.ctr->n_branch_a, 1ULL);
+            double mafi, S, Smean, z;
+            const int r = homo_scalar(sum_g, n, s4[1], vc.sumRn, vc.sumRn2, 0.00001, 2.0, &mafi, &S, &Smean, &z);   // ref :598
+            if (r == 2) { po[0] = po[1] = po[2] = po[3] = NA; }
+            else if (r == 0) { const double pn = d_pnorm(fabs(z), false) * 2; po[0] = po[1] = po[2] = po[3] = pn; }
+            else {
+                spa = true;
+                SrcHomo src; src.rv = A.Rn; src.maf = mafi;
+                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), &iters);
+                po[0] = po[1] = po[2] = ps;
+                po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            }
+        } else {
+            if (writer) atomicAdd(&A.ctr->n_branch_b, 1ULL);
+            const double a = (double)n, b = sum_g, d = s4[3];
+            const double det = a * d - b * b;
+            if (det == 0 || !isfinite(det)) {
+                if (writer) {
+                    o[0] = MAF; o[m_total] = miss_rate;
+                    o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                    o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+                    atomicAdd(&A.ctr->n_singular, 1ULL);
+                }
+                continue;
+            }
+            const double i00 = d / det, i01 = -b / det, i11 = a / det;
+            SrcDenseAdj src;
+            src.R = A.R; src.E = A.E; src.gf = gf;
+            src.a = i00 * vc.sumR + i01 * S1; src.b = i01 * vc.sumR + i11 * S1;
+            double v3[3] = {0, 0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                double r, mm, w; src.get(i, r, mm, w);
+                v3[0] += gf(i) * r; v3[1] += r; v3[2] += r * r;
+            }
+            red.sum<3>(v3);
+            double mafi, S, Smean, z, pspa, pn;
+            const int r = homo_scalar(sum_g, n, v3[0], v3[1], v3[2], A.min_maf, 2.0, &mafi, &S, &Smean, &z);   // ref :616
+            if (r == 2) { pspa = NA; pn = NA; }
+            else if (r == 0) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
+            else {
+                spa = true; src.maf = mafi;
+                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S, 2 * Smean - S), fmin(S, 2 * Smean - S), &iters);
+                pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            }
+            DesignWaldDense ds{A.wd, A.E, gf, n};
+            const int q = ds.q();
+            double pw = NA; int wfail = 0, invalid;
+            if (A.wd.trait == 1) {
+                double se2 = 0;
+                const int rc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
+                if (rc) wfail = rc; else pw = 2 * d_pnorm(-fabs(sh.beta[q - 1] / sqrt(se2)), true);
+            } else {
+                wald_pass_any(ds, i_lo, i_hi, q, true, tile, sh, red, &invalid);
+                wald_solve(sh, q);
+                if (!sh.ok) wfail = 1;
+                else {
+                    const double il = sh.se2, bl = sh.beta[q - 1];
+                    const double rss = wald_pass_any(ds, i_lo, i_hi, q, false, tile, sh, red, &invalid);
+                    const double rdf = (double)(n - q);
+                    pw = d_pt2(bl / sqrt(il * (rss / rdf)), rdf);
+                }
+            }
+            double pc = NA;
+            const int crc = d_cct2(pspa, pw, &pc);
+            if (writer) {
+                if (wfail) atomicAdd(&A.ctr->n_wald_fail, 1ULL);
+                if (crc) atomicAdd(&A.ctr->n_cct_stop, 1ULL);
+            }
+            po[0] = pspa; po[1] = pw; po[2] = crc ? NA : pc; po[3] = pn;
+        }
+        if (writer) {
+            o[0] = MAF; o[m_total] = miss_rate;
+            o[2 * m_total] = po[0]; o[3 * m_total] = po[1]; o[4 * m_total] = po[2]; o[5 * m_total] = po[3];
+            o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+            if (spa) { atomicAdd(&A.ctr->n_spa, 1ULL); atomicAdd(&A.ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+    cl.sync();
+}
+
 }  // namespace spagxe

@@ -155,6 +155,8 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     // opt in to the large dynamic shared memory of the per-SNP SPAGxEmix kernel
     e = cudaFuncSetAttribute(k_mix_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
+    e = cudaFuncSetAttribute(k_cct_dosage_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_cct_dosage_snp)", e);
     e = cudaFuncSetAttribute(k_localance_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_localance_snp)", e);
     if ((e = cudaMalloc((void **)&ctx->quad.x, sizeof(double) * kQBins * kQNodes)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -710,6 +712,76 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     return SPAGXE_OK;
 }
 
+// SPAGxE_CCT on a real-valued matrix (imputed dosages): the 2-bit pipeline refuses values outside {0, 1, 2, NA}, so a
+// double matrix that holds such values is tested by k_cct_dosage_snp instead (one cluster per SNP, g read as doubles).
+// Binary and quantitative traits.
+static int run_cct_dosage(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+    if (g->kind != SPAGXE_GENO_F64) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "dosage input must be a double matrix");
+    if (ctx->wald_trait != SPAGXE_TRAIT_BINARY && ctx->wald_trait != SPAGXE_TRAIT_QUANTITATIVE)
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "Geno.mtx holds non-integer dosages: the survival / categorical Wald tests need hard calls");
+    if (prm->out_location == SPAGXE_LOC_DEVICE) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "dosage input: the result matrix lives on the host");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream();
+    int rc = ensure_vec_mode(ctx, 0, nullptr);
+    if (rc) return rc;
+    const int64_t n = g->n_samples, m = g->n_snps, ld = g->pitch;
+    spagxe_diag dg; memset(&dg, 0, sizeof dg);
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
+    EventPool evp(ctx);
+    cudaEvent_t ev0 = evp.rec(s);
+    const bool on_dev = (g->location == SPAGXE_LOC_DEVICE);
+    const int64_t mc_max = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(m, 1), (256ll << 20) / (n * 8)));
+    const int64_t need_dense = mc_max * n * 8, need_out = std::max<int64_t>(m, 1) * 10;
+    if (!on_dev && need_dense > ctx->cap_dense) { CU(cudaStreamSynchronize(s)); cudaFree(ctx->d_dense); ctx->d_dense = nullptr; CU(cudaMalloc(&ctx->d_dense, need_dense)); ctx->cap_dense = need_dense; }
+    if (need_out > ctx->cap_out) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_out, need_out)); ctx->cap_out = need_out; }
+    cudaLaunchConfig_t cfg = {};
+    const int mcs = 8;
+    const int n_clusters = std::max(1, ctx->num_sms / mcs);
+    cfg.gridDim = dim3((unsigned)(n_clusters * mcs));
+    cfg.blockDim = dim3(kBThreads);
+    cfg.dynamicSmemBytes = branch_b_smem(kMaxQ);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)mcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const double *G = (const double *)g->data;
+    for (int64_t j0 = 0; j0 < m; j0 += mc_max) {
+        const int mc = (int)std::min<int64_t>(mc_max, m - j0);
+        DosageArgs a;
+        if (on_dev) { a.G = G + j0 * ld; a.ld = ld; }
+        else {
+            CU(cudaMemcpy2DAsync(ctx->d_dense, n * 8, G + j0 * ld, ld * 8, n * 8, mc, cudaMemcpyHostToDevice, s));
+            dg.h2d_bytes += n * 8 * mc;
+            a.G = (const double *)ctx->d_dense; a.ld = n;
+        }
+        a.m = mc; a.snp0 = j0; a.m_total = m; a.n = n;
+        a.R = ctx->d_R; a.E = ctx->d_E; a.Rn = ctx->d_Rn; a.vc = ctx->d_vc;
+        a.wd = WaldData{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
+        a.epsilon = prm->epsilon; a.min_maf = prm->min_maf; a.g_model = prm->g_model;
+        a.out = ctx->d_out; a.ctr = ctx->d_ctr;
+        CU(cudaLaunchKernelEx(&cfg, k_cct_dosage_snp, a));
+        ctx->launches++;
+    }
+    cudaEvent_t ev1 = evp.rec(s);
+    Counters hc;
+    CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
+    if (m > 0) {
+        const int64_t old = prm->out_ld > 0 ? prm->out_ld : m;
+        CU(cudaMemcpy2DAsync(out, old * 8, ctx->d_out, m * 8, m * 8, 10, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+    dg.ms_total = ms; dg.ms_tests = ms; dg.d2h_bytes = m * 10 * 8;
+    fill_diag(&dg, hc, m);
+    dg.kernel_launches = ctx->launches;
+    if (diag) *diag = dg;
+    if (hc.n_allmissing) return fail(ctx, SPAGXE_ERR_ARG, "%llu SNP(s) have every genotype missing (the reference stops here)", hc.n_allmissing);
+    if (hc.n_singular) return fail(ctx, SPAGXE_ERR_SINGULAR, "solve(t(W)%%*%%W) is singular for %llu SNP(s)", hc.n_singular);
+    if (hc.n_cct_stop) return fail(ctx, SPAGXE_ERR_CCT_STOP, "CCT() would stop() for %llu SNP(s) (NA or out-of-range p-value)", hc.n_cct_stop);
+    return SPAGXE_OK;
+}
+
 static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag,
                        RunMode mode) {
     if (!ctx) return SPAGXE_ERR_ARG;
@@ -850,8 +922,12 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     dg.kernel_launches = ctx->launches;
     dg.score_bytes = M * pl.row_bytes;
     if (diag) *diag = dg;
-    if (hc.n_nonint) return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
-                                 "Geno.mtx holds values outside {0,1,2,NA}: imputed dosages are not supported by the 2-bit path");
+    if (hc.n_nonint) {
+        // imputed dosages: SPAGxE_CCT has a dense per-SNP path for them; the other loops rest on the 2-bit coding
+        if (mode == RUN_CCT && g->kind == SPAGXE_GENO_F64) return run_cct_dosage(ctx, g, prm, out, diag);
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
+                    "Geno.mtx holds values outside {0,1,2,NA}: imputed dosages are supported by SPAGxE_CCT with a double matrix only");
+    }
     if (hc.n_allmissing) return fail(ctx, SPAGXE_ERR_ARG, "%llu SNP(s) have every genotype missing (the reference stops here)",
                                      hc.n_allmissing);
     if (hc.n_singular) return fail(ctx, SPAGXE_ERR_SINGULAR, "solve(t(W)%%*%%W) is singular for %llu SNP(s)", hc.n_singular);
@@ -899,10 +975,9 @@ extern "C" int spagxe_run_localance(spagxe_ctx *ctx, int64_t n, int64_t m, const
     int rc = ensure_vec_mode(ctx, 1, nullptr);   // R, E and the constants of R on the device (V = E R is not used here)
     if (rc) return rc;
     spagxe_diag dg; memset(&dg, 0, sizeof dg);
-    cudaEvent_t ev0, ev1;
-    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
-    CU(cudaEventRecord(ev0, s));
+    EventPool evp(ctx);
+    cudaEvent_t ev0 = evp.rec(s);
     const int nmat = 2 + n_cov_haplo;
     const int64_t row_bytes = (n + 3) / 4, pitch = round_up(row_bytes, 16);
     // column blocks: the dense staging buffer holds `mc` columns of one matrix (<= 256 MB), the packed rows of all matrices follow
@@ -945,12 +1020,12 @@ extern "C" int spagxe_run_localance(spagxe_ctx *ctx, int64_t n, int64_t m, const
         CU(cudaLaunchKernelEx(&cfg, k_localance_snp, a));
         ctx->launches++;
     }
-    CU(cudaEventRecord(ev1, s));
+    cudaEvent_t ev1 = evp.rec(s);
     Counters hc;
     CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
     if (m > 0) CU(cudaMemcpyAsync(out, ctx->d_out, sizeof(double) * m * 10, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1); cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
     dg.ms_total = ms; dg.ms_tests = ms; dg.d2h_bytes = m * 10 * 8;
     fill_diag(&dg, hc, m);
     dg.kernel_launches = ctx->launches;

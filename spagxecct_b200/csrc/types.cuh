@@ -100,4 +100,13 @@ struct LocalArgs {
     double *out; Counters *ctr;
 };
 
+// SPAGxE_CCT on a dense real-valued genotype matrix (imputed dosages; ref R/SPAGxECCT.R:543-683 with non-integer g)
+struct DosageArgs {
+    const double *G; int64_t ld;       // device, column-major n x m block (NaN = NA)
+    int m; int64_t snp0, m_total, n;
+    const double *R, *E, *Rn; const VecConst *vc; WaldData wd;
+    double epsilon, min_maf; int g_model;
+    double *out; Counters *ctr;
+};
+
 }  // namespace spagxe

@@ -147,11 +147,12 @@ def test_one_snp_entry_point_and_errors(gpu_ctx, oracle):
     v = SPAGxE_CCT_one_SNP("binary", G[:, 0], ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
     ref, *_ = oracle.cct_matrix("binary", G[:, :1], ph["R"], ph["E"], ph["Y"], ph["Cova"])
     assert_parity(v[None, :], ref, P_COLS, S_COLS, label="one_SNP")
-    # imputed (non-integer) dosages are refused loudly, not silently rounded
+    # imputed (non-integer) dosages are never rounded: the vector goes through the dense kernel (tests/test_dosage.py)
     g = G[:, 1].copy(); g[3] = 0.37
-    with pytest.raises(_lib.SpagxeError) as ei:
-        SPAGxE_CCT_one_SNP("binary", g, ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
-    assert ei.value.code == _lib.ERR_UNSUPPORTED
+    v = SPAGxE_CCT_one_SNP("binary", g, ph["R"], ph["E"], phen, ph["Cova"], ctx=gpu_ctx)
+    ref, *_ = oracle.cct_matrix("binary", g[:, None], ph["R"], ph["E"], ph["Y"], ph["Cova"])
+    assert np.isclose(v[0], ref[0, 0], rtol=1e-13)
+    assert_parity(v[None, :], ref, P_COLS, S_COLS, exact_cols=(1,), label="one_SNP dosage")
     # sample-count mismatch
     with pytest.raises(_lib.SpagxeError) as ei:
         gpu_ctx.run_cct(gpu_ctx.geno_desc(_lib.GENO_F64, G.ctypes.data, n - 1, 1, n - 1))
