@@ -39,7 +39,11 @@ template <int KPAD, int MODE>
 __global__ void __launch_bounds__(kMbThreads)
 k_mix_tile(const uint8_t *__restrict__ bed, int64_t pitch, int mc, int64_t n, int k, const double *__restrict__ pcs,
            const double *__restrict__ R, const double *__restrict__ E, const double *__restrict__ beta,
-           const int *__restrict__ asum, const int *__restrict__ nmiss, double *__restrict__ partial, int64_t per_split, int g_model) {
+           const int *__restrict__ asum, const int *__restrict__ nmiss, double *__restrict__ partial, int64_t per_split, int g_model,
+           const VecConst *__restrict__ vcp) {
+    // E enters the lambda-expanded statistics centred by the SNP-invariant c = sum(E R^2) / sum(R^2): with an uncentred E
+    // (a birth year, a large offset) the expansion in lambda would lose log10(E_rms^2 / Var E) digits to cancellation
+    const double e_centre = (MODE == 1) ? vcp->lambda : 0.0;
     constexpr int ROW = (MODE == 0) ? KPAD : KPAD + 6;    // doubles per staged sample row (even)
     constexpr int NP = (MODE == 0) ? KPAD : kMbStats;
     __shared__ __align__(16) double xs[kMbTile * ROW];
@@ -73,7 +77,7 @@ k_mix_tile(const uint8_t *__restrict__ bed, int64_t pitch, int mc, int64_t n, in
 #pragma unroll
             for (int c = 1; c < KPAD; c++) xr[c] = (in && c <= k) ? pcs[i + (int64_t)(c - 1) * n] : 0.0;
             if (MODE == 1) {
-                const double r = in ? R[i] : 0.0, e = in ? E[i] : 0.0, r2 = r * r;
+                const double r = in ? R[i] : 0.0, e = in ? E[i] - e_centre : 0.0, r2 = r * r;
                 xr[KPAD + 0] = r; xr[KPAD + 1] = r2; xr[KPAD + 2] = e * r2; xr[KPAD + 3] = e * r;
                 xr[KPAD + 4] = (e * e) * r2; xr[KPAD + 5] = 0.0;
             }
@@ -194,11 +198,13 @@ __global__ void k_mix_finish(const double *__restrict__ partial, int n_splits, i
             const double pG = d_pnorm(-fabs(Z1), true) * 2;
             slow = !(pG > prm.epsilon);                                               // branch B (ref :1150)
             if (!slow) {
-                const double lambda = a[3] / a[2];                                    // ref :1115
+                // a[3..5] were accumulated with E' = E - c (c = vc.lambda, SNP-invariant): lambda' = lambda - c
+                const double lam_c = a[3] / a[2];
+                const double lambda = lam_c + vc.lambda;                              // ref :1115
                 const double S_GxE = S2 - lambda * S1;
-                // sum R.new m and sum R.new^2 gvar with R.new = (E - lambda) R, expanded in lambda
-                const double Smean = 2 * (a[4] - lambda * a[1]);
-                const double Svar = a[5] - 2 * lambda * a[3] + (lambda * lambda) * a[2];
+                // sum R.new m and sum R.new^2 gvar with R.new = (E - lambda) R = (E' - lambda') R, expanded in lambda'
+                const double Smean = 2 * (a[4] - lam_c * a[1]);
+                const double Svar = a[5] - 2 * lam_c * a[3] + (lam_c * lam_c) * a[2];
                 const double z = (S_GxE - Smean) / sqrt(Svar);
                 slow = !(fabs(z) < prm.cutoff);                                       // SPA (ref :1127)
                 if (slow) {   // everything but the two tail probabilities is final: hand the statistics over
@@ -261,9 +267,9 @@ static cudaError_t run_k(cudaStream_t s, int num_sms, MixScratch &ms, const uint
     if ((e = grow(&ms.hand, &ms.cap_hand, (int64_t)mc)) != cudaSuccess) return e;
     ms.beta_ld = KPAD;
     dim3 grid((unsigned)blocks, (unsigned)n_splits);
-    k_mix_tile<KPAD, 0><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, nullptr, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
+    k_mix_tile<KPAD, 0><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, nullptr, st.asum, st.nmiss, ms.part, per_split, prm.g_model, vc);
     k_mix_beta<KPAD><<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, k, xtx_inv, ms.beta);
-    k_mix_tile<KPAD, 1><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, ms.beta, st.asum, st.nmiss, ms.part, per_split, prm.g_model);
+    k_mix_tile<KPAD, 1><<<grid, kMbThreads, 0, s>>>(d_rows, pitch, mc, n, k, pcs, R, E, ms.beta, st.asum, st.nmiss, ms.part, per_split, prm.g_model, vc);
     k_mix_finish<<<(mc + 127) / 128, 128, 0, s>>>(ms.part, n_splits, mc, j0, M, n, st, vc, ms.want, prm, d_out, b_list, ctr, ms.hand);
     *launches += 4;
     return cudaGetLastError();

@@ -472,9 +472,11 @@ def test_edge_cases_empty_tiny_and_fatal_inputs(gpu_ctx, oracle):
         assert ei.value.code == _lib.ERR_ARG
 
 
-def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir):
+@pytest.mark.parametrize("e_offset", [0.0, 1950.0])
+def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir, e_offset):
     """SPAGxEmix_CCT: the batched common path (mix_batch.cu) against the per-SNP cluster kernel on the same inputs
-    (tiled 3x so that the sample axis spans several splits and a ragged last tile)."""
+    (tiled 3x so that the sample axis spans several splits and a ragged last tile).  e_offset: an uncentred E (a birth
+    year): the batched path expands its statistics in lambda and must not lose digits to cancellation."""
     from spagxecct_b200 import SPAGxEmix_CCT
     x = _mix_inputs(golden_dir, "binary")
     rep = 3
@@ -485,7 +487,7 @@ def test_mix_batched_common_path_matches_per_snp_kernel(gpu_ctx, golden_dir):
     G = tile(x["G"]).copy()
     G[rng.random(G.shape) < 0.001] = np.nan
     PCs = tile(x["PCs"]) + 1e-3 * rng.standard_normal((n, x["PCs"].shape[1]))
-    args = dict(Geno_mtx=np.ascontiguousarray(G), R=tile(x["R"]) - tile(x["R"]).mean(), E=tile(x["E"]),
+    args = dict(Geno_mtx=np.ascontiguousarray(G), R=tile(x["R"]) - tile(x["R"]).mean(), E=tile(x["E"]) + e_offset,
                 Phen_mtx={"Y": tile(x["Y"])}, Cova_mtx=tile(x["Cova"]), topPCs=PCs, epsilon=0.001, Cutoff=2, min_maf=0.0002,
                 ctx=gpu_ctx, quiet=True)
     fast = SPAGxEmix_CCT("binary", **args)
