@@ -18,8 +18,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|spagxe' 
 echo "launch list rc=$?"
 $short > $out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_bb_farm|k_spa_quad|k_finalize_cct|k_score_unpack_mma' -s 8 -c 8 \
-    -o $out/${tag}_prof_cct $short > $out/${tag}_ncu_full.log 2>&1
+    -o /tmp/${tag}_prof_cct $short > $out/${tag}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+# the .ncu-rep stays on the box (gpurun copies back at most 64 MiB): only its text summary travels
+python tools/ncu_summary.py /tmp/${tag}_prof_cct.ncu-rep $out/${tag}_ncu_cct_kernels.txt > /dev/null 2>&1; echo "ncu summary rc=$?"
 shortmix="python bench.py --workload mix --steps 1 --warmup 2 --no-e2e --cpu-sample-snps 0"
 $shortmix > $out/${tag}_plain_mix.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|spagxe' -c 400 --csv \
