@@ -8,8 +8,10 @@
 
 A "step" is one pass of the hot path (2-bit unpack + score + routing + SPA + genotype-adjusted
 branch) over one batch of synthetic UK-Biobank-shaped SNPs that is already resident in HBM.  The
-batch (default 16,384 SNPs x 500,000 samples = 2.05 GB packed) is far larger than the 126 MB L2, so
-no flush is needed between iterations.  One JSON line is printed by rank 0.
+batch (default 65,536 SNPs x 500,000 samples = 8.19 GB packed, eight ~1 GB chunks of the Step-2 pipeline; rounds 1 and
+early 2 used 16,384 SNPs, `--batch-snps 16384` reproduces those lines) is far larger than the 126 MB L2, so no flush
+is needed between iterations.  One call of the north-star job holds 125,000 SNPs per GPU: the per-call costs (one
+branch-B solver-farm launch, result copy) amortise as there.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -25,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SAMPLES = 500_000
+DEFAULT_BATCH_SNPS = 65536
 PREVALENCE = 0.01
 SEED_PHENO = 12345
 SEED_GENO = 20251019
@@ -258,7 +261,7 @@ def run_other(args, kind):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     W, K = max(3, args.warmup), args.steps
-    m = args.batch_snps if args.batch_snps != 16384 else (4096 if kind == "mix" else 8192)
+    m = args.batch_snps if args.batch_snps != DEFAULT_BATCH_SNPS else (4096 if kind == "mix" else 8192)
     x = c4_admixed(m=m, device=dev) if kind == "mix" else c5_families(m=m, device=dev)
     n = x["n"]
     rb = (n + 3) // 4
@@ -365,7 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cct", choices=["cct", "mix", "plus"])
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES)
-    ap.add_argument("--batch-snps", type=int, default=16384)
+    ap.add_argument("--batch-snps", type=int, default=DEFAULT_BATCH_SNPS)
     ap.add_argument("--ref-snps", type=int, default=0)
     ap.add_argument("--cpu-sample-snps", type=int, default=1536)   # ~15 s of one host core at N = 500k
     ap.add_argument("--e2e-steps", type=int, default=10)
