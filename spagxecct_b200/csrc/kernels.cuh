@@ -346,7 +346,7 @@ __device__ double spa_two_tail(const Src &src, const Red &red, int64_t i_lo, int
 // sequence of iterates and the summation order of spa_tail, so the result is bit-identical to spa_two_tail.
 template <class Src, class Red>
 __device__ double spa_two_tail_fused(const Src &src, const Red &red, int64_t i_lo, int64_t i_hi, double s_hi, double s_lo,
-                                     int *iters) {
+                                     int *iters, double max_abs_t = 1.7976931348623157e308) {
     const double tol = 0x1p-13;
     const double sv[2] = {s_hi, s_lo};
     double t[2] = {0, 0}, H1[2] = {0, 0}, diff[2] = {CUDART_INF, CUDART_INF}, pv[2] = {0, 0};
@@ -358,6 +358,8 @@ __device__ double spa_two_tail_fused(const Src &src, const Red &red, int64_t i_l
             if (phase[h] == 0 && ++it[h] > 100) { it[h] = 100; pv[h] = 0.0; phase[h] = 2; }   // maxiter: t = NA -> p = 0 (ref :1846, :1873)
         }
         if (phase[0] == 2 && phase[1] == 2) break;
+        // a source with a bounded domain (the quadrature): an iterate or root outside it hands the SNP back, as spa_tail does
+        if ((phase[0] != 2 && fabs(t[0]) > max_abs_t) || (phase[1] != 2 && fabs(t[1]) > max_abs_t)) { *iters = 0; return -1.0; }
         double v[4] = {0, 0, 0, 0};
 #pragma unroll 2
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__rest
         double p = -1.0;
         if (max_t > 0) {
             SrcQuad src{q.x, q.w, it.maf};
-            p = spa_two_tail(src, red, 0, (int64_t)(*q.count), s_hi, s_lo, max_t, &iters);
+            p = spa_two_tail_fused(src, red, 0, (int64_t)(*q.count), s_hi, s_lo, &iters, max_t);   // both tails in one pass over the nodes
         }
         if (threadIdx.x == 0) {
             if (p < 0) exact_list[atomicAdd(&ctr->spax_count, 1)] = it;
