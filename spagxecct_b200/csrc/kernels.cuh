@@ -513,7 +513,14 @@ __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__rest
     const int count = ctr->spa_count;
     const double max_t = q.range[3];
     BlockRed red{scratch};
-    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+    // dynamic queue: the Newton iteration counts of the items differ by an order of magnitude
+    __shared__ int s_idx;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_idx = atomicAdd(&ctr->work_cursor, 1);
+        __syncthreads();
+        const int idx = s_idx;
+        if (idx >= count) break;
         const SpaItem it = list[idx];
         double s_hi, s_lo;
         spa_item_tails(it, s_hi, s_lo);

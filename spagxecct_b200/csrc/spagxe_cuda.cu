@@ -50,6 +50,7 @@ struct spagxe_ctx {
     // chunk scratch
     int64_t cap_chunk_bytes = 0; uint8_t *d_bed[2] = {nullptr, nullptr};
     int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
+    int64_t cap_spa = 0;                                   // capacity of the saddlepoint work lists (SNPs)
     int64_t cap_partial = 0; double *d_partial = nullptr; int *d_ipartial = nullptr;
     SpaItem *d_spa_list = nullptr, *d_spax_list = nullptr; int *d_b_list = nullptr;
     BItem *d_bitems = nullptr; int64_t cap_bitems = 0;
@@ -376,7 +377,8 @@ static int ensure_vec_mode(spagxe_ctx *ctx, int mode, const double *d_Rn_in) {
 static int launch_spa(spagxe_ctx *ctx, const double *rv, int64_t N, int64_t M, double *d_out) {
     cudaStream_t s = ctx->stream();
     if (ctx->quad_on) {
-        k_spa_quad<<<ctx->num_sms * 4, kSpaQThreads, 0, s>>>(ctx->d_spa_list, ctx->d_ctr, ctx->quad, ctx->d_spax_list, M, d_out);
+        CU(cudaMemsetAsync(&ctx->d_ctr->work_cursor, 0, sizeof(int), s));   // item queue of k_spa_quad
+        k_spa_quad<<<ctx->num_sms * 3, kSpaQThreads, 0, s>>>(ctx->d_spa_list, ctx->d_ctr, ctx->quad, ctx->d_spax_list, M, d_out);   // 3 resident CTAs per SM (80 registers)
         LAUNCH_CHECK();
         k_spa_homo<<<ctx->num_sms * 2, kSpaThreads, 0, s>>>(ctx->d_spax_list, &ctx->d_ctr->spax_count, ctx->d_ctr, rv, N, M, d_out);
         LAUNCH_CHECK();
@@ -446,9 +448,16 @@ static int ensure_chunk_scratch(spagxe_ctx *ctx, const ChunkPlan &pl, bool need_
     }
     if (pl.chunk_m > ctx->cap_m) {
         CU(dev_realloc(&ctx->d_stats, (size_t)6 * pl.chunk_m)); CU(dev_realloc(&ctx->d_istats, (size_t)3 * pl.chunk_m));
-        CU(dev_realloc(&ctx->d_spa_list, pl.chunk_m)); CU(dev_realloc(&ctx->d_b_list, pl.chunk_m));
-        CU(dev_realloc(&ctx->d_spax_list, pl.chunk_m));
+        CU(dev_realloc(&ctx->d_b_list, pl.chunk_m));
         ctx->cap_m = pl.chunk_m;
+    }
+    {   // saddlepoint work lists: the items carry no genotype rows, so they are collected over the chunks of a call and
+        // solved by one launch (a list holds up to 2^20 SNPs' worth; longer calls flush in between)
+        const int64_t want = std::max<int64_t>(pl.chunk_m, std::min<int64_t>(pl.m, 1ll << 20));
+        if (want > ctx->cap_spa) {
+            CU(dev_realloc(&ctx->d_spa_list, want)); CU(dev_realloc(&ctx->d_spax_list, want));
+            ctx->cap_spa = want;
+        }
     }
     if (out_elems > ctx->cap_out) { CU(dev_realloc(&ctx->d_out, out_elems)); ctx->cap_out = out_elems; }
     return SPAGXE_OK;
@@ -847,33 +856,49 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     WaldData wd{ctx->d_Y, ctx->d_cova, ctx->wald_p, ctx->wald_trait};
     PlusConst pc{ctx->R_GRM_R, ctx->R_GRM_RE, ctx->Rnew_GRM_Rnew};
     int buf = 0;
+    int64_t spa_pending = 0;   // SNPs whose saddlepoint items are waiting in the work list
     for (int64_t j0 = 0; j0 < M; j0 += pl.chunk_m, buf ^= 1) {
         const int mc = (int)std::min<int64_t>(pl.chunk_m, M - j0);
         const uint8_t *d_rows = nullptr;
         if ((rc = stage_chunk(ctx, g, pl, j0, mc, buf, &d_rows, &dg.h2d_bytes))) return rc;
-        // reset per-chunk work-list cursors (counters keep accumulating)
-        CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, (mode == RUN_MIX ? 4 : 2) * sizeof(int), s));  // branch-B items persist until flushed
+        // SPAGxEmix: per-chunk work list and queue cursor.  The other loops collect their saddlepoint items over the chunks
+        // (flush_spa) and their branch-B items until a flush.
+        if (mode == RUN_MIX) CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, 4 * sizeof(int), s));
         cudaEvent_t a = evp.rec(s);
         if ((rc = launch_score(ctx, d_rows, pl, mc, st, prm->g_model))) return rc;
         cudaEvent_t b = evp.rec(s);
         score_ev.push_back({a, b});
+        const bool last = (j0 + pl.chunk_m >= M);
+        // one saddlepoint launch for the items of many chunks: the slowest SNP of a launch (a dozen Newton iterations where
+        // the mean is two) sets its duration, so eight launches per 65,536 SNPs cost 0.6 ms and one costs a quarter of that
+        auto flush_spa = [&](const double *rv) -> int {
+            if (spa_pending == 0) return SPAGXE_OK;
+            int r2 = launch_spa(ctx, rv, N, M, d_out);
+            if (r2) return r2;
+            CU(cudaMemsetAsync(&ctx->d_ctr->spa_count, 0, 2 * sizeof(int), s));
+            spa_pending = 0;
+            return SPAGXE_OK;
+        };
         if (mode == RUN_CCT) {
+            if (spa_pending + mc > ctx->cap_spa && (rc = flush_spa(ctx->d_V))) return rc;
             k_finalize_cct<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, prm->epsilon, prm->min_maf, d_out,
                                                             ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch, ctx->d_ctr, prm->g_model);
             LAUNCH_CHECK();
-            if ((rc = launch_spa(ctx, ctx->d_V, N, M, d_out))) return rc;
+            spa_pending += mc;
+            if (last && (rc = flush_spa(ctx->d_V))) return rc;
         } else if (mode == RUN_PLUS) {
+            if (spa_pending + mc > ctx->cap_spa && (rc = flush_spa(ctx->d_Rn))) return rc;
             k_finalize_plus<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, ctx->d_vc, pc, prm->epsilon, prm->cutoff,
                                                              prm->min_maf, d_out, ctx->d_spa_list, ctx->d_bitems, d_rows, pl.dpitch,
                                                              ctx->d_ctr, prm->g_model);
             LAUNCH_CHECK();
-            if ((rc = launch_spa(ctx, ctx->d_Rn, N, M, d_out))) return rc;
+            spa_pending += mc;
+            if (last && (rc = flush_spa(ctx->d_Rn))) return rc;
         } else {
             if ((rc = launch_mix(ctx, d_rows, pl.dpitch, st, j0, mc, M, N, wd, prm, d_out))) return rc;
         }
         // staged rows live in two alternating buffers: pending branch-B items must run before their buffer is reused;
         // caller-owned device rows stay valid for the whole call, so everything is deferred to one launch at the end
-        const bool last = (j0 + pl.chunk_m >= M);
         bool flushed = false;
         cudaEvent_t c = evp.rec(s);
         spa_ev.push_back({b, c});
