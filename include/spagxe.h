@@ -190,6 +190,21 @@ int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params
 int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
                     spagxe_diag *diag);
 
+/* SPAGxEmix_CCT_Plus (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133 -> SPAGxEmix_CCT_Plus_one_SNP :144-427): SPAGxEmix_CCT
+ * with the sparse GRM in every variance (t(R sqrt(g.var.est)) GRM (R sqrt(g.var.est)), :222-232, :260, :269-299, :318-349)
+ * and GetProb_SPA_G_new_adjust (:435-462).  spagxe_set_vectors (R = ResidMat$Resid: the reference's one-SNP function
+ * reads `R` as a free variable), spagxe_set_pcs and spagxe_set_sparse_grm first; no Wald data.
+ * spagxe_set_sparse_grm: the sparseGRM table as 0-based COO triplets, gi / gj = positions of ID1 / ID2 in ResidMat$SubjID
+ * after the reference's filter (:220; the match() calls of :228-229 are done once by the caller).
+ * out: M x 12 like spagxe_run_mix (p.value.spaGxEmix.plus, ...Wald, ...CCT.Wald, p.value.normGxEmix.plus, ...).  For the
+ * SNPs of branch B (p.value.betaG <= epsilon) the reference's Wald test is a mixed model fitted by lme4::glmer / lmer
+ * (:384, :404); that fit is NOT done here: columns 4 and 5 of those rows hold NA_real_, column 3 holds pval.spaGxE, and
+ * the caller (spagxecct_b200/R/SPAGxECCT_cuda.R; api.SPAGxEmix_CCT_Plus) fits the model for those few SNPs and applies
+ * CCT.  diag->n_branch_b counts them.                                                                             */
+int spagxe_set_sparse_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv);
+int spagxe_run_mix_plus(spagxe_ctx *ctx, const spagxe_geno *geno, const spagxe_params *prm, double *out,
+                        spagxe_diag *diag);
+
 /* SPAGxEmixCCT_localance loop body, R/SPAGxECCT.R:1443-1476 -> SPAGxEmixCCT_localance_one_SNP :1496-1647 (with
  * SPAmix_localance_one_SNP :2324-2395 and the binomial(h_i, MAF) saddlepoint functions :2132-2311): ancestry-specific
  * G x E test with local ancestry.  The reference takes R matrices only: G (Geno.mtx, ancestry-specific genotypes), H

@@ -272,6 +272,40 @@ def mix_one_snp(trait, g, R, E, Y, Cova, PCs, epsilon=0.001, cutoff=2.0, min_maf
     return out, route.value, (its[0], its[1]), mafest, rc
 
 
+def mixplus_bed(bed_rows, n, R, E, PCs, grm_i, grm_j, grm_v, epsilon=0.001, cutoff=2.0, min_maf=0.001, pc_pcut=0.05,
+                neg_ratio_cut=0.1, pitch=None, nthreads=1):
+    """SPAGxEmix_CCT_Plus loop (ref R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:100-127 -> :144-427) over packed rows.
+    Branch-B rows carry NA in the Wald / CCT columns (the mixed-model Wald test is the caller's, see spagxe_oracle.c)."""
+    bed_rows = np.ascontiguousarray(bed_rows, dtype=np.uint8).ravel()
+    pitch = pitch or (n + 3) // 4
+    m = bed_rows.size // pitch
+    R, Rp = _d(R); E, Ep = _d(E)
+    PCs, Pp = _f(np.asarray(PCs, dtype=np.float64).reshape(n, -1))
+    k = PCs.shape[1]
+    gi = np.ascontiguousarray(grm_i, dtype=np.int32); gj = np.ascontiguousarray(grm_j, dtype=np.int32)
+    gv, gvp = _d(grm_v)
+    out = np.empty((m, 12), order="F"); route = np.zeros(m, dtype=np.int32); iters = np.zeros((m, 2), dtype=np.int32)
+
+    def run(lo, hi):
+        o = np.empty((hi - lo, 12), order="F")
+        rc = lib().orc_mixplus_bed(C.c_void_p(bed_rows.ctypes.data + lo * pitch), C.c_long(pitch), C.c_long(n),
+                                   C.c_long(hi - lo), Rp, Ep, Pp, C.c_int(k), C.c_long(gi.size), gi.ctypes.data_as(c_ip),
+                                   gj.ctypes.data_as(c_ip), gvp, C.c_double(epsilon), C.c_double(cutoff),
+                                   C.c_double(min_maf), C.c_double(pc_pcut), C.c_double(neg_ratio_cut),
+                                   o.ctypes.data_as(c_dp), C.c_void_p(route.ctypes.data + lo * 4),
+                                   C.c_void_p(iters.ctypes.data + lo * 8))
+        out[lo:hi] = o
+        return rc
+
+    sh = _shards(m, _threads(nthreads) if nthreads != 1 else 1)
+    if len(sh) == 1:
+        rcs = [run(*sh[0])]
+    else:
+        with ThreadPoolExecutor(len(sh)) as ex:
+            rcs = list(ex.map(lambda a: run(*a), sh))
+    return out, route, iters, max(rcs)
+
+
 def localance_matrix(trait, G, H, R, E, Y, Cova, cova_haplo, epsilon=0.001, min_maf=0.0001):
     """SPAGxEmixCCT_localance loop (ref R/SPAGxECCT.R:1443-1476) over (N, M) matrices: G ancestry-specific genotypes,
     H local ancestry counts, cova_haplo a list of (N, M) matrices (Cova.haplo.mtx.list).  OpenMP over SNPs."""

@@ -994,20 +994,12 @@ static double two_tail_spa(const double *Rv, const double *mafvec, double maf, l
     return pval1 + pval2;
 }
 
-int orc_mix_one_snp(int trait, const double *g_in, int g_is_int, const double *R, const double *E,
-                    const double *Y, const double *Cova, int p, const double *PCs, int k, long n,
-                    double epsilon, double cutoff, double min_maf, double pc_pcut, double neg_ratio_cut,
-                    double out[12], int *route, int iters[2], double *mafest_out) {
-    double *g = (double *)malloc(sizeof(double) * n);
-    memcpy(g, g_in, sizeof(double) * n);
-    double MAF, miss; int rt = 0, rc = 0, touched = 0;
-    if (iters) iters[0] = iters[1] = 0;
-    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
-        out[0] = MAF; out[1] = miss; for (int j = 2; j < 12; j++) out[j] = ORC_NA;
-        if (route) *route = 1; free(g); return 0;
-    }
-    double MAC = MAF * 2 * (double)n;
-    double *m = (double *)malloc(sizeof(double) * n);
+/* individual-level allele frequencies of SPAGxEmix_CCT_one_SNP (R/SPAGxECCT.R:1055-1100; the same block opens
+ * SPAGxEmix_CCT_Plus_one_SNP, R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:190-232): g is the imputed / flipped
+ * genotype vector, m receives MAF.est, *negnum_out MAF.est.negative.num; returns the route bits 64 / 128 / 256.    */
+static int mix_af_estimate(const double *g, long n, double MAF, double MAC, const double *PCs, int k, double pc_pcut,
+                           double neg_ratio_cut, double *m, double *negnum_out) {
+    int rt = 0;
     double negnum = 0;
     if (MAC <= 20) {
         for (long i = 0; i < n; i++) m[i] = MAF;
@@ -1059,6 +1051,26 @@ int orc_mix_one_snp(int trait, const double *g_in, int g_is_int, const double *R
         }
         free(X); free(coef); free(se); free(pv);
     }
+    *negnum_out = negnum;
+    return rt;
+}
+
+int orc_mix_one_snp(int trait, const double *g_in, int g_is_int, const double *R, const double *E,
+                    const double *Y, const double *Cova, int p, const double *PCs, int k, long n,
+                    double epsilon, double cutoff, double min_maf, double pc_pcut, double neg_ratio_cut,
+                    double out[12], int *route, int iters[2], double *mafest_out) {
+    double *g = (double *)malloc(sizeof(double) * n);
+    memcpy(g, g_in, sizeof(double) * n);
+    double MAF, miss; int rt = 0, rc = 0, touched = 0;
+    if (iters) iters[0] = iters[1] = 0;
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
+        out[0] = MAF; out[1] = miss; for (int j = 2; j < 12; j++) out[j] = ORC_NA;
+        if (route) *route = 1; free(g); return 0;
+    }
+    double MAC = MAF * 2 * (double)n;
+    double *m = (double *)malloc(sizeof(double) * n);
+    double negnum = 0;
+    rt |= mix_af_estimate(g, n, MAF, MAC, PCs, k, pc_pcut, neg_ratio_cut, m, &negnum);
     if (mafest_out) memcpy(mafest_out, m, sizeof(double) * n);
     double *gv = (double *)malloc(sizeof(double) * n);
     for (long i = 0; i < n; i++) gv[i] = 2 * m[i] * (1 - m[i]);
@@ -1525,5 +1537,140 @@ int orc_plus_bed(const uint8_t *bed, long pitch, long n, long mm, const double *
         }
         free(g);
     }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* SPAGxEmix_CCT_Plus_one_SNP: R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:144-427 (SPAGxEmix_CCT with the sparse GRM
+ * in every variance).  out[12] as orc_mix_one_snp.  The reference reads the residual vector `R` as a free variable
+ * (:235 ff.; its scripts define R = ResidMat$Resid); gi / gj are the 0-based positions of sparseGRM$ID1 / $ID2 in
+ * ResidMat$SubjID (the match() calls of :228-229).  Branch B's Wald test is a mixed model fitted by lme4::glmer / lmer
+ * (:384, :404), which is not restated: out[3] (Wald) and out[4] (CCT) are NA for branch-B SNPs and the caller combines
+ * them (the R wrapper calls glmer / lmer itself for those few SNPs).  route bits as orc_mix_one_snp.               */
+/* GetProb_SPA_G_new_adjust: :435-462 */
+static double getprob_spa_adjust(const double *R, const double *mafvec, long n, double sstat, double var_ratio,
+                                 int lower_tail, int *iter_out) {
+    double zeta, h2; int it, cv;
+    orc_spa_root(R, mafvec, 0, n, sstat, 0.0, &zeta, &it, &cv, &h2);
+    if (iter_out) *iter_out = it;
+    double k1 = H_org(zeta, R, mafvec, 0, n);
+    double k2 = H2(zeta, R, mafvec, 0, n);
+    double temp1 = zeta * sstat - k1;
+    double w = r_sign(zeta) * sqrt(2 * temp1);
+    double v = zeta * sqrt(k2);
+    double a = w + 1 / w * log(v / w);
+    double pval = orc_pnorm(a * sqrt(var_ratio), lower_tail);
+    if (isnan(pval)) pval = 0;
+    return pval;
+}
+/* sum(Value * x[ID1] * y[ID2]) over the GRM table (:230-232, :247-255) */
+static double grm_cross(long nnz, const int32_t *gi, const int32_t *gj, const double *gv, const double *x, const double *y) {
+    ld s = 0; for (long e = 0; e < nnz; e++) s += (gv[e] * x[gi[e]]) * y[gj[e]];
+    return (double)s;
+}
+/* the statistic block shared by both branches (:268-299, :318-349): z, then normal or adjusted saddlepoint p-values */
+static void mixplus_tails(const double *Rv, const double *m, const double *gvar, const double *sq, long n, long nnz,
+                          const int32_t *gi, const int32_t *gj, const double *gv, double S, double cutoff,
+                          double *pspa, double *pn, int *rt, int iters[2]) {
+    double *x = (double *)malloc(sizeof(double) * n);
+    for (long i = 0; i < n; i++) x[i] = Rv[i] * sq[i];
+    ld acc = 0; for (long i = 0; i < n; i++) acc += Rv[i] * m[i];
+    double Smean = 2 * (double)acc;
+    acc = 0; for (long i = 0; i < n; i++) acc += (Rv[i] * Rv[i]) * gvar[i];
+    double Svar_mix = (double)acc;
+    double Svar = grm_cross(nnz, gi, gj, gv, x, x) * 2 - Svar_mix;
+    double z = (S - Smean) / sqrt(Svar);
+    if (fabs(z) < cutoff) {
+        *pn = orc_pnorm(fabs(z), 0) * 2; *pspa = *pn;
+    } else {
+        *rt |= 4;
+        double ratio = Svar_mix / Svar;
+        int i1 = 0, i2 = 0;
+        double pval1 = getprob_spa_adjust(Rv, m, n, fmax(S, 2 * Smean - S), ratio, 0, &i1);
+        double pval2 = getprob_spa_adjust(Rv, m, n, fmin(S, 2 * Smean - S), ratio, 1, &i2);
+        if (iters) { iters[0] = i1; iters[1] = i2; }
+        if (isnan(pval2)) pval2 = pval1;
+        *pspa = pval1 + pval2;
+        *pn = orc_pnorm(fabs(z), 0) + orc_pnorm(-fabs(z), 1);
+    }
+    free(x);
+}
+
+int orc_mixplus_one_snp(const double *g_in, int g_is_int, const double *R, const double *E, const double *PCs, int k,
+                        long n, long nnz, const int32_t *gi, const int32_t *gj, const double *gv,
+                        double epsilon, double cutoff, double min_maf, double pc_pcut, double neg_ratio_cut,
+                        double out[12], int *route, int iters[2]) {
+    double *g = (double *)malloc(sizeof(double) * n);
+    memcpy(g, g_in, sizeof(double) * n);
+    double MAF, miss; int rt = 0, touched = 0;
+    if (iters) iters[0] = iters[1] = 0;
+    if (prologue(g, n, g_is_int, min_maf, &MAF, &miss, &touched, g_gmodel)) {
+        out[0] = MAF; out[1] = miss; for (int j = 2; j < 12; j++) out[j] = ORC_NA;
+        if (route) *route = 1; free(g); return 0;
+    }
+    double MAC = MAF * 2 * (double)n;
+    double *m = (double *)malloc(sizeof(double) * n), *gvar = (double *)malloc(sizeof(double) * n);
+    double *sq = (double *)malloc(sizeof(double) * n), *x = (double *)malloc(sizeof(double) * n);
+    double negnum = 0;
+    rt |= mix_af_estimate(g, n, MAF, MAC, PCs, k, pc_pcut, neg_ratio_cut, m, &negnum);
+    for (long i = 0; i < n; i++) { gvar[i] = 2 * m[i] * (1 - m[i]); sq[i] = sqrt(gvar[i]); x[i] = R[i] * sq[i]; }   /* :222-224 */
+    ld acc = 0; for (long i = 0; i < n; i++) acc += g[i] * R[i];
+    double S1 = (double)acc;
+    acc = 0; for (long i = 0; i < n; i++) acc += R[i] * m[i];
+    double meanS1 = 2 * (double)acc;
+    acc = 0; for (long i = 0; i < n; i++) acc += (R[i] * R[i]) * gvar[i];
+    double VarS1 = grm_cross(nnz, gi, gj, gv, x, x) * 2 - (double)acc;                                             /* :260 */
+    double Z1 = (S1 - meanS1) / sqrt(VarS1);
+    double pnorm1 = orc_pnorm(-fabs(Z1), 1) * 2;
+    double po[5];
+    if (pnorm1 > epsilon) {
+        acc = 0; for (long i = 0; i < n; i++) acc += (g[i] * E[i]) * R[i];
+        double S2 = (double)acc;
+        double *y = (double *)malloc(sizeof(double) * n);
+        for (long i = 0; i < n; i++) y[i] = (R[i] * E[i]) * sq[i];                                                 /* :269 */
+        acc = 0; for (long i = 0; i < n; i++) acc += (gvar[i] * E[i]) * (R[i] * R[i]);
+        double Cov = grm_cross(nnz, gi, gj, gv, x, y) + grm_cross(nnz, gi, gj, gv, y, x) - (double)acc;            /* :279-281 */
+        double lambda = Cov / VarS1;
+        double S_GxE = S2 - lambda * S1;
+        for (long i = 0; i < n; i++) y[i] = (E[i] - lambda) * R[i];
+        double pspa, pn;
+        mixplus_tails(y, m, gvar, sq, n, nnz, gi, gj, gv, S_GxE, cutoff, &pspa, &pn, &rt, iters);
+        po[0] = po[1] = po[2] = pspa; po[3] = pn; po[4] = pnorm1;
+        free(y);
+    } else {
+        rt |= 2;
+        double *R0 = (double *)malloc(sizeof(double) * n);
+        if (adjust_for_g(g, R, n, R0)) {
+            rt |= 32; for (int j = 0; j < 4; j++) po[j] = ORC_NA; po[4] = pnorm1;
+        } else {
+            acc = 0; for (long i = 0; i < n; i++) acc += (g[i] * E[i]) * R0[i];
+            double S0 = (double)acc;
+            for (long i = 0; i < n; i++) R0[i] = E[i] * R0[i];
+            double pspa, pn;
+            mixplus_tails(R0, m, gvar, sq, n, nnz, gi, gj, gv, S0, cutoff, &pspa, &pn, &rt, iters);
+            po[0] = pspa; po[1] = ORC_NA; po[2] = ORC_NA; po[3] = pn; po[4] = pnorm1;   /* Wald (glmer / lmer) and CCT: caller */
+        }
+        free(R0);
+    }
+    out[0] = MAF; out[1] = miss; for (int j = 0; j < 5; j++) out[2 + j] = po[j];
+    out[7] = S1; out[8] = VarS1; out[9] = Z1; out[10] = negnum; out[11] = MAC;
+    if (route) *route = rt;
+    free(g); free(m); free(gvar); free(sq); free(x);
+    return 0;
+}
+
+int orc_mixplus_bed(const uint8_t *bed, long pitch, long n, long mm, const double *R, const double *E, const double *PCs,
+                    int k, long nnz, const int32_t *gi, const int32_t *gj, const double *gv, double epsilon, double cutoff,
+                    double min_maf, double pc_pcut, double neg_ratio_cut, double *out, int *route, int *iters) {
+    double *g = (double *)malloc(sizeof(double) * n);
+    for (long j = 0; j < mm; j++) {
+        double o[12]; int rt, it[2];
+        orc_bed_decode_row(bed + j * pitch, n, g);
+        orc_mixplus_one_snp(g, 0, R, E, PCs, k, n, nnz, gi, gj, gv, epsilon, cutoff, min_maf, pc_pcut, neg_ratio_cut, o, &rt, it);
+        for (int c = 0; c < 12; c++) out[j + c * mm] = o[c];
+        if (route) route[j] = rt;
+        if (iters) { iters[2 * j] = it[0]; iters[2 * j + 1] = it[1]; }
+    }
+    free(g);
     return 0;
 }

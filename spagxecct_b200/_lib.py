@@ -25,7 +25,7 @@ EXPORTS = [
     "spagxe_measure_fp64_peak", "spagxe_score_stats", "spagxe_ctx_set_option", "spagxe_plus_nullmodel",
     "spagxe_set_wald_device", "spagxe_set_wald_survival", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
     "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus", "spagxe_mgpu_set_wald_survival",
-    "spagxe_mgpu_set_pcs", "spagxe_mgpu_set_grm",
+    "spagxe_mgpu_set_pcs", "spagxe_mgpu_set_grm", "spagxe_set_sparse_grm", "spagxe_run_mix_plus",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
 OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL, OPT_MIX_CLUSTER = 1, 2, 3, 4, 5
@@ -107,8 +107,9 @@ def load():
                                  C.c_double, C.c_void_p]
     L.spagxe_plus_nullmodel.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
-    for f in ("spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus"):
+    for f in ("spagxe_run_cct", "spagxe_run_mix", "spagxe_run_plus", "spagxe_run_mix_plus"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
+    L.spagxe_set_sparse_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.spagxe_run_localance.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                        C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
     L.spagxe_bed_counts.argtypes = [C.c_void_p, C.POINTER(Geno), C.c_void_p]
@@ -199,6 +200,12 @@ class Context:
         self._chk(self.L.spagxe_set_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data,
                                         float(R_GRM_R), float(R_GRM_RE), float(Rnew_GRM_Rnew), Rnew.ctypes.data))
 
+    def set_sparse_grm(self, gi, gj, gv):
+        """sparseGRM of SPAGxEmix_CCT_Plus as 0-based COO triplets (no Step-1 scalars)."""
+        gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
+        gv = _f64(gv)
+        self._chk(self.L.spagxe_set_sparse_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data))
+
     def plus_nullmodel(self, gi, gj, gv, R, E):
         """(R_GRM_R, R_GRM_RE, R.new, R.new_GRM_R.new) of SPAGxE_Plus_Nullmodel, computed on the device."""
         gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
@@ -240,6 +247,9 @@ class Context:
 
     def run_plus(self, geno, params=None, out_ptr=None):
         return self._run(self.L.spagxe_run_plus, 8, geno, params, out_ptr)
+
+    def run_mix_plus(self, geno, params=None, out_ptr=None):
+        return self._run(self.L.spagxe_run_mix_plus, 12, geno, params, out_ptr)
 
     def run_localance(self, G, H, cova_haplo=(), params=None):
         """SPAGxEmixCCT_localance loop (ref R/SPAGxECCT.R:1443-1476): G, H and every matrix of cova_haplo are (N, M)."""

@@ -8,6 +8,7 @@ drive; the R wrappers that bind the very same C ABI are in spagxecct_b200/R/).
     SPAGxE_CCT_one_SNP    R/SPAGxECCT.R:543-683
     SPAGxEmix_CCT(_one_SNP)  R/SPAGxECCT.R:916-1002, :1013-1269
     SPAGxE_Plus(_one_SNP)    R/SPAGxEPlus_functions_MYZ.R:159-238, :248-405
+    SPAGxEmix_CCT_Plus(_one_SNP)  R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133, :144-427
     check_input_Resid     R/SPAGxECCT.R:1900-1913
 
 R's `.` in argument names becomes `_` (Geno.mtx -> Geno_mtx).  Phen_mtx is any mapping/DataFrame
@@ -397,6 +398,147 @@ def SPAGxEmix_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, topPCs, epsilon=0
                         missing_cutoff=missing_cutoff, min_maf=min_maf, G_model=G_model,
                         topPCs_pvalue_cutoff=topPCs_pvalue_cutoff,
                         MAF_est_negative_ratio_cutoff=MAF_est_negative_ratio_cutoff, ctx=ctx, device=device, quiet=True)
+    return res.values[0].copy()
+
+
+COLS_MIX_PLUS = ["MAF", "missing.rate", "p.value.spaGxEmix.plus", "p.value.spaGxEmix.plus.Wald",
+                 "p.value.spaGxEmix.plus.CCT.Wald", "p.value.normGxEmix.plus", "p.value.betaG", "Stat.betaG", "Var.betaG",
+                 "z.betaG", "MAF.est.negative.num", "MAC"]
+
+
+def CCT(pvals, weights=None):
+    """The reference's CCT() (R/SPAGxECCT.R:2070-2123) for the handful of p-values a caller combines on the host (the Wald
+    p-values of SPAGxEmix_CCT_Plus' branch B come from the caller's mixed-model fit); same stop() conditions."""
+    import math
+    p = np.asarray(pvals, dtype=np.float64)
+    if np.isnan(p).any():
+        raise RStop("Cannot have NAs in the p-values!")
+    if ((p < 0) | (p > 1)).any():
+        raise RStop("All p-values must be between 0 and 1!")
+    is_zero, is_one = bool((p == 0).any()), bool((p == 1).any())
+    if is_zero and is_one:
+        raise RStop("Cannot have both 0 and 1 p-values!")
+    if is_zero:
+        return 0.0
+    if is_one:
+        p = np.where(p == 1, 0.999, p)     # the reference warns and goes on with 0.999 (:2090-2093)
+    w = np.full(p.size, 1.0 / p.size) if weights is None else np.asarray(weights, dtype=np.float64) / np.sum(weights)
+    small = p < 1e-16
+    # R's sum() accumulates in long double: fsum (exactly rounded) agrees with it for these few terms
+    stat = (math.fsum((wi / pi_) / math.pi for wi, pi_ in zip(w[small], p[small]))
+            + math.fsum(wi * math.tan((0.5 - pi_) * math.pi) for wi, pi_ in zip(w[~small], p[~small])))
+    if stat > 1e15:
+        return (1.0 / stat) / math.pi
+    # 1 - pcauchy(stat): R's pcauchy evaluates atan(1 / x) / pi for |x| > 1 (upper tail first, then 1 - . twice)
+    if abs(stat) > 1:
+        y = math.atan(1.0 / stat) / math.pi
+        low = (0.5 - y + 0.5) if stat > 0 else -y      # R_D_Cval
+    else:
+        low = 0.5 + math.atan(stat) / math.pi
+    return 1.0 - low
+
+
+def _mixplus_grm(ResidMat, sparseGRM):
+    """the ID handling of SPAGxEmix_CCT_Plus_one_SNP (ref mixPlus :212-229): every subject of ResidMat needs GRM
+    information, GRM rows with an ID outside ResidMat are dropped, ID1 / ID2 are matched to their position in SubjID."""
+    if "i" in sparseGRM:
+        return (np.asarray(sparseGRM["i"], dtype=np.int32), np.asarray(sparseGRM["j"], dtype=np.int32),
+                np.asarray(sparseGRM["Value"], dtype=np.float64))
+    ids = [str(x) for x in _col(ResidMat, "SubjID")]
+    id1 = [str(x) for x in sparseGRM["ID1"]]; id2 = [str(x) for x in sparseGRM["ID2"]]
+    in_grm = set(id1) | set(id2)
+    if any(x not in in_grm for x in ids):
+        raise RStop("At least one subject in residual matrix does not have GRM information.")
+    pos = {}
+    for k, x in enumerate(ids):
+        pos.setdefault(x, k)      # match() returns the first position
+    val = np.asarray(sparseGRM["Value"], dtype=np.float64)
+    keep = [e for e in range(len(id1)) if id1[e] in pos and id2[e] in pos]
+    gi = np.array([pos[id1[e]] for e in keep], dtype=np.int32)
+    gj = np.array([pos[id2[e]] for e in keep], dtype=np.int32)
+    return gi, gj, val[keep]
+
+
+def SPAGxEmix_CCT_Plus(traits="binary/quantitative", Geno_mtx=None, ResidMat=None, E=None, Phen_mtx=None, Cova_mtx=None,
+                       topPCs=None, sparseGRM=None, epsilon=0.001, Cutoff=2, impute_method="fixed", missing_cutoff=0.15,
+                       min_maf=0.001, G_model="Add", topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1,
+                       wald=None, ctx=None, device=0, quiet=False):
+    """Drop-in for SPAGxEmix_CCT_Plus (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133): M x 12.  Like the reference it
+    takes an R matrix only (no GenoFile) and prints the SNP counter.  R = ResidMat$Resid (the reference's one-SNP function
+    reads `R` as a free variable, which its scripts define that way).
+
+    Branch B (p.value.betaG <= epsilon) needs the Wald p-value of `E:g` from lme4::glmer / lmer(Y ~ Cova + E + g + g*E +
+    (1 | IID)) (:384, :404), a mixed model that is fitted by the caller, not on the device: `wald(j, g)` receives the
+    column index and the imputed / flipped genotype vector of every such SNP and returns that p-value (NaN -> pval.spaGxE,
+    :389, :409); the result is combined by CCT() here.  With wald=None a call that meets a branch-B SNP raises
+    NotImplementedError; wald="skip" leaves NA in the Wald / CCT columns of those rows."""
+    if traits not in ("binary", "quantitative"):
+        raise RStop('traits must be "binary" or "quantitative"')
+    own = ctx is None
+    ctx = ctx or _lib.Context(device)
+    try:
+        G, _, snp_ids = _split_geno(Geno_mtx)
+        keep, geno = _geno_desc_from_matrix(G)
+        n, m = G.shape
+        if not quiet:
+            print(f'[1] "Sample size is {n}."')
+            print(f'[1] "Number of variants is {m}."')
+        R = np.asarray(_col(ResidMat, "Resid"), dtype=np.float64)
+        _prep_common(ctx, R, E)
+        ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
+        ctx.set_sparse_grm(*_mixplus_grm(ResidMat, sparseGRM))
+        if not quiet:
+            print('[1] "Start Analyzing..."')
+            print(_now())
+            for i in range(1, m + 1):
+                print(f"[1] {i}")
+        prm = _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model,
+                      pc_pvalue_cutoff=topPCs_pvalue_cutoff, neg_ratio_cutoff=MAF_est_negative_ratio_cutoff)
+        out, diag = ctx.run_mix_plus(geno, prm)
+        del keep
+        bb = np.flatnonzero(out[:, 6] <= epsilon)      # NA rows compare False
+        if bb.size and wald is None:
+            raise NotImplementedError(
+                f"SPAGxEmix_CCT_Plus: {bb.size} SNP(s) take the genotype-adjusted branch, whose Wald test is a glmer / lmer "
+                "mixed model fitted by the caller: pass wald=callable (or wald='skip' for NA in those columns)")
+        if bb.size and callable(wald):
+            Gd = np.asarray(G, dtype=np.float64)
+            for j in bb:
+                g = Gd[:, j].copy()
+                if G.dtype.kind == "i":
+                    g[G[:, j] == np.iinfo(np.int32).min] = np.nan
+                maf = np.nanmean(g) / 2
+                g[np.isnan(g)] = 2 * maf
+                if maf > 0.5:
+                    g = 2 - g
+                if G_model == "Dom":
+                    g = np.where(g >= 1, 1.0, 0.0)
+                elif G_model == "Rec":
+                    g = np.where(g <= 1, 0.0, 1.0)
+                pw = float(wald(int(j), g))
+                if np.isnan(pw):
+                    pw = out[j, 2]
+                out[j, 3] = pw
+                out[j, 4] = CCT([out[j, 2], pw])
+        if not quiet:
+            print('[1] "Analysis Complete."')
+            print(_now())
+        return Result(out, snp_ids, COLS_MIX_PLUS, diag)
+    finally:
+        if own:
+            ctx.close()
+
+
+def SPAGxEmix_CCT_Plus_one_SNP(traits, g, ResidMat, E, Phen_mtx, Cova_mtx, topPCs, sparseGRM, epsilon=0.001, Cutoff=2,
+                               impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add",
+                               topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, wald=None, ctx=None, device=0):
+    """Drop-in for SPAGxEmix_CCT_Plus_one_SNP (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:144-427): numeric(12)."""
+    res = SPAGxEmix_CCT_Plus(traits, Geno_mtx=np.asarray(g).reshape(-1, 1), ResidMat=ResidMat, E=E, Phen_mtx=Phen_mtx,
+                             Cova_mtx=Cova_mtx, topPCs=topPCs, sparseGRM=sparseGRM, epsilon=epsilon, Cutoff=Cutoff,
+                             impute_method=impute_method, missing_cutoff=missing_cutoff, min_maf=min_maf, G_model=G_model,
+                             topPCs_pvalue_cutoff=topPCs_pvalue_cutoff,
+                             MAF_est_negative_ratio_cutoff=MAF_est_negative_ratio_cutoff, wald=wald, ctx=ctx, device=device,
+                             quiet=True)
     return res.values[0].copy()
 
 

@@ -346,7 +346,7 @@ __device__ double spa_two_tail(const Src &src, const Red &red, int64_t i_lo, int
 // sequence of iterates and the summation order of spa_tail, so the result is bit-identical to spa_two_tail.
 template <class Src, class Red>
 __device__ double spa_two_tail_fused(const Src &src, const Red &red, int64_t i_lo, int64_t i_hi, double s_hi, double s_lo,
-                                     int *iters, double max_abs_t = 1.7976931348623157e308) {
+                                     int *iters, double max_abs_t = 1.7976931348623157e308, double arg_scale = 1.0) {
     const double tol = 0x1p-13;
     const double sv[2] = {s_hi, s_lo};
     double t[2] = {0, 0}, H1[2] = {0, 0}, diff[2] = {CUDART_INF, CUDART_INF}, pv[2] = {0, 0};
@@ -380,7 +380,8 @@ __device__ double spa_two_tail_fused(const Src &src, const Red &red, int64_t i_l
                 const double temp1 = t[h] * sv[h] - v[2 * h];
                 const double w = d_sign(t[h]) * sqrt(2 * temp1);
                 const double vv = t[h] * sqrt(v[2 * h + 1]);
-                double pval = d_pnorm(w + 1 / w * log(vv / w), h == 1);
+                // arg_scale = sqrt(Var.ratio) of GetProb_SPA_G_new_adjust (mixPlus :456), 1 everywhere else (exact)
+                double pval = d_pnorm((w + 1 / w * log(vv / w)) * arg_scale, h == 1);
                 if (isnan(pval)) pval = 0;
                 pv[h] = pval; phase[h] = 2;
             } else if (phase[h] == 0) {
@@ -1234,14 +1235,22 @@ __global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m
 
 struct MixShared { AfModel af; double xg[kMaxPC + 1]; double pv[kMaxPC + 1]; };
 
-__global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ list, Counters *ctr,
-                                                        const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
-                                                        int64_t snp0, int64_t m_total, int64_t n,
-                                                        const double *__restrict__ R, const double *__restrict__ E,
-                                                        const VecConst *__restrict__ vcp, WaldData wd, MixData md,
-                                                        double epsilon, double cutoff, double *__restrict__ out,
-                                                        double *__restrict__ mcache_all, const double *__restrict__ hbeta,
-                                                        int hbeta_ld, const MixHand *__restrict__ hand) {
+// PLUS: SPAGxEmix_CCT_Plus_one_SNP (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:144-427): the same allele-frequency
+// model, every variance through the sparse GRM with the per-SNP weights sqrt(g.var.est_i) (:222-232, :260, :269-299,
+// :318-349), the saddlepoint p-value scaled by sqrt(Var.ratio) (GetProb_SPA_G_new_adjust, :435-462).  The branch-B
+// Wald test there is a mixed model (lme4::glmer / lmer, :384 / :404) that stays with the caller: columns 4 and 5 of such
+// rows are NA.  m_i is exchanged between the CTAs of the cluster through the per-cluster cache in global memory.
+__device__ __forceinline__ double mixplus_sq(const double *mc, int64_t i) { const double m = __ldcg(mc + i); return sqrt(2 * m * (1 - m)); }
+
+template <bool PLUS>
+__device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Counters *ctr,
+                                             const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
+                                             int64_t snp0, int64_t m_total, int64_t n,
+                                             const double *__restrict__ R, const double *__restrict__ E,
+                                             const VecConst *__restrict__ vcp, WaldData wd, MixData md,
+                                             double epsilon, double cutoff, double *__restrict__ out,
+                                             double *__restrict__ mcache_all, const double *__restrict__ hbeta,
+                                             int hbeta_ld, const MixHand *__restrict__ hand, GrmCoo grm) {
     namespace cg = cooperative_groups;
     extern __shared__ double tile[];
     __shared__ BShared sh;
@@ -1415,6 +1424,22 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
             v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
         }
         red.sum<4>(v4);
+        // edges of the GRM table this CTA sums (PLUS); the barrier inside red.sum has published every CTA's part of mcache
+        const int64_t e_per = (grm.nnz + cs - 1) / cs;
+        const int64_t e_lo = min((int64_t)grm.nnz, e_per * rank), e_hi = min((int64_t)grm.nnz, e_per * (rank + 1));
+        double cov12 = 0;
+        if (PLUS) {
+            double q2[2] = {0, 0};
+            for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+                const int a = grm.gi[e], b = grm.gj[e];
+                const double xa = R[a] * mixplus_sq(mcache, a), xb = R[b] * mixplus_sq(mcache, b), gvv = grm.gv[e];
+                q2[0] += (gvv * xa) * xb;
+                q2[1] += (gvv * xa) * (xb * E[b]) + (gvv * xb) * (xa * E[a]);
+            }
+            red.sum<2>(q2);
+            cov12 = q2[1] - v4[2];                                                    // Cov_S1_S2 (ref mixPlus :279-281)
+            v4[1] = q2[0] * 2 - v4[1];                                                // VarS1 (ref mixPlus :260)
+        }
         const double meanS1 = 2 * v4[0], VarS1 = v4[1];
         const double Z1 = (S1 - meanS1) / sqrt(VarS1);
         const double pG = d_pnorm(-fabs(Z1), true) * 2;
@@ -1425,7 +1450,7 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         double po[4];
         int iters = 0; bool spa = false;
         if (pG > epsilon) {
-            const double lambda = v4[2] / v4[1];                                      // ref :1115
+            const double lambda = PLUS ? cov12 / VarS1 : v4[2] / v4[1];               // ref :1115; mixPlus :285
             const double S_GxE = S2 - lambda * S1;
             src.lambda = lambda; src.adj = 0;
             double v2[2] = {0, 0};
@@ -1434,14 +1459,27 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                 v2[0] += r * m; v2[1] += (r * r) * (2 * m * (1 - m));
             }
             red.sum<2>(v2);
-            const double Smean = 2 * v2[0], Svar = v2[1];
+            double Svar = v2[1], vscale = 1.0;
+            if (PLUS) {   // S_GxE.var through the GRM (ref mixPlus :296), Var.ratio for the saddlepoint (:308-309)
+                double q1[1] = {0};
+                for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+                    const int a = grm.gi[e], b = grm.gj[e];
+                    const double xa = ((E[a] - lambda) * R[a]) * mixplus_sq(mcache, a), xb = ((E[b] - lambda) * R[b]) * mixplus_sq(mcache, b);
+                    q1[0] += (grm.gv[e] * xa) * xb;
+                }
+                red.sum<1>(q1);
+                Svar = q1[0] * 2 - v2[1];
+                vscale = sqrt(v2[1] / Svar);
+            }
+            const double Smean = 2 * v2[0];
             const double z = (S_GxE - Smean) / sqrt(Svar);
             if (fabs(z) < cutoff) {
                 const double pn = d_pnorm(fabs(z), false) * 2;
                 po[0] = po[1] = po[2] = po[3] = pn;
             } else {
                 spa = true;
-                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE), &iters);
+                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE), &iters,
+                                                     1.7976931348623157e308, vscale);
                 po[0] = po[1] = po[2] = ps;
                 po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             }
@@ -1474,23 +1512,39 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
                 v3[0] += gf(i) * r; v3[1] += r * m; v3[2] += (r * r) * (2 * m * (1 - m));
             }
             red.sum<3>(v3);
-            const double S0 = v3[0], Smean = 2 * v3[1], Svar = v3[2];
+            double Svar = v3[2], vscale = 1.0;
+            if (PLUS) {   // S_GxE0.var through the GRM (ref mixPlus :343), Var.ratio (:355-356)
+                double q1[1] = {0};
+                for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+                    const int a = grm.gi[e], b = grm.gj[e];
+                    double ra, rb, m_, w_;
+                    src.get(a, ra, m_, w_); src.get(b, rb, m_, w_);
+                    q1[0] += (grm.gv[e] * (ra * mixplus_sq(mcache, a))) * (rb * mixplus_sq(mcache, b));
+                }
+                red.sum<1>(q1);
+                Svar = q1[0] * 2 - v3[2];
+                vscale = sqrt(v3[2] / Svar);
+            }
+            const double S0 = v3[0], Smean = 2 * v3[1];
             const double z = (S0 - Smean) / sqrt(Svar);
             double pspa, pn;
             if (fabs(z) < cutoff) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
             else {
                 spa = true;
-                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), &iters);
+                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), &iters,
+                                          1.7976931348623157e308, vscale);
                 pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             }
-            int wfail;
-            double pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
-            if (isnan(pw)) pw = pspa;                                                 // ref :1194, :1213, :1232
-            double pc = NA;
-            int crc = d_cct2(pspa, pw, &pc);
-            if (writer) {
-                if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
-                if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
+            double pw = NA, pc = NA;
+            if (!PLUS) {
+                int wfail;
+                pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
+                if (isnan(pw)) pw = pspa;                                             // ref :1194, :1213, :1232
+                int crc = d_cct2(pspa, pw, &pc);
+                if (writer) {
+                    if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
+                    if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
+                }
             }
             po[0] = pspa; po[1] = pw; po[2] = pc; po[3] = pn;
         }
@@ -1502,6 +1556,30 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
         }
     }
     cl.sync();
+}
+
+__global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ list, Counters *ctr,
+                                                        const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
+                                                        int64_t snp0, int64_t m_total, int64_t n,
+                                                        const double *__restrict__ R, const double *__restrict__ E,
+                                                        const VecConst *__restrict__ vcp, WaldData wd, MixData md,
+                                                        double epsilon, double cutoff, double *__restrict__ out,
+                                                        double *__restrict__ mcache_all, const double *__restrict__ hbeta,
+                                                        int hbeta_ld, const MixHand *__restrict__ hand) {
+    mix_snp_body<false>(list, ctr, bed, pitch, st, snp0, m_total, n, R, E, vcp, wd, md, epsilon, cutoff, out, mcache_all, hbeta,
+                        hbeta_ld, hand, GrmCoo{nullptr, nullptr, nullptr, 0});
+}
+// SPAGxEmix_CCT_Plus: every SNP of the chunk's list through the per-SNP route (the GRM forms are not polynomial in the
+// OLS coefficients, so there is no batched path); mcache_all must hold n doubles per cluster
+__global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict__ list, Counters *ctr,
+                                                            const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
+                                                            int64_t snp0, int64_t m_total, int64_t n,
+                                                            const double *__restrict__ R, const double *__restrict__ E,
+                                                            const VecConst *__restrict__ vcp, MixData md, GrmCoo grm,
+                                                            double epsilon, double cutoff, double *__restrict__ out,
+                                                            double *__restrict__ mcache_all) {
+    mix_snp_body<true>(list, ctr, bed, pitch, st, snp0, m_total, n, R, E, vcp, WaldData{nullptr, nullptr, 0, 0}, md, epsilon, cutoff,
+                       out, mcache_all, nullptr, 0, nullptr, grm);
 }
 
 // ===========================================================================

@@ -26,6 +26,7 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
 __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__restrict__ b_list, const int *__restrict__ count_ptr, Counters *ctr, int64_t m_total, int64_t n, const double *__restrict__ R, const double *__restrict__ E, const VecConst *__restrict__ vcp, GrmCoo grm, double cutoff, double *__restrict__ out, int g_model);
 __global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n, double min_maf, double *__restrict__ out, int *b_list, Counters *ctr);
 __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ list, Counters *ctr, const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st, int64_t snp0, int64_t m_total, int64_t n, const double *__restrict__ R, const double *__restrict__ E, const VecConst *__restrict__ vcp, WaldData wd, MixData md, double epsilon, double cutoff, double *__restrict__ out, double *__restrict__ mcache_all, const double *__restrict__ hbeta, int hbeta_ld, const MixHand *__restrict__ hand);
+__global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict__ list, Counters *ctr, const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st, int64_t snp0, int64_t m_total, int64_t n, const double *__restrict__ R, const double *__restrict__ E, const VecConst *__restrict__ vcp, MixData md, GrmCoo grm, double epsilon, double cutoff, double *__restrict__ out, double *__restrict__ mcache_all);
 
 __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A);
 __global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A);

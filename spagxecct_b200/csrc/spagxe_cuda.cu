@@ -46,7 +46,7 @@ struct spagxe_ctx {
     double *d_pcs = nullptr; int n_pcs = 0;
     double *d_xtx_inv = nullptr;
     int64_t grm_nnz = 0; int *d_gi = nullptr, *d_gj = nullptr; double *d_gv = nullptr;
-    double R_GRM_R = 0, R_GRM_RE = 0, Rnew_GRM_Rnew = 0; double *d_Rn_user = nullptr; bool have_grm = false;
+    double R_GRM_R = 0, R_GRM_RE = 0, Rnew_GRM_Rnew = 0; double *d_Rn_user = nullptr; bool have_grm = false, have_coo = false;
     // chunk scratch
     int64_t cap_chunk_bytes = 0; uint8_t *d_bed[2] = {nullptr, nullptr};
     int cap_m = 0; double *d_stats = nullptr; int *d_istats = nullptr;
@@ -156,6 +156,8 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     // opt in to the large dynamic shared memory of the per-SNP SPAGxEmix kernel
     e = cudaFuncSetAttribute(k_mix_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
+    e = cudaFuncSetAttribute(k_mixplus_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mixplus_snp)", e);
     e = cudaFuncSetAttribute(k_cct_dosage_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_cct_dosage_snp)", e);
     e = cudaFuncSetAttribute(k_localance_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
@@ -241,7 +243,7 @@ static int set_vectors_common(spagxe_ctx *ctx, int64_t n, const double *R, const
         // inputs that depend on N are invalidated
         cudaFree(ctx->d_Y); ctx->d_Y = nullptr; cudaFree(ctx->d_cova); ctx->d_cova = nullptr; ctx->wald_trait = 0;
         cudaFree(ctx->d_pcs); ctx->d_pcs = nullptr; ctx->n_pcs = 0;
-        ctx->have_grm = false;
+        ctx->have_grm = false; ctx->have_coo = false;
         ctx->n = n;
     }
     cudaStream_t s = ctx->stream();
@@ -679,14 +681,14 @@ static void fill_diag(spagxe_diag *diag, const Counters &c, int64_t m) {
 
 static const spagxe_params kDefaultParams = {0.001, 2.0, 0.001, 0.15, 0.05, 0.1, 0, 0, 0, 0, 0};
 
-enum RunMode { RUN_CCT = 0, RUN_PLUS = 1, RUN_MIX = 2 };
+enum RunMode { RUN_CCT = 0, RUN_PLUS = 1, RUN_MIX = 2, RUN_MIXPLUS = 3 };
 
 static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, SnpStats st, int64_t j0, int mc, int64_t M,
-                      int64_t N, WaldData wd, const spagxe_params *prm, double *d_out) {
+                      int64_t N, WaldData wd, const spagxe_params *prm, double *d_out, bool plus) {
     cudaStream_t s = ctx->stream();
     k_finalize_mix<<<(mc + 127) / 128, 128, 0, s>>>(st, mc, j0, M, N, prm->min_maf, d_out, ctx->d_b_list, ctx->d_ctr);
     LAUNCH_CHECK();
-    if (!ctx->opt_mix_per_snp) {   // test hook: every SNP through the cluster kernel
+    if (!ctx->opt_mix_per_snp && !plus) {   // test hook: every SNP through the cluster kernel (SPAGxEmix_CCT_Plus: always)
         const MixBatchParams bp{prm->epsilon, prm->cutoff, prm->neg_ratio_cutoff, prm->g_model};
         if (!ctx->mix_scratch) ctx->mix_scratch = mix_scratch_create();
         CU(mix_batch_run(s, ctx->mix_scratch, ctx->num_sms, d_rows, dpitch, st, j0, mc, M, N, ctx->d_R, ctx->d_E, ctx->d_vc, ctx->d_pcs,
@@ -714,6 +716,12 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     }
     double *mcache = ctx->d_mcache;
     const double *hbeta = nullptr; int hbeta_ld = 0; const MixHand *hand = nullptr;
+    if (plus) {
+        GrmCoo grm{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
+        CU(cudaLaunchKernelEx(&cfg, k_mixplus_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, md, grm, prm->epsilon, prm->cutoff, d_out, mcache));
+        ctx->launches++;
+        return SPAGXE_OK;
+    }
     if (!ctx->opt_mix_per_snp) { hbeta = mix_scratch_beta(ctx->mix_scratch, &hbeta_ld); hand = mix_scratch_hand(ctx->mix_scratch); }
     CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out, mcache,
                           hbeta, hbeta_ld, hand));
@@ -797,19 +805,22 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (!prm) prm = &kDefaultParams;
     int rc = validate_geno(ctx, g);
     if (rc) return rc;
-    const char *name = mode == RUN_CCT ? "run_cct" : mode == RUN_PLUS ? "run_plus" : "run_mix";
+    const bool mixplus = (mode == RUN_MIXPLUS);
+    if (mixplus) mode = RUN_MIX;   // the same pipeline; the per-SNP kernel differs (launch_mix)
+    const char *name = mode == RUN_CCT ? "run_cct" : mode == RUN_PLUS ? "run_plus" : mixplus ? "run_mix_plus" : "run_mix";
     const int ncol = mode == RUN_CCT ? 10 : mode == RUN_PLUS ? 8 : 12;
     if (!out) return fail(ctx, SPAGXE_ERR_ARG, "out is NULL");
     if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_vectors first", name);
     if (g->n_samples != ctx->n) return fail(ctx, SPAGXE_ERR_ARG, "geno has %lld samples but R has %lld",
                                             (long long)g->n_samples, (long long)ctx->n);
-    if (mode != RUN_PLUS && ctx->wald_trait == 0)
+    if (mode != RUN_PLUS && !mixplus && ctx->wald_trait == 0)
         return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_wald first (Wald test data)", name);
     if (mode == RUN_PLUS && !ctx->have_grm) return fail(ctx, SPAGXE_ERR_STATE, "run_plus: call spagxe_set_grm first");
-    if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "run_mix: call spagxe_set_pcs first");
-    if (mode == RUN_MIX && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL)
+    if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_pcs first", name);
+    if (mixplus && !ctx->have_coo) return fail(ctx, SPAGXE_ERR_STATE, "run_mix_plus: call spagxe_set_sparse_grm first");
+    if (mode == RUN_MIX && !mixplus && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL)
         return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the survival Wald test is implemented for SPAGxE_CCT only");
-    if (mode == RUN_MIX && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL)
+    if (mode == RUN_MIX && !mixplus && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL)
         return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the categorical Wald test is implemented for SPAGxE_CCT only");
     if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL && !clm_ready(ctx->clm)) {
         CU(cudaSetDevice(ctx->device));
@@ -895,7 +906,7 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
             spa_pending += mc;
             if (last && (rc = flush_spa(ctx->d_Rn))) return rc;
         } else {
-            if ((rc = launch_mix(ctx, d_rows, pl.dpitch, st, j0, mc, M, N, wd, prm, d_out))) return rc;
+            if ((rc = launch_mix(ctx, d_rows, pl.dpitch, st, j0, mc, M, N, wd, prm, d_out, mixplus))) return rc;
         }
         // staged rows live in two alternating buffers: pending branch-B items must run before their buffer is reused;
         // caller-owned device rows stay valid for the whole call, so everything is deferred to one launch at the end
@@ -969,6 +980,9 @@ extern "C" int spagxe_run_plus(spagxe_ctx *ctx, const spagxe_geno *g, const spag
 }
 extern "C" int spagxe_run_mix(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
     return run_generic(ctx, g, prm, out, diag, RUN_MIX);
+}
+extern "C" int spagxe_run_mix_plus(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+    return run_generic(ctx, g, prm, out, diag, RUN_MIXPLUS);
 }
 
 // ---------------------------------------------------------------------------
@@ -1081,8 +1095,27 @@ extern "C" int spagxe_set_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, c
     }
     CU(cudaMemcpy(ctx->d_Rn_user, Rnew, ctx->n * sizeof(double), cudaMemcpyHostToDevice));
     ctx->grm_nnz = nnz; ctx->R_GRM_R = R_GRM_R; ctx->R_GRM_RE = R_GRM_RE; ctx->Rnew_GRM_Rnew = Rnew_GRM_Rnew;
-    ctx->have_grm = true;
+    ctx->have_grm = true; ctx->have_coo = true;
     ctx->vec_mode = -1;
+    return SPAGXE_OK;
+}
+
+// sparseGRM of SPAGxEmix_CCT_Plus (ref R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:216-232): the table alone, no Step-1 scalars
+extern "C" int spagxe_set_sparse_grm(spagxe_ctx *ctx, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv) {
+    if (!ctx) return SPAGXE_ERR_ARG;
+    if (ctx->n <= 0) return fail(ctx, SPAGXE_ERR_STATE, "set_sparse_grm: call spagxe_set_vectors first");
+    if (nnz < 0 || (nnz > 0 && (!gi || !gj || !gv))) return fail(ctx, SPAGXE_ERR_ARG, "set_sparse_grm: bad arguments");
+    { int rc = check_grm_indices(ctx, "set_sparse_grm", nnz, gi, gj, ctx->n); if (rc) return rc; }
+    CU(cudaSetDevice(ctx->device));
+    CU(dev_realloc(&ctx->d_gi, std::max<int64_t>(nnz, 1))); CU(dev_realloc(&ctx->d_gj, std::max<int64_t>(nnz, 1)));
+    CU(dev_realloc(&ctx->d_gv, std::max<int64_t>(nnz, 1)));
+    if (nnz > 0) {
+        CU(cudaMemcpy(ctx->d_gi, gi, nnz * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_gj, gj, nnz * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_gv, gv, nnz * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    ctx->grm_nnz = nnz;
+    ctx->have_coo = true; ctx->have_grm = false;   // SPAGxE_Plus needs its scalars and R.new again (spagxe_set_grm)
     return SPAGXE_OK;
 }
 
