@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port, all host threads)
 
-    python bench.py --workload mix|plus ...                  # configs 4 / 5 (SPAGxEmix_CCT, SPAGxE_Plus), same JSON contract
+    python bench.py --workload mix|plus|mixplus ...                  # configs 4 / 5 (SPAGxEmix_CCT, SPAGxE_Plus), same JSON contract
 
 A "step" is one pass of the hot path (2-bit unpack + score + routing + SPA + genotype-adjusted
 branch) over one batch of synthetic UK-Biobank-shaped SNPs that is already resident in HBM.  The
@@ -246,7 +246,9 @@ def run_reference(args):
 def workload_config_other(kind, n, m, extra):
     rb = (n + 3) // 4
     base = {"mix": "C4: SPAGxEmix_CCT, two-way admixed population, 10 PCs, binary trait with ancestry-specific prevalence 0.1 / 0.01",
-            "plus": "C5: SPAGxE_Plus, 20,000 four-member families + 20,000 singletons, sparse GRM (200,000 entries), Cox martingale residuals"}[kind]
+            "plus": "C5: SPAGxE_Plus, 20,000 four-member families + 20,000 singletons, sparse GRM (200,000 entries), Cox martingale residuals",
+            "mixplus": "C4 data through SPAGxEmix_CCT_Plus: two-way admixed population, 10 PCs, sparse GRM = diagonal + 50,000 pairs at 0.5 "
+                       "(branch-B Wald = caller's glmer, not timed)"}[kind]
     return {"workload": f"{base}, N={n}, {m} SNPs/step/GPU ({m * rb / 1e6:.0f} MB packed .bed rows resident in HBM)", "n_samples": n,
             "snps_per_step_per_gpu": m, "l2_policy": "L2 flushed by a 256 MB write between steps" if m * rb < 3e8 else "inputs larger than L2",
             "sharding": "SNP ranges per rank, no data-path collective", **extra}
@@ -261,8 +263,8 @@ def run_other(args, kind):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     W, K = max(3, args.warmup), args.steps
-    m = args.batch_snps if args.batch_snps != DEFAULT_BATCH_SNPS else (4096 if kind == "mix" else 8192)
-    x = c4_admixed(m=m, device=dev) if kind == "mix" else c5_families(m=m, device=dev)
+    m = args.batch_snps if args.batch_snps != DEFAULT_BATCH_SNPS else {"mix": 4096, "mixplus": 1024}.get(kind, 8192)
+    x = c4_admixed(m=m, device=dev) if kind in ("mix", "mixplus") else c5_families(m=m, device=dev)
     n = x["n"]
     rb = (n + 3) // 4
     ctx = Context(local)
@@ -274,6 +276,14 @@ def run_other(args, kind):
             ctx.set_option(_lib.OPT_MIX_CLUSTER, args.mix_cluster)
         run, ncol, prm_kw = ctx.run_mix, 12, dict(min_maf=1e-5)
         metric = "SNPs/sec at N=200k, 10 PCs (SPAGxEmix_CCT Step-2 loop, device-timed)"
+    elif kind == "mixplus":
+        npair = 50_000
+        x["grm_i"] = np.r_[np.arange(x["n"]), np.arange(1, 2 * npair, 2)].astype(np.int32)
+        x["grm_j"] = np.r_[np.arange(x["n"]), np.arange(0, 2 * npair, 2)].astype(np.int32)
+        x["grm_v"] = np.r_[np.ones(x["n"]), np.full(npair, 0.5)]
+        ctx.set_pcs(x["PCs"]); ctx.set_sparse_grm(x["grm_i"], x["grm_j"], x["grm_v"])
+        run, ncol, prm_kw = ctx.run_mix_plus, 12, dict(min_maf=1e-5)
+        metric = "SNPs/sec at N=200k, 10 PCs, sparse GRM (SPAGxEmix_CCT_Plus Step-2 loop, device-timed)"
     else:
         a, b, Rnew, c = ctx.plus_nullmodel(x["grm_i"], x["grm_j"], x["grm_v"], x["R"], x["E"])
         ctx.set_grm(x["grm_i"], x["grm_j"], x["grm_v"], a, b, c, Rnew)
@@ -320,18 +330,19 @@ def run_other(args, kind):
     ms_score = float(np.mean([d["ms_score"] for d in diags]))
     ms_tests = float(np.mean([d["ms_tests"] for d in diags]))
     dg = diags[-1]
-    k1 = x["PCs"].shape[1] + 1 if kind == "mix" else 0
+    k1 = x["PCs"].shape[1] + 1 if kind in ("mix", "mixplus") else 0
     line = {"metric": metric, "value": m * K / (ms_sum * 1e-3), "unit": "SNPs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_sum / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config_other(kind, n, m, {"n_pcs": k1 - 1} if kind == "mix" else {"grm_nnz": int(x["grm_i"].size)}),
+            "data": "synthetic", "config": workload_config_other(kind, n, m, dict({"n_pcs": k1 - 1} if k1 else {}, **({"grm_nnz": int(x["grm_i"].size)} if kind != "mix" else {}))),
             "e2e": {"value": m * ke / (ms_e * 1e-3), "unit": "SNPs/s", "h2d_bytes_per_step": int(dge["h2d_bytes"]),
                     "d2h_bytes_per_step": int(dge["d2h_bytes"]), "steps": ke},
             "gpu_launches": int(sum(d["kernel_launches"] for d in diags)),
             "roofline": ({"bound": "tensor", "achieved": 2.0 * n * k1 * 2 * m / (ms_tests * 1e-3) / 1e12, "peak": fp64, "unit": "TFLOP/s",
                           "frac": (2.0 * n * k1 * 2 * m / (ms_tests * 1e-3) / 1e12 / fp64) if fp64 else None, "traffic": None,
-                          "kernel": "k_mix_tile + k_mix_finish (allele-frequency projection, fp64 CUDA cores; 'tensor' = compute bound)",
+                          "kernel": ("k_mix_tile + k_mix_finish (allele-frequency projection, fp64 CUDA cores; 'tensor' = compute bound)" if kind == "mix"
+                                     else "k_mixplus_snp (per-SNP cluster kernel: allele-frequency model, GRM forms, saddlepoint; 'tensor' = compute bound)"),
                           "flop_model": "2 passes x 2 N (k+1) flop per SNP (X'g and x_i'beta)", "peak_source": "DFMA loop measured in this run"}
-                         if kind == "mix" else
+                         if k1 else
                          {"bound": "hbm", "achieved": float(dg["score_bytes"]) / (ms_score * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": float(dg["score_bytes"]) / (ms_score * 1e-3) / 1e9 / peak, "traffic": None,
                           "kernel": "k_score_unpack_mma", "peak_source": peak_src}),
@@ -342,15 +353,17 @@ def run_other(args, kind):
     if args.cpu_sample_snps > 0:
         from oracle import oracle as O
         O.build()
-        ns = min(64 if kind == "mix" else 256, m)
+        ns = min(64 if k1 else 256, m)
         t0 = time.perf_counter()
         if kind == "mix":
             ref, *_ = O.mix_bed("binary", x["rows"][: ns * rb], n, x["R"], x["E"], x["Y"], x["Cova"], x["PCs"], min_maf=1e-5)
+        elif kind == "mixplus":
+            ref, *_ = O.mixplus_bed(x["rows"][: ns * rb], n, x["R"], x["E"], x["PCs"], x["grm_i"], x["grm_j"], x["grm_v"], min_maf=1e-5)
         else:
             ref, *_ = O.plus_bed(x["rows"][: ns * rb], n, x["R"], x["E"], Rnew, a, b, c, x["grm_i"], x["grm_j"], x["grm_v"])
         dt = time.perf_counter() - t0
         got = out_dev.cpu().numpy().reshape(ncol, m).T[:ns]
-        pc = [2, 3, 4, 5, 6] if kind == "mix" else [2, 3, 4]
+        pc = [2, 3, 4, 5, 6] if kind == "mix" else ([2, 5, 6] if kind == "mixplus" else [2, 3, 4])
         with np.errstate(all="ignore"):
             chk = float(np.nanmax(np.abs(np.log10(got[:, pc]) - np.log10(ref[:, pc])) / np.maximum(np.abs(np.log10(ref[:, pc])), 1e-3)))
         line["cpu_baseline"] = {"value": ns / dt, "unit": "SNPs/s", "cores": 1, "kind": "port",
@@ -366,7 +379,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cct", choices=["cct", "mix", "plus"])
+    ap.add_argument("--workload", default="cct", choices=["cct", "mix", "plus", "mixplus"])
     ap.add_argument("--n-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--batch-snps", type=int, default=DEFAULT_BATCH_SNPS)
     ap.add_argument("--ref-snps", type=int, default=0)

@@ -251,6 +251,11 @@ int spagxe_mgpu_run_mix(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, 
                         spagxe_diag *diag);
 int spagxe_mgpu_run_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
                          spagxe_diag *diag);
+/* SPAGxEmix_CCT_Plus on several GPUs: spagxe_mgpu_set_inputs (trait 0), spagxe_mgpu_set_pcs, spagxe_mgpu_set_sparse_grm;
+ * out is M x 12 with NA in the Wald / CCT columns of branch-B rows (see spagxe_run_mix_plus).                    */
+int spagxe_mgpu_set_sparse_grm(spagxe_mgpu *mg, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv);
+int spagxe_mgpu_run_mix_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                             spagxe_diag *diag);
 
 /* ---- genotype unpack (K1) exposed for the bit-exact decode checks ----------- */
 /* per-SNP code counts of packed rows: counts[4*j + c], c = 00,01,10,11 (GRAB decode: 2,NA,1,0);

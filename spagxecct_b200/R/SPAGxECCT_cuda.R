@@ -1,6 +1,7 @@
 # SPAGxECCT_cuda.R -- drop-in replacements of the reference's exported Step-2 functions.
 # Same formals, printed lines, column names and stop() behaviour as R/SPAGxECCT.R:455-530 (SPAGxE_CCT), :543-683
-# (SPAGxE_CCT_one_SNP), :916-1002 (SPAGxEmix_CCT), :1013-1269 (SPAGxEmix_CCT_one_SNP) and
+# (SPAGxE_CCT_one_SNP), :916-1002 (SPAGxEmix_CCT), :1013-1269 (SPAGxEmix_CCT_one_SNP),
+# R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133, :144-427 (SPAGxEmix_CCT_Plus, SPAGxEmix_CCT_Plus_one_SNP) and
 # R/SPAGxEPlus_functions_MYZ.R:159-238, :248-405 (SPAGxE_Plus, SPAGxE_Plus_one_SNP); the serial `for(i in 1:n.Geno)` loop
 # is replaced by one .Call into libspagxe_cuda.so.  Step 1 (SPA_G_Get_Resid, the model fit of SPAGxE_Plus_Nullmodel) stays
 # in R.  dyn.load("spagxe_rshim.so") once (it links libspagxe_cuda.so).
@@ -220,6 +221,81 @@ SPAGxE_Plus_one_SNP <- function(g, E, Phen.mtx, Cova.mtx, obj.SPAGxE_Plus_Nullmo
   .spagxe_set_plus(ctx, obj.SPAGxE_Plus_Nullmodel, E)
   gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
   as.numeric(.spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm)))
+}
+
+# SPAGxEmix_CCT_Plus / SPAGxEmix_CCT_Plus_one_SNP (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133, :144-427).  The GPU does
+# the allele-frequency model, every sparse-GRM variance and the adjusted saddlepoint for all SNPs; for the few SNPs of
+# branch B (p.value.betaG <= epsilon) the Wald test is the reference's own lme4::glmer / lmer call (:384, :404), run here
+# in R on the recoded genotype vector, followed by the reference's CCT().  R = ResidMat$Resid (the reference's one-SNP
+# function reads `R` as a free variable that its scripts define this way).
+.spagxe_mixplus_prepare <- function(ctx, ResidMat, E, topPCs, sparseGRM) {
+  ids <- as.character(ResidMat$SubjID)
+  id1 <- as.character(sparseGRM$ID1); id2 <- as.character(sparseGRM$ID2)
+  if (any(!ids %in% unique(c(id1, id2)))) stop("At least one subject in residual matrix does not have GRM information.")
+  g1 <- match(id1, ids); g2 <- match(id2, ids)
+  keep <- !is.na(g1) & !is.na(g2)                                       # filter(ID1 %in% SubjID & ID2 %in% SubjID), :220
+  .Call("spagxe_r_set_vectors", ctx, as.double(ResidMat$Resid), as.double(E))
+  .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
+  .Call("spagxe_r_set_sparse_grm", ctx, g1[keep] - 1L, g2[keep] - 1L, as.double(sparseGRM$Value[keep]))
+}
+
+# the recoding of :171-188 for one column, then the Wald fit of :384-389 / :404-409 and CCT (:393, :413)
+.spagxe_mixplus_wald <- function(traits, g, row, E, Phen.mtx, Cova.mtx, G.model) {
+  MAF <- mean(g, na.rm = TRUE) / 2
+  g[is.na(g)] <- 2 * MAF
+  if (MAF > 0.5) g <- 2 - g
+  if (G.model == "Dom") g <- ifelse(g >= 1, 1, 0)
+  if (G.model == "Rec") g <- ifelse(g <= 1, 0, 1)
+  if (traits == "binary") {
+    data0 <- lme4::glmer(Y ~ as.matrix(Cova.mtx) + E + g + g * E + (1 | IID), family = "binomial", data = Phen.mtx)
+    pval.wald <- summary(data0)$coefficients["E:g", "Pr(>|z|)"]
+  } else {
+    data0 <- lme4::lmer(Y ~ as.matrix(Cova.mtx) + E + g + g * E + (1 | IID), data = Phen.mtx)
+    pval.wald <- summary(data0)$coefficients["E:g", "Pr(>|t|)"]
+  }
+  if (is.na(pval.wald)) pval.wald <- row[3]
+  row[4] <- pval.wald
+  row[5] <- CCT(c(row[3], pval.wald))
+  row
+}
+
+SPAGxEmix_CCT_Plus <- function(traits = "binary/quantitative", Geno.mtx, ResidMat, E, Phen.mtx, Cova.mtx, topPCs, sparseGRM,
+                               epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001,
+                               G.model = "Add", topPCs.pvalue.cutoff = 0.05, MAF.est.negative.ratio.cutoff = 0.1, device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  print(paste0("Sample size is ", nrow(Geno.mtx), "."))
+  print(paste0("Number of variants is ", ncol(Geno.mtx), "."))
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .spagxe_mixplus_prepare(ctx, ResidMat, E, topPCs, sparseGRM)
+  print("Start Analyzing...")
+  print(Sys.time())
+  gi <- list(g = Geno.mtx, n = nrow(Geno.mtx), m = ncol(Geno.mtx), sidx = NULL, nfile = 0, a2 = 0L)
+  output <- .spagxe_run(ctx, 3L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm))
+  for (i in seq_len(ncol(Geno.mtx))) print(i)                            # the reference prints the SNP counter (:103)
+  for (i in which(output[, 7] <= epsilon))
+    output[i, ] <- .spagxe_mixplus_wald(traits, Geno.mtx[, i], output[i, ], E, Phen.mtx, Cova.mtx, G.model)
+  colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxEmix.plus", "p.value.spaGxEmix.plus.Wald",
+                        "p.value.spaGxEmix.plus.CCT.Wald", "p.value.normGxEmix.plus", "p.value.betaG", "Stat.betaG",
+                        "Var.betaG", "z.betaG", "MAF.est.negative.num", "MAC")
+  rownames(output) <- colnames(Geno.mtx)
+  print("Analysis Complete.")
+  print(Sys.time())
+  output
+}
+
+SPAGxEmix_CCT_Plus_one_SNP <- function(traits = "binary/quantitative", g, ResidMat, E, Phen.mtx, Cova.mtx, topPCs, sparseGRM,
+                                       epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15,
+                                       min.maf = 0.001, G.model = "Add", topPCs.pvalue.cutoff = 0.05,
+                                       MAF.est.negative.ratio.cutoff = 0.1, device = 0L) {
+  gm <- .spagxe_gmodel(G.model)
+  ctx <- .Call("spagxe_r_create", as.integer(device))
+  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+  .spagxe_mixplus_prepare(ctx, ResidMat, E, topPCs, sparseGRM)
+  gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
+  row <- as.numeric(.spagxe_run(ctx, 3L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm)))
+  if (!is.na(row[7]) && row[7] <= epsilon) row <- .spagxe_mixplus_wald(traits, g, row, E, Phen.mtx, Cova.mtx, G.model)
+  row
 }
 
 # The GRM quadratic forms of SPAGxE_Plus_Nullmodel (R/SPAGxEPlus_functions_MYZ.R:490-537) on the GPU: call this in place of

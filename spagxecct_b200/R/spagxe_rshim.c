@@ -67,6 +67,12 @@ SEXP spagxe_r_set_grm(SEXP ptr, SEXP gi, SEXP gj, SEXP gv, SEXP scalars, SEXP Rn
                               REAL(scalars)[2], REAL(Rnew)));
     return R_NilValue;
 }
+/* sparseGRM of SPAGxEmix_CCT_Plus: 0-based positions of ID1 / ID2 in ResidMat$SubjID and Value */
+SEXP spagxe_r_set_sparse_grm(SEXP ptr, SEXP gi, SEXP gj, SEXP gv) {
+    spagxe_ctx *ctx = get_ctx(ptr);
+    CHECK(ctx, spagxe_set_sparse_grm(ctx, XLENGTH(gv), INTEGER(gi), INTEGER(gj), REAL(gv)));
+    return R_NilValue;
+}
 /* list(scalars = c(R_GRM_R, R_GRM_RE, R.new_GRM_R.new), R.new = numeric(n)) */
 SEXP spagxe_r_plus_nullmodel(SEXP ptr, SEXP R, SEXP E, SEXP gi, SEXP gj, SEXP gv) {
     spagxe_ctx *ctx = get_ctx(ptr);
@@ -130,17 +136,18 @@ static void attach_diag(SEXP out, const spagxe_diag *d) {
     UNPROTECT(2);
 }
 
-/* which: 0 cct (M x 10), 1 mix (M x 12), 2 plus (M x 8); prm = c(epsilon, Cutoff, min.maf, missing.cutoff, pc.cut, neg.cut) */
+/* which: 0 cct (M x 10), 1 mix (M x 12), 2 plus (M x 8), 3 mix_plus (M x 12); prm = c(epsilon, Cutoff, min.maf, missing.cutoff, pc.cut, neg.cut) */
 SEXP spagxe_r_run(SEXP ptr, SEXP which, SEXP geno, SEXP n_, SEXP m_, SEXP prm, SEXP sidx, SEXP nfile, SEXP a2) {
     spagxe_ctx *ctx = get_ctx(ptr);
     spagxe_geno gd; int64_t *ix = NULL;
     geno_from_sexp(geno, n_, m_, sidx, nfile, a2, &gd, &ix);
     spagxe_params sp; params_from_sexp(prm, &sp);
-    const int w = asInteger(which), ncol = (w == 0) ? 10 : (w == 1 ? 12 : 8);
+    const int w = asInteger(which), ncol = (w == 0) ? 10 : ((w == 1 || w == 3) ? 12 : 8);
     SEXP out = PROTECT(allocMatrix(REALSXP, (int)gd.n_snps, ncol));
     spagxe_diag diag; memset(&diag, 0, sizeof diag);
     int rc = (w == 0) ? spagxe_run_cct(ctx, &gd, &sp, REAL(out), &diag)
            : (w == 1) ? spagxe_run_mix(ctx, &gd, &sp, REAL(out), &diag)
+           : (w == 3) ? spagxe_run_mix_plus(ctx, &gd, &sp, REAL(out), &diag)
                       : spagxe_run_plus(ctx, &gd, &sp, REAL(out), &diag);
     free(ix);
     if (rc != SPAGXE_OK) { UNPROTECT(1); Rf_error("%s", spagxe_last_error(ctx)); }
@@ -217,6 +224,7 @@ static const R_CallMethodDef call_methods[] = {
     {"spagxe_r_set_pcs", (DL_FUNC)&spagxe_r_set_pcs, 2},
     {"spagxe_r_set_grm", (DL_FUNC)&spagxe_r_set_grm, 6},
     {"spagxe_r_plus_nullmodel", (DL_FUNC)&spagxe_r_plus_nullmodel, 6},
+    {"spagxe_r_set_sparse_grm", (DL_FUNC)&spagxe_r_set_sparse_grm, 4},
     {"spagxe_r_run", (DL_FUNC)&spagxe_r_run, 9},
     {"spagxe_r_run_localance", (DL_FUNC)&spagxe_r_run_localance, 5},
     {"spagxe_r_mgpu_create", (DL_FUNC)&spagxe_r_mgpu_create, 1},

@@ -26,6 +26,7 @@ EXPORTS = [
     "spagxe_set_wald_device", "spagxe_set_wald_survival", "spagxe_mgpu_create", "spagxe_mgpu_destroy", "spagxe_mgpu_last_error", "spagxe_mgpu_n_gpus",
     "spagxe_mgpu_set_inputs", "spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus", "spagxe_mgpu_set_wald_survival",
     "spagxe_mgpu_set_pcs", "spagxe_mgpu_set_grm", "spagxe_set_sparse_grm", "spagxe_run_mix_plus",
+    "spagxe_mgpu_set_sparse_grm", "spagxe_mgpu_run_mix_plus",
 ]
 # test / tuning hooks (include/spagxe.h SPAGXE_OPT_*): not part of the reference-facing surface
 OPT_CHUNK_SNPS, OPT_EXACT_SPA, OPT_MIX_PER_SNP, OPT_SCORE_IMPL, OPT_MIX_CLUSTER = 1, 2, 3, 4, 5
@@ -96,7 +97,8 @@ def load():
     L.spagxe_mgpu_last_error.restype = C.c_char_p
     L.spagxe_mgpu_n_gpus.argtypes = [C.c_void_p]
     L.spagxe_mgpu_set_inputs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    for f in ("spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus"):
+    L.spagxe_mgpu_set_sparse_grm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    for f in ("spagxe_mgpu_run_cct", "spagxe_mgpu_run_mix", "spagxe_mgpu_run_plus", "spagxe_mgpu_run_mix_plus"):
         getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Geno), C.c_int, C.POINTER(Params), C.c_void_p, C.POINTER(Diag)]
     L.spagxe_mgpu_set_wald_survival.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.spagxe_mgpu_set_pcs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -354,6 +356,14 @@ class MultiContext:
         gv = _f64(gv); Rnew = _f64(Rnew)
         self._chk(self.L.spagxe_mgpu_set_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data,
                                              float(R_GRM_R), float(R_GRM_RE), float(Rnew_GRM_Rnew), Rnew.ctypes.data))
+
+    def set_sparse_grm(self, gi, gj, gv):
+        gi = np.ascontiguousarray(gi, dtype=np.int32); gj = np.ascontiguousarray(gj, dtype=np.int32)
+        gv = _f64(gv)
+        self._chk(self.L.spagxe_mgpu_set_sparse_grm(self.h, gi.size, gi.ctypes.data, gj.ctypes.data, gv.ctypes.data))
+
+    def run_mix_plus(self, geno, params=None, out_ptr=None):
+        return self.run_cct(geno, params, out_ptr, _fn="spagxe_mgpu_run_mix_plus", _ncol=12)
 
     def run_mix(self, geno, params=None, out_ptr=None):
         return self.run_cct(geno, params, out_ptr, _fn="spagxe_mgpu_run_mix", _ncol=12)

@@ -201,6 +201,9 @@ extern "C" int spagxe_mgpu_set_grm(spagxe_mgpu *mg, int64_t nnz, const int32_t *
                                    double R_GRM_R, double R_GRM_RE, double Rnew_GRM_Rnew, const double *Rnew) {
     MG_EACH(spagxe_set_grm(c, nnz, gi, gj, gv, R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew, Rnew));
 }
+extern "C" int spagxe_mgpu_set_sparse_grm(spagxe_mgpu *mg, int64_t nnz, const int32_t *gi, const int32_t *gj, const double *gv) {
+    MG_EACH(spagxe_set_sparse_grm(c, nnz, gi, gj, gv));
+}
 
 static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
                     spagxe_diag *diag, int which);
@@ -210,6 +213,8 @@ extern "C" int spagxe_mgpu_run_mix(spagxe_mgpu *mg, const spagxe_geno *geno, int
                                    spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 1); }
 extern "C" int spagxe_mgpu_run_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
                                     spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 2); }
+extern "C" int spagxe_mgpu_run_mix_plus(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
+                                        spagxe_diag *diag) { return mgpu_run(mg, geno, n_shards, prm, out, diag, 3); }
 
 static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, const spagxe_params *prm, double *out,
                     spagxe_diag *diag, int which) {
@@ -252,6 +257,7 @@ static int mgpu_run(spagxe_mgpu *mg, const spagxe_geno *geno, int n_shards, cons
             cudaSetDevice(mg->devices[k]);
             rcs[k] = which == 0 ? spagxe_run_cct(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k])
                    : which == 1 ? spagxe_run_mix(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k])
+                   : which == 3 ? spagxe_run_mix_plus(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k])
                                 : spagxe_run_plus(mg->ctx[k], &sh[k], &p0, out + row0[k], &dgs[k]);
         });
     }

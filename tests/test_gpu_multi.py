@@ -97,6 +97,16 @@ def test_mix_plus_and_survival_shard_like_cct(gpu_ctx, golden_dir):
         two, d2 = mg.run_mix(g, dict(epsilon=0.2, min_maf=0.0002))
     assert np.array_equal(np.nan_to_num(two, nan=-1), np.nan_to_num(one, nan=-1))
     assert d2["n_mix_logistic"] == d1["n_mix_logistic"] and d2["newton_iters"] == d1["newton_iters"]
+    # SPAGxEmix_CCT_Plus on the same data with a sib-pair GRM
+    from tests.test_mix_plus import _family_grm
+    gi, gj, gv = _family_grm(n, 3000)
+    gpu_ctx.set_sparse_grm(gi, gj, gv)
+    one_mp, dm1 = gpu_ctx.run_mix_plus(g, dict(epsilon=0.2, min_maf=0.0002))
+    with _lib.MultiContext(2) as mg:
+        mg.set_inputs(x["R"], x["E"]); mg.set_pcs(x["PCs"]); mg.set_sparse_grm(gi, gj, gv)
+        two_mp, dm2 = mg.run_mix_plus(g, dict(epsilon=0.2, min_maf=0.0002))
+    assert np.array_equal(np.nan_to_num(two_mp, nan=-1), np.nan_to_num(one_mp, nan=-1))
+    assert dm2["n_branch_b"] == dm1["n_branch_b"] >= 3 and dm2["newton_iters"] == dm1["newton_iters"]
     # SPAGxE_Plus (sib pairs) and SPAGxE_CCT with a survival trait on the same cohort
     n_fam = 2001; n = 2 * n_fam + 1001
     ph = _surv_pheno(n, 41, 25)
