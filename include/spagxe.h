@@ -145,9 +145,9 @@ int spagxe_set_vectors_device(spagxe_ctx *ctx, int64_t n, const double *dR, cons
 
 /* data of the Wald model Y ~ Cova + E + g + E:g (R/SPAGxECCT.R:622-677): Phen.mtx$Y and
  * as.matrix(Cova.mtx) (N x p column-major, p <= 12).  trait = SPAGXE_TRAIT_*.
- * SPAGXE_TRAIT_CATEGORICAL (R/SPAGxECCT.R:664-677: ordinal::clm(as.factor(Phen.mtx$Y) ~ ..., logit link, flexible
- * thresholds): Y holds the index of every sample's level in sort(unique(Y)), 0 .. J-1 with J <= 8 and every level
- * present; p <= 2; SPAGxE_CCT only.  Survival data go through spagxe_set_wald_survival.   */
+ * SPAGXE_TRAIT_CATEGORICAL (R/SPAGxECCT.R:664-677, :1244-1262: ordinal::clm(as.factor(Phen.mtx$Y) ~ ..., logit link,
+ * flexible thresholds): Y holds the index of every sample's level in sort(unique(Y)), 0 .. J-1 with J <= 8 and every level
+ * present; p <= 2; SPAGxE_CCT and SPAGxEmix_CCT.  Survival data go through spagxe_set_wald_survival.   */
 int spagxe_set_wald(spagxe_ctx *ctx, int trait, const double *Y, const double *cova, int p);
 
 /* same with device pointers (the multi-GPU driver hands over what arrived by the NCCL broadcast) */
@@ -155,7 +155,7 @@ int spagxe_set_wald_device(spagxe_ctx *ctx, int trait, const double *dY, const d
 
 /* traits = "survival" (R/SPAGxECCT.R:622-634): the Wald model is coxph(Surv(Phen.mtx$surv.time, Phen.mtx$event) ~
  * as.matrix(Cova.mtx) + E + g + g*E, iter.max = 1000) with Efron ties; host pointers, event in {0, 1}, p <= 2.
- * SPAGxE_CCT only (spagxe_run_cct); sets the trait to SPAGXE_TRAIT_SURVIVAL.                                    */
+ * SPAGxE_CCT and SPAGxEmix_CCT (:1187-1193; spagxe_run_cct / spagxe_run_mix); sets the trait to SPAGXE_TRAIT_SURVIVAL. */
 int spagxe_set_wald_survival(spagxe_ctx *ctx, const double *surv_time, const double *event, const double *cova, int p);
 
 /* topPCs of SPAGxEmix_CCT (R/SPAGxECCT.R:925, :1066): N x k column-major, k <= 15         */

@@ -156,7 +156,7 @@ SPAGxEmix_CCT <- function(traits = "survival/binary/quantitative/categorical", G
   ctx <- .Call("spagxe_r_create", as.integer(device))
   on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-  .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
   .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
   print("Start Analyzing...")
   print(Sys.time())
@@ -178,7 +178,7 @@ SPAGxEmix_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categor
   ctx <- .Call("spagxe_r_create", as.integer(device))
   on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
   .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-  .Call("spagxe_r_set_wald", ctx, .spagxe_trait(traits), as.double(Phen.mtx$Y), as.matrix(Cova.mtx) + 0)
+  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
   .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
   gi <- list(g = matrix(g, ncol = 1), n = length(g), m = 1L, sidx = NULL, nfile = 0, a2 = 0L)
   as.numeric(.spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm)))

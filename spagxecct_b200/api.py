@@ -369,9 +369,7 @@ def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=No
             print(f'[1] "Sample size is {n}."')
             print(f'[1] "Number of variants is {m}."')
         _prep_common(ctx, R, E)
-        if _trait_code(traits) in (_lib.TRAIT_SURVIVAL, _lib.TRAIT_CATEGORICAL):
-            raise NotImplementedError('SPAGxEmix_CCT: the survival and categorical Wald tests are implemented for SPAGxE_CCT only')
-        ctx.set_wald(_trait_code(traits), _col(Phen_mtx, "Y"), np.asarray(Cova_mtx, dtype=np.float64))
+        _set_wald(ctx, traits, Phen_mtx, Cova_mtx)      # all four traits (ref :1187-1262)
         ctx.set_pcs(np.asarray(topPCs, dtype=np.float64))
         if not quiet:
             print('[1] "Start Analyzing..."')

@@ -51,7 +51,7 @@ struct ClmArgs {
     const int *perm;            // storage position -> sample index (-1: padding)
     const double *x;            // (p + 1) columns x n_pad: E, cova[0..p) gathered
     const uint8_t *chunk_cat;   // category of every 32-sample chunk
-    int p, J, g_model;
+    int p, J, g_model, na_to_spa;
     double *out; Counters *ctr;
     uint8_t *codes;             // per cluster: the item's 2-bit codes in storage order, bit 2 = a real sample
 };
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kClThreads, 1) k_clm_wald(ClmArgs A) {
             double pw = sh.pw;
             atomicAdd(&A.ctr->clm_evals, (unsigned long long)sh.evals);
             if (sh.status == 2 || isnan(pw)) { pw = NA; atomicAdd(&A.ctr->n_wald_fail, 1ULL); }
+            if (A.na_to_spa && isnan(pw)) pw = o[2 * M];                 // SPAGxEmix_CCT (ref :1190, :1249)
             double pc = NA;
             const int crc = d_cct2(o[2 * M], pw, &pc);   // p.spa of this item was written by the solver farm
             if (crc) atomicAdd(&A.ctr->n_cct_stop, 1ULL);
@@ -368,12 +369,12 @@ cudaError_t clm_setup(ClmData *c, cudaStream_t s, int64_t n, const double *h_yca
 }
 
 cudaError_t clm_launch(ClmData *c, cudaStream_t s, int num_sms, const BItem *items, const int *count, int64_t m_total, int g_model,
-                       double *out, Counters *ctr, int64_t *launches) {
+                       double *out, Counters *ctr, int64_t *launches, bool na_to_spa) {
     if (!c || !c->ready) return cudaErrorInvalidValue;
     ClmArgs a;
     a.items = items; a.count = count; a.m_total = m_total; a.n = c->n; a.n_pad = c->n_pad;
     a.perm = c->d_perm; a.x = c->d_x; a.chunk_cat = c->d_chunk_cat; a.p = c->p; a.J = c->J; a.g_model = g_model;
-    a.out = out; a.ctr = ctr;
+    a.out = out; a.ctr = ctr; a.na_to_spa = na_to_spa ? 1 : 0;
     const int n_clusters = std::max(1, num_sms / kClCluster);
     const size_t need = (size_t)n_clusters * (size_t)c->n_pad;
     if (need > c->cap_codes) {

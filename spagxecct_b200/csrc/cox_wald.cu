@@ -53,7 +53,7 @@ struct CoxArgs {
     const int *perm;        // sorted position -> sample index
     const double *x;        // (p + 1) columns x n_eff: E, cova[0..p) gathered and centred
     const int *info;        // bit 0 death, bits 1..: deaths of the tie group ending here
-    int p, g_model, unit_len;
+    int p, g_model, unit_len, na_to_spa;
     double *out; Counters *ctr;
     uint8_t *codes;         // per cluster: the item's 2-bit codes gathered into time order (n_eff bytes each)
 };
@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(kCxThreads, 1) k_cox_wald(CoxArgs A) {
             double pw = sh.pw;
             atomicAdd(&A.ctr->cox_evals, (unsigned long long)(sh.iter + 1));   // likelihood evaluations of this item
             if (sh.status == 2 || isnan(pw)) { pw = NA; atomicAdd(&A.ctr->n_wald_fail, 1ULL); }
+            if (A.na_to_spa && isnan(pw)) pw = o[2 * M];                 // SPAGxEmix_CCT (ref :1190, :1249)
             double pc = NA;
             const int crc = d_cct2(o[2 * M], pw, &pc);   // p.spa of this item was written by the solver farm
             if (crc) atomicAdd(&A.ctr->n_cct_stop, 1ULL);
@@ -476,13 +477,13 @@ cudaError_t cox_setup(CoxData *c, cudaStream_t s, int64_t n, const double *h_tim
 }
 
 cudaError_t cox_launch(CoxData *c, cudaStream_t s, int num_sms, const BItem *items, const int *count, int64_t m_total, int g_model,
-                       double *out, Counters *ctr, int64_t *launches) {
+                       double *out, Counters *ctr, int64_t *launches, bool na_to_spa) {
     if (!c || !c->ready) return cudaErrorInvalidValue;
     CoxArgs a;
     a.items = items; a.count = count; a.m_total = m_total; a.n = c->n; a.n_eff = c->n_eff;
     a.perm = c->d_perm; a.x = c->d_x; a.info = c->d_info; a.p = c->p; a.g_model = g_model;
     a.unit_len = c->unit_len;
-    a.out = out; a.ctr = ctr;
+    a.out = out; a.ctr = ctr; a.na_to_spa = na_to_spa ? 1 : 0;
     cudaLaunchConfig_t cfg = {};
     const int n_clusters = std::max(1, num_sms / kCxCluster);
     const size_t need = (size_t)n_clusters * (size_t)c->n_eff;

@@ -20,6 +20,7 @@ cudaError_t cox_setup(CoxData *c, cudaStream_t s, int64_t n, const double *h_tim
 // Wald p-value and CCT(p.spa, p.wald) for items[0 .. *count): reads p.spa from column 2 of `out` (written by the solver
 // farm earlier on the same stream), writes columns 3 and 4
 cudaError_t cox_launch(CoxData *c, cudaStream_t s, int num_sms, const BItem *items, const int *count, int64_t m_total, int g_model,
-                       double *out, Counters *ctr, int64_t *launches);
+                       double *out, Counters *ctr, int64_t *launches, bool na_to_spa = false);
+// na_to_spa: SPAGxEmix_CCT's rule `if (is.na(pval.wald)) pval.wald = pval.spaGxE` (ref R/SPAGxECCT.R:1190, :1249); SPAGxE_CCT has none
 
 }  // namespace spagxe

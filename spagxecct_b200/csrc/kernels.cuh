@@ -1536,7 +1536,15 @@ __device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Count
                 pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
             }
             double pw = NA, pc = NA;
-            if (!PLUS) {
+            if (!PLUS && (wd.trait == 3 || wd.trait == 4)) {
+                // coxph / clm (ref :1187-1193, :1244-1250): the item goes to the Cox / cumulative-link kernel that follows on the
+                // stream; it reads pval.spaGxE from column 3 of the row and writes the Wald and CCT columns
+                if (writer) {
+                    const int pos = atomicAdd(&ctr->spax_count, 1);
+                    md.wald_items[pos] = BItem{row, (long long)j, asum, nmiss, st.D0[jl], st.T0[jl], g_model ? st.H0[jl] : 0.0,
+                                               g_model ? st.nhom[jl] : 0, 0};
+                }
+            } else if (!PLUS) {
                 int wfail;
                 pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
                 if (isnan(pw)) pw = pspa;                                             // ref :1194, :1213, :1232

@@ -709,7 +709,7 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     Counters *ctr = ctx->d_ctr;
     const double *R = ctx->d_R, *E = ctx->d_E;
     const VecConst *vc = ctx->d_vc;
-    MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff, prm->g_model};
+    MixData md{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff, prm->g_model, ctx->d_bitems};
     {   // per-cluster cache of the individual allele frequencies m_i (N doubles each)
         const int64_t need = (int64_t)n_clusters * N;
         if (need > ctx->cap_mcache) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_mcache, need)); ctx->cap_mcache = need; }
@@ -726,6 +726,14 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
     CU(cudaLaunchKernelEx(&cfg, k_mix_snp, list, ctr, d_rows, dpitch, st, j0, M, N, R, E, vc, wd, md, prm->epsilon, prm->cutoff, d_out, mcache,
                           hbeta, hbeta_ld, hand));
     ctx->launches++;
+    // traits survival / categorical: the Wald test + CCT of the chunk's branch-B SNPs (k_mix_snp appended them to d_bitems)
+    if (wd.trait == SPAGXE_TRAIT_SURVIVAL) {
+        cudaError_t e = cox_launch(ctx->cox, s, ctx->num_sms, ctx->d_bitems, &ctx->d_ctr->spax_count, M, prm->g_model, d_out, ctx->d_ctr, &ctx->launches, true);
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "cox_launch: %s", cudaGetErrorString(e));
+    } else if (wd.trait == SPAGXE_TRAIT_CATEGORICAL) {
+        cudaError_t e = clm_launch(ctx->clm, s, ctx->num_sms, ctx->d_bitems, &ctx->d_ctr->spax_count, M, prm->g_model, d_out, ctx->d_ctr, &ctx->launches, true);
+        if (e != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "clm_launch: %s", cudaGetErrorString(e));
+    }
     return SPAGXE_OK;
 }
 
@@ -818,17 +826,14 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (mode == RUN_PLUS && !ctx->have_grm) return fail(ctx, SPAGXE_ERR_STATE, "run_plus: call spagxe_set_grm first");
     if (mode == RUN_MIX && ctx->n_pcs <= 0) return fail(ctx, SPAGXE_ERR_STATE, "%s: call spagxe_set_pcs first", name);
     if (mixplus && !ctx->have_coo) return fail(ctx, SPAGXE_ERR_STATE, "run_mix_plus: call spagxe_set_sparse_grm first");
-    if (mode == RUN_MIX && !mixplus && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL)
-        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the survival Wald test is implemented for SPAGxE_CCT only");
-    if (mode == RUN_MIX && !mixplus && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL)
-        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "run_mix: the categorical Wald test is implemented for SPAGxE_CCT only");
-    if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL && !clm_ready(ctx->clm)) {
+    const bool wald_dev = (mode == RUN_CCT) || (mode == RUN_MIX && !mixplus);   // loops whose branch B runs a Wald kernel
+    if (wald_dev && ctx->wald_trait == SPAGXE_TRAIT_CATEGORICAL && !clm_ready(ctx->clm)) {
         CU(cudaSetDevice(ctx->device));
         const char *what = "clm_setup";
         cudaError_t ce = clm_setup(ctx->clm, ctx->stream(), ctx->n, ctx->h_ycat.data(), ctx->d_E, ctx->d_cova, ctx->wald_p, &what);
         if (ce != cudaSuccess) return fail(ctx, SPAGXE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(ce));
     }
-    if (mode == RUN_CCT && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL && !cox_ready(ctx->cox)) {
+    if (wald_dev && ctx->wald_trait == SPAGXE_TRAIT_SURVIVAL && !cox_ready(ctx->cox)) {
         CU(cudaSetDevice(ctx->device));
         const char *what = "cox_setup";
         cudaError_t ce = cox_setup(ctx->cox, ctx->stream(), ctx->n, ctx->h_time.data(), ctx->h_event.data(), ctx->d_E, ctx->d_cova,

@@ -87,6 +87,8 @@ struct MixData {
     int k;
     double pc_pcut, neg_ratio_cut;
     int g_model;            // 0 Add, 1 Dom, 2 Rec
+    BItem *wald_items;      // traits survival / categorical: branch-B SNPs are appended here (count: Counters::spax_count) and
+                            // their Wald test + CCT run afterwards in k_cox_wald / k_clm_wald (ref R/SPAGxECCT.R:1187-1262)
 };
 
 // SPAGxEmixCCT_localance (ref R/SPAGxECCT.R:1401-1647): packed 2-bit rows (code -> value: 00 2, 10 1, 11 0; 01 = NA is refused)
