@@ -33,7 +33,7 @@ enum {
     SPAGXE_ERR_CUDA = 1,        /* CUDA runtime failure (message has the detail)          */
     SPAGXE_ERR_ARG = 2,         /* bad argument (NULL, size mismatch, unknown enum)       */
     SPAGXE_ERR_STATE = 3,       /* a required spagxe_set_* call is missing                */
-    SPAGXE_ERR_UNSUPPORTED = 4, /* e.g. non-integer dosages, categorical traits              */
+    SPAGXE_ERR_UNSUPPORTED = 4, /* e.g. non-integer dosages with a survival / categorical trait    */
     SPAGXE_ERR_CCT_STOP = 5,    /* CCT() would stop(): NA / out-of-range p (ref :2072-2087)*/
     SPAGXE_ERR_SINGULAR = 6     /* solve(t(W)%*%W) singular (ref :609)                    */
 };

@@ -306,6 +306,35 @@ def mixplus_bed(bed_rows, n, R, E, PCs, grm_i, grm_j, grm_v, epsilon=0.001, cuto
     return out, route, iters, max(rcs)
 
 
+def plus_one_snp(g, R, E, Rnew, R_GRM_R, R_GRM_RE, Rnew_GRM_Rnew, grm_i, grm_j, grm_v, epsilon=0.001, cutoff=2.0, min_maf=0.001,
+                 g_is_int=False):
+    g, gp = _d(g); n = g.size
+    R, Rp = _d(R); E, Ep = _d(E); Rnew, Rnp = _d(Rnew)
+    gi = np.ascontiguousarray(grm_i, dtype=np.int32); gj = np.ascontiguousarray(grm_j, dtype=np.int32)
+    gv, gvp = _d(grm_v)
+    out = np.empty(8); route = C.c_int(); its = (C.c_int * 2)()
+    lib().orc_plus_one_snp(gp, C.c_int(int(g_is_int)), Rp, Ep, Rnp, C.c_double(R_GRM_R), C.c_double(R_GRM_RE),
+                           C.c_double(Rnew_GRM_Rnew), C.c_long(gi.size), gi.ctypes.data_as(c_ip), gj.ctypes.data_as(c_ip), gvp,
+                           C.c_long(n), C.c_double(epsilon), C.c_double(cutoff), C.c_double(min_maf), out.ctypes.data_as(c_dp),
+                           C.byref(route), its)
+    return out, route.value, (its[0], its[1])
+
+
+def mixplus_one_snp(g, R, E, PCs, grm_i, grm_j, grm_v, epsilon=0.001, cutoff=2.0, min_maf=0.001, pc_pcut=0.05,
+                    neg_ratio_cut=0.1, g_is_int=False):
+    g, gp = _d(g); n = g.size
+    R, Rp = _d(R); E, Ep = _d(E)
+    PCs, Pp = _f(np.asarray(PCs, dtype=np.float64).reshape(n, -1))
+    gi = np.ascontiguousarray(grm_i, dtype=np.int32); gj = np.ascontiguousarray(grm_j, dtype=np.int32)
+    gv, gvp = _d(grm_v)
+    out = np.empty(12); route = C.c_int(); its = (C.c_int * 2)()
+    lib().orc_mixplus_one_snp(gp, C.c_int(int(g_is_int)), Rp, Ep, Pp, C.c_int(PCs.shape[1]), C.c_long(n), C.c_long(gi.size),
+                              gi.ctypes.data_as(c_ip), gj.ctypes.data_as(c_ip), gvp, C.c_double(epsilon), C.c_double(cutoff),
+                              C.c_double(min_maf), C.c_double(pc_pcut), C.c_double(neg_ratio_cut), out.ctypes.data_as(c_dp),
+                              C.byref(route), its)
+    return out, route.value, (its[0], its[1])
+
+
 def localance_matrix(trait, G, H, R, E, Y, Cova, cova_haplo, epsilon=0.001, min_maf=0.0001):
     """SPAGxEmixCCT_localance loop (ref R/SPAGxECCT.R:1443-1476) over (N, M) matrices: G ancestry-specific genotypes,
     H local ancestry counts, cova_haplo a list of (N, M) matrices (Cova.haplo.mtx.list).  OpenMP over SNPs."""

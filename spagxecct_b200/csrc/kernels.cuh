@@ -879,8 +879,45 @@ struct DesignWald {
     }
 };
 // Design of the mix fallback glm(1{round(g) != 0} ~ selected PCs, binomial) (ref :1081-1089)
-struct DesignAf {
-    const double *pcs; int64_t n; int nsel; const int *sel; GFromRow gf;
+struct GDense {   // processed genotype: NA -> 2 MAF, flip, Dom / Rec (ref :562-574)
+    const double *col; double imp; int flip, g_model;
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        double g = col[i];
+        if (isnan(g)) g = imp;
+        if (flip) g = 2 - g;
+        if (g_model == 1) g = (g >= 1) ? 1.0 : 0.0;
+        if (g_model == 2) g = (g <= 1) ? 0.0 : 1.0;
+        return g;
+    }
+};
+struct SrcDenseAdj {  // R.new0_i = E_i (R_i - a - b g_i) (ref :609-612)
+    const double *R, *E; GDense gf; double a, b, maf;
+    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
+        r = E[i] * (R[i] - (a + b * gf(i))); m = maf; w = 1.0;
+    }
+};
+struct DesignWaldDense {
+    WaldData wd; const double *E; GDense gf; int64_t n;
+    __device__ __forceinline__ int q() const { return wd.p + 4; }
+    __device__ __forceinline__ int trait() const { return wd.trait; }
+    __device__ __forceinline__ double y(int64_t i) const { return wd.Y[i]; }
+    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
+        const int p = q - 4;
+        const double g = gf(i), ev = E[i];
+        x[0] = 1.0;
+        for (int c = 0; c < p; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
+        x[p + 1] = ev; x[p + 2] = g; x[p + 3] = ev * g;
+    }
+    template <int Q>
+    __device__ __forceinline__ void fill(int64_t i, double *x) const { fill_rt(i, x, Q); }
+};
+template <class GF> struct WaldDesignOf;
+template <> struct WaldDesignOf<GFromRow> { using type = DesignWald; };
+template <> struct WaldDesignOf<GDense> { using type = DesignWaldDense; };
+
+template <class GF>
+struct DesignAfT {
+    const double *pcs; int64_t n; int nsel; const int *sel; GF gf;
     __device__ __forceinline__ int q() const { return nsel + 1; }
     __device__ __forceinline__ int trait() const { return 1; }
     __device__ __forceinline__ double y(int64_t i) const { return (rint(gf(i)) != 0.0) ? 1.0 : 0.0; }
@@ -949,7 +986,7 @@ __device__ int irls_fit(const Design &ds, int64_t i_lo, int64_t i_hi, double *ti
 template <class GFun>
 __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, int64_t n, int64_t i_lo, int64_t i_hi,
                           double *tile, BShared &sh, const ClusterRed &red, int *fail) {
-    DesignWald ds{wd, E, gf, n};
+    typename WaldDesignOf<GFun>::type ds{wd, E, gf, n};
     const int q = ds.q();
     *fail = 0;
     if (wd.trait == 1) {
@@ -1197,16 +1234,40 @@ __device__ __forceinline__ double af_eval(const AfModel &af, const double *__res
     const double mu = tmp / (1 + tmp);
     return 1 - sqrt(1 - mu);                           // ref :1089
 }
-struct SrcMix {  // residual vector (E - lambda) R or E * (R - fit[class]) with per-sample allele frequency
+// genotype source of the per-SNP SPAGxEmix code: a packed 2-bit row (values and fitted values of W = [1, g] per class) ...
+struct MixGenoRow {
+    GFromRow gf; double fit[4];
+    __device__ __forceinline__ double g(int64_t i) const { return gf(i); }
+    __device__ __forceinline__ void set_fit(double i00, double i01, double i11, double sumR, double S1) {
+        for (int c = 0; c < 4; c++) {
+            const double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
+            fit[c] = wi0 * sumR + wi1 * S1;
+        }
+    }
+    __device__ __forceinline__ double fit_at(int64_t i) const { return fit[(gf.row[i >> 2] >> (2 * (i & 3))) & 3]; }
+};
+// ... or a dense double column (imputed dosages): the same expressions per sample
+struct MixGenoDense {
+    GDense gf; double i00, i01, i11, sumR, S1;
+    __device__ __forceinline__ double g(int64_t i) const { return gf(i); }
+    __device__ __forceinline__ void set_fit(double a00, double a01, double a11, double sR, double s1) { i00 = a00; i01 = a01; i11 = a11; sumR = sR; S1 = s1; }
+    __device__ __forceinline__ double fit_at(int64_t i) const {
+        const double gg = gf(i), wi0 = i00 + gg * i01, wi1 = i01 + gg * i11;
+        return wi0 * sumR + wi1 * S1;
+    }
+};
+template <class MG>
+struct SrcMixT {  // residual vector (E - lambda) R or E * (R - fitted(g_i)) with per-sample allele frequency
     const AfModel *af; const double *pcs; int64_t n;
-    const double *R, *E; const uint8_t *row; double fit[4]; double lambda; int adj;
+    const double *R, *E; MG mg; double lambda; int adj;   // mg by value: the class table stays in registers
     const double *mcache;   // m_i of this SNP, written once by the statistics pass (same thread <-> same samples in every pass)
     __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
-        if (adj) { int c = (row[i >> 2] >> (2 * (i & 3))) & 3; r = E[i] * (R[i] - fit[c]); }
+        if (adj) r = E[i] * (R[i] - mg.fit_at(i));
         else r = (E[i] - lambda) * R[i];
         m = mcache ? mcache[i] : af_eval(*af, pcs, n, i); w = 1.0;
     }
 };
+using SrcMix = SrcMixT<MixGenoRow>;
 
 // K3 for mix: filtered rows are written here; every other SNP goes to the cluster kernel's list
 __global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n, double min_maf,
@@ -1241,6 +1302,256 @@ struct MixShared { AfModel af; double xg[kMaxPC + 1]; double pv[kMaxPC + 1]; };
 // Wald test there is a mixed model (lme4::glmer / lmer, :384 / :404) that stays with the caller: columns 4 and 5 of such
 // rows are NA.  m_i is exchanged between the CTAs of the cluster through the per-cluster cache in global memory.
 __device__ __forceinline__ double mixplus_sq(const double *mc, int64_t i) { const double m = __ldcg(mc + i); return sqrt(2 * m * (1 - m)); }
+
+// where a deferred Wald item of the packed-row kernels comes from (nullptr row: dense genotypes, nothing is deferred)
+struct MixDeferSrc { const uint8_t *row; long long snp; int asum, nmiss, jl; };
+
+// One SNP from the allele-frequency model on (ref R/SPAGxECCT.R:1055-1269; PLUS: R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:190-427).
+// maf, S1 = sum(g R), S2 = sum(g E R), sum_g describe the processed genotype vector mg.g(.); hb: the batched path's OLS
+// coefficients of this SNP or nullptr; o: the SNP's output row.  The kernel parameters are handed through one by one (not
+// in a struct) so that they stay reads of the constant bank after inlining.
+template <bool PLUS, class MG>
+__device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, const int64_t m_total, const int64_t i_lo, const int64_t i_hi,
+                                             const int cs, const int rank, const double *__restrict__ R, const double *__restrict__ E,
+                                             const VecConst &vc, const WaldData &wd, const MixData &md, const double epsilon,
+                                             const double cutoff, const GrmCoo &grm, double *tile, BShared &sh, MixShared &ms,
+                                             double *mcache_in, const SnpStats &st, const ClusterRed &red, const MG &mg, double maf,
+                                             double S1, double S2, double sum_g, const double *hb, double *o, const MixDeferSrc &df) {
+    const int k = md.k, k1 = md.k + 1;
+    const double NA = d_na_real();
+    const double MAC = maf * 2 * (double)n;                                   // ref :1058
+    double negnum = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { ms.af.kind = 0; ms.af.maf = maf; ms.af.k = k; ms.af.nsel = 0; }
+    __syncthreads();
+    if (!(MAC <= 20)) {
+        // ---- lm(g ~ topPCs): X'g, beta = (X'X)^-1 X'g (ref :1066); the batched path has them already ----
+        if (hb) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int a = 0; a < k1; a++) ms.af.beta[a] = hb[a];
+                ms.af.kind = 1;
+            }
+            __syncthreads();
+        } else {
+        for (int c0 = 0; c0 < k1; c0 += 4) {
+            double v4[4] = {0, 0, 0, 0};
+            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+                const double g = mg.g(i);
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    if (c0 + c < k1) v4[c] += g * ((c0 + c == 0) ? 1.0 : md.pcs[i + (int64_t)(c0 + c - 1) * n]);
+            }
+            red.sum<4>(v4);
+            if (threadIdx.x == 0) for (int c = 0; c < 4; c++) if (c0 + c < k1) ms.xg[c0 + c] = v4[c];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int a = 0; a < k1; a++) {
+                double b = 0;
+                for (int c = 0; c < k1; c++) b += md.xtx_inv[a + c * k1] * ms.xg[c];
+                ms.af.beta[a] = b;
+            }
+            ms.af.kind = 1;
+        }
+        __syncthreads();
+        }
+        // fitted values: negative count and residual sum of squares
+        double v2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double f = ms.af.beta[0];
+            for (int c = 0; c < k; c++) f += md.pcs[i + (int64_t)c * n] * ms.af.beta[1 + c];
+            if (f / 2 < 0) v2[0] += 1.0;
+            const double e = mg.g(i) - f;
+            v2[1] += e * e;
+        }
+        red.sum<2>(v2);
+        negnum = v2[0];
+        const double negratio = negnum / (double)n;
+        if (negratio > md.neg_ratio_cut) {                                        // ref :1074
+            const double rdf = (double)(n - k1), resvar = v2[1] / rdf;
+            __syncthreads();
+            if (threadIdx.x < k) {                                                // PC p-values (summary.lm)
+                const int a = 1 + threadIdx.x;
+                const double se = sqrt(md.xtx_inv[a + a * k1] * resvar);
+                ms.pv[a] = d_pt2(ms.af.beta[a] / se, rdf);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int ns = 0;
+                for (int a = 1; a <= k; a++) if (ms.pv[a] < md.pc_pcut) ms.af.sel[ns++] = a - 1;
+                ms.af.nsel = ns;
+                // sum(round(g)) == 0 | sum(2 - round(g)) == 0 from the class counts (ref :1084)
+                ms.af.kind = 0;
+            }
+            __syncthreads();
+            const int nsel = ms.af.nsel;
+            if (nsel > 0) {
+                double vs[2] = {0, 0};
+                for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double gt = rint(mg.g(i)); vs[0] += gt; vs[1] += 2 - gt; }
+                red.sum<2>(vs);
+                if (!(vs[0] == 0 || vs[1] == 0)) {
+                    DesignAfT<decltype(mg.gf)> ds{md.pcs, n, nsel, ms.af.sel, mg.gf};
+                    double se2;
+                    int frc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
+                    (void)frc;   // the reference uses Fit$fitted.values whatever glm() warned about
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        for (int c = 0; c <= nsel; c++) ms.af.beta[c] = sh.beta[c];
+                        ms.af.kind = 2;
+                        if (rank == 0) atomicAdd(&ctr->n_mix_logistic, 1ULL);
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- statistics with per-sample allele frequencies (ref :1102-1108) ----
+    double v4[4] = {0, 0, 0, 0};
+    // m_i is evaluated once per SNP (k loads + k multiply-adds, or an exp and a sqrt) and kept for the later passes
+    double *mcache = mcache_in;
+    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        const double m = af_eval(ms.af, md.pcs, n, i), gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
+        if (mcache) mcache[i] = m;
+        v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
+    }
+    red.sum<4>(v4);
+    // edges of the GRM table this CTA sums (PLUS); the barrier inside red.sum has published every CTA's part of mcache
+    const int64_t e_per = (grm.nnz + cs - 1) / cs;
+    const int64_t e_lo = min((int64_t)grm.nnz, e_per * rank), e_hi = min((int64_t)grm.nnz, e_per * (rank + 1));
+    double cov12 = 0;
+    if (PLUS) {
+        double q2[2] = {0, 0};
+        for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+            const int a = grm.gi[e], b = grm.gj[e];
+            const double xa = R[a] * mixplus_sq(mcache, a), xb = R[b] * mixplus_sq(mcache, b), gvv = grm.gv[e];
+            q2[0] += (gvv * xa) * xb;
+            q2[1] += (gvv * xa) * (xb * E[b]) + (gvv * xb) * (xa * E[a]);
+        }
+        red.sum<2>(q2);
+        cov12 = q2[1] - v4[2];                                                    // Cov_S1_S2 (ref mixPlus :279-281)
+        v4[1] = q2[0] * 2 - v4[1];                                                // VarS1 (ref mixPlus :260)
+    }
+    const double meanS1 = 2 * v4[0], VarS1 = v4[1];
+    const double Z1 = (S1 - meanS1) / sqrt(VarS1);
+    const double pG = d_pnorm(-fabs(Z1), true) * 2;
+    const bool writer = (rank == 0 && threadIdx.x == 0);
+    SrcMixT<MG> src;
+    src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.mg = mg; src.mcache = mcache;
+    double po[4];
+    int iters = 0; bool spa = false;
+    if (pG > epsilon) {
+        const double lambda = PLUS ? cov12 / VarS1 : v4[2] / v4[1];               // ref :1115; mixPlus :285
+        const double S_GxE = S2 - lambda * S1;
+        src.lambda = lambda; src.adj = 0;
+        double v2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, m, w; src.get(i, r, m, w);
+            v2[0] += r * m; v2[1] += (r * r) * (2 * m * (1 - m));
+        }
+        red.sum<2>(v2);
+        double Svar = v2[1], vscale = 1.0;
+        if (PLUS) {   // S_GxE.var through the GRM (ref mixPlus :296), Var.ratio for the saddlepoint (:308-309)
+            double q1[1] = {0};
+            for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+                const int a = grm.gi[e], b = grm.gj[e];
+                const double xa = ((E[a] - lambda) * R[a]) * mixplus_sq(mcache, a), xb = ((E[b] - lambda) * R[b]) * mixplus_sq(mcache, b);
+                q1[0] += (grm.gv[e] * xa) * xb;
+            }
+            red.sum<1>(q1);
+            Svar = q1[0] * 2 - v2[1];
+            vscale = sqrt(v2[1] / Svar);
+        }
+        const double Smean = 2 * v2[0];
+        const double z = (S_GxE - Smean) / sqrt(Svar);
+        if (fabs(z) < cutoff) {
+            const double pn = d_pnorm(fabs(z), false) * 2;
+            po[0] = po[1] = po[2] = po[3] = pn;
+        } else {
+            spa = true;
+            const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE), &iters,
+                                                 1.7976931348623157e308, vscale);
+            po[0] = po[1] = po[2] = ps;
+            po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+        }
+        if (writer) atomicAdd(&ctr->n_branch_a, 1ULL);
+    } else {
+        if (writer) atomicAdd(&ctr->n_branch_b, 1ULL);
+        double v3[3] = {0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = mg.g(i); v3[0] += g * g; }
+        red.sum<3>(v3);
+        const double a = (double)n, b = sum_g, d = v3[0];
+        const double det = a * d - b * b;
+        if (det == 0 || !isfinite(det)) {
+            if (writer) {
+                o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
+                o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+                o[10 * m_total] = negnum; o[11 * m_total] = MAC;
+                atomicAdd(&ctr->n_singular, 1ULL);
+            }
+            return;
+        }
+        const double i00 = d / det, i01 = -b / det, i11 = a / det;
+        src.mg.set_fit(i00, i01, i11, vc.sumR, S1);
+        src.adj = 1; src.lambda = 0;
+        v3[0] = v3[1] = v3[2] = 0;
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, m, w; src.get(i, r, m, w);
+            v3[0] += mg.g(i) * r; v3[1] += r * m; v3[2] += (r * r) * (2 * m * (1 - m));
+        }
+        red.sum<3>(v3);
+        double Svar = v3[2], vscale = 1.0;
+        if (PLUS) {   // S_GxE0.var through the GRM (ref mixPlus :343), Var.ratio (:355-356)
+            double q1[1] = {0};
+            for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+                const int a = grm.gi[e], b = grm.gj[e];
+                double ra, rb, m_, w_;
+                src.get(a, ra, m_, w_); src.get(b, rb, m_, w_);
+                q1[0] += (grm.gv[e] * (ra * mixplus_sq(mcache, a))) * (rb * mixplus_sq(mcache, b));
+            }
+            red.sum<1>(q1);
+            Svar = q1[0] * 2 - v3[2];
+            vscale = sqrt(v3[2] / Svar);
+        }
+        const double S0 = v3[0], Smean = 2 * v3[1];
+        const double z = (S0 - Smean) / sqrt(Svar);
+        double pspa, pn;
+        if (fabs(z) < cutoff) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
+        else {
+            spa = true;
+            pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), &iters,
+                                      1.7976931348623157e308, vscale);
+            pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+        }
+        double pw = NA, pc = NA;
+        if (!PLUS && (wd.trait == 3 || wd.trait == 4)) {
+            // coxph / clm (ref :1187-1193, :1244-1250): the item goes to the Cox / cumulative-link kernel that follows on the
+            // stream; it reads pval.spaGxE from column 3 of the row and writes the Wald and CCT columns
+            if (writer && df.row) {
+                const int pos = atomicAdd(&ctr->spax_count, 1);
+                const int gm = md.g_model, jl = df.jl;
+                md.wald_items[pos] = BItem{df.row, df.snp, df.asum, df.nmiss, st.D0[jl], st.T0[jl], gm ? st.H0[jl] : 0.0, gm ? st.nhom[jl] : 0, 0};
+            }
+        } else if (!PLUS) {
+            int wfail;
+            pw = wald_eg(mg.gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
+            if (isnan(pw)) pw = pspa;                                             // ref :1194, :1213, :1232
+            int crc = d_cct2(pspa, pw, &pc);
+            if (writer) {
+                if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
+                if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
+            }
+        }
+        po[0] = pspa; po[1] = pw; po[2] = pc; po[3] = pn;
+    }
+    if (writer) {
+        o[2 * m_total] = po[0]; o[3 * m_total] = po[1]; o[4 * m_total] = po[2]; o[5 * m_total] = po[3];
+        o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
+        o[10 * m_total] = negnum; o[11 * m_total] = MAC;
+        if (spa) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
+    }
+}
 
 template <bool PLUS>
 __device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Counters *ctr,
@@ -1296,7 +1607,7 @@ __device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Count
             double *mc = mcache_all ? mcache_all + (int64_t)cluster_id * n : nullptr;
             if (mc) for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) mc[i] = af_eval(ms.af, md.pcs, n, i);
             SrcMix src;
-            src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row; src.mcache = mc;
+            src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.mcache = mc;   // adj = 0: mg is not read
             src.lambda = h.lambda; src.adj = 0;
             int iters = 0;
             const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(h.S_GxE, 2 * h.Smean - h.S_GxE),
@@ -1326,242 +1637,10 @@ __device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Count
             S2 = class_dot(gc, st.D1[jl], st.T1[jl], st.H1[jl], vc.sumV);
             sum_g = class_sum(gc, make_gcounts(asum, nmiss, st.nhom[jl], n), 1);
         }
-        const double MAC = pr.maf * 2 * (double)n;                                   // ref :1058
-        double negnum = 0;
-        __syncthreads();
-        if (threadIdx.x == 0) { ms.af.kind = 0; ms.af.maf = pr.maf; ms.af.k = k; ms.af.nsel = 0; }
-        __syncthreads();
-        if (!(MAC <= 20)) {
-            // ---- lm(g ~ topPCs): X'g, beta = (X'X)^-1 X'g (ref :1066); the batched path has them already ----
-            if (hbeta) {
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    for (int a = 0; a < k1; a++) ms.af.beta[a] = hbeta[(int64_t)jl * hbeta_ld + a];
-                    ms.af.kind = 1;
-                }
-                __syncthreads();
-            } else {
-            for (int c0 = 0; c0 < k1; c0 += 4) {
-                double v4[4] = {0, 0, 0, 0};
-                for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-                    const double g = gf(i);
-#pragma unroll
-                    for (int c = 0; c < 4; c++)
-                        if (c0 + c < k1) v4[c] += g * ((c0 + c == 0) ? 1.0 : md.pcs[i + (int64_t)(c0 + c - 1) * n]);
-                }
-                red.sum<4>(v4);
-                if (threadIdx.x == 0) for (int c = 0; c < 4; c++) if (c0 + c < k1) ms.xg[c0 + c] = v4[c];
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int a = 0; a < k1; a++) {
-                    double b = 0;
-                    for (int c = 0; c < k1; c++) b += md.xtx_inv[a + c * k1] * ms.xg[c];
-                    ms.af.beta[a] = b;
-                }
-                ms.af.kind = 1;
-            }
-            __syncthreads();
-            }
-            // fitted values: negative count and residual sum of squares
-            double v2[2] = {0, 0};
-            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-                double f = ms.af.beta[0];
-                for (int c = 0; c < k; c++) f += md.pcs[i + (int64_t)c * n] * ms.af.beta[1 + c];
-                if (f / 2 < 0) v2[0] += 1.0;
-                const double e = gf(i) - f;
-                v2[1] += e * e;
-            }
-            red.sum<2>(v2);
-            negnum = v2[0];
-            const double negratio = negnum / (double)n;
-            if (negratio > md.neg_ratio_cut) {                                        // ref :1074
-                const double rdf = (double)(n - k1), resvar = v2[1] / rdf;
-                __syncthreads();
-                if (threadIdx.x < k) {                                                // PC p-values (summary.lm)
-                    const int a = 1 + threadIdx.x;
-                    const double se = sqrt(md.xtx_inv[a + a * k1] * resvar);
-                    ms.pv[a] = d_pt2(ms.af.beta[a] / se, rdf);
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int ns = 0;
-                    for (int a = 1; a <= k; a++) if (ms.pv[a] < md.pc_pcut) ms.af.sel[ns++] = a - 1;
-                    ms.af.nsel = ns;
-                    // sum(round(g)) == 0 | sum(2 - round(g)) == 0 from the class counts (ref :1084)
-                    ms.af.kind = 0;
-                }
-                __syncthreads();
-                const int nsel = ms.af.nsel;
-                if (nsel > 0) {
-                    double vs[2] = {0, 0};
-                    for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double gt = rint(gf(i)); vs[0] += gt; vs[1] += 2 - gt; }
-                    red.sum<2>(vs);
-                    if (!(vs[0] == 0 || vs[1] == 0)) {
-                        DesignAf ds{md.pcs, n, nsel, ms.af.sel, gf};
-                        double se2;
-                        int frc = irls_fit(ds, i_lo, i_hi, tile, sh, red, &se2);
-                        (void)frc;   // the reference uses Fit$fitted.values whatever glm() warned about
-                        __syncthreads();
-                        if (threadIdx.x == 0) {
-                            for (int c = 0; c <= nsel; c++) ms.af.beta[c] = sh.beta[c];
-                            ms.af.kind = 2;
-                            if (rank == 0) atomicAdd(&ctr->n_mix_logistic, 1ULL);
-                        }
-                        __syncthreads();
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // ---- statistics with per-sample allele frequencies (ref :1102-1108) ----
-        double v4[4] = {0, 0, 0, 0};
-        // m_i is evaluated once per SNP (k loads + k multiply-adds, or an exp and a sqrt) and kept for the later passes
-        double *mcache = mcache_all ? mcache_all + (int64_t)cluster_id * n : nullptr;
-        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-            const double m = af_eval(ms.af, md.pcs, n, i), gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
-            if (mcache) mcache[i] = m;
-            v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
-        }
-        red.sum<4>(v4);
-        // edges of the GRM table this CTA sums (PLUS); the barrier inside red.sum has published every CTA's part of mcache
-        const int64_t e_per = (grm.nnz + cs - 1) / cs;
-        const int64_t e_lo = min((int64_t)grm.nnz, e_per * rank), e_hi = min((int64_t)grm.nnz, e_per * (rank + 1));
-        double cov12 = 0;
-        if (PLUS) {
-            double q2[2] = {0, 0};
-            for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-                const int a = grm.gi[e], b = grm.gj[e];
-                const double xa = R[a] * mixplus_sq(mcache, a), xb = R[b] * mixplus_sq(mcache, b), gvv = grm.gv[e];
-                q2[0] += (gvv * xa) * xb;
-                q2[1] += (gvv * xa) * (xb * E[b]) + (gvv * xb) * (xa * E[a]);
-            }
-            red.sum<2>(q2);
-            cov12 = q2[1] - v4[2];                                                    // Cov_S1_S2 (ref mixPlus :279-281)
-            v4[1] = q2[0] * 2 - v4[1];                                                // VarS1 (ref mixPlus :260)
-        }
-        const double meanS1 = 2 * v4[0], VarS1 = v4[1];
-        const double Z1 = (S1 - meanS1) / sqrt(VarS1);
-        const double pG = d_pnorm(-fabs(Z1), true) * 2;
-        double *o = out + j;
-        const bool writer = (rank == 0 && threadIdx.x == 0);
-        SrcMix src;
-        src.af = &ms.af; src.pcs = md.pcs; src.n = n; src.R = R; src.E = E; src.row = row; src.mcache = mcache;
-        double po[4];
-        int iters = 0; bool spa = false;
-        if (pG > epsilon) {
-            const double lambda = PLUS ? cov12 / VarS1 : v4[2] / v4[1];               // ref :1115; mixPlus :285
-            const double S_GxE = S2 - lambda * S1;
-            src.lambda = lambda; src.adj = 0;
-            double v2[2] = {0, 0};
-            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-                double r, m, w; src.get(i, r, m, w);
-                v2[0] += r * m; v2[1] += (r * r) * (2 * m * (1 - m));
-            }
-            red.sum<2>(v2);
-            double Svar = v2[1], vscale = 1.0;
-            if (PLUS) {   // S_GxE.var through the GRM (ref mixPlus :296), Var.ratio for the saddlepoint (:308-309)
-                double q1[1] = {0};
-                for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-                    const int a = grm.gi[e], b = grm.gj[e];
-                    const double xa = ((E[a] - lambda) * R[a]) * mixplus_sq(mcache, a), xb = ((E[b] - lambda) * R[b]) * mixplus_sq(mcache, b);
-                    q1[0] += (grm.gv[e] * xa) * xb;
-                }
-                red.sum<1>(q1);
-                Svar = q1[0] * 2 - v2[1];
-                vscale = sqrt(v2[1] / Svar);
-            }
-            const double Smean = 2 * v2[0];
-            const double z = (S_GxE - Smean) / sqrt(Svar);
-            if (fabs(z) < cutoff) {
-                const double pn = d_pnorm(fabs(z), false) * 2;
-                po[0] = po[1] = po[2] = po[3] = pn;
-            } else {
-                spa = true;
-                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S_GxE, 2 * Smean - S_GxE), fmin(S_GxE, 2 * Smean - S_GxE), &iters,
-                                                     1.7976931348623157e308, vscale);
-                po[0] = po[1] = po[2] = ps;
-                po[3] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
-            }
-            if (writer) atomicAdd(&ctr->n_branch_a, 1ULL);
-        } else {
-            if (writer) atomicAdd(&ctr->n_branch_b, 1ULL);
-            double v3[3] = {0, 0, 0};
-            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) { double g = gf(i); v3[0] += g * g; }
-            red.sum<3>(v3);
-            const double a = (double)n, b = sum_g, d = v3[0];
-            const double det = a * d - b * b;
-            if (det == 0 || !isfinite(det)) {
-                if (writer) {
-                    o[2 * m_total] = NA; o[3 * m_total] = NA; o[4 * m_total] = NA; o[5 * m_total] = NA;
-                    o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
-                    o[10 * m_total] = negnum; o[11 * m_total] = MAC;
-                    atomicAdd(&ctr->n_singular, 1ULL);
-                }
-                continue;
-            }
-            const double i00 = d / det, i01 = -b / det, i11 = a / det;
-            for (int c = 0; c < 4; c++) {
-                double wi0 = i00 + gf.gval[c] * i01, wi1 = i01 + gf.gval[c] * i11;
-                src.fit[c] = wi0 * vc.sumR + wi1 * S1;
-            }
-            src.adj = 1; src.lambda = 0;
-            v3[0] = v3[1] = v3[2] = 0;
-            for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-                double r, m, w; src.get(i, r, m, w);
-                v3[0] += gf(i) * r; v3[1] += r * m; v3[2] += (r * r) * (2 * m * (1 - m));
-            }
-            red.sum<3>(v3);
-            double Svar = v3[2], vscale = 1.0;
-            if (PLUS) {   // S_GxE0.var through the GRM (ref mixPlus :343), Var.ratio (:355-356)
-                double q1[1] = {0};
-                for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-                    const int a = grm.gi[e], b = grm.gj[e];
-                    double ra, rb, m_, w_;
-                    src.get(a, ra, m_, w_); src.get(b, rb, m_, w_);
-                    q1[0] += (grm.gv[e] * (ra * mixplus_sq(mcache, a))) * (rb * mixplus_sq(mcache, b));
-                }
-                red.sum<1>(q1);
-                Svar = q1[0] * 2 - v3[2];
-                vscale = sqrt(v3[2] / Svar);
-            }
-            const double S0 = v3[0], Smean = 2 * v3[1];
-            const double z = (S0 - Smean) / sqrt(Svar);
-            double pspa, pn;
-            if (fabs(z) < cutoff) { pn = d_pnorm(fabs(z), false) * 2; pspa = pn; }
-            else {
-                spa = true;
-                pspa = spa_two_tail_fused(src, red, i_lo, i_hi, fmax(S0, 2 * Smean - S0), fmin(S0, 2 * Smean - S0), &iters,
-                                          1.7976931348623157e308, vscale);
-                pn = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
-            }
-            double pw = NA, pc = NA;
-            if (!PLUS && (wd.trait == 3 || wd.trait == 4)) {
-                // coxph / clm (ref :1187-1193, :1244-1250): the item goes to the Cox / cumulative-link kernel that follows on the
-                // stream; it reads pval.spaGxE from column 3 of the row and writes the Wald and CCT columns
-                if (writer) {
-                    const int pos = atomicAdd(&ctr->spax_count, 1);
-                    md.wald_items[pos] = BItem{row, (long long)j, asum, nmiss, st.D0[jl], st.T0[jl], g_model ? st.H0[jl] : 0.0,
-                                               g_model ? st.nhom[jl] : 0, 0};
-                }
-            } else if (!PLUS) {
-                int wfail;
-                pw = wald_eg(gf, wd, E, n, i_lo, i_hi, tile, sh, red, &wfail);
-                if (isnan(pw)) pw = pspa;                                             // ref :1194, :1213, :1232
-                int crc = d_cct2(pspa, pw, &pc);
-                if (writer) {
-                    if (wfail) atomicAdd(&ctr->n_wald_fail, 1ULL);
-                    if (crc) atomicAdd(&ctr->n_cct_stop, 1ULL);
-                }
-            }
-            po[0] = pspa; po[1] = pw; po[2] = pc; po[3] = pn;
-        }
-        if (writer) {
-            o[2 * m_total] = po[0]; o[3 * m_total] = po[1]; o[4 * m_total] = po[2]; o[5 * m_total] = po[3];
-            o[6 * m_total] = pG; o[7 * m_total] = S1; o[8 * m_total] = VarS1; o[9 * m_total] = Z1;
-            o[10 * m_total] = negnum; o[11 * m_total] = MAC;
-            if (spa) { atomicAdd(&ctr->n_spa, 1ULL); atomicAdd(&ctr->newton_iters, (unsigned long long)iters); }
-        }
+        MixGenoRow mg; mg.gf = gf;
+        mix_snp_core<PLUS>(ctr, n, m_total, i_lo, i_hi, cs, rank, R, E, vc, wd, md, epsilon, cutoff, grm, tile, sh, ms,
+                           mcache_all ? mcache_all + (int64_t)cluster_id * n : nullptr, st, red, mg, pr.maf, S1, S2, sum_g,
+                           hbeta ? hbeta + (int64_t)jl * hbeta_ld : nullptr, out + j, MixDeferSrc{row, (long long)j, asum, nmiss, jl});
     }
     cl.sync();
 }
@@ -1589,6 +1668,185 @@ __global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict
     mix_snp_body<true>(list, ctr, bed, pitch, st, snp0, m_total, n, R, E, vcp, WaldData{nullptr, nullptr, 0, 0}, md, epsilon, cutoff,
                        out, mcache_all, nullptr, 0, nullptr, grm);
 }
+
+// SPAGxE_Plus on imputed (non-integer) dosages (ref R/SPAGxEPlus_functions_MYZ.R:248-405 on a real-valued g): one cluster per
+// SNP, both branches; the statistics of k_finalize_plus / k_branch_b_plus with the genotype read as doubles.
+__global__ void __launch_bounds__(kBThreads) k_plus_dosage_snp(PlusDosageArgs A) {
+    namespace cg = cooperative_groups;
+    __shared__ BShared sh;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const VecConst vc = *A.vc;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t n = A.n, m_total = A.m_total;
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const long long eper = (A.grm.nnz + cs - 1) / cs;
+    const long long e_lo = min(A.grm.nnz, eper * rank), e_hi = min(A.grm.nnz, eper * (rank + 1));
+    const double NA = d_na_real();
+    const bool writer = (rank == 0 && threadIdx.x == 0);
+    for (int jl = cluster_id; jl < A.m; jl += n_clusters) {
+        const double *col = A.G + (int64_t)jl * A.ld;
+        double *o = A.out + A.snp0 + jl;
+        double a2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = col[i];
+            if (!isnan(g)) { a2[0] += g; a2[1] += 1.0; }
+        }
+        red.sum<2>(a2);
+        const double n_obs = a2[1], n_miss = (double)n - n_obs;
+        if (n_obs == 0) {
+            if (writer) { for (int c = 0; c < 8; c++) o[c * m_total] = NA; o[m_total] = 1.0; atomicAdd(&A.ctr->n_allmissing, 1ULL); }
+            continue;
+        }
+        double MAF = (a2[0] / n_obs) / 2;
+        const double miss_rate = n_miss / (double)n;
+        GDense gf; gf.col = col; gf.imp = 2 * MAF; gf.flip = 0; gf.g_model = A.g_model;
+        if (MAF > 0.5) { MAF = 1 - MAF; gf.flip = 1; }
+        if (writer) { o[0] = MAF; o[m_total] = miss_rate; }
+        if (MAF < A.min_maf) {
+            if (writer) { for (int c = 2; c < 8; c++) o[c * m_total] = NA; atomicAdd(&A.ctr->n_filtered, 1ULL); }
+            continue;
+        }
+        double s4[4] = {0, 0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = gf(i);
+            s4[0] += g * A.R[i]; s4[1] += (g * A.E[i]) * A.R[i]; s4[2] += g; s4[3] += g * g;
+        }
+        red.sum<4>(s4);
+        const double S1 = s4[0], S2 = s4[1], sum_g = s4[2];
+        const double gvar = 2 * MAF * (1 - MAF);
+        const double VarS1 = gvar * A.pc.R_GRM_R;                                   // ref :300
+        const double Z1 = (S1 - 0) / sqrt(VarS1);
+        const double pG = d_pnorm(-fabs(Z1), true) * 2;
+        if (writer) { o[4 * m_total] = pG; o[5 * m_total] = S1; o[6 * m_total] = VarS1; o[7 * m_total] = Z1; }
+        int iters = 0;
+        if (pG > A.epsilon) {
+            if (writer) atomicAdd(&A.ctr->n_branch_a, 1ULL);
+            const double lambda = A.pc.R_GRM_RE / A.pc.R_GRM_R;                     // ref :310
+            const double S_GxE = S2 - lambda * S1;
+            const double Svar = gvar * A.pc.Rnew_GRM_Rnew;
+            const double z = S_GxE / sqrt(Svar);
+            if (fabs(z) < A.cutoff) {
+                const double pn = d_pnorm(fabs(z), false) * 2;
+                if (writer) { o[2 * m_total] = pn; o[3 * m_total] = pn; }
+            } else {
+                const double ratio = (vc.sumRn2 * gvar) / Svar;                      // ref :322-323
+                const double Snew = S_GxE * sqrt(ratio);
+                SrcHomo src; src.rv = A.Rn; src.maf = MAF;
+                const double ps = spa_two_tail_fused(src, red, i_lo, i_hi, fabs(Snew), -fabs(Snew), &iters);
+                if (writer) {
+                    o[2 * m_total] = ps; o[3 * m_total] = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+                    atomicAdd(&A.ctr->n_spa, 1ULL); atomicAdd(&A.ctr->newton_iters, (unsigned long long)iters);
+                }
+            }
+            continue;
+        }
+        if (writer) atomicAdd(&A.ctr->n_branch_b, 1ULL);
+        const double a = (double)n, b = sum_g, d = s4[3];
+        const double det = a * d - b * b;
+        if (det == 0 || !isfinite(det)) {
+            if (writer) { o[2 * m_total] = NA; o[3 * m_total] = NA; atomicAdd(&A.ctr->n_singular, 1ULL); }
+            continue;
+        }
+        const double i00 = d / det, i01 = -b / det, i11 = a / det;
+        SrcDenseAdj src;
+        src.R = A.R; src.E = A.E; src.gf = gf; src.maf = MAF;
+        src.a = i00 * vc.sumR + i01 * S1; src.b = i01 * vc.sumR + i11 * S1;
+        double v3[3] = {0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            double r, mm, w; src.get(i, r, mm, w);
+            v3[0] += gf(i) * r; v3[1] += r; v3[2] += r * r;
+        }
+        red.sum<3>(v3);
+        double vq[1] = {0};                                                        // K7 (ref :356-358)
+        for (long long e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+            double r1, r2, mm, w;
+            src.get(A.grm.gi[e], r1, mm, w); src.get(A.grm.gj[e], r2, mm, w);
+            vq[0] += (A.grm.gv[e] * r1) * r2;
+        }
+        red.sum<1>(vq);
+        const double S0 = v3[0];
+        const double Smean = 2 * v3[1] * MAF;                                      // ref :360
+        const double Svar = 2 * vq[0] * gvar - v3[2] * gvar;                       // ref :361
+        const double z = (S0 - Smean) / sqrt(Svar);
+        double pspa, pnorm_;
+        const bool spa = !(fabs(z) < A.cutoff);
+        if (!spa) { pnorm_ = d_pnorm(fabs(z), false) * 2; pspa = pnorm_; }
+        else {
+            const double ratio = (v3[2] * gvar) / Svar;
+            const double Snew = S0 * sqrt(ratio), Smean_new = Smean * sqrt(ratio);
+            const double dlt = fabs(Snew - Smean_new);
+            pnorm_ = d_pnorm(fabs(z), false) + d_pnorm(-fabs(z), true);
+            pspa = spa_two_tail_fused(src, red, i_lo, i_hi, Smean + dlt, Smean - dlt, &iters);
+        }
+        if (writer) {
+            o[2 * m_total] = pspa; o[3 * m_total] = pnorm_;
+            if (spa) { atomicAdd(&A.ctr->n_spa, 1ULL); atomicAdd(&A.ctr->newton_iters, (unsigned long long)iters); }
+        }
+    }
+    cl.sync();
+}
+
+// SPAGxEmix_CCT / SPAGxEmix_CCT_Plus on imputed (non-integer) dosages: a dense double column per SNP, the prologue of
+// ref :1030-1051 computed here (k_cct_dosage_snp's layout), then the same per-SNP code as the packed-row kernels.
+template <bool PLUS>
+__device__ __forceinline__ void mix_dosage_body(const MixDosageArgs &A) {
+    namespace cg = cooperative_groups;
+    extern __shared__ double tile[];
+    __shared__ BShared sh;
+    __shared__ MixShared ms;
+    cg::cluster_group cl = cg::this_cluster();
+    const int cs = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int cluster_id = blockIdx.x / cs, n_clusters = gridDim.x / cs;
+    const VecConst vc = *A.vc;
+    ClusterRed red{sh.scratch, sh.slot};
+    const int64_t n = A.n, m_total = A.m_total;
+    const int64_t per = ((n + cs - 1) / cs + 3) / 4 * 4;
+    const int64_t i_lo = min(n, per * rank), i_hi = min(n, per * (rank + 1));
+    const double NA = d_na_real();
+    const bool writer = (rank == 0 && threadIdx.x == 0);
+    const SnpStats no_stats{};
+    for (int jl = cluster_id; jl < A.m; jl += n_clusters) {
+        cl.sync();   // every CTA is done with the previous SNP's shared state and allele-frequency cache
+        const double *col = A.G + (int64_t)jl * A.ld;
+        double *o = A.out + A.snp0 + jl;
+        double a2[2] = {0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = col[i];
+            if (!isnan(g)) { a2[0] += g; a2[1] += 1.0; }
+        }
+        red.sum<2>(a2);
+        const double n_obs = a2[1], n_miss = (double)n - n_obs;
+        if (n_obs == 0) {
+            if (writer) { for (int c = 0; c < 12; c++) o[c * m_total] = NA; o[m_total] = 1.0; atomicAdd(&A.ctr->n_allmissing, 1ULL); }
+            continue;
+        }
+        double MAF = (a2[0] / n_obs) / 2;
+        const double miss_rate = n_miss / (double)n;
+        MixGenoDense mg;
+        mg.gf.col = col; mg.gf.imp = 2 * MAF; mg.gf.flip = 0; mg.gf.g_model = A.md.g_model;
+        if (MAF > 0.5) { MAF = 1 - MAF; mg.gf.flip = 1; }
+        if (writer) { o[0] = MAF; o[m_total] = miss_rate; }
+        if (MAF < A.min_maf) {
+            if (writer) { for (int c = 2; c < 12; c++) o[c * m_total] = NA; atomicAdd(&A.ctr->n_filtered, 1ULL); }
+            continue;
+        }
+        double s3[3] = {0, 0, 0};
+        for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+            const double g = mg.g(i);
+            s3[0] += g * A.R[i]; s3[1] += (g * A.E[i]) * A.R[i]; s3[2] += g;
+        }
+        red.sum<3>(s3);
+        mix_snp_core<PLUS>(A.ctr, n, m_total, i_lo, i_hi, cs, rank, A.R, A.E, vc, A.wd, A.md, A.epsilon, A.cutoff, A.grm, tile, sh, ms,
+                           A.mcache_all + (int64_t)cluster_id * n, no_stats, red, mg, MAF, s3[0], s3[1], s3[2], nullptr, o,
+                           MixDeferSrc{nullptr, 0, 0, 0, 0});
+    }
+    cl.sync();
+}
+__global__ void __launch_bounds__(kBThreads) k_mix_dosage_snp(MixDosageArgs A) { mix_dosage_body<false>(A); }
+__global__ void __launch_bounds__(kBThreads) k_mixplus_dosage_snp(MixDosageArgs A) { mix_dosage_body<true>(A); }
 
 // ===========================================================================
 // SPAGxEmixCCT_localance (R/SPAGxECCT.R:1401-1647): ancestry-specific G x E test with local ancestry.  One cluster per
@@ -1833,38 +2091,6 @@ __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A) {
 // SPAGxE_CCT_one_SNP (R/SPAGxECCT.R:543-683) on a real-valued genotype vector (imputed dosages): the 2-bit path above
 // needs g in {0, 1, 2, NA}; a matrix with other values goes through this kernel -- one cluster per SNP, g read as
 // doubles (8 bytes per sample instead of 0.25: a compatibility path, HBM / PCIe bound by its input).
-struct GDense {   // processed genotype: NA -> 2 MAF, flip, Dom / Rec (ref :562-574)
-    const double *col; double imp; int flip, g_model;
-    __device__ __forceinline__ double operator()(int64_t i) const {
-        double g = col[i];
-        if (isnan(g)) g = imp;
-        if (flip) g = 2 - g;
-        if (g_model == 1) g = (g >= 1) ? 1.0 : 0.0;
-        if (g_model == 2) g = (g <= 1) ? 0.0 : 1.0;
-        return g;
-    }
-};
-struct SrcDenseAdj {  // R.new0_i = E_i (R_i - a - b g_i) (ref :609-612)
-    const double *R, *E; GDense gf; double a, b, maf;
-    __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const {
-        r = E[i] * (R[i] - (a + b * gf(i))); m = maf; w = 1.0;
-    }
-};
-struct DesignWaldDense {
-    WaldData wd; const double *E; GDense gf; int64_t n;
-    __device__ __forceinline__ int q() const { return wd.p + 4; }
-    __device__ __forceinline__ int trait() const { return wd.trait; }
-    __device__ __forceinline__ double y(int64_t i) const { return wd.Y[i]; }
-    __device__ __forceinline__ void fill_rt(int64_t i, double *x, int q) const {
-        const int p = q - 4;
-        const double g = gf(i), ev = E[i];
-        x[0] = 1.0;
-        for (int c = 0; c < p; c++) x[1 + c] = wd.cova[i + (int64_t)c * n];
-        x[p + 1] = ev; x[p + 2] = g; x[p + 3] = ev * g;
-    }
-    template <int Q>
-    __device__ __forceinline__ void fill(int64_t i, double *x) const { fill_rt(i, x, Q); }
-};
 
 __global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A) {
     namespace cg = cooperative_groups;

@@ -30,5 +30,8 @@ __global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict
 
 __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A);
 __global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A);
+__global__ void __launch_bounds__(kBThreads) k_plus_dosage_snp(PlusDosageArgs A);
+__global__ void __launch_bounds__(kBThreads) k_mix_dosage_snp(MixDosageArgs A);
+__global__ void __launch_bounds__(kBThreads) k_mixplus_dosage_snp(MixDosageArgs A);
 
 }  // namespace spagxe

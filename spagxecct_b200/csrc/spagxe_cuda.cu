@@ -158,6 +158,10 @@ extern "C" int spagxe_ctx_create(int device, spagxe_ctx **out) {
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_snp)", e);
     e = cudaFuncSetAttribute(k_mixplus_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mixplus_snp)", e);
+    e = cudaFuncSetAttribute(k_mix_dosage_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mix_dosage_snp)", e);
+    e = cudaFuncSetAttribute(k_mixplus_dosage_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_mixplus_dosage_snp)", e);
     e = cudaFuncSetAttribute(k_cct_dosage_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
     if (e != cudaSuccess) return bail("cudaFuncSetAttribute(k_cct_dosage_snp)", e);
     e = cudaFuncSetAttribute(k_localance_snp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)branch_b_smem(kMaxQ));
@@ -740,23 +744,27 @@ static int launch_mix(spagxe_ctx *ctx, const uint8_t *d_rows, int64_t dpitch, Sn
 // SPAGxE_CCT on a real-valued matrix (imputed dosages): the 2-bit pipeline refuses values outside {0, 1, 2, NA}, so a
 // double matrix that holds such values is tested by k_cct_dosage_snp instead (one cluster per SNP, g read as doubles).
 // Binary and quantitative traits.
-static int run_cct_dosage(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag) {
+// kind 0: SPAGxE_CCT; 1: SPAGxEmix_CCT; 2: SPAGxEmix_CCT_Plus (k_mix_dosage_snp / k_mixplus_dosage_snp: the per-SNP SPAGxEmix code on a
+// dense column, M x 12)
+static int run_cct_dosage(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_params *prm, double *out, spagxe_diag *diag, int kind = 0) {
     if (g->kind != SPAGXE_GENO_F64) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "dosage input must be a double matrix");
-    if (ctx->wald_trait != SPAGXE_TRAIT_BINARY && ctx->wald_trait != SPAGXE_TRAIT_QUANTITATIVE)
+    if (kind < 2 && ctx->wald_trait != SPAGXE_TRAIT_BINARY && ctx->wald_trait != SPAGXE_TRAIT_QUANTITATIVE)
         return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "Geno.mtx holds non-integer dosages: the survival / categorical Wald tests need hard calls");
+    const int ncol = kind == 0 ? 10 : (kind == 3 ? 8 : 12);   // kind 3: SPAGxE_Plus (k_plus_dosage_snp)
     if (prm->out_location == SPAGXE_LOC_DEVICE) return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "dosage input: the result matrix lives on the host");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream();
-    int rc = ensure_vec_mode(ctx, 0, nullptr);
+    int rc = ensure_vec_mode(ctx, kind == 0 ? 0 : (kind == 3 ? 1 : 2), kind == 3 ? ctx->d_Rn_user : nullptr);
     if (rc) return rc;
     const int64_t n = g->n_samples, m = g->n_snps, ld = g->pitch;
     spagxe_diag dg; memset(&dg, 0, sizeof dg);
+    ctx->launches = 0;
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), s));
     EventPool evp(ctx);
     cudaEvent_t ev0 = evp.rec(s);
     const bool on_dev = (g->location == SPAGXE_LOC_DEVICE);
     const int64_t mc_max = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(m, 1), (256ll << 20) / (n * 8)));
-    const int64_t need_dense = mc_max * n * 8, need_out = std::max<int64_t>(m, 1) * 10;
+    const int64_t need_dense = mc_max * n * 8, need_out = std::max<int64_t>(m, 1) * ncol;
     if (!on_dev && need_dense > ctx->cap_dense) { CU(cudaStreamSynchronize(s)); cudaFree(ctx->d_dense); ctx->d_dense = nullptr; CU(cudaMalloc(&ctx->d_dense, need_dense)); ctx->cap_dense = need_dense; }
     if (need_out > ctx->cap_out) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_out, need_out)); ctx->cap_out = need_out; }
     cudaLaunchConfig_t cfg = {};
@@ -771,8 +779,51 @@ static int run_cct_dosage(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_pa
     attr[0].val.clusterDim.x = (unsigned)mcs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const double *G = (const double *)g->data;
+    if (kind == 1 || kind == 2) {   // per-cluster cache of the individual allele frequencies m_i
+        const int64_t need = (int64_t)n_clusters * n;
+        if (need > ctx->cap_mcache) { CU(cudaStreamSynchronize(s)); CU(dev_realloc(&ctx->d_mcache, need)); ctx->cap_mcache = need; }
+    }
     for (int64_t j0 = 0; j0 < m; j0 += mc_max) {
         const int mc = (int)std::min<int64_t>(mc_max, m - j0);
+        if (kind == 3) {
+            PlusDosageArgs a;
+            if (on_dev) { a.G = G + j0 * ld; a.ld = ld; }
+            else {
+                CU(cudaMemcpy2DAsync(ctx->d_dense, n * 8, G + j0 * ld, ld * 8, n * 8, mc, cudaMemcpyHostToDevice, s));
+                dg.h2d_bytes += n * 8 * mc;
+                a.G = (const double *)ctx->d_dense; a.ld = n;
+            }
+            a.m = mc; a.snp0 = j0; a.m_total = m; a.n = n;
+            a.R = ctx->d_R; a.E = ctx->d_E; a.Rn = ctx->d_Rn; a.vc = ctx->d_vc;
+            a.pc = PlusConst{ctx->R_GRM_R, ctx->R_GRM_RE, ctx->Rnew_GRM_Rnew};
+            a.grm = GrmCoo{ctx->d_gi, ctx->d_gj, ctx->d_gv, (long long)ctx->grm_nnz};
+            a.epsilon = prm->epsilon; a.cutoff = prm->cutoff; a.min_maf = prm->min_maf; a.g_model = prm->g_model;
+            a.out = ctx->d_out; a.ctr = ctx->d_ctr;
+            cudaLaunchConfig_t cfg0 = cfg; cfg0.dynamicSmemBytes = 0;   // no Wald tile in this kernel
+            CU(cudaLaunchKernelEx(&cfg0, k_plus_dosage_snp, a));
+            ctx->launches++;
+            continue;
+        }
+        if (kind != 0) {
+            MixDosageArgs a;
+            if (on_dev) { a.G = G + j0 * ld; a.ld = ld; }
+            else {
+                CU(cudaMemcpy2DAsync(ctx->d_dense, n * 8, G + j0 * ld, ld * 8, n * 8, mc, cudaMemcpyHostToDevice, s));
+                dg.h2d_bytes += n * 8 * mc;
+                a.G = (const double *)ctx->d_dense; a.ld = n;
+            }
+            a.m = mc; a.snp0 = j0; a.m_total = m; a.n = n;
+            a.R = ctx->d_R; a.E = ctx->d_E; a.vc = ctx->d_vc;
+            a.wd = WaldData{ctx->d_Y, ctx->d_cova, ctx->wald_p, kind == 2 ? 0 : ctx->wald_trait};
+            a.md = MixData{ctx->d_pcs, ctx->d_xtx_inv, ctx->n_pcs, prm->pc_pvalue_cutoff, prm->neg_ratio_cutoff, prm->g_model, nullptr};
+            a.grm = GrmCoo{ctx->d_gi, ctx->d_gj, ctx->d_gv, kind == 2 ? (long long)ctx->grm_nnz : 0};
+            a.epsilon = prm->epsilon; a.cutoff = prm->cutoff; a.min_maf = prm->min_maf;
+            a.out = ctx->d_out; a.ctr = ctx->d_ctr; a.mcache_all = ctx->d_mcache;
+            if (kind == 2) CU(cudaLaunchKernelEx(&cfg, k_mixplus_dosage_snp, a));
+            else CU(cudaLaunchKernelEx(&cfg, k_mix_dosage_snp, a));
+            ctx->launches++;
+            continue;
+        }
         DosageArgs a;
         if (on_dev) { a.G = G + j0 * ld; a.ld = ld; }
         else {
@@ -793,11 +844,11 @@ static int run_cct_dosage(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_pa
     CU(cudaMemcpyAsync(&hc, ctx->d_ctr, sizeof hc, cudaMemcpyDeviceToHost, s));
     if (m > 0) {
         const int64_t old = prm->out_ld > 0 ? prm->out_ld : m;
-        CU(cudaMemcpy2DAsync(out, old * 8, ctx->d_out, m * 8, m * 8, 10, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpy2DAsync(out, old * 8, ctx->d_out, m * 8, m * 8, ncol, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
-    dg.ms_total = ms; dg.ms_tests = ms; dg.d2h_bytes = m * 10 * 8;
+    dg.ms_total = ms; dg.ms_tests = ms; dg.d2h_bytes = m * ncol * 8;
     fill_diag(&dg, hc, m);
     dg.kernel_launches = ctx->launches;
     if (diag) *diag = dg;
@@ -966,8 +1017,9 @@ static int run_generic(spagxe_ctx *ctx, const spagxe_geno *g, const spagxe_param
     if (hc.n_nonint) {
         // imputed dosages: SPAGxE_CCT has a dense per-SNP path for them; the other loops rest on the 2-bit coding
         if (mode == RUN_CCT && g->kind == SPAGXE_GENO_F64) return run_cct_dosage(ctx, g, prm, out, diag);
-        return fail(ctx, SPAGXE_ERR_UNSUPPORTED,
-                    "Geno.mtx holds values outside {0,1,2,NA}: imputed dosages are supported by SPAGxE_CCT with a double matrix only");
+        if (mode == RUN_MIX && g->kind == SPAGXE_GENO_F64) return run_cct_dosage(ctx, g, prm, out, diag, mixplus ? 2 : 1);
+        if (mode == RUN_PLUS && g->kind == SPAGXE_GENO_F64) return run_cct_dosage(ctx, g, prm, out, diag, 3);
+        return fail(ctx, SPAGXE_ERR_UNSUPPORTED, "Geno.mtx holds values outside {0,1,2,NA}: imputed dosages need a double matrix");
     }
     if (hc.n_allmissing) return fail(ctx, SPAGXE_ERR_ARG, "%llu SNP(s) have every genotype missing (the reference stops here)",
                                      hc.n_allmissing);

@@ -103,6 +103,19 @@ struct LocalArgs {
 };
 
 // SPAGxE_CCT on a dense real-valued genotype matrix (imputed dosages; ref R/SPAGxECCT.R:543-683 with non-integer g)
+struct MixDosageArgs {   // SPAGxEmix_CCT / SPAGxEmix_CCT_Plus on a dense column block (imputed dosages)
+    const double *G; int64_t ld;       // device, column-major n x m block (NaN = NA)
+    int m; int64_t snp0, m_total, n;
+    const double *R, *E; const VecConst *vc; WaldData wd; MixData md; GrmCoo grm;
+    double epsilon, cutoff, min_maf;
+    double *out; Counters *ctr; double *mcache_all;
+};
+struct PlusDosageArgs {  // SPAGxE_Plus on a dense column block (imputed dosages)
+    const double *G; int64_t ld; int m; int64_t snp0, m_total, n;
+    const double *R, *E, *Rn; const VecConst *vc; PlusConst pc; GrmCoo grm;
+    double epsilon, cutoff, min_maf; int g_model;
+    double *out; Counters *ctr;
+};
 struct DosageArgs {
     const double *G; int64_t ld;       // device, column-major n x m block (NaN = NA)
     int m; int64_t snp0, m_total, n;

@@ -11,6 +11,7 @@ python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_default.json 2> $out/$
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err; echo "ref rc=$?"
 python bench.py --workload mix --steps 5 --warmup 3 > $out/${tag}_bench_mix.json 2> $out/${tag}_bench_mix.err; echo "mix rc=$?"
 python bench.py --workload plus --steps 10 --warmup 3 > $out/${tag}_bench_plus.json 2> $out/${tag}_bench_plus.err; echo "plus rc=$?"
+python bench.py --workload mixplus --steps 3 --warmup 3 > $out/${tag}_bench_mixplus.json 2> $out/${tag}_bench_mixplus.err; echo "mixplus rc=$?"
 short="python bench.py --steps 2 --warmup 3 --no-e2e --cpu-sample-snps 0"
 $short > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|spagxe' -c 400 --csv \
