@@ -522,7 +522,7 @@ def main():
         dg = diags[-1]
         # bounded CPU sample of the very same batch (first rows), single thread
         cpu = None
-        if args.cpu_sample_snps > 0:
+        if args.cpu_sample_snps > 0 and world == 1:     # the CPU baseline is timed on rank 0 at N = 1 only
             ns = min(args.cpu_sample_snps, m)
             rows_host = bed[:ns, :rb].contiguous().cpu().numpy().ravel()
             rate, dt, mm = oracle_sample_rate(ph, rows_host, n, 1)
@@ -537,6 +537,16 @@ def main():
                    "sample": f"first {mm} SNPs of the timed batch at N={n} ({dt:.1f} s); restated reference (C oracle, -O2), not the R interpreter",
                    "parity_first_snps": {"snps": nchk, "max_rel_dlog10p_vs_gpu": chk, "n_spa": int(((route & 4) > 0).sum()),
                                          "n_branch_b": int(((route & 2) > 0).sum())}}
+            # ... and of the batch's genotype-adjusted SNPs (branch B: adjusted residual SPA + glm.fit Wald + CCT), up to 16
+            full = out_dev.cpu().numpy().reshape(10, m).T
+            bsel = np.flatnonzero(full[:, 6] <= 0.001)[:16]
+            if bsel.size:
+                rows_b = np.ascontiguousarray(bed[torch.as_tensor(bsel, device=bed.device), :rb].cpu().numpy()).ravel()
+                ref_b, route_b, *_ = O.cct_bed("binary", rows_b, n, ph["R"], ph["E"], ph["Y"], ph["Cova"], nthreads=os.cpu_count())
+                with np.errstate(all="ignore"):
+                    chk_b = float(np.nanmax(np.abs(np.log10(full[bsel][:, pc]) - np.log10(ref_b[:, pc])) / np.maximum(np.abs(np.log10(ref_b[:, pc])), 1e-3)))
+                cpu["parity_branch_b_snps"] = {"snps": int(bsel.size), "max_rel_dlog10p_vs_gpu": chk_b,
+                                               "n_branch_b": int(((route_b & 2) > 0).sum()), "n_spa": int(((route_b & 4) > 0).sum())}
             rr = r_reference_rate(ph, rows_host, n, min(32, ns))
             if rr:
                 cpu["r_interpreter"] = rr

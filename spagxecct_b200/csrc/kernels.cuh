@@ -1364,6 +1364,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
             if (f / 2 < 0) v2[0] += 1.0;
             const double e = mg.g(i) - f;
             v2[1] += e * e;
+            if (mcache_in) mcache_in[i] = f / 2;   // Fit.lm$fitted.values / 2: the statistics pass clamps it instead of a second walk over the PCs
         }
         red.sum<2>(v2);
         negnum = v2[0];
@@ -1411,8 +1412,12 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
     double v4[4] = {0, 0, 0, 0};
     // m_i is evaluated once per SNP (k loads + k multiply-adds, or an exp and a sqrt) and kept for the later passes
     double *mcache = mcache_in;
+    const bool fitted_cached = (mcache != nullptr) && ms.af.kind == 1;   // kind 1 <=> the fitted-values pass above ran and stands
     for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-        const double m = af_eval(ms.af, md.pcs, n, i), gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
+        double m;
+        if (fitted_cached) { m = mcache[i]; if (m <= 0) m = 0; if (m >= 1) m = 1; }   // same thread wrote it; af_eval's clamp (ref :1095-1096)
+        else m = af_eval(ms.af, md.pcs, n, i);
+        const double gv = 2 * m * (1 - m), r = R[i], r2 = r * r;
         if (mcache) mcache[i] = m;
         v4[0] += r * m; v4[1] += r2 * gv; v4[2] += (gv * E[i]) * r2;
     }
