@@ -282,6 +282,8 @@ def run_other(args, kind):
         x["grm_j"] = np.r_[np.arange(x["n"]), np.arange(0, 2 * npair, 2)].astype(np.int32)
         x["grm_v"] = np.r_[np.ones(x["n"]), np.full(npair, 0.5)]
         ctx.set_pcs(x["PCs"]); ctx.set_sparse_grm(x["grm_i"], x["grm_j"], x["grm_v"])
+        if args.mix_cluster:
+            ctx.set_option(_lib.OPT_MIX_CLUSTER, args.mix_cluster)
         run, ncol, prm_kw = ctx.run_mix_plus, 12, dict(min_maf=1e-5)
         metric = "SNPs/sec at N=200k, 10 PCs, sparse GRM (SPAGxEmix_CCT_Plus Step-2 loop, device-timed)"
     else:

@@ -59,7 +59,7 @@ struct spagxe_ctx {
     int8_t *d_bmat = nullptr; int64_t cap_bmat = 0; BmatInfo *d_binfo = nullptr; long long *d_acc = nullptr; int cap_acc = 0;
     bool use_tc = true; int tc_cfg = 0;
     // test / tuning hooks (spagxe_ctx_set_option); no environment variable is ever read by this library
-    int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false; int opt_mix_cluster = 8;
+    int64_t opt_chunk_snps = 0; bool opt_exact_spa = false, opt_mix_per_snp = false; int opt_mix_cluster = 4;   // 4..6 CTAs per SNP measure alike at N = 200,000 (8: 6 % slower, 2: 12 % slower)
     int64_t cap_out = 0; double *d_out = nullptr;
     int64_t cap_dense = 0; void *d_dense = nullptr;
     int64_t cap_local = 0; uint8_t *d_local = nullptr;     // SPAGxEmixCCT_localance: packed rows of g, haplo and the haplotype covariates
