@@ -256,6 +256,61 @@ def _prep_common(ctx, R, E):
     return R, E
 
 
+class _MultiGpu:
+    """A _lib.MultiContext behind the single-GPU Context's method names, for the loops that take `n_gpus` (the SNPs are
+    cut into contiguous ranges over the GPUs of the node; R / E / Y / Cova reach them by one NCCL broadcast)."""
+
+    def __init__(self, n_gpus):
+        self.mg = _lib.MultiContext(n_gpus)
+        self._vec = None
+        self._sent = False
+
+    def close(self):
+        self.mg.close()
+
+    def set_vectors(self, R, E):
+        self._vec = (R, E); self._sent = False
+
+    def _send(self, trait=0, Y=None, cova=None):
+        self.mg.set_inputs(self._vec[0], self._vec[1], trait, Y, cova)
+        self._sent = True
+
+    def set_wald(self, trait, Y, cova):
+        self._send(int(trait), Y, cova)
+
+    def set_wald_survival(self, surv_time, event, cova):
+        self._send()
+        self.mg.set_wald_survival(surv_time, event, cova)
+
+    def _ready(self):
+        if not self._sent:
+            self._send()
+
+    def set_pcs(self, pcs):
+        self._ready(); self.mg.set_pcs(pcs)
+
+    def set_grm(self, *a):
+        self._ready(); self.mg.set_grm(*a)
+
+    def set_sparse_grm(self, *a):
+        self._ready(); self.mg.set_sparse_grm(*a)
+
+    def run_mix(self, geno, prm):
+        return self.mg.run_mix(geno, prm)
+
+    def run_plus(self, geno, prm):
+        return self.mg.run_plus(geno, prm)
+
+    def run_mix_plus(self, geno, prm):
+        return self.mg.run_mix_plus(geno, prm)
+
+
+def _make_ctx(ctx, device, n_gpus):
+    if ctx is not None:
+        return ctx
+    return _MultiGpu(n_gpus) if n_gpus > 1 else _lib.Context(device)
+
+
 def _params(epsilon, Cutoff, impute_method, missing_cutoff, min_maf, G_model, **kw):
     if impute_method != "fixed":
         raise NotImplementedError('only impute.method = "fixed" exists in the reference')
@@ -353,11 +408,12 @@ def SPAGxE_CCT_one_SNP(traits, g, R, E, Phen_mtx, Cova_mtx, epsilon=0.001, Cutof
 def SPAGxEmix_CCT(traits="survival/binary/quantitative/categorical", GenoFile=None, GenoFileIndex=None,
                   control=None, Geno_mtx=None, R=None, E=None, Phen_mtx=None, Cova_mtx=None, topPCs=None,
                   epsilon=0.001, Cutoff=2, impute_method="fixed", missing_cutoff=0.15, min_maf=0.001, G_model="Add",
-                  topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, ctx=None, device=0, quiet=False):
-    """Drop-in for SPAGxEmix_CCT (R/SPAGxECCT.R:916-1002): M x 12. (No ID check: commented out at :955.)"""
+                  topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1, ctx=None, device=0, quiet=False, n_gpus=1):
+    """Drop-in for SPAGxEmix_CCT (R/SPAGxECCT.R:916-1002): M x 12. (No ID check: commented out at :955.)
+    n_gpus > 1 (an addition to the reference's formals): contiguous SNP ranges over the GPUs of the node."""
     _trait_code(traits)
     own = ctx is None
-    ctx = ctx or _lib.Context(device)
+    ctx = _make_ctx(ctx, device, n_gpus)
     try:
         if Geno_mtx is None:
             geno, keep, n, m, snp_ids, _ = _read_geno_file(GenoFile, GenoFileIndex, _col(Phen_mtx, "ID"), control)
@@ -460,7 +516,7 @@ def _mixplus_grm(ResidMat, sparseGRM):
 def SPAGxEmix_CCT_Plus(traits="binary/quantitative", Geno_mtx=None, ResidMat=None, E=None, Phen_mtx=None, Cova_mtx=None,
                        topPCs=None, sparseGRM=None, epsilon=0.001, Cutoff=2, impute_method="fixed", missing_cutoff=0.15,
                        min_maf=0.001, G_model="Add", topPCs_pvalue_cutoff=0.05, MAF_est_negative_ratio_cutoff=0.1,
-                       wald=None, ctx=None, device=0, quiet=False):
+                       wald=None, ctx=None, device=0, quiet=False, n_gpus=1):
     """Drop-in for SPAGxEmix_CCT_Plus (R/SPAmixGxECCTPlus_functions_MYZ_2024-09-17.R:38-133): M x 12.  Like the reference it
     takes an R matrix only (no GenoFile) and prints the SNP counter.  R = ResidMat$Resid (the reference's one-SNP function
     reads `R` as a free variable, which its scripts define that way).
@@ -473,7 +529,7 @@ def SPAGxEmix_CCT_Plus(traits="binary/quantitative", Geno_mtx=None, ResidMat=Non
     if traits not in ("binary", "quantitative"):
         raise RStop('traits must be "binary" or "quantitative"')
     own = ctx is None
-    ctx = ctx or _lib.Context(device)
+    ctx = _make_ctx(ctx, device, n_gpus)
     try:
         G, _, snp_ids = _split_geno(Geno_mtx)
         keep, geno = _geno_desc_from_matrix(G)
@@ -542,12 +598,12 @@ def SPAGxEmix_CCT_Plus_one_SNP(traits, g, ResidMat, E, Phen_mtx, Cova_mtx, topPC
 
 def SPAGxE_Plus(GenoFile=None, GenoFileIndex=None, control=None, Geno_mtx=None, E=None, Phen_mtx=None,
                 Cova_mtx=None, obj_SPAGxE_Plus_Nullmodel=None, epsilon=0.001, Cutoff=2, impute_method="fixed",
-                missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0, quiet=False):
+                missing_cutoff=0.15, min_maf=0.001, G_model="Add", ctx=None, device=0, quiet=False, n_gpus=1):
     """Drop-in for SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:159-238): M x 8.
     obj_SPAGxE_Plus_Nullmodel: mapping with R, R_GRM_R, R_GRM_RE, R.new, R.new_GRM_R.new and sparseGRM
     (ID1/ID2 as 0-based sample indices `i`,`j` or as id strings matched against ResidMat$SubjID, Value)."""
     own = ctx is None
-    ctx = ctx or _lib.Context(device)
+    ctx = _make_ctx(ctx, device, n_gpus)
     try:
         obj = obj_SPAGxE_Plus_Nullmodel
         if Geno_mtx is None:

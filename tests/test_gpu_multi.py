@@ -66,6 +66,31 @@ def test_api_n_gpus_argument(gpu_ctx):
     assert np.array_equal(np.nan_to_num(a.values, nan=-1), np.nan_to_num(b.values, nan=-1))
 
 
+@needs2
+def test_api_n_gpus_for_mix_plus_and_mixplus(gpu_ctx, golden_dir):
+    """n_gpus of SPAGxEmix_CCT / SPAGxE_Plus / SPAGxEmix_CCT_Plus: the 2-GPU matrices equal the single-GPU ones bit for bit."""
+    from spagxecct_b200 import SPAGxE_Plus, SPAGxEmix_CCT, SPAGxEmix_CCT_Plus
+    from tests.test_mix_plus import _gpu_inputs
+    x = _gpu_inputs(golden_dir)
+    n = x["n"]
+    gi, gj, gv = x["grm"]
+    kw = dict(Geno_mtx=x["G"], R=x["R"], E=x["E"], Phen_mtx={"Y": x["Y"]}, Cova_mtx=x["Cova"], topPCs=x["PCs"], epsilon=0.2, min_maf=0.0002, quiet=True)
+    one = SPAGxEmix_CCT("binary", ctx=gpu_ctx, **kw)
+    two = SPAGxEmix_CCT("binary", n_gpus=2, **kw)
+    assert np.array_equal(np.nan_to_num(two.values, nan=-1), np.nan_to_num(one.values, nan=-1))
+    kw = dict(Geno_mtx=x["G"], ResidMat={"SubjID": np.arange(n), "Resid": x["R"]}, E=x["E"], Phen_mtx={"Y": x["Y"]}, Cova_mtx=x["Cova"],
+              topPCs=x["PCs"], sparseGRM={"i": gi, "j": gj, "Value": gv}, epsilon=0.2, min_maf=0.0002, wald="skip", quiet=True)
+    one = SPAGxEmix_CCT_Plus("binary", ctx=gpu_ctx, **kw)
+    two = SPAGxEmix_CCT_Plus("binary", n_gpus=2, **kw)
+    assert np.array_equal(np.nan_to_num(two.values, nan=-1), np.nan_to_num(one.values, nan=-1)) and one.diag["n_branch_b"] >= 3
+    a, b, Rnew, c = gpu_ctx.plus_nullmodel(gi, gj, gv, x["R"], x["E"])
+    obj = {"R": x["R"], "R_GRM_R": a, "R_GRM_RE": b, "R.new": Rnew, "R.new_GRM_R.new": c, "sparseGRM": {"i": gi, "j": gj, "Value": gv}}
+    kw = dict(Geno_mtx=x["G"], E=x["E"], Phen_mtx={"ID": np.arange(n)}, Cova_mtx=x["Cova"], obj_SPAGxE_Plus_Nullmodel=obj, epsilon=0.2, quiet=True)
+    one = SPAGxE_Plus(ctx=gpu_ctx, **kw)
+    two = SPAGxE_Plus(n_gpus=2, **kw)
+    assert np.array_equal(np.nan_to_num(two.values, nan=-1), np.nan_to_num(one.values, nan=-1))
+
+
 def test_single_gpu_multicontext_is_the_plain_path(gpu_ctx):
     """n_gpus = 1 needs no NCCL and must equal the single-context result (runs on every box)."""
     n, m = 5003, 40
