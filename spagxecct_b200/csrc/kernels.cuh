@@ -15,10 +15,18 @@
 #include "stat_common.cuh"
 #include <cooperative_groups.h>
 
+// The kernels are spread over several translation units so that the heavy ones (minutes of ptxas each) compile side by
+// side: a .cu file defines SPAGXE_TU before including this header and gets the kernels of its group only (0: all of them).
+#ifndef SPAGXE_TU
+#define SPAGXE_TU 0
+#endif
+#define SPAGXE_IN_TU(x) (SPAGXE_TU == 0 || SPAGXE_TU == (x))
+
 namespace spagxe {
 
 // ---------------------------------------------------------------------------
 // K0: SNP-invariant vector statistics.  One CTA (deterministic tree).
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(1024) k_vec_prep1(const double *__restrict__ R, const double *__restrict__ E,
                                                     int64_t n, VecConst *vc) {
     __shared__ double scratch[3 * 32];
@@ -33,7 +41,9 @@ __global__ void __launch_bounds__(1024) k_vec_prep1(const double *__restrict__ R
     bad = __syncthreads_count(bad);
     if (threadIdx.x == 0) { vc->sumR = v[0]; vc->sumR2 = v[1]; vc->sumER2 = v[2]; vc->lambda = v[2] / v[1]; vc->nonfinite = bad; }
 }
+#endif
 // mode 0: V = R.new (CCT); mode 1: V = E*R (mix / plus).  Rn_in != NULL: use the caller's R.new (plus).
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(1024) k_vec_prep2(const double *__restrict__ R, const double *__restrict__ E,
                                                     const double *__restrict__ Rn_in, int64_t n, int mode,
                                                     double *__restrict__ Rn, double *__restrict__ V, VecConst *vc) {
@@ -51,6 +61,7 @@ __global__ void __launch_bounds__(1024) k_vec_prep2(const double *__restrict__ R
     block_sum<4>(v, scratch);
     if (threadIdx.x == 0) { vc->sumRn = v[0]; vc->sumRn2 = v[1]; vc->sumV = v[2]; vc->sumV2 = v[3]; }
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // K1 helpers
@@ -98,6 +109,7 @@ __global__ void k_pack_dense(const T *__restrict__ G, int64_t ld, int64_t n, int
 
 // GRAB.ReadGeno's sample subset / reorder and allele order as a device gather, 2 bits -> 2 bits (ref :484-487).
 // One thread per output 32-bit word (16 samples); idx == NULL keeps the sample order; padding samples get code 11.
+#if SPAGXE_IN_TU(1)
 __global__ void k_bed_prepare(const uint8_t *__restrict__ src, int64_t spitch, uint32_t *__restrict__ dst, int64_t dpitch_words,
                               int64_t n, int m, const int64_t *__restrict__ idx, int count_a2) {
     const int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -121,8 +133,10 @@ __global__ void k_bed_prepare(const uint8_t *__restrict__ src, int64_t spitch, u
     }
     dst[(int64_t)j * dpitch_words + w] = word;
 }
+#endif
 
 // per-code counts (exact integers). One warp per SNP row; pitch multiple of 4.
+#if SPAGXE_IN_TU(1)
 __global__ void k_bed_counts(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, long long *counts) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= m) return;
@@ -149,7 +163,9 @@ __global__ void k_bed_counts(const uint8_t *__restrict__ bed, int64_t pitch, int
         counts[4 * warp + 3] = n - c0 - c1 - c2;
     }
 }
+#endif
 
+#if SPAGXE_IN_TU(1)
 __global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int64_t n, int m, double *__restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
@@ -157,8 +173,10 @@ __global__ void k_bed_decode(const uint8_t *__restrict__ bed, int64_t pitch, int
     int c = (bed[(int64_t)j * pitch + (i >> 2)] >> (2 * (i & 3))) & 3;
     out[(int64_t)j * n + i] = (c == 0) ? 2.0 : (c == 2) ? 1.0 : (c == 3) ? 0.0 : d_na_real();
 }
+#endif
 
 // K3 for SPAGxE_CCT (ref :543-603).  One thread per SNP of the chunk.
+#if SPAGXE_IN_TU(1)
 __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                const VecConst *__restrict__ vcp, double epsilon, double min_maf,
                                double *__restrict__ out, SpaItem *spa_list, BItem *b_list, const uint8_t *bed,
@@ -226,6 +244,7 @@ __global__ void k_finalize_cct(SnpStats st, int m_chunk, int64_t snp0, int64_t m
     if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl],
                                     g_model ? st.H0[jl] : 0.0, g_model ? st.nhom[jl] : 0, 0};
 }
+#endif
 
 // Reduction policies: every thread of every participating CTA gets the same fixed-order total.
 struct BlockRed {
@@ -429,6 +448,7 @@ __device__ __forceinline__ double cheb_node(int j) {  // cos((2j+1) pi / (2 kQNo
     return cospi((2.0 * j + 1.0) / (2.0 * kQNodes));
 }
 
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(1024) k_quad_range(const double *__restrict__ rv, int64_t n, Quad q) {
     __shared__ double smin[32], smax[32];
     double mn = CUDART_INF, mx = -CUDART_INF;
@@ -443,6 +463,8 @@ __global__ void __launch_bounds__(1024) k_quad_range(const double *__restrict__ 
         q.range[0] = mn; q.range[1] = mx; q.range[2] = h; q.range[3] = ok ? kQTheta / h : 0.0;
     }
 }
+#endif
+#if SPAGXE_IN_TU(1)
 __global__ void k_quad_accumulate(const double *__restrict__ rv, int64_t n, Quad q) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const double mn = q.range[0], h = q.range[2];
@@ -462,7 +484,9 @@ __global__ void k_quad_accumulate(const double *__restrict__ rv, int64_t n, Quad
         atomicAdd((unsigned long long *)&q.wfix[b * kQNodes + j], (unsigned long long)__double2ll_rn(L * kQScale));
     }
 }
+#endif
 // nodes + weights, compacted in a fixed order to the bins that hold samples (single CTA, deterministic)
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(1024) k_quad_finish(Quad q) {
     constexpr int kTotal = kQBins * kQNodes, kPer = (kTotal + 1023) / 1024;
     __shared__ int s_cnt[1024];
@@ -489,6 +513,7 @@ __global__ void __launch_bounds__(1024) k_quad_finish(Quad q) {
         }
     }
 }
+#endif
 struct SrcQuad {
     const double *x, *wq; double maf;
     __device__ __forceinline__ void get(int64_t i, double &r, double &m, double &w) const { r = x[i]; m = maf; w = wq[i]; }
@@ -507,6 +532,7 @@ __device__ __forceinline__ void spa_item_write(const SpaItem &it, double p, int 
 }
 
 // quadrature SPA: one CTA per item; items whose |t| leaves the covered range go to the exact list
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__restrict__ list, Counters *ctr, Quad q,
                                                             SpaItem *__restrict__ exact_list, int64_t m_total,
                                                             double *__restrict__ out) {
@@ -539,8 +565,10 @@ __global__ void __launch_bounds__(kSpaQThreads) k_spa_quad(const SpaItem *__rest
         }
     }
 }
+#endif
 
 // exact SPA: persistent CTAs popping work items, N exp() per CGF evaluation
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restrict__ list, const int *count_ptr,
                                                            Counters *ctr, const double *__restrict__ rv, int64_t n,
                                                            int64_t m_total, double *__restrict__ out) {
@@ -557,6 +585,7 @@ __global__ void __launch_bounds__(kSpaThreads) k_spa_homo(const SpaItem *__restr
         if (threadIdx.x == 0) spa_item_write(it, p, iters, m_total, out, ctr);
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // K5: branch B (ref :604-678).  One thread-block CLUSTER per SNP: each CTA owns a contiguous slice of
@@ -573,7 +602,7 @@ struct SrcAdj {  // R.new0_i = E_i * (R_i - fit[class_i]) computed from the pack
 
 // Solve the equilibrated SPD system (single thread). A: q x q (ld kMaxQ), b: rhs.
 // Returns false when a Cholesky pivot collapses (rank deficient design).
-__device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, double *inv_last) {
+static __device__ bool chol_solve(double (*A)[kMaxQ], double *b, int q, double *x, double *inv_last) {
     double sc[kMaxQ];
     for (int i = 0; i < q; i++) { if (!(A[i][i] > 0)) return false; sc[i] = 1.0 / sqrt(A[i][i]); }
     for (int i = 0; i < q; i++) for (int j = 0; j < q; j++) A[i][j] *= sc[i] * sc[j];
@@ -1014,6 +1043,7 @@ __device__ double wald_eg(const GFun &gf, const WaldData &wd, const double *E, i
 // SPAGxE_Plus (R/SPAGxEPlus_functions_MYZ.R:248-405)
 // Step-1 scalars of SPAGxE_Plus_Nullmodel (ref R/SPAGxEPlus_functions_MYZ.R:490-537): the three sparse-GRM quadratic
 // forms and R.new = (E - lambda) R with lambda = R_GRM_RE / R_GRM_R.  One CTA, fixed-order sums (runs once per analysis).
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(1024) k_plus_nullmodel(const double *__restrict__ R, const double *__restrict__ E,
                                                          int64_t n, GrmCoo grm, double *__restrict__ Rnew,
                                                          double *__restrict__ out3) {
@@ -1045,8 +1075,10 @@ __global__ void __launch_bounds__(1024) k_plus_nullmodel(const double *__restric
     block_sum<2>(w, scratch);
     if (threadIdx.x == 0) out3[2] = w[0] * 2 - w[1];         // :537
 }
+#endif
 
 // K3 for SPAGxE_Plus: V = E*R, so D1/T1 carry sum(g*E*R).  One thread per SNP.  out is M x 8.
+#if SPAGXE_IN_TU(1)
 __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n,
                                 const VecConst *__restrict__ vcp, PlusConst pc, double epsilon, double cutoff,
                                 double min_maf, double *__restrict__ out, SpaItem *spa_list, BItem *b_list,
@@ -1113,8 +1145,10 @@ __global__ void k_finalize_plus(SnpStats st, int m_chunk, int64_t snp0, int64_t 
     if (want_b) b_list[pos] = BItem{bed + (int64_t)jl * pitch, (long long)j, st.asum[jl], st.nmiss[jl], st.D0[jl], st.T0[jl],
                                     g_model ? st.H0[jl] : 0.0, g_model ? st.nhom[jl] : 0, 0};
 }
+#endif
 
 // branch B of SPAGxE_Plus (ref :342-400): cluster per SNP; K7 = sparse-GRM quadratic form of R.new0
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__restrict__ b_list, const int *__restrict__ count_ptr, Counters *ctr,
                                                               int64_t m_total, int64_t n,
                                                               const double *__restrict__ R, const double *__restrict__ E,
@@ -1206,6 +1240,7 @@ __global__ void __launch_bounds__(kBThreads) k_branch_b_plus(const BItem *__rest
     }
     cl.sync();
 }
+#endif
 
 
 // ===========================================================================
@@ -1270,6 +1305,7 @@ struct SrcMixT {  // residual vector (E - lambda) R or E * (R - fitted(g_i)) wit
 using SrcMix = SrcMixT<MixGenoRow>;
 
 // K3 for mix: filtered rows are written here; every other SNP goes to the cluster kernel's list
+#if SPAGXE_IN_TU(1)
 __global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m_total, int64_t n, double min_maf,
                                double *__restrict__ out, int *b_list, Counters *ctr) {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1293,6 +1329,7 @@ __global__ void k_finalize_mix(SnpStats st, int m_chunk, int64_t snp0, int64_t m
     int pos = list_reserve(&ctr->b_count, want);
     if (want) b_list[pos] = jl;
 }
+#endif
 
 struct MixShared { AfModel af; double xg[kMaxPC + 1]; double pv[kMaxPC + 1]; };
 
@@ -1650,6 +1687,7 @@ __device__ __forceinline__ void mix_snp_body(const int *__restrict__ list, Count
     cl.sync();
 }
 
+#if SPAGXE_IN_TU(1)
 __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ list, Counters *ctr,
                                                         const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
                                                         int64_t snp0, int64_t m_total, int64_t n,
@@ -1661,8 +1699,10 @@ __global__ void __launch_bounds__(kBThreads) k_mix_snp(const int *__restrict__ l
     mix_snp_body<false>(list, ctr, bed, pitch, st, snp0, m_total, n, R, E, vcp, wd, md, epsilon, cutoff, out, mcache_all, hbeta,
                         hbeta_ld, hand, GrmCoo{nullptr, nullptr, nullptr, 0});
 }
+#endif
 // SPAGxEmix_CCT_Plus: every SNP of the chunk's list through the per-SNP route (the GRM forms are not polynomial in the
 // OLS coefficients, so there is no batched path); mcache_all must hold n doubles per cluster
+#if SPAGXE_IN_TU(4)
 __global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict__ list, Counters *ctr,
                                                             const uint8_t *__restrict__ bed, int64_t pitch, SnpStats st,
                                                             int64_t snp0, int64_t m_total, int64_t n,
@@ -1673,9 +1713,11 @@ __global__ void __launch_bounds__(kBThreads) k_mixplus_snp(const int *__restrict
     mix_snp_body<true>(list, ctr, bed, pitch, st, snp0, m_total, n, R, E, vcp, WaldData{nullptr, nullptr, 0, 0}, md, epsilon, cutoff,
                        out, mcache_all, nullptr, 0, nullptr, grm);
 }
+#endif
 
 // SPAGxE_Plus on imputed (non-integer) dosages (ref R/SPAGxEPlus_functions_MYZ.R:248-405 on a real-valued g): one cluster per
 // SNP, both branches; the statistics of k_finalize_plus / k_branch_b_plus with the genotype read as doubles.
+#if SPAGXE_IN_TU(3)
 __global__ void __launch_bounds__(kBThreads) k_plus_dosage_snp(PlusDosageArgs A) {
     namespace cg = cooperative_groups;
     __shared__ BShared sh;
@@ -1793,6 +1835,7 @@ __global__ void __launch_bounds__(kBThreads) k_plus_dosage_snp(PlusDosageArgs A)
     }
     cl.sync();
 }
+#endif
 
 // SPAGxEmix_CCT / SPAGxEmix_CCT_Plus on imputed (non-integer) dosages: a dense double column per SNP, the prologue of
 // ref :1030-1051 computed here (k_cct_dosage_snp's layout), then the same per-SNP code as the packed-row kernels.
@@ -1850,8 +1893,12 @@ __device__ __forceinline__ void mix_dosage_body(const MixDosageArgs &A) {
     }
     cl.sync();
 }
+#if SPAGXE_IN_TU(3)
 __global__ void __launch_bounds__(kBThreads) k_mix_dosage_snp(MixDosageArgs A) { mix_dosage_body<false>(A); }
+#endif
+#if SPAGXE_IN_TU(3)
 __global__ void __launch_bounds__(kBThreads) k_mixplus_dosage_snp(MixDosageArgs A) { mix_dosage_body<true>(A); }
+#endif
 
 // ===========================================================================
 // SPAGxEmixCCT_localance (R/SPAGxECCT.R:1401-1647): ancestry-specific G x E test with local ancestry.  One cluster per
@@ -1905,7 +1952,7 @@ struct LocalShared { int map[kMaxQ]; int nq; int last_kept; };
 
 // which columns of the design survive lm()'s / glm()'s rank check: Cholesky of the equilibrated Gram matrix, a pivot
 // below 1e-13 (remaining norm < 3e-7 of the column norm; dqrdc2 uses 1e-7) marks the column as aliased
-__device__ void local_alias_map(const double (*NE)[kMaxQ], int q0, LocalShared &ls) {
+static __device__ void local_alias_map(const double (*NE)[kMaxQ], int q0, LocalShared &ls) {
     double A[kMaxQ][kMaxQ], sc[kMaxQ];
     int kept[kMaxQ], nk = 0;
     for (int i = 0; i < q0; i++) sc[i] = (NE[i][i] > 0) ? 1.0 / sqrt(NE[i][i]) : 0.0;
@@ -1930,6 +1977,7 @@ __device__ void local_alias_map(const double (*NE)[kMaxQ], int q0, LocalShared &
     ls.last_kept = (nk > 0 && kept[nk - 1] == q0 - 1) ? 1 : 0;
 }
 
+#if SPAGXE_IN_TU(2)
 __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A) {
     namespace cg = cooperative_groups;
     extern __shared__ double tile[];
@@ -2091,12 +2139,14 @@ __global__ void __launch_bounds__(kBThreads) k_localance_snp(LocalArgs A) {
     }
     cl.sync();
 }
+#endif
 
 // ===========================================================================
 // SPAGxE_CCT_one_SNP (R/SPAGxECCT.R:543-683) on a real-valued genotype vector (imputed dosages): the 2-bit path above
 // needs g in {0, 1, 2, NA}; a matrix with other values goes through this kernel -- one cluster per SNP, g read as
 // doubles (8 bytes per sample instead of 0.25: a compatibility path, HBM / PCIe bound by its input).
 
+#if SPAGXE_IN_TU(4)
 __global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A) {
     namespace cg = cooperative_groups;
     extern __shared__ double tile[];
@@ -2227,5 +2277,6 @@ __global__ void __launch_bounds__(kBThreads) k_cct_dosage_snp(DosageArgs A) {
     }
     cl.sync();
 }
+#endif
 
 }  // namespace spagxe

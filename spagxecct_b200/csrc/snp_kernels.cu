@@ -2,6 +2,7 @@
 // R-matrix packing, decode / counts, the per-SNP epilogues with routing, the SPA kernels (quadrature and exact), the
 // SPAGxE_Plus sparse-GRM branch B and the per-SNP SPAGxEmix kernel.  Compiled on its own (the template-heavy cluster
 // kernels take minutes) so that the host pipeline in spagxe_cuda.cu rebuilds in seconds.
+#define SPAGXE_TU 1   // the small kernels and k_mix_snp; snp_kernels_tu{2,3,4}.cu hold the other heavy kernels
 #include <cuda_runtime.h>
 #include <climits>
 #include "snp_kernels.h"
