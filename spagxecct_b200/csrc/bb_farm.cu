@@ -30,7 +30,7 @@ namespace spagxe {
 constexpr int kFWarps = 16;
 constexpr int kFThreads = kFWarps * 32;
 constexpr int kFJ = 2;             // units per (solver, CTA): halves of the CTA's slice
-constexpr int kFBatch = 64;        // items advanced in lock step
+constexpr int kFBatch = 128;       // items advanced in lock step (a 65,536-SNP call at epsilon = 0.001 holds 66 +- 8 branch-B SNPs: one batch)
 constexpr int kFRegQ = 6;          // widest design with register accumulators
 constexpr int kFMaxIt = 25;        // glm.fit maxit
 
