@@ -266,3 +266,51 @@ def test_mixplus_api_wald_callback(gpu_ctx, oracle, golden_dir):
     one = SPAGxEmix_CCT_Plus_one_SNP("binary", x["G"][:, j0], resid, x["E"], {"Y": x["Y"]}, x["Cova"], x["PCs"], grm, epsilon=0.2,
                                      min_maf=0.0002, ctx=gpu_ctx)
     assert np.allclose(one, skip.values[j0], rtol=1e-12, equal_nan=True)
+
+
+def test_mixplus_host_logic_with_a_recording_context():
+    """CPU: the branch-B completion of the Python mirror (genotype recoding handed to `wald`, NaN -> pval.spaGxE, host CCT,
+    refusal without a callback) driven through a stand-in for the device context (no compute)."""
+    from spagxecct_b200 import CCT, SPAGxEmix_CCT_Plus
+
+    n, m = 50, 4
+    rng = np.random.default_rng(2)
+    G = rng.binomial(2, 0.7, (n, m)).astype(float)      # MAF > 0.5: the callback must see the flipped coding
+    G[3, 1] = np.nan
+    canned = np.full((m, 12), 0.5, order="F")
+    canned[:, 6] = [0.5, 1e-5, 1e-9, np.nan]             # p.value.betaG: SNPs 1 and 2 take branch B, SNP 3 is filtered
+    canned[1:3, 3:5] = np.nan
+    canned[1:3, 2] = [0.02, 0.03]
+    canned[3, 2:] = np.nan
+    calls = []
+
+    class Ctx:
+        def set_vectors(self, R, E): calls.append(("vec", R.size))
+        def set_pcs(self, pcs): calls.append(("pcs", pcs.shape))
+        def set_sparse_grm(self, gi, gj, gv): calls.append(("grm", gi.tolist(), gj.tolist(), gv.tolist()))
+        def run_mix_plus(self, geno, prm): return canned.copy(order="F"), {"n_branch_b": 2}
+
+    ids = [f"s{i}" for i in range(n)]
+    resid = {"SubjID": ids, "Resid": rng.standard_normal(n)}
+    grm = {"ID1": ids + ["s1", "zz"], "ID2": ids + ["s0", "s0"], "Value": [1.0] * n + [0.5, 0.25]}
+    kw = dict(Geno_mtx=G, ResidMat=resid, E=rng.standard_normal(n), Phen_mtx={"Y": np.zeros(n)}, Cova_mtx=np.zeros((n, 1)),
+              topPCs=rng.standard_normal((n, 2)), sparseGRM=grm, ctx=Ctx(), quiet=True)
+    with pytest.raises(NotImplementedError):
+        SPAGxEmix_CCT_Plus("binary", **kw)
+    assert calls[2][0] == "grm" and len(calls[2][1]) == n + 1 and calls[2][1][-1] == 1 and calls[2][2][-1] == 0   # the row with "zz" is dropped
+    seen = {}
+
+    def wald(j, g):
+        seen[j] = g.copy()
+        return np.nan if j == 1 else 0.004
+
+    res = SPAGxEmix_CCT_Plus("binary", wald=wald, **kw)
+    assert sorted(seen) == [1, 2]
+    maf1 = np.nanmean(G[:, 1]) / 2
+    g1 = np.where(np.isnan(G[:, 1]), 2 * maf1, G[:, 1])
+    assert np.array_equal(seen[1], 2 - g1) and np.array_equal(seen[2], 2 - G[:, 2])
+    assert res.values[1, 3] == 0.02 and res.values[1, 4] == CCT([0.02, 0.02])            # NaN -> pval.spaGxE (:389)
+    assert res.values[2, 3] == 0.004 and res.values[2, 4] == CCT([0.03, 0.004])
+    assert np.array_equal(res.values[[0, 3]], canned[[0, 3]], equal_nan=True)
+    with pytest.raises(Exception):
+        SPAGxEmix_CCT_Plus("survival", **kw)
