@@ -7,7 +7,8 @@
 # in R.  dyn.load("spagxe_rshim.so") once (it links libspagxe_cuda.so).
 #
 # Additions to the reference's formals (all optional, defaults reproduce the reference call):
-#   n.gpus   number of GPUs of the node to spread the SNPs over (SPAGxE_CCT only; one NCCL broadcast of R/E/Y/Cova)
+#   n.gpus   number of GPUs of the node to spread the SNPs over (SPAGxE_CCT, SPAGxEmix_CCT, SPAGxE_Plus; one NCCL broadcast
+#            of R/E/Y/Cova)
 #   device   CUDA ordinal for single-GPU calls
 # The result carries attr(, "diag"): routing counts and device times of the call.
 
@@ -148,19 +149,34 @@ SPAGxE_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categorica
 SPAGxEmix_CCT <- function(traits = "survival/binary/quantitative/categorical", GenoFile = NULL, GenoFileIndex = NULL,
                           control = list(AllMarkers = TRUE), Geno.mtx = NULL, R, E, Phen.mtx, Cova.mtx, topPCs,
                           epsilon = 0.001, Cutoff = 2, impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001,
-                          G.model = "Add", topPCs.pvalue.cutoff = 0.05, MAF.est.negative.ratio.cutoff = 0.1, device = 0L) {
+                          G.model = "Add", topPCs.pvalue.cutoff = 0.05, MAF.est.negative.ratio.cutoff = 0.1, n.gpus = 1L,
+                          device = 0L) {
   gm <- .spagxe_gmodel(G.model)
   gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)   # no ID check: commented out in the reference (:955)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  ctx <- .Call("spagxe_r_create", as.integer(device))
-  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
-  .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
-  .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
-  .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
+  prm <- c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .spagxe_run(ctx, 1L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, topPCs.pvalue.cutoff, MAF.est.negative.ratio.cutoff, gm))
+  if (n.gpus > 1L) {
+    mg <- .Call("spagxe_r_mgpu_create", as.integer(n.gpus))
+    on.exit(.Call("spagxe_r_mgpu_destroy", mg), add = TRUE)
+    if (.spagxe_trait(traits) == 3L) {
+      .Call("spagxe_r_mgpu_set_vectors", mg, as.double(R), as.double(E))
+      .Call("spagxe_r_mgpu_set_wald_survival", mg, as.double(Phen.mtx$surv.time), as.double(Phen.mtx$event), as.matrix(Cova.mtx) + 0)
+    } else {
+      .Call("spagxe_r_mgpu_set_inputs", mg, as.double(R), as.double(E), .spagxe_trait(traits), .spagxe_wald_y(traits, Phen.mtx), as.matrix(Cova.mtx) + 0)
+    }
+    .Call("spagxe_r_mgpu_set_pcs", mg, as.matrix(topPCs) + 0)
+    output <- .Call("spagxe_r_mgpu_run", mg, 1L, gi$g, gi$n, gi$m, prm, gi$sidx, as.double(gi$nfile), gi$a2)
+  } else {
+    ctx <- .Call("spagxe_r_create", as.integer(device))
+    on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+    .Call("spagxe_r_set_vectors", ctx, as.double(R), as.double(E))
+    .spagxe_set_wald(ctx, traits, Phen.mtx, Cova.mtx)
+    .Call("spagxe_r_set_pcs", ctx, as.matrix(topPCs) + 0)
+    output <- .spagxe_run(ctx, 1L, gi, prm)
+  }
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE", "p.value.spaGxE.Wald", "p.value.spaGxE.CCT.Wald",
                         "p.value.normGxE", "p.value.betaG", "Stat.betaG", "Var.betaG", "z.betaG",
                         "MAF.est.negative.num", "MAC")
@@ -193,18 +209,30 @@ SPAGxEmix_CCT_one_SNP <- function(traits = "survival/binary/quantitative/categor
 
 SPAGxE_Plus <- function(GenoFile = NULL, GenoFileIndex = NULL, control = list(AllMarkers = TRUE), Geno.mtx = NULL, E,
                         Phen.mtx, Cova.mtx, obj.SPAGxE_Plus_Nullmodel, epsilon = 0.001, Cutoff = 2,
-                        impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001, G.model = "Add", device = 0L) {
+                        impute.method = "fixed", missing.cutoff = 0.15, min.maf = 0.001, G.model = "Add", n.gpus = 1L,
+                        device = 0L) {
   gm <- .spagxe_gmodel(G.model)
   obj <- obj.SPAGxE_Plus_Nullmodel
   gi <- .spagxe_geno(GenoFile, GenoFileIndex, control, Geno.mtx, Phen.mtx$ID)
   print(paste0("Sample size is ", gi$n, "."))
   print(paste0("Number of variants is ", gi$m, "."))
-  ctx <- .Call("spagxe_r_create", as.integer(device))
-  on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
-  .spagxe_set_plus(ctx, obj, E)
+  prm <- c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm)
   print("Start Analyzing...")
   print(Sys.time())
-  output <- .spagxe_run(ctx, 2L, gi, c(epsilon, Cutoff, min.maf, missing.cutoff, 0.05, 0.1, gm))
+  if (n.gpus > 1L) {
+    ids <- as.character(obj$ResidMat$SubjID)
+    mg <- .Call("spagxe_r_mgpu_create", as.integer(n.gpus))
+    on.exit(.Call("spagxe_r_mgpu_destroy", mg), add = TRUE)
+    .Call("spagxe_r_mgpu_set_vectors", mg, as.double(obj$R), as.double(E))
+    .Call("spagxe_r_mgpu_set_grm", mg, match(as.character(obj$sparseGRM$ID1), ids) - 1L, match(as.character(obj$sparseGRM$ID2), ids) - 1L,
+          as.double(obj$sparseGRM$Value), c(obj$R_GRM_R, obj$R_GRM_RE, obj$R.new_GRM_R.new), as.double(obj$R.new))
+    output <- .Call("spagxe_r_mgpu_run", mg, 2L, gi$g, gi$n, gi$m, prm, gi$sidx, as.double(gi$nfile), gi$a2)
+  } else {
+    ctx <- .Call("spagxe_r_create", as.integer(device))
+    on.exit(.Call("spagxe_r_destroy", ctx), add = TRUE)
+    .spagxe_set_plus(ctx, obj, E)
+    output <- .spagxe_run(ctx, 2L, gi, prm)
+  }
   colnames(output) <- c("MAF", "missing.rate", "p.value.spaGxE.plus", "p.value.normGxE.plus", "p.value.betaG",
                         "Stat.betaG", "Var.betaG", "z.betaG")
   rownames(output) <- gi$snp

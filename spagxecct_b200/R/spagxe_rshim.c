@@ -215,6 +215,52 @@ SEXP spagxe_r_mgpu_run_cct(SEXP ptr, SEXP geno, SEXP n_, SEXP m_, SEXP prm, SEXP
     return out;
 }
 
+/* the other loops on several GPUs: inputs without Wald data (trait 0), the per-analysis extras, one generic run.
+ * which: 1 mix (M x 12), 2 plus (M x 8), 3 mix_plus (M x 12) */
+SEXP spagxe_r_mgpu_set_vectors(SEXP ptr, SEXP R, SEXP E) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    if (spagxe_mgpu_set_inputs(mg, XLENGTH(R), REAL(R), REAL(E), 0, NULL, NULL, 0) != SPAGXE_OK) Rf_error("%s", spagxe_mgpu_last_error(mg));
+    return R_NilValue;
+}
+SEXP spagxe_r_mgpu_set_wald_survival(SEXP ptr, SEXP time, SEXP event, SEXP cova) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    if (spagxe_mgpu_set_wald_survival(mg, REAL(time), REAL(event), REAL(cova), ncols(cova)) != SPAGXE_OK) Rf_error("%s", spagxe_mgpu_last_error(mg));
+    return R_NilValue;
+}
+SEXP spagxe_r_mgpu_set_pcs(SEXP ptr, SEXP pcs) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    if (spagxe_mgpu_set_pcs(mg, REAL(pcs), ncols(pcs)) != SPAGXE_OK) Rf_error("%s", spagxe_mgpu_last_error(mg));
+    return R_NilValue;
+}
+SEXP spagxe_r_mgpu_set_grm(SEXP ptr, SEXP gi, SEXP gj, SEXP gv, SEXP scalars, SEXP Rnew) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    if (spagxe_mgpu_set_grm(mg, XLENGTH(gv), INTEGER(gi), INTEGER(gj), REAL(gv), REAL(scalars)[0], REAL(scalars)[1], REAL(scalars)[2],
+                            REAL(Rnew)) != SPAGXE_OK) Rf_error("%s", spagxe_mgpu_last_error(mg));
+    return R_NilValue;
+}
+SEXP spagxe_r_mgpu_set_sparse_grm(SEXP ptr, SEXP gi, SEXP gj, SEXP gv) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    if (spagxe_mgpu_set_sparse_grm(mg, XLENGTH(gv), INTEGER(gi), INTEGER(gj), REAL(gv)) != SPAGXE_OK) Rf_error("%s", spagxe_mgpu_last_error(mg));
+    return R_NilValue;
+}
+SEXP spagxe_r_mgpu_run(SEXP ptr, SEXP which, SEXP geno, SEXP n_, SEXP m_, SEXP prm, SEXP sidx, SEXP nfile, SEXP a2) {
+    spagxe_mgpu *mg = get_mgpu(ptr);
+    spagxe_geno gd; int64_t *ix = NULL;
+    geno_from_sexp(geno, n_, m_, sidx, nfile, a2, &gd, &ix);
+    spagxe_params sp; params_from_sexp(prm, &sp);
+    const int w = asInteger(which), ncol = (w == 2) ? 8 : 12;
+    SEXP out = PROTECT(allocMatrix(REALSXP, (int)gd.n_snps, ncol));
+    spagxe_diag diag; memset(&diag, 0, sizeof diag);
+    int rc = (w == 1) ? spagxe_mgpu_run_mix(mg, &gd, 1, &sp, REAL(out), &diag)
+           : (w == 2) ? spagxe_mgpu_run_plus(mg, &gd, 1, &sp, REAL(out), &diag)
+                      : spagxe_mgpu_run_mix_plus(mg, &gd, 1, &sp, REAL(out), &diag);
+    free(ix);
+    if (rc != SPAGXE_OK) { UNPROTECT(1); Rf_error("%s", spagxe_mgpu_last_error(mg)); }
+    attach_diag(out, &diag);
+    UNPROTECT(1);
+    return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"spagxe_r_create", (DL_FUNC)&spagxe_r_create, 1},
     {"spagxe_r_destroy", (DL_FUNC)&spagxe_r_destroy, 1},
@@ -231,6 +277,12 @@ static const R_CallMethodDef call_methods[] = {
     {"spagxe_r_mgpu_destroy", (DL_FUNC)&spagxe_r_mgpu_destroy, 1},
     {"spagxe_r_mgpu_set_inputs", (DL_FUNC)&spagxe_r_mgpu_set_inputs, 6},
     {"spagxe_r_mgpu_run_cct", (DL_FUNC)&spagxe_r_mgpu_run_cct, 8},
+    {"spagxe_r_mgpu_set_vectors", (DL_FUNC)&spagxe_r_mgpu_set_vectors, 3},
+    {"spagxe_r_mgpu_set_wald_survival", (DL_FUNC)&spagxe_r_mgpu_set_wald_survival, 4},
+    {"spagxe_r_mgpu_set_pcs", (DL_FUNC)&spagxe_r_mgpu_set_pcs, 2},
+    {"spagxe_r_mgpu_set_grm", (DL_FUNC)&spagxe_r_mgpu_set_grm, 6},
+    {"spagxe_r_mgpu_set_sparse_grm", (DL_FUNC)&spagxe_r_mgpu_set_sparse_grm, 4},
+    {"spagxe_r_mgpu_run", (DL_FUNC)&spagxe_r_mgpu_run, 9},
     {NULL, NULL, 0}};
 
 void R_init_spagxe_rshim(DllInfo *dll) {
