@@ -1373,6 +1373,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
         } else {
         for (int c0 = 0; c0 < k1; c0 += 4) {
             double v4[4] = {0, 0, 0, 0};
+            #pragma unroll 4
             for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
                 const double g = mg.g(i);
 #pragma unroll
@@ -1395,6 +1396,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
         }
         // fitted values: negative count and residual sum of squares
         double v2[2] = {0, 0};
+        #pragma unroll 4
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
             double f = ms.af.beta[0];
             for (int c = 0; c < k; c++) f += md.pcs[i + (int64_t)c * n] * ms.af.beta[1 + c];
@@ -1450,6 +1452,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
     // m_i is evaluated once per SNP (k loads + k multiply-adds, or an exp and a sqrt) and kept for the later passes
     double *mcache = mcache_in;
     const bool fitted_cached = (mcache != nullptr) && ms.af.kind == 1;   // kind 1 <=> the fitted-values pass above ran and stands
+    #pragma unroll 4
     for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
         double m;
         if (fitted_cached) { m = mcache[i]; if (m <= 0) m = 0; if (m >= 1) m = 1; }   // same thread wrote it; af_eval's clamp (ref :1095-1096)
@@ -1465,6 +1468,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
     double cov12 = 0;
     if (PLUS) {
         double q2[2] = {0, 0};
+        #pragma unroll 4
         for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
             const int a = grm.gi[e], b = grm.gj[e];
             const double xa = R[a] * mixplus_sq(mcache, a), xb = R[b] * mixplus_sq(mcache, b), gvv = grm.gv[e];
@@ -1488,6 +1492,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
         const double S_GxE = S2 - lambda * S1;
         src.lambda = lambda; src.adj = 0;
         double v2[2] = {0, 0};
+        #pragma unroll 4
         for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
             double r, m, w; src.get(i, r, m, w);
             v2[0] += r * m; v2[1] += (r * r) * (2 * m * (1 - m));
@@ -1496,6 +1501,7 @@ __device__ __forceinline__ void mix_snp_core(Counters *ctr, const int64_t n, con
         double Svar = v2[1], vscale = 1.0;
         if (PLUS) {   // S_GxE.var through the GRM (ref mixPlus :296), Var.ratio for the saddlepoint (:308-309)
             double q1[1] = {0};
+            #pragma unroll 4
             for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
                 const int a = grm.gi[e], b = grm.gj[e];
                 const double xa = ((E[a] - lambda) * R[a]) * mixplus_sq(mcache, a), xb = ((E[b] - lambda) * R[b]) * mixplus_sq(mcache, b);
